@@ -1,0 +1,687 @@
+// oracle/divquant_oracle.cpp -- TEST INFRASTRUCTURE ONLY.  NOT PART OF THE PRODUCT.
+//
+// An independent CPU restatement of the reference's DivQuant hot path (caomw/ClusteringSegmentation-1,
+// DivQuant/*).  It exists to check the CUDA path in csrc/ and is itself pinned two ways:
+//   (1) against the seven known-answer palettes of the reference's Test/DivQuantTest.m
+//       (tests/golden/divquant_kat.json), and
+//   (2) against the UNMODIFIED reference sources compiled from /root/reference into
+//       oracle/_ref/libdivquant_ref.so (tests/test_oracle_vs_ref.py; fixtures in tests/golden/).
+// Parity status: PINNED (both of the above pass bit-for-bit, including the floating-point
+// summation order of the weighted path, which this file follows operation by operation).
+//
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+// load this library.  Every function cites the reference file:line it restates.  The arithmetic
+// is written so that g++ evaluates the same IEEE-754 double operations in the same order as the
+// reference build (compile with -ffp-contract=off; see oracle/Makefile).
+#include "divquant_oracle.h"
+
+#include <algorithm>
+#include <cassert>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+namespace {
+
+inline uint32_t chan_r(uint32_t p) { return (p >> 16) & 0xFFu; }
+inline uint32_t chan_g(uint32_t p) { return (p >> 8) & 0xFFu; }
+inline uint32_t chan_b(uint32_t p) { return p & 0xFFu; }
+inline double sq(double x) { return x * x; }
+
+struct Vec3 {
+  double r, g, b;
+};
+
+// ---------------------------------------------------------------------------------------------
+// 24-bit colour histogram.  Reference: calc_color_table, DivQuantMapColors.cpp:82-203.
+// The reference keeps a 20 023-bucket chained hash (HASH macro :55-62) whose chains are pushed at
+// the head, then walks buckets in ascending order.  The emission order matters downstream because
+// the weighted statistics are summed sequentially in doubles in exactly that order.
+// ---------------------------------------------------------------------------------------------
+const int kBuckets = 20023;
+
+inline int bucket_of(uint32_t r, uint32_t g, uint32_t b) {
+  long h = (long)r * 33023 + (long)g * 30013 + (long)b * 27011;
+  return (int)((h & 0x7fffffff) % kBuckets);
+}
+
+struct ChainNode {
+  uint32_t colour;  // 0x00RRGGBB
+  uint32_t count;
+  int next;  // index of the next node in the chain, -1 = end
+};
+
+}  // namespace
+
+extern "C" int oracle_calc_color_table(const uint32_t *in, uint32_t /*num_pixels*/, uint32_t num_rows,
+                                       uint32_t num_cols, int dec_factor, uint32_t *unique_out,
+                                       double *weights_out, uint32_t *counts_out) {
+  if (dec_factor <= 0) {
+    fprintf(stderr, "Decimation factor ( %d ) should be positive !\n", dec_factor);
+    return -1;
+  }
+  std::vector<int> head(kBuckets, -1);
+  std::vector<ChainNode> nodes;
+  // Sampling grid, including the reference's `ic + ir * numRows` addressing (:124) -- harmless in
+  // practice because the only caller passes numRows == 1 (quant_util.cpp:60).
+  for (int ir = 0; ir < (int)num_rows; ir += dec_factor) {
+    for (int ic = 0; ic < (int)num_cols; ic += dec_factor) {
+      uint32_t colour = in[ic + ir * (int)num_rows] & 0x00FFFFFFu;
+      int h = bucket_of(chan_r(colour), chan_g(colour), chan_b(colour));
+      int at = head[h];
+      while (at >= 0 && nodes[at].colour != colour) at = nodes[at].next;
+      if (at >= 0) {
+        nodes[at].count++;
+      } else {
+        ChainNode fresh = {colour, 1u, head[h]};  // push at the chain head (:157-158)
+        head[h] = (int)nodes.size();
+        nodes.push_back(fresh);
+      }
+    }
+  }
+  // Frequencies -> probabilities (:172).
+  double norm = 1.0 / (std::ceil(num_rows / (double)dec_factor) * std::ceil(num_cols / (double)dec_factor));
+  int emitted = 0;
+  for (int h = 0; h < kBuckets; ++h) {
+    for (int at = head[h]; at >= 0; at = nodes[at].next) {
+      unique_out[emitted] = nodes[at].colour;
+      if (weights_out) weights_out[emitted] = norm * (int)nodes[at].count;  // (:185) bucket->value is int
+      if (counts_out) counts_out[emitted] = nodes[at].count;
+      ++emitted;
+    }
+  }
+  return emitted;
+}
+
+// Reference: cut_bits, DivQuantUni.cpp:28-100 (validate_num_bits, DivQuantMisc.cpp:36-46).
+extern "C" int oracle_cut_bits(const uint32_t *in, uint32_t num_pixels, uint32_t *out, int rbits, int gbits,
+                               int bbits) {
+  const int bits[3] = {rbits, gbits, bbits};
+  for (int i = 0; i < 3; ++i) {
+    if (!(0 < bits[i] && bits[i] <= 8)) {
+      fprintf(stderr, "Number of bits per channel ( %d ) must be in [1,8] !\n", bits[i]);
+      return 0;
+    }
+  }
+  const uint32_t sr = 8 - rbits, sg = 8 - gbits, sb = 8 - bbits;
+  if (sr == sg && sr == sb) {
+    // Whole-word variant (:60-74): the alpha byte is masked away, then everything shifts together.
+    const uint32_t byte_mask = (0xFFu >> sr) << sr;
+    const uint32_t word_mask = (byte_mask << 16) | (byte_mask << 8) | byte_mask;
+    for (uint32_t i = 0; i < num_pixels; ++i) out[i] = (in[i] & word_mask) >> sr;
+  } else {
+    for (uint32_t i = 0; i < num_pixels; ++i) {
+      uint32_t p = in[i];
+      out[i] = ((chan_r(p) >> sr) << 16) | ((chan_g(p) >> sg) << 8) | (chan_b(p) >> sb);
+    }
+  }
+  return 1;
+}
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// Divisive phase.  Reference: DivQuantCluster<UW,MT,KM=true>, DivQuantCluster.cpp:133-1097, and
+// DivQuantClusterInitMeanAndVar, :49-123.
+//
+// `uniform` mirrors the UW template flag: every point carries weight `w_uniform` and the reference
+// accumulates plain integers (u32 chunks of <= 0xFFFF points, :440-455), which is exact, so one
+// exact u64 accumulation per pass is the same number.  Otherwise `w[i]` are the doubles produced
+// by calc_color_table and every sum is a sequential double accumulation in point order.
+// ---------------------------------------------------------------------------------------------
+struct PassSums {
+  double mean_r, mean_g, mean_b;  // sum of w*c   (weighted)   | unused (uniform)
+  double var_r, var_g, var_b;     // sum of w*c^2 (weighted)
+  double weight;                  // sum of w     (weighted)
+  uint64_t i_r, i_g, i_b;         // integer sums (uniform)
+  uint64_t i_rr, i_gg, i_bb;
+  uint64_t count;  // number of points taken
+};
+
+struct DivisiveState {
+  int num_points;
+  const uint32_t *data;
+  const double *w;  // nullptr when uniform
+  double w_uniform;
+  bool uniform;
+};
+
+// Global weighted mean / variance of all points (:60-104).
+void initial_mean_and_var(const DivisiveState &s, Vec3 *mean, Vec3 *var) {
+  double mr = 0.0, mg = 0.0, mb = 0.0, vr = 0.0, vg = 0.0, vb = 0.0;
+  for (int ip = 0; ip < s.num_points; ++ip) {
+    uint32_t p = s.data[ip];
+    uint32_t R = chan_r(p), G = chan_g(p), B = chan_b(p);
+    if (s.uniform) {
+      mr += R;
+      mg += G;
+      mb += B;
+      vr += (R * R);
+      vg += (G * G);
+      vb += (B * B);
+    } else {
+      double wt = s.w[ip];
+      mr += wt * R;
+      mg += wt * G;
+      mb += wt * B;
+      vr += wt * (R * R);
+      vg += wt * (G * G);
+      vb += wt * (B * B);
+    }
+  }
+  if (s.uniform) {
+    mr *= s.w_uniform;
+    mg *= s.w_uniform;
+    mb *= s.w_uniform;
+    vr *= s.w_uniform;
+    vg *= s.w_uniform;
+    vb *= s.w_uniform;
+  }
+  vr -= sq(mr);
+  vg -= sq(mg);
+  vb -= sq(mb);
+  mean->r = mr;
+  mean->g = mg;
+  mean->b = mb;
+  var->r = vr;
+  var->g = vg;
+  var->b = vb;
+}
+
+}  // namespace
+
+extern "C" int oracle_quant_varpart_fast(uint32_t num_pixels, const uint32_t *in, uint32_t num_rows,
+                                         uint32_t num_cols, uint32_t *num_clusters, uint32_t *colortable,
+                                         int num_bits, int dec_factor, int max_iters, int all_pixels_unique,
+                                         oracle_split_record *records, int *num_records) {
+  assert(0 < num_bits && num_bits <= 8);  // (:1115-1118)
+  assert(max_iters >= 1);                 // KM is hard-wired true; 0 iterations is degenerate
+  if (num_records) *num_records = 0;
+
+  // ---- path selection, quant_varpart_fast :1130-1147 ----
+  std::vector<uint32_t> points;
+  std::vector<double> weights;
+  DivisiveState s;
+  if (all_pixels_unique && num_bits == 8 && dec_factor == 1) {
+    s.uniform = true;
+    s.w_uniform = 1.0 / (std::ceil(1 / (double)1) * std::ceil((int)num_pixels / (double)1));  // (:215)
+    s.w = nullptr;
+    s.data = in;
+    s.num_points = (int)num_pixels;
+  } else {
+    std::vector<uint32_t> sampled;
+    const uint32_t *src = in;
+    if (!(!all_pixels_unique && num_bits == 8)) {
+      sampled.resize(num_pixels);
+      oracle_cut_bits(in, num_pixels, sampled.data(), num_bits, num_bits, num_bits);
+      src = sampled.data();
+    }
+    points.resize(num_pixels);
+    weights.resize(num_pixels);
+    int u = oracle_calc_color_table(src, num_pixels, num_rows, num_cols, dec_factor, points.data(),
+                                    weights.data(), nullptr);
+    assert(u > 0);
+    s.uniform = false;
+    s.w_uniform = 0.0;
+    s.w = weights.data();
+    s.data = points.data();
+    s.num_points = u;
+  }
+
+  const int K = (int)*num_clusters;
+  assert(K > 0);
+  const int U = s.num_points;
+
+  // Per-cluster bookkeeping (all zero-initialised like the reference's `new T[n]()`, :296-324).
+  std::vector<double> weight(K, 0.0), tse(K, 0.0);
+  std::vector<int> size(K, 0);
+  std::vector<Vec3> mean(K, Vec3{0, 0, 0}), var(K, Vec3{0, 0, 0});
+  std::vector<uint32_t> member(U, 0u);
+
+  // The cluster being split: `cur` lists original point indices in ascending order (the reference
+  // keeps tmp_data/point_index, :929-1019; before the first gather it is the identity).
+  std::vector<int> cur(U);
+  for (int i = 0; i < U; ++i) cur[i] = i;
+
+  int old_index = 0;
+  weight[0] = 1.0;
+  size[0] = U;
+  int cur_n = U;
+  const int last_it = max_iters - 1;
+
+  for (int new_index = 1; new_index < K; ++new_index) {
+    const double tw = weight[old_index];
+    Vec3 tm, tv;
+    if (new_index == 1) {
+      initial_mean_and_var(s, &tm, &tv);
+    } else {
+      tm = mean[old_index];
+      tv = var[old_index];
+    }
+
+    // Cutting axis = channel of largest variance, cut at the mean (:388-403). The blue branch does
+    // not refresh max_val in the reference; nothing reads it afterwards.
+    double best = tv.r;
+    int axis = 0;
+    double cut = tm.r;
+    if (best < tv.g) {
+      best = tv.g;
+      axis = 1;
+      cut = tm.g;
+    }
+    if (best < tv.b) {
+      axis = 2;
+      cut = tm.b;
+    }
+
+    Vec3 &nm = mean[new_index];
+    Vec3 &nv = var[new_index];
+    Vec3 &om = mean[old_index];
+    nm = Vec3{0, 0, 0};
+
+    // ---- split pass (:438-559): points strictly above the cut seed the new cluster ----
+    double nw = 0.0;
+    {
+      uint64_t ir = 0, ig = 0, ib = 0, cnt = 0;
+      for (int j = 0; j < cur_n; ++j) {
+        int idx = cur[j];
+        uint32_t p = s.data[idx];
+        uint32_t R = chan_r(p), G = chan_g(p), B = chan_b(p);
+        double proj = (axis == 0) ? R : ((axis == 1) ? G : B);
+        if (cut < proj) {
+          if (s.uniform) {
+            ir += R;
+            ig += G;
+            ib += B;
+            cnt += 1;
+          } else {
+            double wt = s.w[idx];
+            nm.r += wt * R;
+            nm.g += wt * G;
+            nm.b += wt * B;
+            nw += wt;
+          }
+        }
+      }
+      if (s.uniform) {
+        nm.r += (double)ir;
+        nm.g += (double)ig;
+        nm.b += (double)ib;
+        nm.r *= s.w_uniform;
+        nm.g *= s.w_uniform;
+        nm.b *= s.w_uniform;
+        nw = (uint32_t)cnt * s.w_uniform;
+      }
+    }
+    double ow = tw - nw;
+    nm.r /= nw;
+    nm.g /= nw;
+    nm.b /= nw;
+    // 'combined mean' (:579-581)
+    om.r = (tw * tm.r - nw * nm.r) / ow;
+    om.g = (tw * tm.g - nw * nm.g) / ow;
+    om.b = (tw * tm.b - nw * nm.b) / ow;
+
+    // ---- local 2-means refinement (:613-811) ----
+    int new_size = 0;
+    for (int it = 0; it < max_iters; ++it) {
+      const double lhs =
+          0.5 * (sq(om.r) - sq(nm.r) + sq(om.g) - sq(nm.g) + sq(om.b) - sq(nm.b));  // (:616-619)
+      const double rr = om.r - nm.r, rg = om.g - nm.g, rb = om.b - nm.b;
+      nw = 0.0;
+      new_size = 0;
+      nm = Vec3{0, 0, 0};
+      nv = Vec3{0, 0, 0};
+      uint64_t ir = 0, ig = 0, ib = 0, irr = 0, igg = 0, ibb = 0;
+      for (int j = 0; j < cur_n; ++j) {
+        int idx = cur[j];
+        uint32_t p = s.data[idx];
+        uint32_t R = chan_r(p), G = chan_g(p), B = chan_b(p);
+        double red = R, green = G, blue = B;
+        if (lhs < ((rr * red) + (rg * green) + (rb * blue))) {
+          // closer to the old centre (:683)
+          if (it == last_it) member[idx] = (uint32_t)old_index;
+        } else {
+          if (s.uniform) {
+            ir += R;
+            ig += G;
+            ib += B;
+            if (it == last_it) {
+              irr += R * R;
+              igg += G * G;
+              ibb += B * B;
+            }
+          } else {
+            double wt = s.w[idx];
+            nm.r += wt * red;
+            nm.g += wt * green;
+            nm.b += wt * blue;
+            if (it == last_it) {
+              nv.r += wt * (R * R);
+              nv.g += wt * (G * G);
+              nv.b += wt * (B * B);
+            }
+            nw += wt;
+          }
+          if (it == last_it) member[idx] = (uint32_t)new_index;
+          new_size++;
+        }
+      }
+      if (s.uniform) {
+        nm.r += (double)ir;
+        nm.g += (double)ig;
+        nm.b += (double)ib;
+        nv.r += (double)irr;
+        nv.g += (double)igg;
+        nv.b += (double)ibb;
+        nm.r *= s.w_uniform;
+        nm.g *= s.w_uniform;
+        nm.b *= s.w_uniform;
+        nw = new_size * s.w_uniform;
+        nv.r *= s.w_uniform;
+        nv.g *= s.w_uniform;
+        nv.b *= s.w_uniform;
+      }
+      nm.r /= nw;
+      nm.g /= nw;
+      nm.b /= nw;
+      ow = tw - nw;
+      om.r = (tw * tm.r - nw * nm.r) / ow;
+      om.g = (tw * tm.g - nw * nm.g) / ow;
+      om.b = (tw * tm.b - nw * nm.b) / ow;
+    }
+
+    size[old_index] = cur_n - new_size;
+    size[new_index] = new_size;
+
+    oracle_split_record rec;
+    memset(&rec, 0, sizeof(rec));
+    rec.new_index = new_index;
+    rec.old_index = old_index;
+    rec.cut_axis = axis;
+    rec.num_points = cur_n;
+    rec.new_size = new_size;
+    rec.cut_pos = cut;
+    rec.total_weight = tw;
+    rec.new_weight = nw;
+    rec.old_weight = ow;
+    rec.new_mean[0] = nm.r, rec.new_mean[1] = nm.g, rec.new_mean[2] = nm.b;
+    rec.old_mean[0] = om.r, rec.old_mean[1] = om.g, rec.old_mean[2] = om.b;
+
+    if (new_index == K - 1) {
+      // Last split: the reference leaves without touching var/weight/tse (:823-832).
+      rec.is_last = 1;
+      if (records) records[new_index - 1] = rec;
+      if (num_records) *num_records = new_index;
+      break;
+    }
+
+    // Variances: new side from its own sums, old side by the 'combined variance' formula (:836-855).
+    nv.r = nv.r / nw - sq(nm.r);
+    nv.g = nv.g / nw - sq(nm.g);
+    nv.b = nv.b / nw - sq(nm.b);
+    Vec3 &ov = var[old_index];
+    ov.r = ((tw * tv.r - nw * (nv.r + sq(nm.r - tm.r))) / ow) - sq(om.r - tm.r);
+    ov.g = ((tw * tv.g - nw * (nv.g + sq(nm.g - tm.g))) / ow) - sq(om.g - tm.g);
+    ov.b = ((tw * tv.b - nw * (nv.b + sq(nm.b - tm.b))) / ow) - sq(om.b - tm.b);
+    weight[old_index] = ow;
+    weight[new_index] = nw;
+    tse[old_index] = ow * (ov.r + ov.g + ov.b);
+    tse[new_index] = nw * (nv.r + nv.g + nv.b);
+
+    rec.new_var[0] = nv.r, rec.new_var[1] = nv.g, rec.new_var[2] = nv.b;
+    rec.old_var[0] = ov.r, rec.old_var[1] = ov.g, rec.old_var[2] = ov.b;
+    rec.new_tse = tse[new_index];
+    rec.old_tse = tse[old_index];
+    if (records) records[new_index - 1] = rec;
+    if (num_records) *num_records = new_index;
+
+    // Next victim: strictly-greater scan seeded with DBL_MIN, so old_index goes stale when no
+    // cluster has a TSE above it (:876-887).
+    double top = DBL_MIN;
+    for (int ic = 0; ic <= new_index; ++ic) {
+      if (top < tse[ic]) {
+        top = tse[ic];
+        old_index = ic;
+      }
+    }
+
+    // Gather its points in ascending original order (:929-1019).
+    cur_n = 0;
+    for (int ip = 0; ip < U; ++ip) {
+      if (member[ip] == (uint32_t)old_index) cur[cur_n++] = ip;
+    }
+    if (cur_n != size[old_index]) {
+      fprintf(stderr, "Cluster to be split is expected to be of size %d not %d !\n", size[old_index], cur_n);
+      abort();
+    }
+  }
+
+  // Palette = rounded means of the non-empty clusters in index order (:1030-1065).
+  const int shift = 8 - num_bits;
+  int empty = 0, emitted = 0;
+  for (int ic = 0; ic < K; ++ic) {
+    if (size[ic] > 0) {
+      uint32_t R = ((uint8_t)(mean[ic].r + 0.5)) << shift;
+      uint32_t G = ((uint8_t)(mean[ic].g + 0.5)) << shift;
+      uint32_t B = ((uint8_t)(mean[ic].b + 0.5)) << shift;
+      colortable[emitted++] = (R << 16) | (G << 8) | B;
+    } else {
+      ++empty;
+    }
+  }
+  *num_clusters = (uint32_t)(K - empty);
+  return empty;
+}
+
+namespace {
+
+// Reference Pixel_Int (DivQuantHeader.h:40-44): the element type std::sort permutes.  Keeping the
+// same layout and comparator keeps libstdc++'s (unstable) introsort permutation identical.
+struct PaletteEntry {
+  int red, green, blue;
+  int weight;  // r+g+b
+};
+
+inline bool by_sum(const PaletteEntry &a, const PaletteEntry &b) { return a.weight < b.weight; }
+
+struct SearchTables {
+  std::vector<PaletteEntry> sorted;
+  int lut_init[3 * 255 + 1];
+};
+
+// Reference: map_colors_mps set-up, DivQuantMapColors.cpp:267-383.
+void build_tables(const uint32_t *colortable, int n, SearchTables *t) {
+  std::vector<PaletteEntry> v((size_t)n);
+  for (int i = 0; i < n; ++i) {
+    uint32_t p = colortable[i];
+    v[i].red = (int)chan_r(p);
+    v[i].green = (int)chan_g(p);
+    v[i].blue = (int)chan_b(p);
+    v[i].weight = v[i].red + v[i].green + v[i].blue;
+  }
+  std::sort(v.begin(), v.end(), by_sum);
+  t->sorted = v;
+
+  const int lut_n = 3 * 255 + 1;
+  int low, high;
+  // Entry 0 owns sums below the rounded midpoint of the first two sums; the last entry owns sums
+  // from the rounded midpoint of the last two (:331-358). Single-colour palettes use 1 for both.
+  low = (n >= 2) ? (int)(0.5 * (v[0].weight + v[1].weight) + 0.5) : 1;
+  for (int k = 0; k < low; ++k) t->lut_init[k] = 0;
+  high = (n >= 2) ? (int)(0.5 * (v[n - 2].weight + v[n - 1].weight) + 0.5) : 1;
+  for (int k = high; k < lut_n; ++k) t->lut_init[k] = n - 1;
+  for (int ic = 1; ic < n - 1; ++ic) {
+    low = (int)(0.5 * (v[ic - 1].weight + v[ic].weight) + 0.5);
+    high = (int)(0.5 * (v[ic].weight + v[ic + 1].weight) + 0.5);
+    for (int k = low; k < high; ++k) t->lut_init[k] = ic;
+  }
+}
+
+inline int dist2(int r, int g, int b, const PaletteEntry &e) {
+  int d = r - e.red, acc = d * d;
+  d = g - e.green;
+  acc += d * d;
+  d = b - e.blue;
+  acc += d * d;
+  return acc;
+}
+
+inline uint32_t pack(const PaletteEntry &e) {
+  return ((uint32_t)(uint8_t)e.red << 16) | ((uint32_t)(uint8_t)e.green << 8) | (uint32_t)(uint8_t)e.blue;
+}
+
+}  // namespace
+
+extern "C" void oracle_build_search_tables(const uint32_t *colortable, int num_colors, uint32_t *sorted_out,
+                                           int32_t *lut_init_out) {
+  SearchTables t;
+  build_tables(colortable, num_colors, &t);
+  for (int i = 0; i < num_colors; ++i) sorted_out[i] = pack(t.sorted[i]);
+  for (int i = 0; i < 766; ++i) lut_init_out[i] = t.lut_init[i];
+}
+
+// Reference: map_colors_mps search loop, DivQuantMapColors.cpp:385-532.
+extern "C" void oracle_map_colors_mps(const uint32_t *in, uint32_t num_pixels, uint32_t *out,
+                                      const uint32_t *colortable, int num_colors) {
+  assert(num_colors > 0);
+  SearchTables t;
+  build_tables(colortable, num_colors, &t);
+  const PaletteEntry *pal = t.sorted.data();
+  // Lower bound on the distance from the gap in channel sums: (int)(d*d/3.0)  (:285-311).
+  std::vector<int> bound(2 * 765 + 1);
+  for (int d = 0; d <= 765; ++d) bound[765 + d] = bound[765 - d] = (int)((d * d) / 3.0);
+  const int *lb = bound.data() + 765;
+
+  for (uint32_t i = 0; i < num_pixels; ++i) {
+    uint32_t p = in[i];
+    int r = (int)chan_r(p), g = (int)chan_g(p), b = (int)chan_b(p);
+    int sum = r + g + b;
+    int win = t.lut_init[sum];
+    int best = dist2(r, g, b, pal[win]);
+    int hi = win, lo = win;
+    bool go_up = true, go_down = true;
+    while (go_up || go_down) {
+      if (go_up) {
+        ++hi;
+        if (hi > num_colors - 1 || lb[sum - pal[hi].weight] >= best) {
+          go_up = false;
+        } else {
+          int d = dist2(r, g, b, pal[hi]);
+          if (d < best) {
+            best = d;
+            win = hi;
+          }
+        }
+      }
+      if (go_down) {
+        --lo;
+        if (lo < 0 || lb[sum - pal[lo].weight] >= best) {
+          go_down = false;
+        } else {
+          int d = dist2(r, g, b, pal[lo]);
+          if (d < best) {
+            best = d;
+            win = lo;
+          }
+        }
+      }
+    }
+    out[i] = pack(pal[win]);  // alpha cleared (:523-527)
+  }
+}
+
+// Closed form of the same search: argmin over the whole sorted palette of
+// (distance, visiting rank) with rank(s)=0, rank(s+d)=2d-1, rank(s-d)=2d.
+extern "C" void oracle_map_colors_bruteforce(const uint32_t *in, uint32_t num_pixels, uint32_t *out,
+                                             const uint32_t *colortable, int num_colors) {
+  assert(num_colors > 0);
+  SearchTables t;
+  build_tables(colortable, num_colors, &t);
+  const PaletteEntry *pal = t.sorted.data();
+  for (uint32_t i = 0; i < num_pixels; ++i) {
+    uint32_t p = in[i];
+    int r = (int)chan_r(p), g = (int)chan_g(p), b = (int)chan_b(p);
+    int s = t.lut_init[r + g + b];
+    int64_t best_key = INT64_MAX;
+    int win = s;
+    for (int k = 0; k < num_colors; ++k) {
+      int rank = (k == s) ? 0 : (k > s ? 2 * (k - s) - 1 : 2 * (s - k));
+      int64_t key = ((int64_t)dist2(r, g, b, pal[k]) << 32) | (int64_t)rank;
+      if (key < best_key) {
+        best_key = key;
+        win = k;
+      }
+    }
+    out[i] = pack(pal[win]);
+  }
+}
+
+// Reference: quant_recurse, quant_util.cpp:20-158.
+extern "C" void oracle_quant_recurse(uint32_t num_pixels, const uint32_t *in, uint32_t *out,
+                                     uint32_t *num_clusters, uint32_t *colortable, int all_pixels_unique) {
+  oracle_quant_varpart_fast(num_pixels, in, 1, num_pixels, num_clusters, colortable, 8, 1, 10,
+                            all_pixels_unique, nullptr, nullptr);
+  // First occurrence of each palette word survives, order kept (:93-118).
+  int n = (int)*num_clusters, kept = 0;
+  for (int i = 0; i < n; ++i) {
+    bool seen = false;
+    for (int j = 0; j < kept && !seen; ++j) seen = (colortable[j] == colortable[i]);
+    if (!seen) colortable[kept++] = colortable[i];
+  }
+  *num_clusters = (uint32_t)kept;
+  oracle_map_colors_mps(in, num_pixels, out, colortable, kept);
+}
+
+// Reference: mapQuantPixelsToColortableIndexes, superpixels/OpenCVUtil.cpp:787-849 (pixel -> index
+// map filled in palette order, so the LAST duplicate wins; alpha is forced opaque on both sides).
+extern "C" int oracle_colortable_indexes(const uint32_t *quant_pixels, uint32_t num_pixels,
+                                         const uint32_t *colortable, int num_colors, uint32_t *labels_out) {
+  for (uint32_t i = 0; i < num_pixels; ++i) {
+    uint32_t want = quant_pixels[i] & 0x00FFFFFFu;
+    int found = -1;
+    for (int k = 0; k < num_colors; ++k)
+      if ((colortable[k] & 0x00FFFFFFu) == want) found = k;
+    if (found < 0) return -1;
+    labels_out[i] = (uint32_t)found;
+  }
+  return 0;
+}
+
+extern "C" uint64_t oracle_hash_words(const uint32_t *words, uint64_t n) {
+  uint64_t h = 0xcbf29ce484222325ull;
+  for (uint64_t i = 0; i < n; ++i) {
+    h ^= words[i];
+    h *= 0x100000001b3ull;
+  }
+  return h;
+}
+
+extern "C" void oracle_generate(int kind, uint32_t width, uint32_t height, uint64_t seed, uint32_t *out) {
+  uint64_t s = seed;
+  for (uint32_t y = 0; y < height; ++y) {
+    for (uint32_t x = 0; x < width; ++x) {
+      s += 0x9E3779B97F4A7C15ull;
+      uint64_t z = s;
+      z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+      z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+      z ^= z >> 31;
+      uint32_t px;
+      if (kind == 1) {
+        int r = (int)(x * 255u / width), g = (int)(y * 255u / height);
+        int b = (int)((x + y) * 255u / (width + height));
+        int n = (int)(z % 9) - 4;
+        r = std::min(255, std::max(0, r + n));
+        g = std::min(255, std::max(0, g + n));
+        b = std::min(255, std::max(0, b + n));
+        px = 0xFF000000u + ((uint32_t)r << 16) + ((uint32_t)g << 8) + (uint32_t)b;
+      } else {
+        px = 0xFF000000u + (uint32_t)(z & 0xFFFFFFu);
+      }
+      out[(size_t)y * width + x] = px;
+    }
+  }
+}

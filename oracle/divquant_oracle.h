@@ -1,0 +1,79 @@
+/* oracle/divquant_oracle.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * C-ABI of the CPU restatement of the reference's DivQuant path (see divquant_oracle.cpp).
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load this library, and only as the checker.  The product (csrc/) never links or calls it.
+ */
+#ifndef DIVQUANT_ORACLE_H
+#define DIVQUANT_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* One record per executed split of the divisive phase (reference loop DivQuantCluster.cpp:346-1027). */
+typedef struct {
+  int32_t new_index;     /* cluster created by this split                         */
+  int32_t old_index;     /* cluster that was split                                */
+  int32_t cut_axis;      /* 0=R 1=G 2=B                                           */
+  int32_t num_points;    /* unique-colour points in the cluster before the split  */
+  int32_t new_size;      /* points that ended in new_index after the last LKM it. */
+  int32_t is_last;       /* 1 when new_index == K-1 (variance/TSE not computed)   */
+  double cut_pos;
+  double total_weight, new_weight, old_weight;
+  double new_mean[3], old_mean[3];
+  double new_var[3], old_var[3];   /* undefined when is_last */
+  double new_tse, old_tse;         /* undefined when is_last */
+} oracle_split_record;
+
+/* calc_color_table (DivQuantMapColors.cpp:82-203).  Returns U, or -1 on dec_factor<=0.
+ * unique_out / weights_out need capacity for every sampled pixel. counts_out may be NULL. */
+int oracle_calc_color_table(const uint32_t *in, uint32_t num_pixels, uint32_t num_rows, uint32_t num_cols,
+                            int dec_factor, uint32_t *unique_out, double *weights_out, uint32_t *counts_out);
+
+/* cut_bits (DivQuantUni.cpp:28-100). Returns 0 when a bit count is rejected (output untouched). */
+int oracle_cut_bits(const uint32_t *in, uint32_t num_pixels, uint32_t *out, int rbits, int gbits, int bbits);
+
+/* quant_varpart_fast (DivQuantCluster.cpp:1099-1179).  *num_clusters in: requested K, out: actual.
+ * records (capacity >= K-1) may be NULL; *num_records receives the number of splits executed.
+ * Returns the number of empty clusters that were dropped. */
+int oracle_quant_varpart_fast(uint32_t num_pixels, const uint32_t *in, uint32_t num_rows, uint32_t num_cols,
+                              uint32_t *num_clusters, uint32_t *colortable, int num_bits, int dec_factor,
+                              int max_iters, int all_pixels_unique, oracle_split_record *records,
+                              int *num_records);
+
+/* map_colors_mps (DivQuantMapColors.cpp:243-539), restated as the reference's pruned two-way search. */
+void oracle_map_colors_mps(const uint32_t *in, uint32_t num_pixels, uint32_t *out, const uint32_t *colortable,
+                           int num_colors);
+
+/* Same result through the closed form argmin_k (dist, rank) of SURVEY.md section 8a (no pruning). */
+void oracle_map_colors_bruteforce(const uint32_t *in, uint32_t num_pixels, uint32_t *out,
+                                  const uint32_t *colortable, int num_colors);
+
+/* Sorted palette and start-index table exactly as map_colors_mps builds them
+ * (DivQuantMapColors.cpp:314-383).  sorted_out[num_colors], lut_init_out[766]. */
+void oracle_build_search_tables(const uint32_t *colortable, int num_colors, uint32_t *sorted_out,
+                                int32_t *lut_init_out);
+
+/* quant_recurse (quant_util.cpp:20-158): quantize (max_iters 10, 8 bits, no decimation),
+ * first-occurrence palette dedup, remap.  Silent (no timing lines). */
+void oracle_quant_recurse(uint32_t num_pixels, const uint32_t *in, uint32_t *out, uint32_t *num_clusters,
+                          uint32_t *colortable, int all_pixels_unique);
+
+/* Label image: index of each mapped pixel in the caller's palette, last duplicate wins
+ * (superpixels/OpenCVUtil.cpp:787-849). Returns 0, or -1 if a pixel is not in the palette. */
+int oracle_colortable_indexes(const uint32_t *quant_pixels, uint32_t num_pixels, const uint32_t *colortable,
+                              int num_colors, uint32_t *labels_out);
+
+/* FNV-1a style fingerprint over u32 words used by SURVEY.md section 8c. */
+uint64_t oracle_hash_words(const uint32_t *words, uint64_t n);
+
+/* Synthetic generators of SURVEY.md section 8d (splitmix64). kind 1 = G1 natural-like, 2 = G2 uniform. */
+void oracle_generate(int kind, uint32_t width, uint32_t height, uint64_t seed, uint32_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
