@@ -1,0 +1,188 @@
+"""clusteringsegmentation-1_b200 -- B200-native DivQuant colour quantizer (host-side Python mirror).
+
+The product is ``libdivquant_b200.so`` (hand-written CUDA for sm_100a behind the C ABI declared in
+``include/divquant_b200.h``).  This module is a thin ctypes mirror of the reference's interface for
+that path (``quant_recurse``, ``quant_varpart_fast``, ``map_colors_mps``, ``calc_color_table``,
+``cut_bits`` -- DivQuant/DivQuantHeader.h:52-96, DivQuant/quant_util.h:10) used by ``tests/`` and
+``bench.py``.  It never computes anything itself and has no CPU fallback: if the shared library is
+missing it raises, and the library aborts when there is no sm_100a device.
+
+The directory name is not a Python identifier; import it with
+``importlib.import_module("clusteringsegmentation-1_b200")``.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdivquant_b200.so")
+INCLUDE_DIR = os.path.join(os.path.dirname(_HERE), "include")
+
+_u32p = C.POINTER(C.c_uint32)
+_f64p = C.POINTER(C.c_double)
+
+
+class SplitRecord(C.Structure):
+    """dq_split_record (include/divquant_b200.h), same fields as the oracle's record."""
+    _fields_ = [("new_index", C.c_int32), ("old_index", C.c_int32), ("cut_axis", C.c_int32),
+                ("num_points", C.c_int32), ("new_size", C.c_int32), ("is_last", C.c_int32),
+                ("cut_pos", C.c_double), ("total_weight", C.c_double), ("new_weight", C.c_double),
+                ("old_weight", C.c_double), ("new_mean", C.c_double * 3), ("old_mean", C.c_double * 3),
+                ("new_var", C.c_double * 3), ("old_var", C.c_double * 3), ("new_tse", C.c_double),
+                ("old_tse", C.c_double)]
+
+
+class CallStats(C.Structure):
+    _fields_ = [("num_pixels", C.c_uint32), ("num_points", C.c_uint32), ("requested_colors", C.c_uint32),
+                ("actual_colors", C.c_uint32), ("empty_clusters", C.c_uint32), ("split_rounds", C.c_uint32),
+                ("splits_computed", C.c_uint32), ("remap_path", C.c_uint32), ("kernel_launches", C.c_uint32),
+                ("reserved", C.c_uint32 * 7)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
+
+
+def build(verbose=False):
+    """Compile libdivquant_b200.so in-tree (nvcc, sm_100a only)."""
+    subprocess.run(["make", "-C", _HERE, "-j4"], check=True, stdout=None if verbose else subprocess.DEVNULL)
+
+
+def load_library(path=LIB_PATH):
+    if not os.path.exists(path):
+        raise FileNotFoundError(
+            f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (there is no CPU fallback)")
+    lib = C.CDLL(path)
+    vp = C.c_void_p
+    sigs = {
+        "dq_version": (C.c_char_p, []),
+        "dq_quant_recurse": (None, [C.c_uint32, _u32p, _u32p, _u32p, _u32p, C.c_int]),
+        "dq_quant_varpart_fast": (None, [C.c_uint32, _u32p, _u32p, C.c_uint32, C.c_uint32, _u32p, _u32p, C.c_int,
+                                         C.c_int, C.c_int, C.c_int]),
+        "dq_map_colors_mps": (None, [_u32p, C.c_uint32, _u32p, _u32p, C.c_int]),
+        "dq_calc_color_table": (C.c_int, [_u32p, C.c_uint32, _u32p, C.c_uint32, C.c_uint32, C.c_int,
+                                          C.POINTER(C.c_int), _f64p]),
+        "dq_cut_bits": (None, [_u32p, C.c_uint32, _u32p, C.c_ubyte, C.c_ubyte, C.c_ubyte]),
+        "dq_get_double_scale": (C.c_double, [_u32p, C.c_uint32]),
+        "dq_validate_num_bits": (C.c_int, [C.c_ubyte]),
+        "dq_set_display_timings": (None, [C.c_int]),
+        "dq_context_create": (vp, [C.c_int]),
+        "dq_context_destroy": (None, [vp]),
+        "dq_default_context": (vp, []),
+        "dq_context_stream": (vp, [vp]),
+        "dq_context_synchronize": (None, [vp]),
+        "dq_context_last_stats": (None, [vp, C.POINTER(CallStats)]),
+        "dq_quant_recurse_device": (None, [vp, C.c_uint32, vp, vp, _u32p, _u32p, C.c_int]),
+        "dq_map_colors_device": (None, [vp, vp, C.c_uint32, vp, _u32p, C.c_int, C.c_int]),
+        "dq_quant_varpart_device": (None, [vp, C.c_uint32, vp, C.c_uint32, C.c_uint32, _u32p, _u32p, C.c_int,
+                                           C.c_int, C.c_int, C.c_int]),
+        "dq_quant_recurse_ctx": (None, [vp, C.c_uint32, _u32p, _u32p, _u32p, _u32p, C.c_int]),
+        "dq_debug_split_points": (C.c_uint32, [vp, _u32p, _u32p, C.c_uint32, C.c_double, C.c_uint32, C.c_int, C.c_int,
+                                               _u32p, C.POINTER(SplitRecord), _f64p, _u32p]),
+        "dq_debug_histogram": (C.c_uint32, [vp, _u32p, C.c_uint32, _u32p, _u32p]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+EXPORTED_C_SYMBOLS = [
+    "dq_version", "dq_quant_recurse", "dq_quant_varpart_fast", "dq_map_colors_mps", "dq_calc_color_table", "dq_cut_bits",
+    "dq_get_double_scale", "dq_validate_num_bits", "dq_set_display_timings", "dq_context_create", "dq_context_destroy",
+    "dq_default_context", "dq_context_stream", "dq_context_synchronize", "dq_context_last_stats",
+    "dq_quant_recurse_device", "dq_map_colors_device", "dq_quant_varpart_device", "dq_quant_recurse_ctx",
+    "dq_debug_split_points", "dq_debug_histogram",
+]
+
+# The reference's own symbol names, exported for relinking the reference's callers.
+REFERENCE_SYMBOLS = [
+    "_Z18quant_varpart_fastjPKjPjjjS1_S1_iiii", "_Z14map_colors_mpsPKjjPjS1_i", "_Z16calc_color_tablePKjjPjjjiPi",
+    "_Z16get_double_scalePKjj", "_Z8cut_bitsPKjjPjhhh", "_Z17validate_num_bitsh", "_Z9check_memi", "_Z11start_timerv",
+    "_Z10stop_timerl", "_Z8timediffll", "quant_recurse",
+]
+
+
+def _u32(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.uint32).ravel())
+
+
+def _p(a, t=_u32p):
+    return a.ctypes.data_as(t)
+
+
+class DivQuant:
+    """Host-pointer mirror of the reference entry points (numpy in, numpy out)."""
+
+    def __init__(self, lib=None, timings=False):
+        self.lib = lib or load_library()
+        self.lib.dq_set_display_timings(1 if timings else 0)
+
+    # -- reference entry points ----------------------------------------------------------------
+    def quant_recurse(self, pixels, k, all_unique=0):
+        px = _u32(pixels)
+        out = np.zeros_like(px)
+        ct = np.zeros(max(int(k), 1), np.uint32)
+        nk = C.c_uint32(k)
+        self.lib.dq_quant_recurse(px.size, _p(px), _p(out), C.byref(nk), _p(ct), all_unique)
+        return out, ct[:nk.value].copy()
+
+    def quant_varpart_fast(self, pixels, k, num_bits=8, dec_factor=1, max_iters=10, all_unique=0, rows=1, cols=None):
+        px = _u32(pixels)
+        cols = px.size if cols is None else cols
+        tmp = np.zeros_like(px)
+        ct = np.zeros(max(int(k), 1), np.uint32)
+        nk = C.c_uint32(k)
+        self.lib.dq_quant_varpart_fast(px.size, _p(px), _p(tmp), rows, cols, C.byref(nk), _p(ct), num_bits, dec_factor,
+                                       max_iters, all_unique)
+        return ct[:nk.value].copy(), int(k) - nk.value
+
+    def map_colors_mps(self, pixels, colortable):
+        px = _u32(pixels)
+        ct = _u32(colortable).copy()
+        out = np.zeros_like(px)
+        self.lib.dq_map_colors_mps(_p(px), px.size, _p(out), _p(ct), ct.size)
+        return out
+
+    def calc_color_table(self, pixels, dec_factor=1, rows=1, cols=None):
+        px = _u32(pixels)
+        cols = px.size if cols is None else cols
+        uniq = np.zeros(px.size, np.uint32)
+        w = np.zeros(px.size, np.float64)
+        n = C.c_int(0)
+        rc = self.lib.dq_calc_color_table(_p(px), px.size, _p(uniq), rows, cols, dec_factor, C.byref(n), _p(w, _f64p))
+        if rc != 0:
+            return None
+        return uniq[:n.value].copy(), w[:n.value].copy()
+
+    def cut_bits(self, pixels, rbits, gbits, bbits):
+        px = _u32(pixels)
+        out = np.zeros_like(px)
+        self.lib.dq_cut_bits(_p(px), px.size, _p(out), rbits, gbits, bbits)
+        return out
+
+    # -- diagnostics ---------------------------------------------------------------------------
+    def last_stats(self, ctx=None):
+        st = CallStats()
+        self.lib.dq_context_last_stats(ctx or self.lib.dq_default_context(), C.byref(st))
+        return st.as_dict()
+
+    def histogram(self, pixels):
+        px = _u32(pixels)
+        col = np.zeros(px.size, np.uint32)
+        cnt = np.zeros(px.size, np.uint32)
+        u = self.lib.dq_debug_histogram(self.lib.dq_default_context(), _p(px), px.size, _p(col), _p(cnt))
+        return col[:u].copy(), cnt[:u].copy()
+
+    def split_points(self, colours, counts, norm, k, max_iters=10, num_bits=8):
+        col = _u32(colours)
+        cnt = _u32(counts)
+        ct = np.zeros(max(int(k), 1), np.uint32)
+        recs = (SplitRecord * max(int(k), 1))()
+        means = np.zeros(3 * max(int(k), 1), np.float64)
+        sizes = np.zeros(max(int(k), 1), np.uint32)
+        n = self.lib.dq_debug_split_points(self.lib.dq_default_context(), _p(col), _p(cnt), col.size, norm, k, max_iters,
+                                           num_bits, _p(ct), recs, _p(means, _f64p), _p(sizes))
+        return ct[:n].copy(), [recs[i] for i in range(max(int(k) - 1, 0))], means.reshape(-1, 3), sizes

@@ -1,0 +1,684 @@
+// dq_context.cu -- host side of libdivquant_b200.so: contexts, buffer management, the pipeline
+// that strings the kernels together, and the extern "C" layer of include/divquant_b200.h.
+//
+// Pipeline of quant_recurse (reference: DivQuant/quant_util.cpp:20-158):
+//   H2D pixels -> hist_insert/hist_collect (or points_from_pixels when allPixelsUnique)
+//              -> split_kernel (persistent, cooperative)           = quant_varpart_fast
+//              -> D2H palette; host: drop empty/duplicate entries, std::sort by r+g+b, lut_init
+//              -> map_unique + map_gather (unique-colour table) or map_pixels (brute force)
+//              -> D2H pixels
+// The product has no CPU path for any per-pixel or per-point work; the host only handles the <= K
+// palette words exactly as the reference's scalar code does.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "../../include/divquant_b200.h"
+#include "dq_kernels.cuh"
+#include "dq_split.cuh"
+
+namespace {
+
+using namespace dq;
+
+template <typename T>
+struct DevBuf {
+  T *ptr = nullptr;
+  size_t cap = 0;
+  void ensure(size_t n) {
+    if (n <= cap) return;
+    if (ptr) DQ_CUDA_CHECK(cudaFree(ptr));
+    size_t want = n + n / 8 + 64;  // grow with slack so that slowly growing inputs do not realloc
+    DQ_CUDA_CHECK(cudaMalloc(&ptr, want * sizeof(T)));
+    cap = want;
+  }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+  }
+};
+
+// Small control block shared with the kernels (one allocation, one memset per call).
+struct ControlBlock {
+  uint32_t ucount;
+  uint32_t pad0[3];
+  uint64_t root_acc[kAccWords];
+  uint32_t ctl[kCtlWords];
+  unsigned int barrier;
+  uint32_t pad1[3];
+  uint32_t result[4];
+};
+
+// Reference Pixel_Int (DivQuantHeader.h:40-44): element type handed to std::sort, kept identical in
+// layout so that libstdc++'s introsort produces the reference's permutation of equal sums.
+struct PaletteEntry {
+  int red, green, blue;
+  int weight;
+};
+inline bool palette_less(const PaletteEntry &a, const PaletteEntry &b) { return a.weight < b.weight; }
+
+constexpr int kLutEntries = 3 * 255 + 1;
+
+}  // namespace
+
+struct dq_context {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  uint32_t *d_table = nullptr;  // 2^24 counters / mapped colours, all zero between calls
+  ControlBlock *d_cb = nullptr;
+  ControlBlock *h_cb = nullptr;  // pinned
+  DevBuf<uint32_t> d_in, d_out, d_uniq;
+  DevBuf<uint2> d_pts0, d_pts1;
+  DevBuf<uint64_t> d_keys;
+  // sized by K
+  DevBuf<SplitNode> d_nodes;
+  DevBuf<SplitJob> d_jobs;
+  DevBuf<uint64_t> d_acc;
+  DevBuf<int32_t> d_ctl_i32;
+  DevBuf<double> d_ctl_f64;
+  DevBuf<uint32_t> d_palette, d_cluster_size, d_sorted;
+  DevBuf<double> d_cluster_mean;
+  DevBuf<SplitRecord> d_records;
+  DevBuf<int4> d_pal_scratch;
+  int *d_lut = nullptr;
+  // pinned staging for the palette-sized transfers
+  uint32_t *h_small = nullptr;
+  size_t h_small_words = 0;
+  dq_call_stats stats;
+  int display_timings = 1;
+
+  void ensure_small(size_t words) {
+    if (words <= h_small_words) return;
+    if (h_small) DQ_CUDA_CHECK(cudaFreeHost(h_small));
+    DQ_CUDA_CHECK(cudaMallocHost(&h_small, words * sizeof(uint32_t)));
+    h_small_words = words;
+  }
+};
+
+namespace {
+
+void require_device(dq_context *ctx) { DQ_CUDA_CHECK(cudaSetDevice(ctx->device)); }
+
+// ---- host handling of the <= K palette words ------------------------------------------------------
+
+// First occurrence of each word survives, order kept (quant_util.cpp:93-118).
+uint32_t dedup_palette(uint32_t *colortable, uint32_t n) {
+  uint32_t kept = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    bool seen = false;
+    for (uint32_t j = 0; j < kept && !seen; ++j) seen = (colortable[j] == colortable[i]);
+    if (!seen) colortable[kept++] = colortable[i];
+  }
+  return kept;
+}
+
+// Sorted palette + start-index table of map_colors_mps (DivQuantMapColors.cpp:267-383).
+void build_search_tables(const uint32_t *colortable, int n, uint32_t *sorted_out, int *lut_out) {
+  std::vector<PaletteEntry> v((size_t)n);
+  for (int i = 0; i < n; ++i) {
+    const uint32_t p = colortable[i];
+    v[i].blue = (int)(p & 0xFF);
+    v[i].green = (int)((p >> 8) & 0xFF);
+    v[i].red = (int)((p >> 16) & 0xFF);
+    v[i].weight = v[i].red + v[i].green + v[i].blue;
+  }
+  std::sort(v.begin(), v.end(), palette_less);
+  for (int i = 0; i < n; ++i)
+    sorted_out[i] = ((uint32_t)v[i].red << 16) | ((uint32_t)v[i].green << 8) | (uint32_t)v[i].blue;
+  int low = (n >= 2) ? (int)(0.5 * (v[0].weight + v[1].weight) + 0.5) : 1;
+  for (int k = 0; k < low; ++k) lut_out[k] = 0;
+  int high = (n >= 2) ? (int)(0.5 * (v[n - 2].weight + v[n - 1].weight) + 0.5) : 1;
+  for (int k = high; k < kLutEntries; ++k) lut_out[k] = n - 1;
+  for (int ic = 1; ic < n - 1; ++ic) {
+    low = (int)(0.5 * (v[ic - 1].weight + v[ic].weight) + 0.5);
+    high = (int)(0.5 * (v[ic].weight + v[ic + 1].weight) + 0.5);
+    for (int k = low; k < high; ++k) lut_out[k] = ic;
+  }
+}
+
+// ---- device pipeline stages -----------------------------------------------------------------------
+
+void reset_control(dq_context *ctx) {
+  DQ_CUDA_CHECK(cudaMemsetAsync(ctx->d_cb, 0, sizeof(ControlBlock), ctx->stream));
+}
+
+// Runs the divisive phase on ctx->d_pts0[0..U).  U is read on the device from d_cb->ucount.
+// Leaves palette/result/ctl in ctx->h_cb / ctx->h_small after a stream synchronisation.
+// Returns the number of palette entries.
+uint32_t run_split(dq_context *ctx, uint32_t point_capacity, double norm, uint32_t K, int max_iters, int num_bits,
+                   uint32_t *colortable_out, dq_split_record *records_out, double *mean_out, uint32_t *size_out) {
+  if (max_iters < 1 || max_iters > kSplitMaxIters) {
+    fprintf(stderr, "divquant_b200: max_iters ( %d ) must be in [1,%d] (the reference hard-wires local k-means on)\n",
+            max_iters, kSplitMaxIters);
+    abort();
+  }
+  const uint32_t node_cap = 4 * K + 8;
+  ctx->d_pts1.ensure(point_capacity);
+  ctx->d_nodes.ensure(node_cap);
+  ctx->d_jobs.ensure((size_t)2 * K);
+  ctx->d_acc.ensure(split_acc_words(K, max_iters));
+  ctx->d_ctl_i32.ensure((size_t)2 * K + node_cap + 16);
+  ctx->d_ctl_f64.ensure((size_t)K + node_cap + 16);
+  ctx->d_palette.ensure(K);
+  ctx->d_cluster_size.ensure(K);
+  ctx->d_cluster_mean.ensure((size_t)3 * K);
+  if (records_out) ctx->d_records.ensure(K);
+
+  SplitArgs a;
+  memset(&a, 0, sizeof(a));
+  a.pts[0] = ctx->d_pts0.ptr;
+  a.pts[1] = ctx->d_pts1.ptr;
+  a.num_points = 0;
+  a.num_points_dev = &ctx->d_cb->ucount;
+  a.num_colors = K;
+  a.max_iters = max_iters;
+  a.shift = 8 - num_bits;
+  a.norm = norm;
+  a.nodes = ctx->d_nodes.ptr;
+  a.node_cap = node_cap;
+  a.jobs = ctx->d_jobs.ptr;
+  a.acc = ctx->d_acc.ptr;
+  a.root_acc = ctx->d_cb->root_acc;
+  a.ctl = ctx->d_cb->ctl;
+  a.barrier = &ctx->d_cb->barrier;
+  a.g_cluster_node = ctx->d_ctl_i32.ptr;
+  a.g_cluster_tse = ctx->d_ctl_f64.ptr;
+  a.palette = ctx->d_palette.ptr;
+  a.result = ctx->d_cb->result;
+  a.cluster_mean = ctx->d_cluster_mean.ptr;
+  a.cluster_size = ctx->d_cluster_size.ptr;
+  a.records = records_out ? ctx->d_records.ptr : nullptr;
+
+  const SplitLaunch plan = split_plan(ctx->device, K);
+  split_launch(a, plan, ctx->stream);
+  ctx->stats.kernel_launches++;
+
+  ctx->ensure_small((size_t)K + 16);
+  DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->h_small, ctx->d_palette.ptr, K * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->h_cb, ctx->d_cb, sizeof(ControlBlock), cudaMemcpyDeviceToHost, ctx->stream));
+  DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->h_cb->ctl[kCtlError] != 0) {
+    fprintf(stderr, "divquant_b200: split controller ran out of node slots (internal error)\n");
+    abort();
+  }
+  const uint32_t actual = ctx->h_cb->result[0], empty = ctx->h_cb->result[1];
+  memcpy(colortable_out, ctx->h_small, actual * sizeof(uint32_t));
+  if (empty) fprintf(stderr, "# empty clusters: %d\n", (int)empty);  // (:1067-1070)
+  ctx->stats.num_points = ctx->h_cb->ucount;
+  ctx->stats.requested_colors = K;
+  ctx->stats.actual_colors = actual;
+  ctx->stats.empty_clusters = empty;
+  ctx->stats.split_rounds = ctx->h_cb->ctl[kCtlRounds];
+  ctx->stats.splits_computed = ctx->h_cb->ctl[kCtlSplits];
+  if (records_out && K > 1)
+    DQ_CUDA_CHECK(cudaMemcpy(records_out, ctx->d_records.ptr, (size_t)(K - 1) * sizeof(SplitRecord), cudaMemcpyDeviceToHost));
+  if (mean_out) DQ_CUDA_CHECK(cudaMemcpy(mean_out, ctx->d_cluster_mean.ptr, (size_t)3 * K * sizeof(double), cudaMemcpyDeviceToHost));
+  if (size_out) DQ_CUDA_CHECK(cudaMemcpy(size_out, ctx->d_cluster_size.ptr, (size_t)K * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  return actual;
+}
+
+// The reference trusts numRows/numCols blindly (its sampling loop addresses inPixels[ic + ir*numRows],
+// DivQuantMapColors.cpp:120-124); a stray index would be an illegal device address here, so refuse it.
+void check_sampling(uint32_t n, uint32_t rows, uint32_t cols, uint32_t dec) {
+  if (rows == 0 || cols == 0) {
+    fprintf(stderr, "divquant_b200: numRows and numCols must be positive\n");
+    abort();
+  }
+  const uint64_t last_r = ((uint64_t)(rows - 1) / dec) * dec, last_c = ((uint64_t)(cols - 1) / dec) * dec;
+  if (last_c + last_r * rows >= n) {
+    fprintf(stderr, "divquant_b200: sampling grid %u x %u (step %u) reaches beyond the %u input pixels\n", rows, cols, dec, n);
+    abort();
+  }
+}
+
+// Histogram of d_in into the table + unique list; leaves U in d_cb->ucount (device).
+void run_histogram(dq_context *ctx, const uint32_t *d_in, uint32_t n, uint32_t rows, uint32_t cols, uint32_t dec, int bits) {
+  check_sampling(n, rows, cols, dec);
+  ctx->d_uniq.ensure(n);
+  hist_insert(d_in, n, rows, cols, dec, bits, ctx->d_table, ctx->d_uniq.ptr, &ctx->d_cb->ucount, ctx->sm_count, ctx->stream);
+  ctx->stats.kernel_launches++;
+}
+
+void upload_search_tables(dq_context *ctx, const uint32_t *colortable, int k) {
+  ctx->ensure_small((size_t)k + kLutEntries + 16);
+  uint32_t *h_sorted = ctx->h_small;
+  int *h_lut = reinterpret_cast<int *>(ctx->h_small + k);
+  build_search_tables(colortable, k, h_sorted, h_lut);
+  ctx->d_sorted.ensure(k);
+  DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->d_sorted.ptr, h_sorted, (size_t)k * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->d_lut, h_lut, kLutEntries * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  // h_small is reused by later calls: the copies above must have been issued from it before then;
+  // every caller synchronises the stream before returning.
+}
+
+void remap_bruteforce(dq_context *ctx, const uint32_t *d_in, uint32_t n, uint32_t *d_out, int k) {
+  if (k > map_smem_palette_limit()) ctx->d_pal_scratch.ensure(k);
+  map_pixels(d_in, n, d_out, ctx->d_sorted.ptr, k, ctx->d_lut, ctx->d_pal_scratch.ptr, ctx->sm_count, ctx->stream);
+  ctx->stats.kernel_launches += (k > map_smem_palette_limit()) ? 2 : 1;
+  ctx->stats.remap_path = 1;
+}
+
+// Table path: requires the unique list of exactly these pixels in d_uniq / d_cb->ucount.
+void remap_through_table(dq_context *ctx, const uint32_t *d_in, uint32_t n, uint32_t *d_out, int k, uint32_t u_hint) {
+  map_unique(ctx->d_uniq.ptr, &ctx->d_cb->ucount, u_hint, ctx->d_table, ctx->d_sorted.ptr, k, ctx->d_lut, ctx->sm_count,
+             ctx->stream);
+  map_gather(d_in, n, d_out, ctx->d_table, ctx->sm_count, ctx->stream);
+  table_clear(ctx->d_uniq.ptr, &ctx->d_cb->ucount, u_hint, ctx->d_table, ctx->sm_count, ctx->stream);
+  ctx->stats.kernel_launches += 3;
+  ctx->stats.remap_path = 2;
+}
+
+double sample_norm(uint32_t rows, uint32_t cols, int dec) {
+  // norm_factor of calc_color_table (:172) == get_double_scale (:215) when rows = 1, dec = 1
+  return 1.0 / (std::ceil(rows / (double)dec) * std::ceil(cols / (double)dec));
+}
+
+void check_quant_args(uint32_t n, uint32_t k, int num_bits) {
+  if (!dq_validate_num_bits((unsigned char)num_bits)) abort();  // assert(0) in the reference (:1115-1118)
+  if (n == 0 || k == 0) {
+    fprintf(stderr, "divquant_b200: numPixels and the requested number of clusters must be positive\n");
+    abort();  // assert(num_points > 0) / assert(num_colors > 0) (:249, :266)
+  }
+}
+
+// quant_varpart_fast on device-resident pixels; keeps the unique list (when one was built) valid for
+// a following table remap.  Returns true if the histogram table is still dirty (caller must clear).
+bool quantize_device(dq_context *ctx, uint32_t n, const uint32_t *d_in, uint32_t rows, uint32_t cols, uint32_t *k_inout,
+                     uint32_t *colortable, int num_bits, int dec, int max_iters, int all_unique, dq_split_record *records,
+                     double *mean_out, uint32_t *size_out) {
+  const uint32_t K = *k_inout;
+  check_quant_args(n, K, num_bits);
+  reset_control(ctx);
+  bool table_dirty = false;
+  double norm;
+  uint32_t point_cap;
+  if (all_unique && num_bits == 8 && dec == 1) {
+    // uniform weight: every pixel is a point (DivQuantCluster.cpp:1130-1132)
+    ctx->d_pts0.ensure(n);
+    points_from_pixels(d_in, n, ctx->d_pts0.ptr, ctx->sm_count, ctx->stream);
+    ctx->stats.kernel_launches++;
+    ctx->h_cb->ucount = n;
+    DQ_CUDA_CHECK(cudaMemcpyAsync(&ctx->d_cb->ucount, &ctx->h_cb->ucount, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    norm = sample_norm(1, n, 1);
+    point_cap = n;
+  } else {
+    if (dec <= 0) {
+      fprintf(stderr, "Decimation factor ( %d ) should be positive !\n", dec);
+      abort();  // the reference dereferences the NULL it gets back (:1136); fail loudly instead
+    }
+    const uint32_t samples = ((rows + dec - 1) / dec) * ((cols + dec - 1) / dec);
+    ctx->d_pts0.ensure(samples);
+    run_histogram(ctx, d_in, n, rows, cols, (uint32_t)dec, num_bits);
+    hist_collect(ctx->d_uniq.ptr, &ctx->d_cb->ucount, samples, ctx->d_table, ctx->d_pts0.ptr, ctx->sm_count, ctx->stream);
+    ctx->stats.kernel_launches++;
+    table_dirty = true;
+    norm = sample_norm(rows, cols, dec);
+    point_cap = samples;
+  }
+  *k_inout = run_split(ctx, point_cap, norm, K, max_iters, num_bits, colortable, records, mean_out, size_out);
+  return table_dirty;
+}
+
+void quant_recurse_device_impl(dq_context *ctx, uint32_t n, const uint32_t *d_in, uint32_t *d_out, uint32_t *k_inout,
+                               uint32_t *colortable, int all_unique, double *ms_quant, double *ms_map) {
+  auto t0 = std::chrono::steady_clock::now();
+  const bool dirty = quantize_device(ctx, n, d_in, 1, n, k_inout, colortable, 8, 1, 10, all_unique, nullptr, nullptr, nullptr);
+  auto t1 = std::chrono::steady_clock::now();
+  uint32_t k = dedup_palette(colortable, *k_inout);
+  *k_inout = k;
+  ctx->stats.actual_colors = k;
+  upload_search_tables(ctx, colortable, (int)k);
+  const uint32_t U = ctx->stats.num_points;
+  if (dirty && (uint64_t)U * 2 <= n) {
+    remap_through_table(ctx, d_in, n, d_out, (int)k, U);
+  } else {
+    if (dirty) {
+      table_clear(ctx->d_uniq.ptr, &ctx->d_cb->ucount, U, ctx->d_table, ctx->sm_count, ctx->stream);
+      ctx->stats.kernel_launches++;
+    }
+    remap_bruteforce(ctx, d_in, n, d_out, (int)k);
+  }
+  DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  auto t2 = std::chrono::steady_clock::now();
+  if (ms_quant) *ms_quant = std::chrono::duration<double, std::milli>(t1 - t0).count();
+  if (ms_map) *ms_map = std::chrono::duration<double, std::milli>(t2 - t1).count();
+}
+
+std::mutex g_default_mutex;
+dq_context *g_default = nullptr;
+int g_display_timings = -1;
+
+int display_timings_default() {
+  if (g_display_timings < 0) {
+    const char *e = getenv("DIVQUANT_B200_TIMINGS");
+    g_display_timings = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_display_timings;
+}
+
+}  // namespace
+
+// =====================================================================================================
+// extern "C" layer
+// =====================================================================================================
+extern "C" {
+
+const char *dq_version(void) { return "divquant_b200 0.1 (sm_100a)"; }
+
+dq_context *dq_context_create(int device) {
+  int count = 0;
+  cudaError_t err = cudaGetDeviceCount(&count);
+  if (err != cudaSuccess || count == 0) {
+    fprintf(stderr, "divquant_b200: no CUDA device available (%s); this library has no CPU fallback\n",
+            err != cudaSuccess ? cudaGetErrorString(err) : "device count is 0");
+    abort();
+  }
+  dq_context *ctx = new dq_context();
+  if (device < 0) DQ_CUDA_CHECK(cudaGetDevice(&device));
+  ctx->device = device;
+  DQ_CUDA_CHECK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  DQ_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) {
+    fprintf(stderr, "divquant_b200: device %d (%s, sm_%d%d) is not a Blackwell sm_100a part\n", device, prop.name,
+            prop.major, prop.minor);
+    abort();
+  }
+  ctx->sm_count = prop.multiProcessorCount;
+  DQ_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  DQ_CUDA_CHECK(cudaMalloc(&ctx->d_table, (size_t)kColourBins * sizeof(uint32_t)));
+  DQ_CUDA_CHECK(cudaMemsetAsync(ctx->d_table, 0, (size_t)kColourBins * sizeof(uint32_t), ctx->stream));
+  DQ_CUDA_CHECK(cudaMalloc(&ctx->d_cb, sizeof(ControlBlock)));
+  DQ_CUDA_CHECK(cudaMallocHost(&ctx->h_cb, sizeof(ControlBlock)));
+  DQ_CUDA_CHECK(cudaMalloc(&ctx->d_lut, kLutEntries * sizeof(int)));
+  memset(&ctx->stats, 0, sizeof(ctx->stats));
+  ctx->display_timings = display_timings_default();
+  DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  return ctx;
+}
+
+void dq_context_destroy(dq_context *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  ctx->d_in.release();
+  ctx->d_out.release();
+  ctx->d_uniq.release();
+  ctx->d_pts0.release();
+  ctx->d_pts1.release();
+  ctx->d_keys.release();
+  ctx->d_nodes.release();
+  ctx->d_jobs.release();
+  ctx->d_acc.release();
+  ctx->d_ctl_i32.release();
+  ctx->d_ctl_f64.release();
+  ctx->d_palette.release();
+  ctx->d_cluster_size.release();
+  ctx->d_sorted.release();
+  ctx->d_cluster_mean.release();
+  ctx->d_records.release();
+  ctx->d_pal_scratch.release();
+  cudaFree(ctx->d_table);
+  cudaFree(ctx->d_cb);
+  cudaFree(ctx->d_lut);
+  cudaFreeHost(ctx->h_cb);
+  if (ctx->h_small) cudaFreeHost(ctx->h_small);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+dq_context *dq_default_context(void) {
+  std::lock_guard<std::mutex> lock(g_default_mutex);
+  if (!g_default) g_default = dq_context_create(-1);
+  return g_default;
+}
+
+void *dq_context_stream(dq_context *ctx) { return (void *)ctx->stream; }
+
+void dq_context_synchronize(dq_context *ctx) {
+  require_device(ctx);
+  DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}
+
+void dq_context_last_stats(const dq_context *ctx, dq_call_stats *out) { *out = ctx->stats; }
+
+void dq_set_display_timings(int enabled) {
+  g_display_timings = enabled ? 1 : 0;
+  std::lock_guard<std::mutex> lock(g_default_mutex);
+  if (g_default) g_default->display_timings = g_display_timings;
+}
+
+int dq_validate_num_bits(unsigned char num_bits) {
+  if (!(0 < num_bits && num_bits <= 8)) {
+    fprintf(stderr, "Number of bits per channel ( %d ) must be in [1,8] !\n", num_bits);
+    return 0;
+  }
+  return 1;
+}
+
+double dq_get_double_scale(const uint32_t * /*inPixels*/, uint32_t numPixels) { return sample_norm(1, numPixels, 1); }
+
+// ---- device-pointer entry points ----
+
+void dq_quant_recurse_device(dq_context *ctx, uint32_t numPixels, const uint32_t *d_in, uint32_t *d_out,
+                             uint32_t *numClustersPtr, uint32_t *outColortablePtr, int allPixelsUnique) {
+  require_device(ctx);
+  memset(&ctx->stats, 0, sizeof(ctx->stats));
+  ctx->stats.num_pixels = numPixels;
+  quant_recurse_device_impl(ctx, numPixels, d_in, d_out, numClustersPtr, outColortablePtr, allPixelsUnique, nullptr, nullptr);
+}
+
+void dq_quant_varpart_device(dq_context *ctx, uint32_t numPixels, const uint32_t *d_in, uint32_t numRows, uint32_t numCols,
+                             uint32_t *numClustersPtr, uint32_t *colortablePtr, int num_bits, int dec_factor, int max_iters,
+                             int allPixelsUnique) {
+  require_device(ctx);
+  memset(&ctx->stats, 0, sizeof(ctx->stats));
+  ctx->stats.num_pixels = numPixels;
+  const bool dirty = quantize_device(ctx, numPixels, d_in, numRows, numCols, numClustersPtr, colortablePtr, num_bits,
+                                     dec_factor, max_iters, allPixelsUnique, nullptr, nullptr, nullptr);
+  if (dirty) {
+    table_clear(ctx->d_uniq.ptr, &ctx->d_cb->ucount, ctx->stats.num_points, ctx->d_table, ctx->sm_count, ctx->stream);
+    ctx->stats.kernel_launches++;
+    DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  }
+}
+
+void dq_map_colors_device(dq_context *ctx, const uint32_t *d_in, uint32_t numPixels, uint32_t *d_out,
+                          const uint32_t *colortablePtr, int colormapSize, int prefer_table) {
+  require_device(ctx);
+  memset(&ctx->stats, 0, sizeof(ctx->stats));
+  ctx->stats.num_pixels = numPixels;
+  if (colormapSize <= 0) {
+    fprintf(stderr, "divquant_b200: map_colors_mps needs a non-empty colortable\n");
+    abort();  // assert(num_colors > 0) (:266)
+  }
+  ctx->stats.actual_colors = (uint32_t)colormapSize;
+  upload_search_tables(ctx, colortablePtr, colormapSize);
+  bool done = false;
+  if (prefer_table && numPixels >= (1u << 16)) {
+    // A histogram costs about one pass over the pixels; it pays off when few colours repeat often.
+    reset_control(ctx);
+    run_histogram(ctx, d_in, numPixels, 1, numPixels, 1, 8);
+    DQ_CUDA_CHECK(cudaMemcpyAsync(&ctx->h_cb->ucount, &ctx->d_cb->ucount, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    const uint32_t U = ctx->h_cb->ucount;
+    ctx->stats.num_points = U;
+    if ((uint64_t)U * 4 <= numPixels) {
+      remap_through_table(ctx, d_in, numPixels, d_out, colormapSize, U);
+      done = true;
+    } else {
+      table_clear(ctx->d_uniq.ptr, &ctx->d_cb->ucount, U, ctx->d_table, ctx->sm_count, ctx->stream);
+      ctx->stats.kernel_launches++;
+    }
+  }
+  if (!done) remap_bruteforce(ctx, d_in, numPixels, d_out, colormapSize);
+  DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}
+
+// ---- host-pointer entry points ----
+
+void dq_quant_recurse_ctx(dq_context *ctx, uint32_t numPixels, const uint32_t *inPixelsPtr, uint32_t *outPixelsPtr,
+                          uint32_t *numClustersPtr, uint32_t *outColortablePtr, int allPixelsUnique) {
+  require_device(ctx);
+  memset(&ctx->stats, 0, sizeof(ctx->stats));
+  ctx->stats.num_pixels = numPixels;
+  check_quant_args(numPixels, *numClustersPtr, 8);
+  ctx->d_in.ensure(numPixels);
+  ctx->d_out.ensure(numPixels);
+  DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->d_in.ptr, inPixelsPtr, (size_t)numPixels * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  double ms_quant = 0, ms_map = 0;
+  quant_recurse_device_impl(ctx, numPixels, ctx->d_in.ptr, ctx->d_out.ptr, numClustersPtr, outColortablePtr, allPixelsUnique,
+                            &ms_quant, &ms_map);
+  auto t0 = std::chrono::steady_clock::now();
+  DQ_CUDA_CHECK(cudaMemcpyAsync(outPixelsPtr, ctx->d_out.ptr, (size_t)numPixels * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  ms_map += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  if (ctx->display_timings) {
+    // the reference's two stdout lines (quant_util.cpp:62-66, 141-145), wall clock instead of clock()
+    printf("quant_varpart_fast() elapsed: %ld ms aka %0.2f s\n", (long)ms_quant, (float)((long)ms_quant / 1000.0f));
+    printf("map_colors_mps() elapsed: %ld ms aka %0.2f s\n", (long)ms_map, (float)((long)ms_map / 1000.0f));
+  }
+}
+
+void dq_quant_recurse(uint32_t numPixels, const uint32_t *inPixelsPtr, uint32_t *outPixelsPtr, uint32_t *numClustersPtr,
+                      uint32_t *outColortablePtr, int allPixelsUnique) {
+  dq_quant_recurse_ctx(dq_default_context(), numPixels, inPixelsPtr, outPixelsPtr, numClustersPtr, outColortablePtr,
+                       allPixelsUnique);
+}
+
+void dq_quant_varpart_fast(uint32_t numPixels, const uint32_t *inPixels, uint32_t * /*tmpPixels*/, uint32_t numRows,
+                           uint32_t numCols, uint32_t *numClustersPtr, uint32_t *colortablePtr, int num_bits, int dec_factor,
+                           int max_iters, int allPixelsUnique) {
+  dq_context *ctx = dq_default_context();
+  require_device(ctx);
+  ctx->d_in.ensure(numPixels);
+  DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->d_in.ptr, inPixels, (size_t)numPixels * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  dq_quant_varpart_device(ctx, numPixels, ctx->d_in.ptr, numRows, numCols, numClustersPtr, colortablePtr, num_bits, dec_factor,
+                          max_iters, allPixelsUnique);
+}
+
+void dq_map_colors_mps(const uint32_t *inPixelsPtr, uint32_t numPixels, uint32_t *outPixelsPtr, const uint32_t *colortablePtr,
+                       int colormapSize) {
+  dq_context *ctx = dq_default_context();
+  require_device(ctx);
+  if (numPixels == 0) return;
+  ctx->d_in.ensure(numPixels);
+  ctx->d_out.ensure(numPixels);
+  DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->d_in.ptr, inPixelsPtr, (size_t)numPixels * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  dq_map_colors_device(ctx, ctx->d_in.ptr, numPixels, ctx->d_out.ptr, colortablePtr, colormapSize, 1);
+  DQ_CUDA_CHECK(cudaMemcpyAsync(outPixelsPtr, ctx->d_out.ptr, (size_t)numPixels * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}
+
+void dq_cut_bits(const uint32_t *inPixels, uint32_t numPixels, uint32_t *outPixels, unsigned char num_bits_red,
+                 unsigned char num_bits_green, unsigned char num_bits_blue) {
+  if (!dq_validate_num_bits(num_bits_red) || !dq_validate_num_bits(num_bits_green) || !dq_validate_num_bits(num_bits_blue))
+    return;  // silent return after the message, like the reference (DivQuantUni.cpp:41-46)
+  if (numPixels == 0) return;
+  dq_context *ctx = dq_default_context();
+  require_device(ctx);
+  ctx->d_in.ensure(numPixels);
+  ctx->d_out.ensure(numPixels);
+  DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->d_in.ptr, inPixels, (size_t)numPixels * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  cut_bits_device(ctx->d_in.ptr, numPixels, ctx->d_out.ptr, num_bits_red, num_bits_green, num_bits_blue, ctx->sm_count, ctx->stream);
+  DQ_CUDA_CHECK(cudaMemcpyAsync(outPixels, ctx->d_out.ptr, (size_t)numPixels * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}
+
+int dq_calc_color_table(const uint32_t *inPixels, uint32_t numPixels, uint32_t *outPixels, uint32_t numRows, uint32_t numCols,
+                        int dec_factor, int *num_colors, double *weightsOut) {
+  if (dec_factor <= 0) {
+    fprintf(stderr, "Decimation factor ( %d ) should be positive !\n", dec_factor);
+    return -1;
+  }
+  dq_context *ctx = dq_default_context();
+  require_device(ctx);
+  memset(&ctx->stats, 0, sizeof(ctx->stats));
+  const uint32_t dec = (uint32_t)dec_factor;
+  const uint32_t samples = ((numRows + dec - 1) / dec) * ((numCols + dec - 1) / dec);
+  *num_colors = 0;
+  if (samples == 0) return 0;
+  ctx->d_in.ensure(numPixels);
+  ctx->d_pts0.ensure(samples);
+  DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->d_in.ptr, inPixels, (size_t)numPixels * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  reset_control(ctx);
+  check_sampling(numPixels, numRows, numCols, dec);
+  ctx->d_uniq.ensure(samples);
+  hist_insert(ctx->d_in.ptr, numPixels, numRows, numCols, dec, 8, ctx->d_table, ctx->d_uniq.ptr, &ctx->d_cb->ucount,
+              ctx->sm_count, ctx->stream);
+  hist_collect(ctx->d_uniq.ptr, &ctx->d_cb->ucount, samples, ctx->d_table, ctx->d_pts0.ptr, ctx->sm_count, ctx->stream);
+  DQ_CUDA_CHECK(cudaMemcpyAsync(&ctx->h_cb->ucount, &ctx->d_cb->ucount, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  const uint32_t U = ctx->h_cb->ucount;
+  // emission order of the reference: (bucket asc, first-seen desc) keys computed on the device
+  ctx->d_keys.ensure(U);
+  order_keys(ctx->d_in.ptr, numRows, numCols, dec, 8, ctx->d_uniq.ptr, ctx->d_pts0.ptr, U, ctx->d_table, ctx->d_keys.ptr,
+             ctx->sm_count, ctx->stream);
+  std::vector<uint64_t> keys(U);
+  std::vector<uint2> pts(U);
+  DQ_CUDA_CHECK(cudaMemcpyAsync(keys.data(), ctx->d_keys.ptr, (size_t)U * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  DQ_CUDA_CHECK(cudaMemcpyAsync(pts.data(), ctx->d_pts0.ptr, (size_t)U * sizeof(uint2), cudaMemcpyDeviceToHost, ctx->stream));
+  DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  std::vector<uint32_t> order(U);
+  for (uint32_t i = 0; i < U; ++i) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
+  const double norm = sample_norm(numRows, numCols, dec_factor);
+  for (uint32_t i = 0; i < U; ++i) {
+    outPixels[i] = pts[order[i]].x;
+    if (weightsOut) weightsOut[i] = norm * (int)pts[order[i]].y;  // (:185)
+  }
+  *num_colors = (int)U;
+  ctx->stats.num_points = U;
+  return 0;
+}
+
+// ---- test hooks ----
+
+uint32_t dq_debug_split_points(dq_context *ctx, const uint32_t *colours, const uint32_t *counts, uint32_t num_points,
+                               double norm, uint32_t num_colors, int max_iters, int num_bits, uint32_t *colortable,
+                               dq_split_record *records, double *cluster_mean, uint32_t *cluster_size) {
+  require_device(ctx);
+  memset(&ctx->stats, 0, sizeof(ctx->stats));
+  static_assert(sizeof(dq_split_record) == sizeof(SplitRecord), "record layouts must match");
+  std::vector<uint2> pts(num_points);
+  for (uint32_t i = 0; i < num_points; ++i) pts[i] = make_uint2(colours[i] & 0x00FFFFFFu, counts ? counts[i] : 1u);
+  ctx->d_pts0.ensure(num_points);
+  reset_control(ctx);
+  DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->d_pts0.ptr, pts.data(), (size_t)num_points * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->h_cb->ucount = num_points;
+  DQ_CUDA_CHECK(cudaMemcpyAsync(&ctx->d_cb->ucount, &ctx->h_cb->ucount, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  return run_split(ctx, num_points, norm, num_colors, max_iters, num_bits, colortable,
+                   reinterpret_cast<dq_split_record *>(records), cluster_mean, cluster_size);
+}
+
+uint32_t dq_debug_histogram(dq_context *ctx, const uint32_t *inPixels, uint32_t numPixels, uint32_t *colours, uint32_t *counts) {
+  require_device(ctx);
+  memset(&ctx->stats, 0, sizeof(ctx->stats));
+  if (numPixels == 0) return 0;
+  ctx->d_in.ensure(numPixels);
+  ctx->d_pts0.ensure(numPixels);
+  DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->d_in.ptr, inPixels, (size_t)numPixels * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  reset_control(ctx);
+  run_histogram(ctx, ctx->d_in.ptr, numPixels, 1, numPixels, 1, 8);
+  hist_collect(ctx->d_uniq.ptr, &ctx->d_cb->ucount, numPixels, ctx->d_table, ctx->d_pts0.ptr, ctx->sm_count, ctx->stream);
+  table_clear(ctx->d_uniq.ptr, &ctx->d_cb->ucount, numPixels, ctx->d_table, ctx->sm_count, ctx->stream);
+  DQ_CUDA_CHECK(cudaMemcpyAsync(&ctx->h_cb->ucount, &ctx->d_cb->ucount, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  const uint32_t U = ctx->h_cb->ucount;
+  std::vector<uint2> pts(U);
+  DQ_CUDA_CHECK(cudaMemcpy(pts.data(), ctx->d_pts0.ptr, (size_t)U * sizeof(uint2), cudaMemcpyDeviceToHost));
+  for (uint32_t i = 0; i < U; ++i) {
+    colours[i] = pts[i].x;
+    counts[i] = pts[i].y;
+  }
+  ctx->stats.num_points = U;
+  return U;
+}
+
+}  // extern "C"

@@ -1,0 +1,29 @@
+// dq_kernels.cuh -- host-callable launchers of the histogram and remap kernels.
+#pragma once
+
+#include "dq_common.cuh"
+
+namespace dq {
+
+// ---- dq_hist.cu ----
+void hist_insert(const uint32_t *d_in, uint32_t n, uint32_t num_rows, uint32_t num_cols, uint32_t dec, int num_bits,
+                 uint32_t *d_table, uint32_t *d_uniq, uint32_t *d_ucount, int sm_count, cudaStream_t st);
+void hist_collect(const uint32_t *d_uniq, const uint32_t *d_ucount, uint32_t u_hint, const uint32_t *d_table, uint2 *d_pts,
+                  int sm_count, cudaStream_t st);
+void table_clear(const uint32_t *d_uniq, const uint32_t *d_ucount, uint32_t u_hint, uint32_t *d_table, int sm_count,
+                 cudaStream_t st);
+void points_from_pixels(const uint32_t *d_in, uint32_t n, uint2 *d_pts, int sm_count, cudaStream_t st);
+void cut_bits_device(const uint32_t *d_in, uint32_t n, uint32_t *d_out, int rbits, int gbits, int bbits, int sm_count,
+                     cudaStream_t st);
+void order_keys(const uint32_t *d_in, uint32_t num_rows, uint32_t num_cols, uint32_t dec, int num_bits, const uint32_t *d_uniq,
+                const uint2 *d_pts, uint32_t u, uint32_t *d_table, uint64_t *d_keys, int sm_count, cudaStream_t st);
+
+// ---- dq_map.cu ----
+int map_smem_palette_limit();
+void map_pixels(const uint32_t *d_in, uint32_t n, uint32_t *d_out, const uint32_t *d_sorted, int num_colors,
+                const int *d_lut, int4 *d_pal_scratch, int sm_count, cudaStream_t st);
+void map_unique(const uint32_t *d_uniq, const uint32_t *d_ucount, uint32_t u_hint, uint32_t *d_table,
+                const uint32_t *d_sorted, int num_colors, const int *d_lut, int sm_count, cudaStream_t st);
+void map_gather(const uint32_t *d_in, uint32_t n, uint32_t *d_out, const uint32_t *d_table, int sm_count, cudaStream_t st);
+
+}  // namespace dq

@@ -1,0 +1,120 @@
+// dq_split.cuh -- data structures of the divisive (variance split + local 2-means) phase.
+//
+// Reference: DivQuantCluster<UW,MT,KM>, DivQuant/DivQuantCluster.cpp:133-1097.
+//
+// The reference performs K-1 data-dependent splits one after another.  What a split produces
+// (the two child centres, weights, variances, TSEs and point sets) is a pure function of the
+// split cluster's own points and of the (weight, mean, variance) it inherited when it was created;
+// only WHICH clusters get split, and the index each child receives, depend on the global
+// max-TSE priority (:876-887).  The device therefore keeps a binary tree of "nodes":
+//   * every round splits a batch of leaves at once (one persistent kernel, grid barriers between
+//     the 1 + max_iters dependent passes of a round);
+//   * a scalar "controller" (CTA 0) replays the reference's sequential selection over the cached
+//     split results, stalls when it needs a split that has not been computed yet, and requests the
+//     stalled leaf plus the leaves whose TSE rank is within the remaining split budget.
+// Sums over points are exact u64 integer sums of count*c (and count*c*c); the reference's scalar
+// formulas are then evaluated in IEEE double without FMA contraction, in the reference's order.
+#pragma once
+
+#include "dq_common.cuh"
+
+namespace dq {
+
+constexpr int kSplitThreads = 1024;  // one CTA per SM
+constexpr int kSplitTile = 1024;     // points per tile (unit of work distribution)
+constexpr int kSplitMaxIters = 32;   // the reference ships max_iters = 10 (quant_util.cpp:31)
+constexpr int kAccWords = 8;         // per (job, pass): cnt, sumR, sumG, sumB, npts, sumRR, sumGG, sumBB
+
+enum AccSlot { kAccCnt = 0, kAccR = 1, kAccG = 2, kAccB = 3, kAccPts = 4, kAccRR = 5, kAccGG = 6, kAccBB = 7 };
+
+// A cluster at some moment of the reference's sequence.
+struct SplitNode {
+  double tw;      // total weight            (weight[], :293)
+  double tm[3];   // componentwise mean      (mean[],   :316)
+  double tv[3];   // componentwise variance  (var[],    :322)
+  double tse;     // total squared error     (tse[],    :310)
+  double cut;     // cutting position chosen when this node was scheduled for a split
+  uint32_t begin; // its points are pts[buf][begin .. begin+size)
+  uint32_t size;  // number of unique-colour points
+  int32_t buf;
+  int32_t child;  // node id of the "old" child (the "new" child is child+1); -1 = not split yet
+  int32_t axis;   // cutting axis chosen when scheduled
+  int32_t pad;
+};
+
+// A split being computed in the current round.
+struct SplitJob {
+  double cut;
+  double tw;
+  double tm[3];
+  int32_t node;
+  int32_t axis;
+  uint32_t begin;
+  uint32_t size;
+  int32_t buf;
+  uint32_t tile0;    // first tile of this job in the round's tile numbering
+  uint32_t cur_old;  // scatter cursors of the partition pass (relative to the child segment)
+  uint32_t cur_new;
+  int32_t child0;    // node id reserved for the "old" child (child0+1 = "new" child)
+  int32_t pad;
+};
+
+// Mirrors oracle_split_record (oracle/divquant_oracle.h) so tests can compare field by field.
+struct SplitRecord {
+  int32_t new_index, old_index, cut_axis, num_points, new_size, is_last;
+  double cut_pos;
+  double total_weight, new_weight, old_weight;
+  double new_mean[3], old_mean[3];
+  double new_var[3], old_var[3];
+  double new_tse, old_tse;
+};
+
+enum CtlSlot {
+  kCtlJobs = 0,    // jobs in the current round
+  kCtlTiles = 1,   // tiles in the current round
+  kCtlDone = 2,    // 1 when the controller has finished
+  kCtlNodes = 3,   // nodes allocated so far
+  kCtlRounds = 4,  // rounds executed (diagnostics)
+  kCtlSplits = 5,  // splits computed, including speculative ones (diagnostics)
+  kCtlError = 6,   // non-zero = internal inconsistency
+  kCtlWords = 8
+};
+
+struct SplitArgs {
+  uint2 *pts[2];        // (colour 0x00RRGGBB, count) double buffer, capacity U each
+  uint32_t num_points;  // U (ignored when num_points_dev != nullptr)
+  const uint32_t *num_points_dev;  // U produced on the device by the histogram
+  uint32_t num_colors;  // requested K
+  int32_t max_iters;    // >= 1
+  int32_t shift;        // 8 - num_bits
+  double norm;          // 1 / #sampled pixels  (data_weight / norm_factor)
+  SplitNode *nodes;
+  uint32_t node_cap;
+  SplitJob *jobs;       // [2][K], double-buffered by round parity
+  uint64_t *acc;        // [2][K][max_iters+1][kAccWords]
+  uint64_t *root_acc;   // [kAccWords]
+  uint32_t *ctl;        // [kCtlWords]
+  unsigned int *barrier;
+  // controller arrays in global memory, used when they do not fit in shared memory
+  int32_t *g_cluster_node;  // [K]
+  double *g_cluster_tse;    // [K]
+  int32_t use_smem_ctl;
+  // outputs
+  uint32_t *palette;      // [K]   non-empty clusters in index order (:1030-1065)
+  uint32_t *result;       // [0] = number of clusters emitted, [1] = number of empty clusters
+  double *cluster_mean;   // [K][3]   (diagnostics / tests)
+  uint32_t *cluster_size; // [K]
+  SplitRecord *records;   // [K-1] or nullptr
+};
+
+// Launch description computed on the host.
+struct SplitLaunch {
+  int grid;
+  size_t smem_bytes;
+};
+
+SplitLaunch split_plan(int device, uint32_t num_colors);
+void split_launch(const SplitArgs &args, const SplitLaunch &plan, cudaStream_t stream);
+size_t split_acc_words(uint32_t num_colors, int max_iters);
+
+}  // namespace dq

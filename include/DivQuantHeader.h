@@ -1,0 +1,64 @@
+/* DivQuantHeader.h -- drop-in replacement for the reference's DivQuant/DivQuantHeader.h.
+ *
+ * Written from scratch for libdivquant_b200.so: it declares the same C++-linkage functions, with the
+ * same signatures, that reference callers (ClusteringSegmentation/ClusteringSegmentation.cpp, the
+ * XCTest files) include today, so that they compile and link unchanged against the B200 library.
+ * Reference declarations: DivQuant/DivQuantHeader.h:33-96.  The functions are implemented in
+ * clusteringsegmentation-1_b200/csrc/dq_compat.cpp on top of the C ABI in divquant_b200.h.
+ */
+#ifndef DivQuantHeader_h
+#define DivQuantHeader_h
+
+#include <stdint.h>
+#include <time.h>
+
+#include <vector>
+
+#define MAX_RGB (255)
+#define MAX_RGB_SQR (65025)
+#define MAX_COLORS (256)
+
+typedef unsigned char uchar;
+typedef unsigned short ushort;
+typedef unsigned int uint;
+typedef unsigned long ulong;
+
+typedef struct {
+  int red, green, blue;
+  int weight;
+} Pixel_Int;
+
+typedef struct {
+  double red, green, blue;
+  double weight;
+} Pixel_Double;
+
+/* DivQuantMisc.cpp:18-46 */
+clock_t start_timer(void);
+double stop_timer(const clock_t start);
+long timediff(clock_t t1, clock_t t2);
+int validate_num_bits(const uchar num_bits);
+
+/* DivQuantMapColors.cpp:43-51, 205-220 */
+void check_mem(const int failed);
+double get_double_scale(const uint32_t *inPixels, const uint32_t numPixels);
+
+/* DivQuantMapColors.cpp:243-539 */
+void map_colors_mps(const uint32_t *inPixelsPtr, uint32_t numPixels, uint32_t *outPixelsPtr,
+                    uint32_t *outColortablePtr, int colormapSize);
+
+/* DivQuantMapColors.cpp:82-203.  Returns new double[*num_colors]; the caller delete[]s it. */
+double *calc_color_table(const uint32_t *inPixels, const uint32_t numPixels, uint32_t *outPixels,
+                         const uint32_t numRows, const uint32_t numCols, const int dec_factor, int *num_colors);
+
+/* DivQuantUni.cpp:28-100 */
+void cut_bits(const uint32_t *inPixels, const uint32_t numPixels, uint32_t *outPixels, const uchar num_bits_red,
+              const uchar num_bits_green, const uchar num_bits_blue);
+
+/* DivQuantCluster.cpp:1099-1179 */
+void quant_varpart_fast(const uint32_t numPixels, const uint32_t *inPixels, uint32_t *tmpPixels,
+                        const uint32_t numRows, const uint32_t numCols, uint32_t *numClustersPtr,
+                        uint32_t *colortablePtr, const int num_bits, const int dec_factor, const int max_iters,
+                        const int allPixelsUnique);
+
+#endif /* DivQuantHeader_h */

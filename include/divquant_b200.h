@@ -1,0 +1,156 @@
+/* divquant_b200.h -- C ABI of the B200-native DivQuant colour quantizer (libdivquant_b200.so).
+ *
+ * This is the drop-in boundary for the ONE hot path of caomw/ClusteringSegmentation-1 that this
+ * repository accelerates: the DivQuant quantizer (24-bit colour histogram -> divisive variance split
+ * with local 2-means -> nearest-palette remap).  Every entry point is plain C: pointers and sizes,
+ * no C++ or torch types.  Each one names the reference interface it replaces (file:line under the
+ * reference root).  INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * Pixel format everywhere: uint32_t 0xAARRGGBB; alpha is ignored on input and zero on output
+ * (DivQuantMapColors.cpp:125-127, 523-527).
+ *
+ * Error behaviour follows the reference: void functions, no error codes; fatal conditions (CUDA
+ * failure, out of memory, internal inconsistency) print to stderr and abort()
+ * (check_mem, DivQuantMapColors.cpp:43-51; DivQuantCluster.cpp:1021-1026).  There is no CPU
+ * fallback: without a usable sm_100a device the library aborts with a message.
+ */
+#ifndef DIVQUANT_B200_H
+#define DIVQUANT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------------
+ * 1. Reference-signature entry points (HOST pointers, default context on the current CUDA device).
+ *    Same names as the reference with a dq_ prefix; same argument order and meaning.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Replaces  extern "C" quant_recurse        DivQuant/quant_util.h:10, quant_util.cpp:20-158.
+ * Quantize to *numClustersPtr colours (max_iters 10, 8 bits, no decimation), drop duplicate palette
+ * words (first occurrence wins), remap every pixel.  *numClustersPtr: in = requested K, out = actual.
+ * outPixelsPtr and outColortablePtr must hold numPixels and K words. */
+void dq_quant_recurse(uint32_t numPixels, const uint32_t *inPixelsPtr, uint32_t *outPixelsPtr,
+                      uint32_t *numClustersPtr, uint32_t *outColortablePtr, int allPixelsUnique);
+
+/* Replaces  quant_varpart_fast              DivQuant/DivQuantHeader.h:82-94, DivQuantCluster.cpp:1099-1179.
+ * tmpPixels (capacity numPixels) is scratch exactly as in the reference and is left unspecified. */
+void dq_quant_varpart_fast(uint32_t numPixels, const uint32_t *inPixels, uint32_t *tmpPixels, uint32_t numRows,
+                           uint32_t numCols, uint32_t *numClustersPtr, uint32_t *colortablePtr, int num_bits,
+                           int dec_factor, int max_iters, int allPixelsUnique);
+
+/* Replaces  map_colors_mps                  DivQuant/DivQuantHeader.h:61, DivQuantMapColors.cpp:243-539.
+ * The colortable is read, never written. */
+void dq_map_colors_mps(const uint32_t *inPixelsPtr, uint32_t numPixels, uint32_t *outPixelsPtr,
+                       const uint32_t *colortablePtr, int colormapSize);
+
+/* Replaces  calc_color_table                DivQuant/DivQuantHeader.h:63-70, DivQuantMapColors.cpp:82-203.
+ * The reference returns `new double[U]`; a C ABI cannot, so the caller passes weightsOut (capacity:
+ * the number of sampled pixels, ceil(numRows/dec)*ceil(numCols/dec)).  Unique colours are emitted in the
+ * reference's order (hash bucket ascending, most recently first-seen colour first inside a bucket).
+ * Returns 0, or -1 when dec_factor <= 0 (the reference prints a message and returns NULL). */
+int dq_calc_color_table(const uint32_t *inPixels, uint32_t numPixels, uint32_t *outPixels, uint32_t numRows,
+                        uint32_t numCols, int dec_factor, int *num_colors, double *weightsOut);
+
+/* Replaces  cut_bits                        DivQuant/DivQuantHeader.h:72-79, DivQuantUni.cpp:28-100.
+ * In-place (inPixels == outPixels) is allowed.  Invalid bit counts: message on stderr, no output. */
+void dq_cut_bits(const uint32_t *inPixels, uint32_t numPixels, uint32_t *outPixels, unsigned char num_bits_red,
+                 unsigned char num_bits_green, unsigned char num_bits_blue);
+
+/* Replaces  get_double_scale                DivQuant/DivQuantHeader.h:55-57, DivQuantMapColors.cpp:205-220. */
+double dq_get_double_scale(const uint32_t *inPixels, uint32_t numPixels);
+
+/* Replaces  validate_num_bits               DivQuant/DivQuantHeader.h:96, DivQuantMisc.cpp:36-46. */
+int dq_validate_num_bits(unsigned char num_bits);
+
+/* When non-zero (default 1) dq_quant_recurse prints the reference's two timing lines on stdout
+ * (quant_util.cpp:62-66, 141-145).  Also settable with DIVQUANT_B200_TIMINGS=0 in the environment. */
+void dq_set_display_timings(int enabled);
+
+/* ------------------------------------------------------------------------------------------------
+ * 2. Explicit contexts and DEVICE-pointer entry points (what a pipeline that already keeps frames in
+ *    HBM, and bench.py's device-resident leg, call).  One context = one CUDA device + one stream +
+ *    its scratch (the 64 MB direct colour table, point buffers, controller state).  A context is not
+ *    thread-safe; use one per thread/stream.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct dq_context dq_context;
+
+/* device < 0 : use the current device. Aborts on failure like every other entry point. */
+dq_context *dq_context_create(int device);
+void dq_context_destroy(dq_context *ctx);
+/* The lazily created context behind the section-1 entry points. */
+dq_context *dq_default_context(void);
+/* cudaStream_t of the context, as a void* (so that this header needs no CUDA headers). */
+void *dq_context_stream(dq_context *ctx);
+void dq_context_synchronize(dq_context *ctx);
+
+/* What the last call on a context did (for tests, bench.py and tracing). */
+typedef struct {
+  uint32_t num_pixels;
+  uint32_t num_points;       /* U: unique colours (or pixels on the allPixelsUnique path)   */
+  uint32_t requested_colors; /* K asked for                                                */
+  uint32_t actual_colors;    /* palette entries returned                                   */
+  uint32_t empty_clusters;   /* clusters dropped as empty (DivQuantCluster.cpp:1058-1069)  */
+  uint32_t split_rounds;     /* rounds of the persistent split kernel                      */
+  uint32_t splits_computed;  /* splits evaluated, speculative ones included                */
+  uint32_t remap_path;       /* 0 none, 1 brute force over pixels, 2 unique-colour table   */
+  uint32_t kernel_launches;  /* kernels launched by the call                               */
+  uint32_t reserved[7];
+} dq_call_stats;
+void dq_context_last_stats(const dq_context *ctx, dq_call_stats *out);
+
+/* quant_recurse with pixels already resident in HBM.  d_in / d_out are device pointers on the
+ * context's device; colortable and numClustersPtr are host pointers.  Synchronous with respect to
+ * the host on return (the palette has to come back for the reference's std::sort of it). */
+void dq_quant_recurse_device(dq_context *ctx, uint32_t numPixels, const uint32_t *d_in, uint32_t *d_out,
+                             uint32_t *numClustersPtr, uint32_t *outColortablePtr, int allPixelsUnique);
+
+/* map_colors_mps with pixels resident in HBM (colortable on the host). Asynchronous on the context's
+ * stream except for the small palette upload. prefer_table: 1 = histogram + per-unique-colour table
+ * when profitable, 0 = always brute force over pixels. */
+void dq_map_colors_device(dq_context *ctx, const uint32_t *d_in, uint32_t numPixels, uint32_t *d_out,
+                          const uint32_t *colortablePtr, int colormapSize, int prefer_table);
+
+/* quant_varpart_fast with pixels resident in HBM; palette returned to host memory. */
+void dq_quant_varpart_device(dq_context *ctx, uint32_t numPixels, const uint32_t *d_in, uint32_t numRows,
+                             uint32_t numCols, uint32_t *numClustersPtr, uint32_t *colortablePtr, int num_bits,
+                             int dec_factor, int max_iters, int allPixelsUnique);
+
+/* Host-pointer quant_recurse on an explicit context (what dq_quant_recurse forwards to). */
+void dq_quant_recurse_ctx(dq_context *ctx, uint32_t numPixels, const uint32_t *inPixelsPtr, uint32_t *outPixelsPtr,
+                          uint32_t *numClustersPtr, uint32_t *outColortablePtr, int allPixelsUnique);
+
+/* ------------------------------------------------------------------------------------------------
+ * 3. Test hooks (used by tests/ to compare intermediate results with the oracle).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Field-for-field mirror of oracle_split_record (oracle/divquant_oracle.h). */
+typedef struct {
+  int32_t new_index, old_index, cut_axis, num_points, new_size, is_last;
+  double cut_pos;
+  double total_weight, new_weight, old_weight;
+  double new_mean[3], old_mean[3];
+  double new_var[3], old_var[3];
+  double new_tse, old_tse;
+} dq_split_record;
+
+/* Runs only the divisive phase on caller-supplied (colour, count) points (host arrays).
+ * norm = 1/#sampled pixels.  records (capacity K-1), cluster_mean (K*3) and cluster_size (K) may be NULL.
+ * Returns the number of palette entries written to colortable (capacity K). */
+uint32_t dq_debug_split_points(dq_context *ctx, const uint32_t *colours, const uint32_t *counts, uint32_t num_points,
+                               double norm, uint32_t num_colors, int max_iters, int num_bits, uint32_t *colortable,
+                               dq_split_record *records, double *cluster_mean, uint32_t *cluster_size);
+
+/* Unique colours and counts of host pixels, in unspecified order. Returns U. Capacity numPixels each. */
+uint32_t dq_debug_histogram(dq_context *ctx, const uint32_t *inPixels, uint32_t numPixels, uint32_t *colours,
+                            uint32_t *counts);
+
+const char *dq_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIVQUANT_B200_H */

@@ -83,6 +83,8 @@ class Oracle:
         L.oracle_quant_varpart_fast.restype = C.c_int
         L.oracle_quant_varpart_fast.argtypes = [C.c_uint32, _u32p, C.c_uint32, C.c_uint32, _u32p, _u32p, C.c_int,
                                                 C.c_int, C.c_int, C.c_int, C.POINTER(SplitRecord), _i32p]
+        L.oracle_quant_varpart_fast_exact.restype = C.c_int
+        L.oracle_quant_varpart_fast_exact.argtypes = L.oracle_quant_varpart_fast.argtypes
         L.oracle_map_colors_mps.restype = None
         L.oracle_map_colors_mps.argtypes = [_u32p, C.c_uint32, _u32p, _u32p, C.c_int]
         L.oracle_map_colors_bruteforce.restype = None
@@ -119,14 +121,15 @@ class Oracle:
 
     # -- quantize -------------------------------------------------------------------------
     def quant_varpart_fast(self, pixels, k, num_bits=8, dec_factor=1, max_iters=10, all_unique=0,
-                           with_records=False):
+                           with_records=False, exact_counts=False):
         px = _u32(pixels)
         ct = np.zeros(max(k, 1), np.uint32)
         nk = C.c_uint32(k)
         recs = (SplitRecord * max(k, 1))()
         nrec = C.c_int32(0)
-        empty = self.lib.oracle_quant_varpart_fast(px.size, _ptr(px), 1, px.size, C.byref(nk), _ptr(ct), num_bits,
-                                                   dec_factor, max_iters, all_unique, recs, C.byref(nrec))
+        fn = self.lib.oracle_quant_varpart_fast_exact if exact_counts else self.lib.oracle_quant_varpart_fast
+        empty = fn(px.size, _ptr(px), 1, px.size, C.byref(nk), _ptr(ct), num_bits,
+                   dec_factor, max_iters, all_unique, recs, C.byref(nrec))
         pal = ct[:nk.value].copy()
         if with_records:
             return pal, empty, [recs[i] for i in range(nrec.value)]

@@ -132,21 +132,15 @@ namespace {
 // exact u64 accumulation per pass is the same number.  Otherwise `w[i]` are the doubles produced
 // by calc_color_table and every sum is a sequential double accumulation in point order.
 // ---------------------------------------------------------------------------------------------
-struct PassSums {
-  double mean_r, mean_g, mean_b;  // sum of w*c   (weighted)   | unused (uniform)
-  double var_r, var_g, var_b;     // sum of w*c^2 (weighted)
-  double weight;                  // sum of w     (weighted)
-  uint64_t i_r, i_g, i_b;         // integer sums (uniform)
-  uint64_t i_rr, i_gg, i_bb;
-  uint64_t count;  // number of points taken
-};
-
 struct DivisiveState {
   int num_points;
   const uint32_t *data;
   const double *w;  // nullptr when uniform
   double w_uniform;
   bool uniform;
+  // Device-arithmetic model only (oracle_quant_varpart_fast_exact): integer multiplicity of each
+  // point.  nullptr = 1, which is the reference's own uniform path.
+  const uint32_t *counts;
 };
 
 // Global weighted mean / variance of all points (:60-104).
@@ -156,12 +150,13 @@ void initial_mean_and_var(const DivisiveState &s, Vec3 *mean, Vec3 *var) {
     uint32_t p = s.data[ip];
     uint32_t R = chan_r(p), G = chan_g(p), B = chan_b(p);
     if (s.uniform) {
-      mr += R;
-      mg += G;
-      mb += B;
-      vr += (R * R);
-      vg += (G * G);
-      vb += (B * B);
+      double c = s.counts ? (double)s.counts[ip] : 1.0;  // exact integers either way
+      mr += c * R;
+      mg += c * G;
+      mb += c * B;
+      vr += c * (R * R);
+      vg += c * (G * G);
+      vb += c * (B * B);
     } else {
       double wt = s.w[ip];
       mr += wt * R;
@@ -193,22 +188,23 @@ void initial_mean_and_var(const DivisiveState &s, Vec3 *mean, Vec3 *var) {
 
 }  // namespace
 
-extern "C" int oracle_quant_varpart_fast(uint32_t num_pixels, const uint32_t *in, uint32_t num_rows,
-                                         uint32_t num_cols, uint32_t *num_clusters, uint32_t *colortable,
-                                         int num_bits, int dec_factor, int max_iters, int all_pixels_unique,
-                                         oracle_split_record *records, int *num_records) {
+static int varpart_impl(uint32_t num_pixels, const uint32_t *in, uint32_t num_rows, uint32_t num_cols,
+                        uint32_t *num_clusters, uint32_t *colortable, int num_bits, int dec_factor,
+                        int max_iters, int all_pixels_unique, oracle_split_record *records, int *num_records,
+                        bool exact_counts) {
   assert(0 < num_bits && num_bits <= 8);  // (:1115-1118)
   assert(max_iters >= 1);                 // KM is hard-wired true; 0 iterations is degenerate
   if (num_records) *num_records = 0;
 
   // ---- path selection, quant_varpart_fast :1130-1147 ----
-  std::vector<uint32_t> points;
+  std::vector<uint32_t> points, counts;
   std::vector<double> weights;
   DivisiveState s;
   if (all_pixels_unique && num_bits == 8 && dec_factor == 1) {
     s.uniform = true;
     s.w_uniform = 1.0 / (std::ceil(1 / (double)1) * std::ceil((int)num_pixels / (double)1));  // (:215)
     s.w = nullptr;
+    s.counts = nullptr;
     s.data = in;
     s.num_points = (int)num_pixels;
   } else {
@@ -221,14 +217,23 @@ extern "C" int oracle_quant_varpart_fast(uint32_t num_pixels, const uint32_t *in
     }
     points.resize(num_pixels);
     weights.resize(num_pixels);
+    counts.resize(num_pixels);
     int u = oracle_calc_color_table(src, num_pixels, num_rows, num_cols, dec_factor, points.data(),
-                                    weights.data(), nullptr);
+                                    weights.data(), counts.data());
     assert(u > 0);
     s.uniform = false;
     s.w_uniform = 0.0;
     s.w = weights.data();
+    s.counts = nullptr;
     s.data = points.data();
     s.num_points = u;
+    if (exact_counts) {
+      // Device-arithmetic model: the same scalar formulas, but every sum over points is an exact
+      // integer sum of count*c scaled once by norm = 1/#samples (what csrc/ computes on the GPU).
+      s.uniform = true;
+      s.counts = counts.data();
+      s.w_uniform = 1.0 / (std::ceil(num_rows / (double)dec_factor) * std::ceil(num_cols / (double)dec_factor));
+    }
   }
 
   const int K = (int)*num_clusters;
@@ -293,10 +298,11 @@ extern "C" int oracle_quant_varpart_fast(uint32_t num_pixels, const uint32_t *in
         double proj = (axis == 0) ? R : ((axis == 1) ? G : B);
         if (cut < proj) {
           if (s.uniform) {
-            ir += R;
-            ig += G;
-            ib += B;
-            cnt += 1;
+            uint64_t c = s.counts ? s.counts[idx] : 1u;
+            ir += c * R;
+            ig += c * G;
+            ib += c * B;
+            cnt += c;
           } else {
             double wt = s.w[idx];
             nm.r += wt * R;
@@ -313,7 +319,7 @@ extern "C" int oracle_quant_varpart_fast(uint32_t num_pixels, const uint32_t *in
         nm.r *= s.w_uniform;
         nm.g *= s.w_uniform;
         nm.b *= s.w_uniform;
-        nw = (uint32_t)cnt * s.w_uniform;
+        nw = (double)cnt * s.w_uniform;
       }
     }
     double ow = tw - nw;
@@ -335,7 +341,7 @@ extern "C" int oracle_quant_varpart_fast(uint32_t num_pixels, const uint32_t *in
       new_size = 0;
       nm = Vec3{0, 0, 0};
       nv = Vec3{0, 0, 0};
-      uint64_t ir = 0, ig = 0, ib = 0, irr = 0, igg = 0, ibb = 0;
+      uint64_t ir = 0, ig = 0, ib = 0, irr = 0, igg = 0, ibb = 0, cnt = 0;
       for (int j = 0; j < cur_n; ++j) {
         int idx = cur[j];
         uint32_t p = s.data[idx];
@@ -346,13 +352,15 @@ extern "C" int oracle_quant_varpart_fast(uint32_t num_pixels, const uint32_t *in
           if (it == last_it) member[idx] = (uint32_t)old_index;
         } else {
           if (s.uniform) {
-            ir += R;
-            ig += G;
-            ib += B;
+            uint64_t c = s.counts ? s.counts[idx] : 1u;
+            ir += c * R;
+            ig += c * G;
+            ib += c * B;
+            cnt += c;
             if (it == last_it) {
-              irr += R * R;
-              igg += G * G;
-              ibb += B * B;
+              irr += c * (R * R);
+              igg += c * (G * G);
+              ibb += c * (B * B);
             }
           } else {
             double wt = s.w[idx];
@@ -380,7 +388,7 @@ extern "C" int oracle_quant_varpart_fast(uint32_t num_pixels, const uint32_t *in
         nm.r *= s.w_uniform;
         nm.g *= s.w_uniform;
         nm.b *= s.w_uniform;
-        nw = new_size * s.w_uniform;
+        nw = (double)cnt * s.w_uniform;  // == new_size * data_weight when every count is 1 (:788)
         nv.r *= s.w_uniform;
         nv.g *= s.w_uniform;
         nv.b *= s.w_uniform;
@@ -475,6 +483,23 @@ extern "C" int oracle_quant_varpart_fast(uint32_t num_pixels, const uint32_t *in
   }
   *num_clusters = (uint32_t)(K - empty);
   return empty;
+}
+
+extern "C" int oracle_quant_varpart_fast(uint32_t num_pixels, const uint32_t *in, uint32_t num_rows,
+                                         uint32_t num_cols, uint32_t *num_clusters, uint32_t *colortable,
+                                         int num_bits, int dec_factor, int max_iters, int all_pixels_unique,
+                                         oracle_split_record *records, int *num_records) {
+  return varpart_impl(num_pixels, in, num_rows, num_cols, num_clusters, colortable, num_bits, dec_factor,
+                      max_iters, all_pixels_unique, records, num_records, false);
+}
+
+extern "C" int oracle_quant_varpart_fast_exact(uint32_t num_pixels, const uint32_t *in, uint32_t num_rows,
+                                               uint32_t num_cols, uint32_t *num_clusters,
+                                               uint32_t *colortable, int num_bits, int dec_factor,
+                                               int max_iters, int all_pixels_unique,
+                                               oracle_split_record *records, int *num_records) {
+  return varpart_impl(num_pixels, in, num_rows, num_cols, num_clusters, colortable, num_bits, dec_factor,
+                      max_iters, all_pixels_unique, records, num_records, true);
 }
 
 namespace {

@@ -44,6 +44,16 @@ int oracle_quant_varpart_fast(uint32_t num_pixels, const uint32_t *in, uint32_t 
                               int max_iters, int all_pixels_unique, oracle_split_record *records,
                               int *num_records);
 
+/* NOT the reference's arithmetic: a CPU model of the device path's arithmetic, kept here so that CPU
+ * tests can measure how far it is from the reference.  Identical control flow and scalar formulas,
+ * but in the weighted path every sum over points is the exact integer sum of count*c (and count*c*c),
+ * scaled once by 1/#samples -- i.e. the reference's own uniform-weight arithmetic applied to
+ * (colour, count) points.  Summation order therefore cannot matter. */
+int oracle_quant_varpart_fast_exact(uint32_t num_pixels, const uint32_t *in, uint32_t num_rows,
+                                    uint32_t num_cols, uint32_t *num_clusters, uint32_t *colortable,
+                                    int num_bits, int dec_factor, int max_iters, int all_pixels_unique,
+                                    oracle_split_record *records, int *num_records);
+
 /* map_colors_mps (DivQuantMapColors.cpp:243-539), restated as the reference's pruned two-way search. */
 void oracle_map_colors_mps(const uint32_t *in, uint32_t num_pixels, uint32_t *out, const uint32_t *colortable,
                            int num_colors);
