@@ -81,6 +81,8 @@ def load_library(path=LIB_PATH):
         "dq_debug_split_points": (C.c_uint32, [vp, _u32p, _u32p, C.c_uint32, C.c_double, C.c_uint32, C.c_int, C.c_int,
                                                _u32p, C.POINTER(SplitRecord), _f64p, _u32p]),
         "dq_debug_histogram": (C.c_uint32, [vp, _u32p, C.c_uint32, _u32p, _u32p]),
+        "dq_host_dedup_palette": (C.c_uint32, [_u32p, C.c_uint32]),
+        "dq_host_build_search_tables": (None, [_u32p, C.c_int, _u32p, C.POINTER(C.c_int32)]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)
@@ -94,7 +96,7 @@ EXPORTED_C_SYMBOLS = [
     "dq_get_double_scale", "dq_validate_num_bits", "dq_set_display_timings", "dq_context_create", "dq_context_destroy",
     "dq_default_context", "dq_context_stream", "dq_context_synchronize", "dq_context_last_stats",
     "dq_quant_recurse_device", "dq_map_colors_device", "dq_quant_varpart_device", "dq_quant_recurse_ctx",
-    "dq_debug_split_points", "dq_debug_histogram",
+    "dq_debug_split_points", "dq_debug_histogram", "dq_host_dedup_palette", "dq_host_build_search_tables",
 ]
 
 # The reference's own symbol names, exported for relinking the reference's callers.
@@ -162,6 +164,19 @@ class DivQuant:
         out = np.zeros_like(px)
         self.lib.dq_cut_bits(_p(px), px.size, _p(out), rbits, gbits, bbits)
         return out
+
+    # -- host-only palette handling (no device) ------------------------------------------------
+    def host_dedup_palette(self, colortable):
+        ct = _u32(colortable).copy()
+        n = self.lib.dq_host_dedup_palette(_p(ct), ct.size)
+        return ct[:n].copy()
+
+    def host_build_search_tables(self, colortable):
+        ct = _u32(colortable).copy()
+        srt = np.zeros_like(ct)
+        lut = np.zeros(766, np.int32)
+        self.lib.dq_host_build_search_tables(_p(ct), ct.size, _p(srt), lut.ctypes.data_as(C.POINTER(C.c_int32)))
+        return srt, lut
 
     # -- diagnostics ---------------------------------------------------------------------------
     def last_stats(self, ctx=None):

@@ -370,6 +370,12 @@ extern "C" {
 
 const char *dq_version(void) { return "divquant_b200 0.1 (sm_100a)"; }
 
+uint32_t dq_host_dedup_palette(uint32_t *colortable, uint32_t num_colors) { return dedup_palette(colortable, num_colors); }
+
+void dq_host_build_search_tables(const uint32_t *colortable, int num_colors, uint32_t *sorted_out, int32_t *lut_init_out) {
+  build_search_tables(colortable, num_colors, sorted_out, lut_init_out);
+}
+
 dq_context *dq_context_create(int device) {
   int count = 0;
   cudaError_t err = cudaGetDeviceCount(&count);

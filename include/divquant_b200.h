@@ -148,6 +148,14 @@ uint32_t dq_debug_split_points(dq_context *ctx, const uint32_t *colours, const u
 uint32_t dq_debug_histogram(dq_context *ctx, const uint32_t *inPixels, uint32_t numPixels, uint32_t *colours,
                             uint32_t *counts);
 
+/* Host-only pieces of the path (no device needed): the palette handling the shim does between the
+ * kernels, exposed so that CPU-only tests can check it against the oracle.
+ *   dq_host_dedup_palette       first occurrence wins, order kept (quant_util.cpp:93-118); returns the new size.
+ *   dq_host_build_search_tables sorted palette (the reference's std::sort by r+g+b) and lut_init[766]
+ *                               (DivQuantMapColors.cpp:267-383). */
+uint32_t dq_host_dedup_palette(uint32_t *colortable, uint32_t num_colors);
+void dq_host_build_search_tables(const uint32_t *colortable, int num_colors, uint32_t *sorted_out, int32_t *lut_init_out);
+
 const char *dq_version(void);
 
 #ifdef __cplusplus
