@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py -- Mpixels/s of DivQuant quantize+map (quant_recurse), K=256, 3840x2160 (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+One "step" = one whole quant_recurse (24-bit histogram -> divisive split with 10 local 2-means
+iterations -> palette dedup/sort -> remap) of one synthetic 3840x2160 frame (generator G1 of
+SURVEY.md 8d, seed 12345+frame).  N > 1: every rank owns one GPU and its own stream of frames
+(frame-sharded, no collective: weak scaling); value = all ranks' pixels / max-over-ranks device time.
+
+Printed JSON line (rank 0): see the task contract.  value = device-resident throughput (inputs in HBM,
+CUDA events on the library's stream); e2e = the same call through the host-pointer C ABI with pinned
+host buffers, H2D and D2H inside the timed region; roofline = dominant kernel against the measured
+HBM peak; cpu_baseline = the reference's own code (oracle/_ref) on one host core.
+"""
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WIDTH, HEIGHT, K = 3840, 2160, 256
+NPIX = WIDTH * HEIGHT
+RING = 6  # distinct frames resident in HBM: 6 x 33 MB = 199 MB > 126 MB of L2
+METRIC = "Mpixels/sec DivQuant quantize+map (K=256, 4K)"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms while the timed region runs (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation on the host cores
+# ------------------------------------------------------------------------------------------------
+def _ref_worker(args):
+    seed, frames = args
+    from oracle import Oracle, Reference, muted
+    o = Oracle()
+    try:
+        r = Reference()
+        kind = "reference"
+    except FileNotFoundError:
+        r, kind = o, "port"
+    done = 0
+    t0 = time.perf_counter()
+    for f in range(frames):
+        px = o.generate(1, WIDTH, HEIGHT, seed + f)
+        with muted():
+            r.quant_recurse(px, K, 0)
+        done += 1
+    return kind, done, time.perf_counter() - t0
+
+
+def cpu_reference_time(frames_per_worker, workers, pool=None):
+    """Frame-parallel over `workers` processes (the reference itself is single-threaded)."""
+    t0 = time.perf_counter()
+    if workers == 1 or pool is None:
+        res = [_ref_worker((12345, frames_per_worker))]
+    else:
+        res = pool.map(_ref_worker, [(12345 + 1000 * w, frames_per_worker) for w in range(workers)])
+    wall = time.perf_counter() - t0
+    return res[0][0], sum(r[1] for r in res), wall
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU code (oracle/_ref when it was compiled, else the oracle
+    port) on every host core, frame-parallel; one step = every worker quantizes one 4K frame."""
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    workers = os.cpu_count() or 1
+    steps, warmup = args.steps, max(args.warmup, 0)
+    pool = mp.get_context("fork").Pool(workers) if workers > 1 else None
+    for _ in range(min(warmup, 1)):
+        cpu_reference_time(1, workers, pool)
+    t0 = time.perf_counter()
+    total_frames = 0
+    kind = "reference"
+    for _ in range(steps):
+        kind, frames, _ = cpu_reference_time(1, workers, pool)
+        total_frames += frames
+    wall = time.perf_counter() - t0
+    if pool:
+        pool.close()
+    value = total_frames * NPIX / wall / 1e6
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Mpixels/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": 1e3 * wall / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64+u32", "data": "synthetic",
+            "config": {"workload": f"{WIDTH}x{HEIGHT} RGBA G1 natural-like, K={K}, quant_recurse (10 LKM iterations)",
+                       "frames_per_step": workers},
+            "cpu_baseline": {"value": value, "unit": "Mpixels/s", "cores": workers, "kind": kind,
+                             "sample": f"{workers} processes x 1 frame per step, {steps} steps, reference compiled from its own sources"},
+            "e2e": {"value": value, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import ctypes as C
+    import torch
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    pkg = importlib.import_module("clusteringsegmentation-1_b200")
+    from oracle import Oracle, Reference, muted  # input generator + cpu_baseline leg only
+
+    o = Oracle()
+    lib = pkg.load_library()
+    lib.dq_set_display_timings(0)
+    ctx = lib.dq_context_create(local_rank)
+    stream = torch.cuda.ExternalStream(lib.dq_context_stream(ctx), device=torch.device("cuda", local_rank))
+
+    # synthetic frames: rank r, ring slot s -> seed 12345 + r*RING + s
+    host_frames = [torch.from_numpy(o.generate(1, WIDTH, HEIGHT, 12345 + rank * RING + s).view(np.int32)).pin_memory()
+                   for s in range(RING)]
+    dev_frames = [f.cuda(non_blocking=False) for f in host_frames]
+    dev_out = torch.empty(NPIX, dtype=torch.int32, device="cuda")
+    host_out = torch.empty(NPIX, dtype=torch.int32).pin_memory()
+    ct = np.zeros(K, np.uint32)
+    ctp = ct.ctypes.data_as(C.POINTER(C.c_uint32))
+    nk = C.c_uint32(K)
+    stats = pkg.CallStats()
+
+    def step_device(i):
+        nk.value = K
+        lib.dq_quant_recurse_device(ctx, NPIX, dev_frames[i % RING].data_ptr(), dev_out.data_ptr(), C.byref(nk), ctp, 0)
+
+    def step_host(i):
+        nk.value = K
+        lib.dq_quant_recurse_ctx(ctx, NPIX, C.cast(host_frames[i % RING].data_ptr(), C.POINTER(C.c_uint32)),
+                                 C.cast(host_out.data_ptr(), C.POINTER(C.c_uint32)), C.byref(nk), ctp, 0)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, steps, warmup):
+        for i in range(warmup):
+            step_fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches = 0
+        e0.record(stream)
+        for i in range(steps):
+            step_fn(warmup + i)
+            lib.dq_context_last_stats(ctx, C.byref(stats))
+            launches += stats.kernel_launches
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if dist:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches
+
+    steps, warmup = args.steps, max(args.warmup, 3)
+
+    # -- parity spot check before timing anything (rank 0, one frame, against the reference build) --
+    step_device(0)
+    torch.cuda.synchronize()
+    parity = None
+    if rank == 0 and not args.skip_parity:
+        try:
+            checker, kind = Reference(), "reference"
+        except FileNotFoundError:
+            checker, kind = o, "port"
+        with muted():
+            ref_out, ref_pal = checker.quant_recurse(host_frames[0].numpy().view(np.uint32), K, 0)
+        got = dev_out.cpu().numpy().view(np.uint32)
+        parity = bool(np.array_equal(ref_pal, ct[:nk.value]) and np.array_equal(ref_out, got))
+        log(f"[bench] parity vs {kind}: {'bit-exact' if parity else 'MISMATCH'}")
+
+    # -- device-resident throughput --
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    ms_dev, launches = timed(step_device, steps, warmup)
+    clock_info = clocks.stop()
+    value = world * steps * NPIX / (ms_dev * 1e-3) / 1e6
+
+    # -- end to end through the host-pointer API (pinned buffers; H2D + D2H inside) --
+    ms_e2e, _ = timed(step_host, steps, warmup)
+    e2e_value = world * steps * NPIX / (ms_e2e * 1e-3) / 1e6
+
+    # -- per-stage device times (CUDA events inside the library) for the roofline --
+    lib.dq_context_set_profiling(ctx, 1)
+    stage_acc = np.zeros(7)
+    for i in range(steps):
+        step_device(warmup + i)
+        lib.dq_context_last_stats(ctx, C.byref(stats))
+        stage_acc += np.array(list(stats.stage_ms))
+    lib.dq_context_set_profiling(ctx, 0)
+    stage_ms = dict(zip(pkg.CallStats.STAGES, (stage_acc / steps).tolist()))
+    lib.dq_context_last_stats(ctx, C.byref(stats))
+    info = stats.as_dict()
+
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peaks()
+    # algorithmic HBM bytes per pixel of each kernel: hist_insert reads 4 B/pixel;
+    # map_gather reads 4 + writes 4 B/pixel.  The split kernel works on U << N points.
+    kernels = {
+        "hist_insert": {"ms": stage_ms["hist_insert"], "bytes": 4.0 * NPIX},
+        "split": {"ms": stage_ms["split"], "bytes": None},
+        "map_gather": {"ms": stage_ms["map_gather"], "bytes": 8.0 * NPIX},
+    }
+    for k in kernels.values():
+        k["gbs"] = (k["bytes"] / (k["ms"] * 1e-3) / 1e9) if k["bytes"] and k["ms"] > 0 else None
+    hbm_kernels = {n: k for n, k in kernels.items() if k["bytes"]}
+    dom = max(hbm_kernels, key=lambda n: hbm_kernels[n]["ms"])
+    achieved = kernels[dom]["gbs"]
+    # pipe roofline of SURVEY.md 8d for the whole step: N*K distance evaluations x 4 lane-instr
+    sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    sm_clock = (clock_info.get("sm_max_mhz") or 1965.0) * 1e6
+    t_pipe_ms = NPIX * K * 4 / (sm_count * 128 * sm_clock) * 1e3
+    ms_step = ms_dev / steps
+
+    cpu = None
+    if not args.skip_cpu:
+        frames = args.cpu_frames
+        kind, done, wall = cpu_reference_time(frames, 1)
+        cpu = {"value": done * NPIX / wall / 1e6, "unit": "Mpixels/s", "cores": 1, "kind": kind,
+               "sample": f"{done} frames of the same workload, one thread (the reference is single-threaded), {wall:.1f} s"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32+f64",
+        "data": "synthetic",
+        "config": {"workload": f"{WIDTH}x{HEIGHT} RGBA G1 natural-like, K={K}, quant_recurse (histogram + split with 10 LKM iterations + remap)",
+                   "frames_per_rank": RING, "sharding": "frames (one stream of frames per GPU, no collective)" if world > 1 else "single GPU",
+                   "l2": f"inputs rotate over {RING} distinct frames = {RING * NPIX * 4 / 1e6:.0f} MB > 126 MB L2",
+                   "remap_variant": "unique-colour table (U*K evaluations + N gathers)" if info["remap_path"] == 2 else "brute force N*K",
+                   "unique_colours": info["num_points"], "split_rounds": info["split_rounds"], "splits_computed": info["splits_computed"]},
+        "clocks": clock_info,
+        "e2e": {"value": e2e_value, "unit": "Mpixels/s", "h2d_bytes_per_step": NPIX * 4, "d2h_bytes_per_step": NPIX * 4 + K * 4 + 96,
+                "ms_per_step": ms_e2e / steps, "host_buffers": "pinned"},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak if achieved else None, "traffic": None, "peak_source": peak_src,
+                     "note": "algorithmic bytes of the dominant streaming kernel / its CUDA-event time; the split kernel is latency-bound (see stage_ms)"},
+        "pipe_roofline": {"definition": "SURVEY.md 8d: N*K distance evaluations x 4 lane-instr / (SMs x 128 lanes x SM clock)",
+                          "t_roof_ms": t_pipe_ms, "t_measured_ms": ms_step, "frac": t_pipe_ms / ms_step,
+                          "note": "remap_variant says which formulation produced the time; >1 would be an algorithmic win, not pipe efficiency"},
+        "stage_ms": stage_ms,
+        "parity": parity,
+    }
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if dist:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-frames", type=int, default=10, help="frames of the single-thread CPU baseline sample")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-parity", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    import __graft_entry__ as entry
+    if local_rank == 0:
+        entry.build()
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -38,10 +38,14 @@ class CallStats(C.Structure):
     _fields_ = [("num_pixels", C.c_uint32), ("num_points", C.c_uint32), ("requested_colors", C.c_uint32),
                 ("actual_colors", C.c_uint32), ("empty_clusters", C.c_uint32), ("split_rounds", C.c_uint32),
                 ("splits_computed", C.c_uint32), ("remap_path", C.c_uint32), ("kernel_launches", C.c_uint32),
-                ("reserved", C.c_uint32 * 7)]
+                ("stage_ms", C.c_float * 7)]
+
+    STAGES = ("hist_insert", "hist_collect", "split", "map_unique_or_bruteforce", "map_gather", "table_clear", "total")
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
+        d = {n: getattr(self, n) for n, _ in self._fields_ if n != "stage_ms"}
+        d["stage_ms"] = {s: float(self.stage_ms[i]) for i, s in enumerate(self.STAGES)}
+        return d
 
 
 def build(verbose=False):
@@ -73,6 +77,7 @@ def load_library(path=LIB_PATH):
         "dq_context_stream": (vp, [vp]),
         "dq_context_synchronize": (None, [vp]),
         "dq_context_last_stats": (None, [vp, C.POINTER(CallStats)]),
+        "dq_context_set_profiling": (None, [vp, C.c_int]),
         "dq_quant_recurse_device": (None, [vp, C.c_uint32, vp, vp, _u32p, _u32p, C.c_int]),
         "dq_map_colors_device": (None, [vp, vp, C.c_uint32, vp, _u32p, C.c_int, C.c_int]),
         "dq_quant_varpart_device": (None, [vp, C.c_uint32, vp, C.c_uint32, C.c_uint32, _u32p, _u32p, C.c_int,
@@ -94,7 +99,7 @@ def load_library(path=LIB_PATH):
 EXPORTED_C_SYMBOLS = [
     "dq_version", "dq_quant_recurse", "dq_quant_varpart_fast", "dq_map_colors_mps", "dq_calc_color_table", "dq_cut_bits",
     "dq_get_double_scale", "dq_validate_num_bits", "dq_set_display_timings", "dq_context_create", "dq_context_destroy",
-    "dq_default_context", "dq_context_stream", "dq_context_synchronize", "dq_context_last_stats",
+    "dq_default_context", "dq_context_stream", "dq_context_synchronize", "dq_context_last_stats", "dq_context_set_profiling",
     "dq_quant_recurse_device", "dq_map_colors_device", "dq_quant_varpart_device", "dq_quant_recurse_ctx",
     "dq_debug_split_points", "dq_debug_histogram", "dq_host_dedup_palette", "dq_host_build_search_tables",
 ]

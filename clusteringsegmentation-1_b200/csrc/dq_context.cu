@@ -91,6 +91,11 @@ struct dq_context {
   size_t h_small_words = 0;
   dq_call_stats stats;
   int display_timings = 1;
+  int profiling = 0;
+  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  void mark(int i) {
+    if (profiling) DQ_CUDA_CHECK(cudaEventRecord(ev[i], stream));
+  }
 
   void ensure_small(size_t words) {
     if (words <= h_small_words) return;
@@ -194,8 +199,10 @@ uint32_t run_split(dq_context *ctx, uint32_t point_capacity, double norm, uint32
   a.cluster_size = ctx->d_cluster_size.ptr;
   a.records = records_out ? ctx->d_records.ptr : nullptr;
 
-  const SplitLaunch plan = split_plan(ctx->device, K);
+  const SplitLaunch plan = split_plan(ctx->sm_count, K);
+  ctx->mark(2);
   split_launch(a, plan, ctx->stream);
+  ctx->mark(3);
   ctx->stats.kernel_launches++;
 
   ctx->ensure_small((size_t)K + 16);
@@ -258,17 +265,25 @@ void upload_search_tables(dq_context *ctx, const uint32_t *colortable, int k) {
 
 void remap_bruteforce(dq_context *ctx, const uint32_t *d_in, uint32_t n, uint32_t *d_out, int k) {
   if (k > map_smem_palette_limit()) ctx->d_pal_scratch.ensure(k);
+  ctx->mark(4);
   map_pixels(d_in, n, d_out, ctx->d_sorted.ptr, k, ctx->d_lut, ctx->d_pal_scratch.ptr, ctx->sm_count, ctx->stream);
+  ctx->mark(5);
+  ctx->mark(6);
+  ctx->mark(7);
   ctx->stats.kernel_launches += (k > map_smem_palette_limit()) ? 2 : 1;
   ctx->stats.remap_path = 1;
 }
 
 // Table path: requires the unique list of exactly these pixels in d_uniq / d_cb->ucount.
 void remap_through_table(dq_context *ctx, const uint32_t *d_in, uint32_t n, uint32_t *d_out, int k, uint32_t u_hint) {
+  ctx->mark(4);
   map_unique(ctx->d_uniq.ptr, &ctx->d_cb->ucount, u_hint, ctx->d_table, ctx->d_sorted.ptr, k, ctx->d_lut, ctx->sm_count,
              ctx->stream);
+  ctx->mark(5);
   map_gather(d_in, n, d_out, ctx->d_table, ctx->sm_count, ctx->stream);
+  ctx->mark(6);
   table_clear(ctx->d_uniq.ptr, &ctx->d_cb->ucount, u_hint, ctx->d_table, ctx->sm_count, ctx->stream);
+  ctx->mark(7);
   ctx->stats.kernel_launches += 3;
   ctx->stats.remap_path = 2;
 }
@@ -294,12 +309,14 @@ bool quantize_device(dq_context *ctx, uint32_t n, const uint32_t *d_in, uint32_t
   const uint32_t K = *k_inout;
   check_quant_args(n, K, num_bits);
   reset_control(ctx);
+  ctx->mark(0);
   bool table_dirty = false;
   double norm;
   uint32_t point_cap;
   if (all_unique && num_bits == 8 && dec == 1) {
     // uniform weight: every pixel is a point (DivQuantCluster.cpp:1130-1132)
     ctx->d_pts0.ensure(n);
+    ctx->mark(1);
     points_from_pixels(d_in, n, ctx->d_pts0.ptr, ctx->sm_count, ctx->stream);
     ctx->stats.kernel_launches++;
     ctx->h_cb->ucount = n;
@@ -314,6 +331,7 @@ bool quantize_device(dq_context *ctx, uint32_t n, const uint32_t *d_in, uint32_t
     const uint32_t samples = ((rows + dec - 1) / dec) * ((cols + dec - 1) / dec);
     ctx->d_pts0.ensure(samples);
     run_histogram(ctx, d_in, n, rows, cols, (uint32_t)dec, num_bits);
+    ctx->mark(1);
     hist_collect(ctx->d_uniq.ptr, &ctx->d_cb->ucount, samples, ctx->d_table, ctx->d_pts0.ptr, ctx->sm_count, ctx->stream);
     ctx->stats.kernel_launches++;
     table_dirty = true;
@@ -344,6 +362,20 @@ void quant_recurse_device_impl(dq_context *ctx, uint32_t n, const uint32_t *d_in
     remap_bruteforce(ctx, d_in, n, d_out, (int)k);
   }
   DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->profiling) {
+    auto span = [&](int a, int b) {
+      float ms = 0.f;
+      DQ_CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->ev[a], ctx->ev[b]));
+      return ms;
+    };
+    ctx->stats.stage_ms[0] = span(0, 1);
+    ctx->stats.stage_ms[1] = span(1, 2);
+    ctx->stats.stage_ms[2] = span(2, 3);
+    ctx->stats.stage_ms[3] = span(4, 5);
+    ctx->stats.stage_ms[4] = span(5, 6);
+    ctx->stats.stage_ms[5] = span(6, 7);
+    ctx->stats.stage_ms[6] = span(0, 7);
+  }
   auto t2 = std::chrono::steady_clock::now();
   if (ms_quant) *ms_quant = std::chrono::duration<double, std::milli>(t1 - t0).count();
   if (ms_map) *ms_map = std::chrono::duration<double, std::milli>(t2 - t1).count();
@@ -403,6 +435,7 @@ dq_context *dq_context_create(int device) {
   DQ_CUDA_CHECK(cudaMallocHost(&ctx->h_cb, sizeof(ControlBlock)));
   DQ_CUDA_CHECK(cudaMalloc(&ctx->d_lut, kLutEntries * sizeof(int)));
   memset(&ctx->stats, 0, sizeof(ctx->stats));
+  for (int i = 0; i < 8; ++i) DQ_CUDA_CHECK(cudaEventCreate(&ctx->ev[i]));
   ctx->display_timings = display_timings_default();
   DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   return ctx;
@@ -434,6 +467,7 @@ void dq_context_destroy(dq_context *ctx) {
   cudaFree(ctx->d_lut);
   cudaFreeHost(ctx->h_cb);
   if (ctx->h_small) cudaFreeHost(ctx->h_small);
+  for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->ev[i]);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -452,6 +486,8 @@ void dq_context_synchronize(dq_context *ctx) {
 }
 
 void dq_context_last_stats(const dq_context *ctx, dq_call_stats *out) { *out = ctx->stats; }
+
+void dq_context_set_profiling(dq_context *ctx, int enabled) { ctx->profiling = enabled ? 1 : 0; }
 
 void dq_set_display_timings(int enabled) {
   g_display_timings = enabled ? 1 : 0;

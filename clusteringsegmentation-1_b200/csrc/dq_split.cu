@@ -629,11 +629,9 @@ static size_t split_ctl_smem(uint32_t K, uint32_t node_cap) {
   return (size_t)K * 8 + (size_t)node_cap * 8 + (size_t)K * 4 + (size_t)node_cap * 4 + (size_t)K * 4 + 64;
 }
 
-SplitLaunch split_plan(int device, uint32_t num_colors) {
+SplitLaunch split_plan(int sm_count, uint32_t num_colors) {
   SplitLaunch plan;
-  cudaDeviceProp prop;
-  DQ_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
-  plan.grid = prop.multiProcessorCount;
+  plan.grid = sm_count;  // one persistent CTA per SM
   const uint32_t node_cap = 4 * num_colors + 8;
   size_t base = ((sizeof(CtaShared) + 15) & ~size_t(15)) + (((size_t)(num_colors + 1) * 4 + 15) & ~size_t(15));
   size_t with_ctl = base + split_ctl_smem(num_colors, node_cap);

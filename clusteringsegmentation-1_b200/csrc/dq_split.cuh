@@ -113,7 +113,7 @@ struct SplitLaunch {
   size_t smem_bytes;
 };
 
-SplitLaunch split_plan(int device, uint32_t num_colors);
+SplitLaunch split_plan(int sm_count, uint32_t num_colors);
 void split_launch(const SplitArgs &args, const SplitLaunch &plan, cudaStream_t stream);
 size_t split_acc_words(uint32_t num_colors, int max_iters);
 

@@ -98,9 +98,15 @@ typedef struct {
   uint32_t splits_computed;  /* splits evaluated, speculative ones included                */
   uint32_t remap_path;       /* 0 none, 1 brute force over pixels, 2 unique-colour table   */
   uint32_t kernel_launches;  /* kernels launched by the call                               */
-  uint32_t reserved[7];
+  /* Device time of each stage in milliseconds (CUDA events on the context's stream); only filled
+   * while profiling is enabled with dq_context_set_profiling, else 0:
+   * [0] hist_insert  [1] hist_collect / points_from_pixels  [2] split kernel
+   * [3] map_unique or brute-force map  [4] map_gather  [5] table_clear  [6] whole call */
+  float stage_ms[7];
 } dq_call_stats;
 void dq_context_last_stats(const dq_context *ctx, dq_call_stats *out);
+/* Per-stage CUDA-event timing of dq_quant_recurse_device / _ctx calls (off by default). */
+void dq_context_set_profiling(dq_context *ctx, int enabled);
 
 /* quant_recurse with pixels already resident in HBM.  d_in / d_out are device pointers on the
  * context's device; colortable and numClustersPtr are host pointers.  Synchronous with respect to
