@@ -86,6 +86,7 @@ def load_library(path=LIB_PATH):
         "dq_debug_split_points": (C.c_uint32, [vp, _u32p, _u32p, C.c_uint32, C.c_double, C.c_uint32, C.c_int, C.c_int,
                                                _u32p, C.POINTER(SplitRecord), _f64p, _u32p]),
         "dq_debug_histogram": (C.c_uint32, [vp, _u32p, C.c_uint32, _u32p, _u32p]),
+        "dq_debug_split_timeline": (C.c_uint32, [vp, C.c_int, C.POINTER(C.c_uint64), C.c_uint32]),
         "dq_host_dedup_palette": (C.c_uint32, [_u32p, C.c_uint32]),
         "dq_host_build_search_tables": (None, [_u32p, C.c_int, _u32p, C.POINTER(C.c_int32)]),
     }
@@ -101,7 +102,7 @@ EXPORTED_C_SYMBOLS = [
     "dq_get_double_scale", "dq_validate_num_bits", "dq_set_display_timings", "dq_context_create", "dq_context_destroy",
     "dq_default_context", "dq_context_stream", "dq_context_synchronize", "dq_context_last_stats", "dq_context_set_profiling",
     "dq_quant_recurse_device", "dq_map_colors_device", "dq_quant_varpart_device", "dq_quant_recurse_ctx",
-    "dq_debug_split_points", "dq_debug_histogram", "dq_host_dedup_palette", "dq_host_build_search_tables",
+    "dq_debug_split_points", "dq_debug_histogram", "dq_debug_split_timeline", "dq_host_dedup_palette", "dq_host_build_search_tables",
 ]
 
 # The reference's own symbol names, exported for relinking the reference's callers.

@@ -85,6 +85,12 @@ struct dq_context {
   DevBuf<double> d_cluster_mean;
   DevBuf<SplitRecord> d_records;
   DevBuf<int4> d_pal_scratch;
+  DevBuf<unsigned long long> d_timeline;
+  DevBuf<unsigned long long> d_slots;
+  DevBuf<uint32_t> d_cursors;
+  DevBuf<uint32_t> d_progress;
+  int split_version = 2;  // 1 = generic kernel, 2 = latency-optimised kernel (falls back to 1 when it cannot run)
+  int trace_split = 0;
   int *d_lut = nullptr;
   // pinned staging for the palette-sized transfers
   uint32_t *h_small = nullptr;
@@ -198,10 +204,31 @@ uint32_t run_split(dq_context *ctx, uint32_t point_capacity, double norm, uint32
   a.cluster_mean = ctx->d_cluster_mean.ptr;
   a.cluster_size = ctx->d_cluster_size.ptr;
   a.records = records_out ? ctx->d_records.ptr : nullptr;
+  if (ctx->trace_split) {
+    ctx->d_timeline.ensure(8192);
+    DQ_CUDA_CHECK(cudaMemsetAsync(ctx->d_timeline.ptr, 0, sizeof(unsigned long long), ctx->stream));
+    a.timeline = ctx->d_timeline.ptr;
+    a.timeline_cap = 8192;
+  }
 
-  const SplitLaunch plan = split_plan(ctx->sm_count, K);
+  const bool use_v2 = ctx->split_version == 2 && K <= kSplit2MaxColors;
   ctx->mark(2);
-  split_launch(a, plan, ctx->stream);
+  if (use_v2) {
+    Split2Extra x;
+    const size_t slot_cap = split2_slot_capacity(point_capacity, K, ctx->sm_count);
+    ctx->d_slots.ensure(2 * slot_cap * kAccWords);
+    ctx->d_cursors.ensure((size_t)4 * K);
+    ctx->d_nodes.ensure((size_t)8 * K + 16);
+    a.nodes = ctx->d_nodes.ptr;
+    x.slots = ctx->d_slots.ptr;
+    x.slot_cap = (uint32_t)slot_cap;
+    x.cursors = ctx->d_cursors.ptr;
+    ctx->d_progress.ensure(1024);
+    x.progress = ctx->d_progress.ptr;
+    split2_launch(a, x, split2_plan(ctx->sm_count, K), ctx->stream);
+  } else {
+    split_launch(a, split_plan(ctx->sm_count, K), ctx->stream);
+  }
   ctx->mark(3);
   ctx->stats.kernel_launches++;
 
@@ -210,7 +237,16 @@ uint32_t run_split(dq_context *ctx, uint32_t point_capacity, double norm, uint32
   DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->h_cb, ctx->d_cb, sizeof(ControlBlock), cudaMemcpyDeviceToHost, ctx->stream));
   DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   if (ctx->h_cb->ctl[kCtlError] != 0) {
-    fprintf(stderr, "divquant_b200: split controller ran out of node slots (internal error)\n");
+    fprintf(stderr, "divquant_b200: split controller failed (code %u, kernel v%d, detail %u/%u/%u, barrier counter %u; internal error)\n",
+            ctx->h_cb->ctl[kCtlError], use_v2 ? 2 : 1, ctx->h_cb->ctl[kCtlWords - 1], ctx->h_cb->ctl[kCtlJobs],
+            ctx->h_cb->ctl[kCtlTiles], ctx->h_cb->ctl[kCtlNodes]);
+    if (use_v2) {
+      std::vector<uint32_t> prog(ctx->sm_count);
+      cudaMemcpy(prog.data(), ctx->d_progress.ptr, prog.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "  last stage per CTA:");
+      for (size_t i = 0; i < prog.size(); ++i) fprintf(stderr, " %u", prog[i]);
+      fprintf(stderr, "\n");
+    }
     abort();
   }
   const uint32_t actual = ctx->h_cb->result[0], empty = ctx->h_cb->result[1];
@@ -437,6 +473,7 @@ dq_context *dq_context_create(int device) {
   memset(&ctx->stats, 0, sizeof(ctx->stats));
   for (int i = 0; i < 8; ++i) DQ_CUDA_CHECK(cudaEventCreate(&ctx->ev[i]));
   ctx->display_timings = display_timings_default();
+  if (const char *e = getenv("DIVQUANT_B200_SPLIT")) ctx->split_version = (e[0] == '1') ? 1 : 2;
   DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   return ctx;
 }
@@ -462,6 +499,10 @@ void dq_context_destroy(dq_context *ctx) {
   ctx->d_cluster_mean.release();
   ctx->d_records.release();
   ctx->d_pal_scratch.release();
+  ctx->d_timeline.release();
+  ctx->d_slots.release();
+  ctx->d_cursors.release();
+  ctx->d_progress.release();
   cudaFree(ctx->d_table);
   cudaFree(ctx->d_cb);
   cudaFree(ctx->d_lut);
@@ -680,6 +721,17 @@ int dq_calc_color_table(const uint32_t *inPixels, uint32_t numPixels, uint32_t *
 }
 
 // ---- test hooks ----
+
+uint32_t dq_debug_split_timeline(dq_context *ctx, int enable, uint64_t *pairs_out, uint32_t capacity_pairs) {
+  require_device(ctx);
+  ctx->trace_split = enable ? 1 : 0;
+  if (!pairs_out || !ctx->d_timeline.ptr) return 0;
+  unsigned long long n = 0;
+  DQ_CUDA_CHECK(cudaMemcpy(&n, ctx->d_timeline.ptr, sizeof(n), cudaMemcpyDeviceToHost));
+  if (n > capacity_pairs) n = capacity_pairs;
+  DQ_CUDA_CHECK(cudaMemcpy(pairs_out, ctx->d_timeline.ptr + 1, (size_t)n * 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return (uint32_t)n;
+}
 
 uint32_t dq_debug_split_points(dq_context *ctx, const uint32_t *colours, const uint32_t *counts, uint32_t num_points,
                                double norm, uint32_t num_colors, int max_iters, int num_bits, uint32_t *colortable,

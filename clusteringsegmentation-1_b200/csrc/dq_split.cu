@@ -12,40 +12,12 @@
 // [, count*R^2, count*G^2, count*B^2]} with warp shuffles + one global atomic per CTA and word; the
 // parameters of the next pass are re-derived from those sums by every CTA that needs them, so a
 // pass costs exactly one grid barrier.
-#include "dq_split.cuh"
+#include "dq_split_math.cuh"
 
 #include <cfloat>
 
 namespace dq {
 namespace {
-
-struct Means {
-  double nw, ow;
-  double nm[3], om[3];
-};
-
-// new/old weights and centres from the integer sums of a pass
-// (:561-581 after the split pass, :780-810 after an LKM iteration; uniform-weight form).
-__device__ __forceinline__ void derive_means(double tw, const double *tm, double norm, uint64_t cnt,
-                                             uint64_t sr, uint64_t sg, uint64_t sb, Means &m) {
-  m.nw = fmul(__ull2double_rn(cnt), norm);
-  m.nm[0] = fdiv(fmul(__ull2double_rn(sr), norm), m.nw);
-  m.nm[1] = fdiv(fmul(__ull2double_rn(sg), norm), m.nw);
-  m.nm[2] = fdiv(fmul(__ull2double_rn(sb), norm), m.nw);
-  m.ow = fsub(tw, m.nw);
-#pragma unroll
-  for (int c = 0; c < 3; ++c) m.om[c] = fdiv(fsub(fmul(tw, tm[c]), fmul(m.nw, m.nm[c])), m.ow);
-}
-
-// What every thread needs to classify a point in the current pass.
-struct PassParams {
-  double a;     // pass 0: cut position; later: lhs (:616-619)
-  double r[3];  // rhs = old_mean - new_mean (:621-623)
-  int32_t axis;
-  int32_t buf;
-  uint32_t begin;
-  uint32_t size;
-};
 
 struct CtaShared {
   uint64_t red[32][kAccWords];
@@ -60,16 +32,6 @@ struct CtaShared {
   int32_t njobs, ncand, budget, scan_carry;
   int32_t warp_tmp[32];
 };
-
-__device__ __forceinline__ bool goes_new(const PassParams &pp, bool split_pass, uint32_t colour) {
-  const uint32_t R = (colour >> 16) & 0xFFu, G = (colour >> 8) & 0xFFu, B = colour & 0xFFu;
-  if (split_pass) {
-    const uint32_t ch = (pp.axis == 0) ? R : ((pp.axis == 1) ? G : B);
-    return pp.a < (double)ch;  // (:473)
-  }
-  const double dot = fadd(fadd(fmul(pp.r[0], (double)R), fmul(pp.r[1], (double)G)), fmul(pp.r[2], (double)B));
-  return !(pp.a < dot);  // (:683) -- false on NaN, exactly like the reference's else branch
-}
 
 // Block-wide sum of `words` u64 values per thread, result added atomically to dst[0..words).
 template <int WORDS>
@@ -135,6 +97,17 @@ struct CtlArrays {
   uint32_t *tiles;        // [K+1]  scratch: tiles per job -> tile0
 };
 
+__device__ __forceinline__ void trace(const SplitArgs &A, int tag, int arg) {
+  if (A.timeline != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+    const unsigned long long n = A.timeline[0];
+    if (2 * n + 3 < A.timeline_cap) {
+      A.timeline[1 + 2 * n] = ((unsigned long long)tag << 32) | (unsigned)arg;
+      A.timeline[2 + 2 * n] = clock64();
+      A.timeline[0] = n + 1;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Controller, executed by CTA 0 between rounds.
 // ---------------------------------------------------------------------------------------------
@@ -163,7 +136,7 @@ __device__ void controller(const SplitArgs &A, CtaShared &S, const CtlArrays &C,
       root.buf = 0;
       root.child = -1;
       root.axis = 0;
-      root.pad = 0;
+      root.parent = -1;
       A.nodes[0] = root;
       C.node_child[0] = -1;
       C.node_tse[0] = 0.0;
@@ -205,7 +178,7 @@ __device__ void controller(const SplitArgs &A, CtaShared &S, const CtlArrays &C,
       n.tse = tse_n;
       o.cut = n.cut = 0.0;
       o.axis = n.axis = 0;
-      o.pad = n.pad = 0;
+      o.parent = n.parent = job.node;
       o.child = n.child = -1;
       o.buf = n.buf = job.buf ^ 1;
       const uint32_t size_new = (uint32_t)npts;
@@ -224,6 +197,7 @@ __device__ void controller(const SplitArgs &A, CtaShared &S, const CtlArrays &C,
     }
   }
   __syncthreads();
+  trace(A, kTracePhaseA, S.prev_jobs);
 
   // ---- phase B: replay the reference's sequential selection over the cached splits ----
   if (tid < 32) {
@@ -301,6 +275,7 @@ __device__ void controller(const SplitArgs &A, CtaShared &S, const CtlArrays &C,
   __syncthreads();
 
   const int new_index = S.new_index, old_index = S.old_index;
+  trace(A, kTracePhaseB, new_index);
   if (new_index >= K) {
     // ---- finished: palette = rounded means of non-empty clusters in index order (:1030-1065) ----
     if (tid == 0) S.scan_carry = 0;
@@ -440,6 +415,7 @@ __device__ void controller(const SplitArgs &A, CtaShared &S, const CtlArrays &C,
     if ((uint32_t)S.node_count > A.node_cap) A.ctl[kCtlError] = 1;
   }
   __syncthreads();
+  trace(A, kTracePhaseC, njobs);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -501,10 +477,13 @@ __global__ void __launch_bounds__(kSplitThreads, 1) split_kernel(const SplitArgs
       A.acc[i] = 0;
   }
   grid_barrier(A.barrier, bar_target);
+  trace(A, kTraceRoot, 0);
 
   for (int round = 0;; ++round) {
+    trace(A, kTraceRoundBegin, round);
     if (blockIdx.x == 0) controller(A, S, C, round);
     grid_barrier(A.barrier, bar_target);
+    trace(A, kTraceCtlBarrier, round);
     if (ld_cg_u32(A.ctl + kCtlDone) != 0 || ld_cg_u32(A.ctl + kCtlError) != 0) break;
     const int par = round & 1;
     const int njobs = (int)ld_cg_u32(A.ctl + kCtlJobs);
@@ -615,6 +594,7 @@ __global__ void __launch_bounds__(kSplitThreads, 1) split_kernel(const SplitArgs
         }
       }
       if (!partition) grid_barrier(A.barrier, bar_target);
+      trace(A, partition ? kTracePartition : kTracePass, pass);
     }
   }
 }

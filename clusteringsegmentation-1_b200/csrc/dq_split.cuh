@@ -39,7 +39,7 @@ struct SplitNode {
   int32_t buf;
   int32_t child;  // node id of the "old" child (the "new" child is child+1); -1 = not split yet
   int32_t axis;   // cutting axis chosen when scheduled
-  int32_t pad;
+  int32_t parent; // node this one was split from (-1 for the root)
 };
 
 // A split being computed in the current round.
@@ -68,6 +68,9 @@ struct SplitRecord {
   double new_var[3], old_var[3];
   double new_tse, old_tse;
 };
+
+// timeline tags
+enum TraceTag { kTraceRoundBegin = 1, kTracePhaseA = 2, kTracePhaseB = 3, kTracePhaseC = 4, kTraceCtlBarrier = 5, kTracePass = 6, kTracePartition = 7, kTraceRoot = 8 };
 
 enum CtlSlot {
   kCtlJobs = 0,    // jobs in the current round
@@ -105,6 +108,9 @@ struct SplitArgs {
   double *cluster_mean;   // [K][3]   (diagnostics / tests)
   uint32_t *cluster_size; // [K]
   SplitRecord *records;   // [K-1] or nullptr
+  // optional trace: CTA 0 appends (tag, SM clock) pairs; [0] = number of pairs (tracing aid, see tools/)
+  unsigned long long *timeline;
+  uint32_t timeline_cap;
 };
 
 // Launch description computed on the host.
@@ -113,8 +119,22 @@ struct SplitLaunch {
   size_t smem_bytes;
 };
 
+// v1: generic kernel (any K; controller on CTA 0, one grid barrier per pass)
 SplitLaunch split_plan(int sm_count, uint32_t num_colors);
 void split_launch(const SplitArgs &args, const SplitLaunch &plan, cudaStream_t stream);
 size_t split_acc_words(uint32_t num_colors, int max_iters);
+
+// v2: latency-optimised kernel (K <= kSplit2MaxColors): replicated controller, CTA-local narrow jobs,
+// tag-in-data exchange of partial sums for wide jobs.  See dq_split2.cu.
+constexpr uint32_t kSplit2MaxColors = 512;
+struct Split2Extra {
+  unsigned long long *slots;  // [2][slot_cap][kAccWords] tagged words, zeroed by the kernel
+  uint32_t slot_cap;
+  uint32_t *cursors;          // [2][K][2] scatter cursors of wide jobs
+  uint32_t *progress;         // [grid] last stage each CTA reached (diagnostics of an expired wait)
+};
+size_t split2_slot_capacity(uint32_t point_capacity, uint32_t num_colors, int sm_count);
+SplitLaunch split2_plan(int sm_count, uint32_t num_colors);
+void split2_launch(const SplitArgs &args, const Split2Extra &extra, const SplitLaunch &plan, cudaStream_t stream);
 
 }  // namespace dq

@@ -1,0 +1,1115 @@
+// dq_split2.cu -- latency-optimised divisive phase (K <= kSplit2MaxColors), one persistent
+// cooperative sm_100a kernel.
+//
+// Reference: DivQuantCluster, DivQuant/DivQuantCluster.cpp:133-1097 (same formulation as dq_split.cu:
+// a tree of speculatively computed splits + an exact replay of the reference's max-TSE sequence).
+// What is different from the generic kernel is how the dependency chain is kept short:
+//
+//  * Replicated controller.  Every CTA keeps the whole controller state (TSE, child, size, parent of
+//    every node) in its own shared memory and takes the same decisions from the same data, so a round
+//    needs ONE grid barrier and no broadcast.
+//  * Threshold policy instead of a sequential replay per round.  The reference pops the max-TSE leaf
+//    K-1 times; since a child's TSE is below its parent's, the popped set is the K-1 largest TSEs of
+//    the tree.  A leaf is therefore worth splitting only while fewer than K-1 known nodes have a larger
+//    TSE -- a fully parallel test.  The exact sequence (cluster numbering, DBL_MIN / stale-index quirks)
+//    is reconstructed once at the end: in parallel when the TSE order is strict (verified), otherwise
+//    by the reference's sequential scan, replicated in every CTA (which may request more splits).
+//  * Narrow jobs (<= 4096 points) run entirely inside one CTA: points live in registers for all
+//    1 + max_iters passes, reductions are warp shuffles + shared memory, no global traffic.
+//  * Wide jobs span many CTAs.  Partial sums are exchanged through per-(job, CTA) slots of 8-byte
+//    words that carry their own 16-bit pass tag next to the 48-bit value, so publishing is a plain
+//    store and gathering is one polling L2 read: no atomics, no fences, no barrier per pass.
+#include <cfloat>
+
+#include "dq_split_math.cuh"
+
+namespace dq {
+namespace {
+
+constexpr int kWarps = 16;
+constexpr int T = 32 * kWarps;  // 16 warps, up to 128 registers per thread: points stay in registers without spills
+constexpr uint32_t kWideTile = 1024;  // points per wide tile
+constexpr int kWidePPT = 4;           // points per thread when a CTA classifies its share of a wide job
+constexpr int kNarrowPPT = 8;         // points per thread of a narrow job (kept in registers for all passes)
+constexpr uint32_t kNarrowMax = kNarrowPPT * T;
+constexpr int kWideCache = 4;         // wide jobs whose constants a CTA keeps in shared memory
+constexpr unsigned long long kValueMask = (1ull << 48) - 1ull;
+
+struct JobConst {
+  double tw, tm[3], cut;
+  int32_t axis, buf;
+  uint32_t begin, size;
+};
+
+struct Shared2 {
+  uint64_t red[32][kAccWords];
+  uint64_t tot[kAccWords];
+  PassParams pp;
+  SplitNode root;
+  SplitNode cur;  // node being split by a narrow job / finalised by an owner
+  JobConst wide[kWideCache];
+  int32_t n_nodes, n_prev, njobs, prev_njobs;
+  int32_t nwide_tiles, n_mywide, n_mynarrow;
+  int32_t mode;  // 0 = threshold policy, 1 = replicated sequential replay
+  int32_t done, bad;
+  int32_t new_index, old_index;
+  int32_t scan_carry;
+  int32_t warp_tmp[32];
+  uint32_t cur_old, cur_new;
+  uint32_t num_points;
+};
+
+struct Arrays {
+  double *tse;         // [cap]
+  int32_t *child;      // [cap]
+  uint32_t *size;      // [cap]
+  int32_t *parent;     // [cap]
+  int32_t *jobnode;    // [K]
+  uint32_t *tile0;     // [K+1] wide-tile prefix
+  uint32_t *slot0;     // [K+1] slot prefix
+  uint32_t *nidx;      // [K+1] narrow ordinal prefix
+  uint16_t *mywide;    // [K]
+  uint16_t *mynarrow;  // [K]
+  int32_t *cnode;      // [K]   cluster -> node (final assignment / sequential replay)
+  double *ctse;        // [K]
+  int32_t *cand;       // [K]
+  int32_t *rank;       // [cap]  number of known nodes with a larger TSE (final assignment)
+};
+
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int *p) {
+  unsigned int v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Every wait on another CTA is bounded: a persistent spinning kernel must never be able to wedge the
+// device.  After kSpinCycles without progress the waiter records where it was stuck in ctl[] and
+// raises ctl[kCtlError]; every other waiter sees the flag and leaves too, and the host reports it.
+constexpr long long kSpinCycles = 400000000ll;  // ~0.2 s at 1.9 GHz; a healthy wait is microseconds
+
+__device__ __forceinline__ bool spin_expired(const SplitArgs &A, long long t0, unsigned &polls, int what, int arg) {
+  if ((++polls & 1023u) != 0) return false;
+  if (ld_relaxed_u32(A.ctl + kCtlError) != 0) return true;
+  if (clock64() - t0 > kSpinCycles) {
+    if (atomicCAS(A.ctl + kCtlError, 0u, 3u) == 0u) {
+      A.ctl[kCtlWords - 1] = (uint32_t)what;
+      A.ctl[kCtlJobs] = (uint32_t)arg;
+      A.ctl[kCtlTiles] = blockIdx.x;
+      A.ctl[kCtlNodes] = ld_relaxed_u32(A.barrier);
+    }
+    return true;
+  }
+  return false;
+}
+
+#define DQ_PROGRESS(code) \
+  do {                     \
+    if (threadIdx.x == 0) X.progress[blockIdx.x] = (uint32_t)(code); \
+  } while (0)
+
+// CTA-uniform view of the error flag.
+__device__ __forceinline__ bool cta_error(const SplitArgs &A, Shared2 &S) {
+  __syncthreads();
+  if (threadIdx.x == 0) S.bad = (int32_t)ld_relaxed_u32(A.ctl + kCtlError);
+  __syncthreads();
+  const bool e = S.bad != 0;
+  __syncthreads();
+  return e;
+}
+
+// Grid barrier: relaxed polling (no L1 invalidation per poll), one fence on each side.
+__device__ __forceinline__ void grid_barrier2(const SplitArgs &A, unsigned int &target, uint32_t *progress = nullptr) {
+  unsigned int *counter = A.barrier;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += gridDim.x;
+    if (progress) progress[blockIdx.x] = 900000u + target;
+    __threadfence();
+    atomicAdd(counter, 1u);
+    const long long t0 = clock64();
+    unsigned polls = 0;
+    while (ld_relaxed_u32(counter) < target) {
+      if (spin_expired(A, t0, polls, 1, (int)target)) break;
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void trace2(const SplitArgs &A, int tag, int arg) {
+  if (A.timeline != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+    const unsigned long long n = A.timeline[0];
+    if (2 * n + 3 < A.timeline_cap) {
+      A.timeline[1 + 2 * n] = ((unsigned long long)tag << 32) | (unsigned)arg;
+      A.timeline[2 + 2 * n] = clock64();
+      A.timeline[0] = n + 1;
+    }
+  }
+}
+
+// ---- block-level helpers ----------------------------------------------------------------------------
+
+// Warp sum of values below 2^50 with the REDUX unit: three 16/16/18-bit limbs, upper limbs skipped
+// when the whole warp has none (2 cycles per REDUX per SM against 10 shuffles for a 64-bit butterfly).
+__device__ __forceinline__ uint64_t warp_sum_limbs(uint64_t v) {
+  uint64_t s = __reduce_add_sync(0xffffffffu, (unsigned)(v & 0xFFFFu));
+  if (__any_sync(0xffffffffu, (v >> 16) != 0)) {
+    s += (uint64_t)__reduce_add_sync(0xffffffffu, (unsigned)((v >> 16) & 0xFFFFu)) << 16;
+    if (__any_sync(0xffffffffu, (v >> 32) != 0)) s += (uint64_t)__reduce_add_sync(0xffffffffu, (unsigned)(v >> 32)) << 32;
+  }
+  return s;
+}
+
+// Sum of v[0..WORDS) over the first `warps` warps of the CTA into S.tot (visible to all threads on
+// return).  Threads of the other warps must pass zeros or simply not matter: they are not read.
+template <int WORDS>
+__device__ __forceinline__ void block_total(Shared2 &S, const uint64_t (&v)[kAccWords], int warps = kWarps) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp < warps) {
+#pragma unroll
+    for (int w = 0; w < WORDS; ++w) {
+      const uint64_t s = warp_sum_limbs(v[w]);
+      if (lane == 0) S.red[warp][w] = s;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < WORDS * 32) {
+    const int w = threadIdx.x >> 5;
+    const uint64_t s = warp_sum_u64(lane < warps ? S.red[lane][w] : 0ull);
+    if (lane == 0) S.tot[w] = s;
+  }
+  __syncthreads();
+}
+
+// In-place exclusive scan of a[0..n) in shared memory; total left in S.scan_carry.
+__device__ void block_scan(Shared2 &S, uint32_t *a, int n) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per = (n + T - 1) / T;
+  const int lo = min(tid * per, n), hi = min(lo + per, n);
+  uint32_t sum = 0;
+  for (int i = lo; i < hi; ++i) sum += a[i];
+  uint32_t incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) S.warp_tmp[warp] = (int32_t)incl;
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t w = lane < kWarps ? (uint32_t)S.warp_tmp[lane] : 0u;
+    uint32_t wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += t;
+    }
+    S.warp_tmp[lane] = (int32_t)(wi - w);
+    if (lane == 31) S.scan_carry = (int32_t)wi;
+  }
+  __syncthreads();
+  uint32_t run = (uint32_t)S.warp_tmp[warp] + (incl - sum);
+  for (int i = lo; i < hi; ++i) {
+    const uint32_t t = a[i];
+    a[i] = run;
+    run += t;
+  }
+  __syncthreads();
+}
+
+// Appends, in ascending order, every i in [lo, hi) with pred(i) to out[*count..]; all threads call.
+template <typename Pred, typename Out>
+__device__ void ordered_compact(Shared2 &S, int lo, int hi, Pred pred, Out out, int32_t *count) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int base = lo; base < hi; base += T) {
+    const int i = base + tid;
+    const bool p = (i < hi) && pred(i);
+    const unsigned ballot = __ballot_sync(0xffffffffu, p);
+    if (lane == 0) S.warp_tmp[warp] = __popc(ballot);
+    __syncthreads();
+    // every warp scans the 32 warp counts itself (one shuffle ladder, no extra barrier)
+    const int mine = lane < kWarps ? S.warp_tmp[lane] : 0;
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    const int before = *count + __shfl_sync(0xffffffffu, incl - mine, warp);
+    if (p) out(before + __popc(ballot & ((1u << lane) - 1u)), i);
+    __syncthreads();
+    if (tid == 0) *count += total;
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ SplitNode load_node(const SplitArgs &A, const Shared2 &S, int id) {
+  if (id == 0) return S.root;
+  SplitNode nd;
+  const double *src = reinterpret_cast<const double *>(A.nodes + id);
+  double *dst = reinterpret_cast<double *>(&nd);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(SplitNode) / 8); ++i) dst[i] = __ldcg(src + i);
+  return nd;
+}
+
+// Classification parameters of the next pass from the totals in S.tot, computed by warp 0
+// (one lane per channel), left in S.pp.  Caller synchronises afterwards.
+__device__ __forceinline__ void derive_params_warp0(Shared2 &S, const JobConst &jc, double norm) {
+  if (threadIdx.x < 32) {
+    const int c = min((int)threadIdx.x, 2);
+    const double nw = fmul(__ull2double_rn(S.tot[kAccCnt]), norm);
+    const double nm = fdiv(fmul(__ull2double_rn(S.tot[kAccR + c]), norm), nw);
+    const double ow = fsub(jc.tw, nw);
+    const double om = fdiv(fsub(fmul(jc.tw, jc.tm[c]), fmul(nw, nm)), ow);
+    const double a = fsq(om), b = fsq(nm);
+    const double a1 = __shfl_sync(0xffffffffu, a, 1), b1 = __shfl_sync(0xffffffffu, b, 1);
+    const double a2 = __shfl_sync(0xffffffffu, a, 2), b2 = __shfl_sync(0xffffffffu, b, 2);
+    if (threadIdx.x < 3) S.pp.r[c] = fsub(om, nm);
+    if (threadIdx.x == 0) {
+      double l = fsub(a, b);  // (:616-619), left to right
+      l = fadd(l, a1);
+      l = fsub(l, b1);
+      l = fadd(l, a2);
+      l = fsub(l, b2);
+      S.pp.a = fmul(0.5, l);
+      S.pp.axis = jc.axis;
+      S.pp.buf = jc.buf;
+      S.pp.begin = jc.begin;
+      S.pp.size = jc.size;
+    }
+  }
+}
+
+__device__ __forceinline__ void set_split_params(Shared2 &S, const JobConst &jc) {
+  if (threadIdx.x == 0) {
+    S.pp.a = jc.cut;
+    S.pp.r[0] = S.pp.r[1] = S.pp.r[2] = 0.0;
+    S.pp.axis = jc.axis;
+    S.pp.buf = jc.buf;
+    S.pp.begin = jc.begin;
+    S.pp.size = jc.size;
+  }
+}
+
+__device__ __forceinline__ JobConst job_const_of(const SplitNode &nd) {
+  JobConst jc;
+  jc.tw = nd.tw;
+  jc.tm[0] = nd.tm[0], jc.tm[1] = nd.tm[1], jc.tm[2] = nd.tm[2];
+  choose_cut(nd.tv, nd.tm, jc.axis, jc.cut);
+  jc.buf = nd.buf;
+  jc.begin = nd.begin;
+  jc.size = nd.size;
+  return jc;
+}
+
+__device__ __forceinline__ void add_point(uint64_t (&v)[kAccWords], uint2 p, bool with_squares) {
+  const uint64_t cnt = p.y, R = (p.x >> 16) & 0xFFu, G = (p.x >> 8) & 0xFFu, B = p.x & 0xFFu;
+  v[kAccCnt] += cnt;
+  v[kAccR] += cnt * R;
+  v[kAccG] += cnt * G;
+  v[kAccB] += cnt * B;
+  v[kAccPts] += 1;
+  if (with_squares) {
+    v[kAccRR] += cnt * (R * R);
+    v[kAccGG] += cnt * (G * G);
+    v[kAccBB] += cnt * (B * B);
+  }
+}
+
+// Owner of a finished split writes its two children (totals of the last pass in S.tot, parent in S.cur).
+__device__ __forceinline__ void write_children(const SplitArgs &A, Shared2 &S, int node_id, int child0, const JobConst &jc) {
+  if (threadIdx.x == 0) {
+    SplitNode o, n;
+    make_children(S.cur, node_id, child0, A.norm, S.tot, o, n);
+    A.nodes[child0] = o;
+    A.nodes[child0 + 1] = n;
+    SplitNode *p = A.nodes + node_id;
+    p->child = child0;
+    p->axis = jc.axis;
+    p->cut = jc.cut;
+  }
+}
+
+// ---- exchange of partial sums between the CTAs of a wide job ------------------------------------------
+
+template <int WORDS>
+__device__ __forceinline__ void publish(unsigned long long *slots, uint32_t slot, const Shared2 &S, unsigned tag) {
+  if (threadIdx.x < WORDS)
+    st_relaxed_u64(slots + (size_t)slot * kAccWords + threadIdx.x, ((unsigned long long)tag << 48) | S.tot[threadIdx.x]);
+}
+
+// Waits for the m participants' words of this pass and leaves their sums in S.tot.
+__device__ __forceinline__ void gather(const SplitArgs &A, Shared2 &S, const unsigned long long *slots, uint32_t slot0,
+                                       int m, int words, unsigned tag) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int w = tid & 7;
+  unsigned long long sum = 0;
+  if (w < words) {
+    for (int i = tid >> 3; i < m; i += T / 8) {
+      const unsigned long long *p = slots + (size_t)(slot0 + i) * kAccWords + w;
+      unsigned long long v;
+      const long long t0 = clock64();
+      unsigned polls = 0;
+      do {
+        v = ld_relaxed_u64(p);
+      } while ((unsigned)(v >> 48) != tag && !spin_expired(A, t0, polls, 2, (int)((tag << 16) | (unsigned)i)));
+      sum += v & kValueMask;
+    }
+  }
+  sum += __shfl_xor_sync(0xffffffffu, sum, 8);
+  sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+  if (lane < 8) S.red[warp][lane] = sum;
+  __syncthreads();
+  if (tid < kAccWords * 32) {
+    const int ww = tid >> 5;
+    const uint64_t s = warp_sum_u64(lane < kWarps ? S.red[lane][ww] : 0ull);
+    if (lane == 0) S.tot[ww] = s;
+  }
+  __syncthreads();
+}
+
+// ---- final assignment of cluster indices --------------------------------------------------------------
+
+// Palette = rounded means of the non-empty clusters in index order (:1030-1065). cnode[ic] = node of cluster ic.
+__device__ void emit_palette(const SplitArgs &A, Shared2 &S, const Arrays &R) {
+  const int tid = threadIdx.x, lane = tid & 31, K = (int)A.num_colors;
+  if (tid == 0) S.scan_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < K; base += T) {
+    const int ic = base + tid;
+    uint32_t colour = 0, size = 0;
+    if (ic < K) {
+      double mean[3] = {0.0, 0.0, 0.0};  // K == 1 never assigns mean[0]
+      if (K > 1) {
+        const SplitNode nd = load_node(A, S, R.cnode[ic]);
+        size = nd.size;
+        mean[0] = nd.tm[0], mean[1] = nd.tm[1], mean[2] = nd.tm[2];
+      } else {
+        size = S.num_points;
+      }
+      if (size > 0) {
+        const uint32_t Rr = (__double2uint_rz(fadd(mean[0], 0.5)) & 0xFFu) << A.shift;
+        const uint32_t Gg = (__double2uint_rz(fadd(mean[1], 0.5)) & 0xFFu) << A.shift;
+        const uint32_t Bb = (__double2uint_rz(fadd(mean[2], 0.5)) & 0xFFu) << A.shift;
+        colour = (Rr << 16) | (Gg << 8) | Bb;
+      }
+      A.cluster_size[ic] = size;
+      A.cluster_mean[3 * ic + 0] = mean[0];
+      A.cluster_mean[3 * ic + 1] = mean[1];
+      A.cluster_mean[3 * ic + 2] = mean[2];
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, size > 0);
+    if (lane == 0) S.warp_tmp[tid >> 5] = __popc(ballot);
+    __syncthreads();
+    int before = S.scan_carry;
+    for (int w = 0; w < (tid >> 5); ++w) before += S.warp_tmp[w];
+    if (size > 0) A.palette[before + __popc(ballot & ((1u << lane) - 1u))] = colour;
+    __syncthreads();
+    if (tid == 0) {
+      int tot = 0;
+      for (int w = 0; w < kWarps; ++w) tot += S.warp_tmp[w];
+      S.scan_carry += tot;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    A.result[0] = (uint32_t)S.scan_carry;
+    A.result[1] = (uint32_t)(K - S.scan_carry);
+  }
+}
+
+__device__ void write_record(const SplitArgs &A, const Shared2 &S, int node, int child, int new_index, int old_index) {
+  // the parent comes from global memory even for the root: its owner stored axis/cut there
+  const SplitNode p = A.nodes[node], o = load_node(A, S, child), n = load_node(A, S, child + 1);
+  SplitRecord r;
+  r.new_index = new_index;
+  r.old_index = old_index;
+  r.cut_axis = p.axis;
+  r.num_points = (int32_t)p.size;
+  r.new_size = (int32_t)n.size;
+  r.is_last = (new_index == (int)A.num_colors - 1);
+  r.cut_pos = p.cut;
+  r.total_weight = p.tw;
+  r.new_weight = n.tw;
+  r.old_weight = o.tw;
+  for (int c = 0; c < 3; ++c) {
+    r.new_mean[c] = n.tm[c];
+    r.old_mean[c] = o.tm[c];
+    r.new_var[c] = n.tv[c];
+    r.old_var[c] = o.tv[c];
+  }
+  r.new_tse = n.tse;
+  r.old_tse = o.tse;
+  A.records[new_index - 1] = r;
+}
+
+// Parallel reconstruction of the reference's sequence when the TSE order is strict.
+//
+// With key(root) = +inf: the nodes the reference pops are L = the K-1 known nodes of largest TSE, in
+// descending TSE order, PROVIDED every one of them is a computed split, has a TSE above DBL_MIN, is
+// strictly below its parent (so the parent is popped first) and no two compared values are equal
+// (ties are resolved by cluster index in the reference, :882).  All of that is checked; on any doubt
+// S.bad is set and the caller falls back to the sequential scan.  On success R.cnode[ic] = node of
+// final cluster ic: the split popped at step t creates cluster t from its "new" child, the "old"
+// child inherits the parent's index.
+__device__ void fast_assignment(const SplitArgs &A, Shared2 &S, const Arrays &R) {
+  const int tid = threadIdx.x, K = (int)A.num_colors, n = S.n_nodes;
+  if (tid == 0) {
+    S.bad = 0;
+    S.scan_carry = 0;  // |L|
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += T) {
+    const double t = R.tse[i];
+    int above = n, equal = 1;
+    if (t == t) {  // NaN is never selected (:882)
+      above = 0;
+      equal = 0;
+      for (int m2 = 0; m2 < n; ++m2) {
+        const double u = R.tse[m2];
+        above += (u > t);
+        equal += (u == t);
+      }
+    }
+    R.rank[i] = above;
+    if (above < K - 1) {
+      atomicAdd(&S.scan_carry, 1);
+      bool ok = (equal == 1) && (R.child[i] >= 0) && (t > DBL_MIN);
+      if (i != 0) ok = ok && (R.tse[R.parent[i]] > t);
+      if (!ok) S.bad = 1;
+    } else if (above == K - 1 && equal != 1) {
+      S.bad = 1;  // tie right at the boundary
+    }
+  }
+  __syncthreads();
+  if (S.scan_carry != K - 1 && tid == 0) S.bad = 1;
+  __syncthreads();
+  if (S.bad) return;
+  for (int i = tid; i < n; i += T) {
+    const bool popped = R.rank[i] < K - 1;
+    const bool final_cluster = !popped && i != 0 && R.rank[R.parent[i]] < K - 1;
+    if (!popped && !final_cluster) continue;
+    // cluster index carried by node i: up the chain of "old" children to the nearest "new" child
+    int cur = i, idx = 0;
+    while (cur != 0) {
+      const int p = R.parent[cur];
+      if (cur == R.child[p] + 1) {
+        idx = R.rank[p] + 1;
+        break;
+      }
+      cur = p;
+    }
+    if (popped) {
+      if (A.records != nullptr && blockIdx.x == 0) write_record(A, S, i, R.child[i], R.rank[i] + 1, idx);
+    } else {
+      R.cnode[idx] = i;
+    }
+  }
+  __syncthreads();
+}
+
+// The reference's sequential selection (:876-887) over the cached splits, replicated in every CTA.
+// Leaves S.done = 1 when all K-1 splits were consumed; otherwise fills the job list with the stalled
+// split plus the leaves inside the remaining budget (ordered by cluster index).
+__device__ void sequential_controller(const SplitArgs &A, Shared2 &S, const Arrays &R) {
+  const int tid = threadIdx.x, lane = tid & 31, K = (int)A.num_colors;
+  if (tid < 32) {
+    int new_index = S.new_index, old_index = S.old_index;
+    while (new_index < K) {
+      const int node = R.cnode[old_index];
+      const int child = R.child[node];
+      if (child < 0) break;
+      __syncwarp();
+      if (lane == 0) {
+        R.cnode[old_index] = child;
+        R.cnode[new_index] = child + 1;
+        if (A.records != nullptr && blockIdx.x == 0) write_record(A, S, node, child, new_index, old_index);
+      }
+      if (new_index == K - 1) {
+        new_index = K;
+        break;
+      }
+      if (lane == 0) {
+        R.ctse[old_index] = R.tse[child];
+        R.ctse[new_index] = R.tse[child + 1];
+      }
+      __syncwarp();
+      double best = DBL_MIN;
+      int best_i = -1;
+      for (int ic = lane; ic <= new_index; ic += 32) {
+        const double t = R.ctse[ic];
+        if (best < t) {
+          best = t;
+          best_i = ic;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+        const bool take = (oi >= 0) && (best_i < 0 || best < ob || (ob == best && oi < best_i));
+        if (take) {
+          best = ob;
+          best_i = oi;
+        }
+      }
+      if (best_i >= 0) old_index = best_i;
+      ++new_index;
+    }
+    if (lane == 0) {
+      S.new_index = new_index;
+      S.old_index = old_index;
+    }
+  }
+  __syncthreads();
+  const int new_index = S.new_index, old_index = S.old_index;
+  if (new_index >= K) {
+    if (tid == 0) {
+      S.done = 1;
+      S.njobs = 0;
+    }
+    __syncthreads();
+    return;
+  }
+  // requests: the stalled cluster + the top-(R-1) other unsplit clusters by (tse desc, index asc)
+  const int budget = (K - new_index) - 1;
+  if (tid == 0) {
+    S.njobs = 0;
+    S.scan_carry = 0;
+  }
+  __syncthreads();
+  int32_t *ncand = &S.scan_carry;
+  // candidates in cluster-index order
+  ordered_compact(
+      S, 0, new_index,
+      [&](int ic) { return ic != old_index && R.child[R.cnode[ic]] < 0 && (R.ctse[ic] > DBL_MIN); },
+      [&](int pos, int ic) { R.cand[pos] = ic; }, ncand);
+  const int nc = *ncand;
+  __syncthreads();
+  // mark the clusters to split: flag = -(ic+1) stays, others removed
+  for (int i = tid; i < nc; i += T) {
+    const int ic = R.cand[i];
+    bool take = true;
+    if (nc > budget) {
+      const double mine = R.ctse[ic];
+      int rank = 0;
+      for (int q = 0; q < nc; ++q) {
+        const int oc = R.cand[q];
+        const double t = R.ctse[oc];
+        rank += (t > mine) || (t == mine && oc < ic);
+      }
+      take = rank < budget;
+    }
+    R.cand[i] = take ? ic : -1;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    R.jobnode[0] = R.cnode[old_index];  // the stalled split first
+    S.njobs = 1;
+  }
+  __syncthreads();
+  ordered_compact(
+      S, 0, nc, [&](int i) { return R.cand[i] >= 0; }, [&](int pos, int i) { R.jobnode[pos] = R.cnode[R.cand[i]]; },
+      &S.njobs);
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// The kernel
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512, 1) split2_kernel(const SplitArgs A, const Split2Extra X) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Shared2 &S = *reinterpret_cast<Shared2 *>(smem_raw);
+  const int K = (int)A.num_colors, P = A.max_iters, G = (int)gridDim.x, b = (int)blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const uint32_t cap = A.node_cap;
+
+  Arrays R;
+  {
+    unsigned char *cur = smem_raw + ((sizeof(Shared2) + 15) & ~size_t(15));
+    R.tse = reinterpret_cast<double *>(cur);
+    cur += (size_t)cap * 8;
+    R.ctse = reinterpret_cast<double *>(cur);
+    cur += (size_t)K * 8;
+    R.child = reinterpret_cast<int32_t *>(cur);
+    cur += (size_t)cap * 4;
+    R.size = reinterpret_cast<uint32_t *>(cur);
+    cur += (size_t)cap * 4;
+    R.parent = reinterpret_cast<int32_t *>(cur);
+    cur += (size_t)cap * 4;
+    R.rank = reinterpret_cast<int32_t *>(cur);
+    cur += (size_t)cap * 4;
+    R.jobnode = reinterpret_cast<int32_t *>(cur);
+    cur += (size_t)K * 4;
+    R.cnode = reinterpret_cast<int32_t *>(cur);
+    cur += (size_t)K * 4;
+    R.cand = reinterpret_cast<int32_t *>(cur);
+    cur += (size_t)K * 4;
+    R.tile0 = reinterpret_cast<uint32_t *>(cur);
+    cur += (size_t)(K + 1) * 4;
+    R.slot0 = reinterpret_cast<uint32_t *>(cur);
+    cur += (size_t)(K + 1) * 4;
+    R.nidx = reinterpret_cast<uint32_t *>(cur);
+    cur += (size_t)(K + 1) * 4;
+    R.mywide = reinterpret_cast<uint16_t *>(cur);
+    cur += (size_t)K * 2;
+    R.mynarrow = reinterpret_cast<uint16_t *>(cur);
+  }
+
+  const uint32_t U = A.num_points_dev ? ld_cg_u32(A.num_points_dev) : A.num_points;
+  unsigned int bar_target = 0;
+
+  // ---- global statistics of all points (DivQuantClusterInitMeanAndVar, :60-104) + scratch reset ----
+  {
+    uint64_t v[kAccWords] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (size_t i = (size_t)b * T + tid; i < U; i += (size_t)G * T) add_point(v, ld_cg_u2(A.pts[0] + i), true);
+    block_total<kAccWords>(S, v);
+    if (tid < kAccWords && S.tot[tid] != 0)
+      atomicAdd(reinterpret_cast<unsigned long long *>(A.root_acc + tid), (unsigned long long)S.tot[tid]);
+    const size_t slot_words = (size_t)2 * X.slot_cap * kAccWords;
+    for (size_t i = (size_t)b * T + tid; i < slot_words; i += (size_t)G * T) X.slots[i] = 0ull;
+    for (size_t i = (size_t)b * T + tid; i < (size_t)4 * K; i += (size_t)G * T) X.cursors[i] = 0u;
+  }
+  grid_barrier2(A, bar_target);
+  trace2(A, kTraceRoot, 0);
+
+  if (tid == 0) {
+    SplitNode root;
+    root.tw = 1.0;  // weight[0] = 1.0 (:343)
+    for (int c = 0; c < 3; ++c) {
+      root.tm[c] = fmul(__ull2double_rn(ld_cg_u64(A.root_acc + kAccR + c)), A.norm);  // (:107-112)
+      root.tv[c] = fsub(fmul(__ull2double_rn(ld_cg_u64(A.root_acc + kAccRR + c)), A.norm), fsq(root.tm[c]));
+    }
+    root.tse = 0.0;
+    root.cut = 0.0;
+    root.begin = 0;
+    root.size = U;
+    root.buf = 0;
+    root.child = -1;
+    root.axis = 0;
+    root.parent = -1;
+    S.root = root;
+    if (b == 0) A.nodes[0] = root;
+    R.tse[0] = __longlong_as_double(0x7ff0000000000000ll);  // +inf: the first split is unconditional
+    R.child[0] = -1;
+    R.size[0] = U;
+    R.parent[0] = -1;
+    S.num_points = U;
+    S.n_nodes = 1;
+    S.n_prev = 1;  // nothing to absorb in round 0: the root's entries above are final (its TSE key is +inf)
+    S.njobs = 0;
+    S.prev_njobs = 0;
+    S.mode = 0;
+    S.done = 0;
+    S.new_index = 1;
+    S.old_index = 0;
+  }
+  __syncthreads();
+
+  for (int round = 0;; ++round) {
+    if (cta_error(A, S)) break;  // somebody's wait expired
+    trace2(A, kTraceRoundBegin, round);
+    // ================= controller (replicated) =================
+    // (a) absorb the children created in the previous round
+    {
+      const int n_prev = S.n_prev, n_now = S.n_nodes;
+      for (int i = n_prev + tid; i < n_now; i += T) {
+        const SplitNode *nd = A.nodes + i;
+        R.tse[i] = __ldcg(&nd->tse);
+        R.size[i] = __ldcg(&nd->size);
+        R.child[i] = -1;
+        R.parent[i] = R.jobnode[(i - n_prev) >> 1];
+      }
+      for (int j = tid; j < S.prev_njobs; j += T) R.child[R.jobnode[j]] = n_prev + 2 * j;
+    }
+    __syncthreads();
+    trace2(A, kTracePhaseA, S.prev_njobs);
+
+    // (b) which leaves to split next
+    if (K <= 1) {
+      if (tid == 0) S.done = 1;
+      __syncthreads();
+    } else if (S.mode == 0) {
+      const int n_now = S.n_nodes, lo = (round == 0) ? 0 : S.n_prev;
+      const bool need_count = n_now > K - 1;
+      if (tid == 0) S.njobs = 0;
+      __syncthreads();
+      ordered_compact(
+          S, lo, n_now,
+          [&](int i) {
+            const double t = R.tse[i];
+            if (!(t > DBL_MIN)) return false;
+            if (!need_count) return true;
+            int above = 0;
+            for (int m2 = 0; m2 < n_now; ++m2) above += (R.tse[m2] > t);
+            return above < K - 1;
+          },
+          [&](int pos, int i) {
+            if (pos < K) R.jobnode[pos] = i;
+          },
+          &S.njobs);
+      __syncthreads();
+      // node slots: the threshold policy may use the lower half, the sequential policy needs the rest
+      // (many equal TSEs could also request more than K leaves at once: let the exact scan decide then)
+      if (S.njobs > K || (S.njobs > 0 && (uint32_t)(S.n_nodes + 2 * S.njobs) > cap / 2)) {
+        if (tid == 0) {
+          S.mode = 1;
+          R.cnode[0] = 0;
+          R.ctse[0] = 0.0;
+        }
+        __syncthreads();
+      } else if (S.njobs == 0) {
+        fast_assignment(A, S, R);
+        if (S.bad) {
+          if (tid == 0) {
+            S.mode = 1;
+            R.cnode[0] = 0;
+            R.ctse[0] = 0.0;
+          }
+        } else if (tid == 0) {
+          S.done = 1;
+        }
+        __syncthreads();
+      }
+    }
+    if (K > 1 && S.mode == 1 && !S.done) sequential_controller(A, S, R);
+    trace2(A, kTracePhaseB, S.njobs);
+
+    if (S.done) {
+      if (b == 0) {
+        emit_palette(A, S, R);
+        if (tid == 0) {
+          A.ctl[kCtlDone] = 1;
+          A.ctl[kCtlNodes] = (uint32_t)S.n_nodes;
+          A.ctl[kCtlRounds] = (uint32_t)round;
+        }
+      }
+      break;
+    }
+    if ((uint32_t)(S.n_nodes + 2 * S.njobs) > cap || (unsigned)(1 + (round + 1) * (P + 1)) > 0xFFFFu) {
+      if (b == 0 && tid == 0) A.ctl[kCtlError] = 1;
+      break;
+    }
+
+    // (c) work decomposition of this round
+    const int njobs = S.njobs;
+    for (int j = tid; j < njobs; j += T) {
+      const uint32_t sz = R.size[R.jobnode[j]];
+      const bool wide = sz > kNarrowMax;
+      const uint32_t tiles = wide ? (sz + kWideTile - 1) / kWideTile : 0u;
+      R.tile0[j] = tiles;
+      R.slot0[j] = min(tiles, (uint32_t)G);
+      R.nidx[j] = wide ? 0u : 1u;
+    }
+    __syncthreads();
+    block_scan(S, R.tile0, njobs);
+    if (tid == 0) {
+      R.tile0[njobs] = (uint32_t)S.scan_carry;
+      S.nwide_tiles = S.scan_carry;
+    }
+    block_scan(S, R.slot0, njobs);
+    if (tid == 0) R.slot0[njobs] = (uint32_t)S.scan_carry;
+    block_scan(S, R.nidx, njobs);
+    if (tid == 0) {
+      R.nidx[njobs] = (uint32_t)S.scan_carry;
+      S.n_mywide = 0;
+      S.n_mynarrow = 0;
+    }
+    __syncthreads();
+    if (R.slot0[njobs] > X.slot_cap) {
+      if (b == 0 && tid == 0) A.ctl[kCtlError] = 2;
+      break;
+    }
+    const int child_base = S.n_nodes;
+    const int nwide_tiles = S.nwide_tiles;
+    ordered_compact(
+        S, 0, njobs,
+        [&](int j) {
+          const uint32_t tiles = R.tile0[j + 1] - R.tile0[j];
+          if (tiles == 0) return false;
+          const uint32_t i = (uint32_t)(b + G - (int)(R.tile0[j] % (uint32_t)G)) % (uint32_t)G;
+          return i < min(tiles, (uint32_t)G);
+        },
+        [&](int pos, int j) { R.mywide[pos] = (uint16_t)j; }, &S.n_mywide);
+    ordered_compact(
+        S, 0, njobs,
+        [&](int j) {
+          if (R.nidx[j + 1] == R.nidx[j]) return false;
+          return (int)(((uint32_t)nwide_tiles + R.nidx[j]) % (uint32_t)G) == b;
+        },
+        [&](int pos, int j) { R.mynarrow[pos] = (uint16_t)j; }, &S.n_mynarrow);
+    __syncthreads();
+    if (tid == 0) {
+      S.prev_njobs = njobs;
+      S.n_prev = S.n_nodes;
+      S.n_nodes += 2 * njobs;
+      if (b == 0) {
+        A.ctl[kCtlSplits] += (uint32_t)njobs;
+        A.ctl[kCtlJobs] = (uint32_t)njobs;
+      }
+    }
+    // scatter cursors of the next round are cleared now (nobody touches that parity in this round)
+    {
+      uint32_t *other = X.cursors + (size_t)((round & 1) ^ 1) * 2 * K;
+      for (int i = b * T + tid; i < 2 * K; i += G * T) other[i] = 0u;
+    }
+    const int n_mywide = S.n_mywide, n_mynarrow = S.n_mynarrow;
+    for (int mw = tid; mw < min(n_mywide, kWideCache); mw += T) {
+      // (executed by <= kWideCache threads) constants of the first few wide jobs stay in shared memory
+      S.wide[mw] = job_const_of(load_node(A, S, R.jobnode[R.mywide[mw]]));
+    }
+    __syncthreads();
+    trace2(A, kTracePhaseC, njobs);
+    DQ_PROGRESS(round * 10000 + 1000 + n_mywide * 10 + n_mynarrow);
+
+    // ================= wide jobs: all passes, partial sums exchanged through tagged slots =================
+    // A CTA's share of a wide job = tiles me, me+G, ... of kWideTile points.  It is classified by as few
+    // warps as possible (kWidePPT points per thread): the warp reductions, not the arithmetic, are what a
+    // pass costs, so fewer, busier warps are faster.
+    const unsigned seq0 = 1u + (unsigned)round * (unsigned)(P + 1);
+    auto wide_const = [&](int mw) -> JobConst {
+      if (mw < kWideCache) return S.wide[mw];
+      return job_const_of(load_node(A, S, R.jobnode[R.mywide[mw]]));
+    };
+    // q-th point of this CTA's share -> offset inside the job's segment
+    auto share_offset = [&](uint32_t q, uint32_t me) -> uint32_t {
+      return ((q / kWideTile) * (uint32_t)G + me) * kWideTile + (q % kWideTile);
+    };
+    auto share_points = [&](uint32_t tiles, uint32_t me, uint32_t size) -> uint32_t {
+      if (me >= tiles) return 0u;
+      const uint32_t mine = (tiles - me + (uint32_t)G - 1) / (uint32_t)G;  // my tiles
+      const uint32_t last = me + (mine - 1) * (uint32_t)G;                 // my last tile
+      const uint32_t tail = (last == tiles - 1) ? size - last * kWideTile : kWideTile;
+      return (mine - 1) * kWideTile + tail;
+    };
+    for (int pass = 0; pass <= P; ++pass) {
+      unsigned long long *slots_w = X.slots + (size_t)(pass & 1) * X.slot_cap * kAccWords;
+      const unsigned long long *slots_r = X.slots + (size_t)((pass & 1) ^ 1) * X.slot_cap * kAccWords;
+      for (int mw = 0; mw < n_mywide; ++mw) {
+        const int j = R.mywide[mw];
+        const JobConst jc = wide_const(mw);
+        const uint32_t tiles = R.tile0[j + 1] - R.tile0[j];
+        const int m = (int)min(tiles, (uint32_t)G);
+        const uint32_t me = (uint32_t)(b + G - (int)(R.tile0[j] % (uint32_t)G)) % (uint32_t)G;
+        const uint32_t n_my = share_points(tiles, me, jc.size);
+        const uint32_t nthr = min((uint32_t)T, ((n_my + kWidePPT - 1) / kWidePPT + 31u) & ~31u);
+        // prefetch the first points of this CTA's share while the previous pass's totals arrive
+        uint2 pre[kWidePPT];
+#pragma unroll
+        for (int k = 0; k < kWidePPT; ++k) {
+          const uint32_t q = (uint32_t)tid + (uint32_t)k * nthr;
+          pre[k] = make_uint2(0, 0);
+          if ((uint32_t)tid < nthr && q < n_my) pre[k] = ld_cg_u2(A.pts[jc.buf] + jc.begin + share_offset(q, me));
+        }
+        if (pass == 0) {
+          set_split_params(S, jc);
+        } else {
+          gather(A, S, slots_r, R.slot0[j], m, 5, (seq0 + pass - 1) & 0xFFFFu);
+          derive_params_warp0(S, jc, A.norm);
+        }
+        __syncthreads();
+        const PassParams pp = S.pp;
+        uint64_t v[kAccWords] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if ((uint32_t)tid < nthr) {
+#pragma unroll
+          for (int k = 0; k < kWidePPT; ++k) {
+            const uint32_t q = (uint32_t)tid + (uint32_t)k * nthr;
+            if (q < n_my && goes_new(pp, pass == 0, pre[k].x)) add_point(v, pre[k], pass == P);
+          }
+          for (uint32_t q = (uint32_t)tid + kWidePPT * nthr; q < n_my; q += nthr) {
+            const uint2 p = ld_cg_u2(A.pts[jc.buf] + jc.begin + share_offset(q, me));
+            if (goes_new(pp, pass == 0, p.x)) add_point(v, p, pass == P);
+          }
+        }
+        if (pass == P) {
+          block_total<kAccWords>(S, v, (int)(nthr >> 5));
+          publish<kAccWords>(slots_w, R.slot0[j] + me, S, (seq0 + pass) & 0xFFFFu);
+        } else {
+          block_total<5>(S, v, (int)(nthr >> 5));
+          publish<5>(slots_w, R.slot0[j] + me, S, (seq0 + pass) & 0xFFFFu);
+        }
+        __syncthreads();
+      }
+      if (n_mywide) trace2(A, kTracePass, pass);
+      DQ_PROGRESS(round * 10000 + 2000 + pass);
+    }
+    // partition of the wide jobs + children
+    for (int mw = 0; mw < n_mywide; ++mw) {
+      const int j = R.mywide[mw];
+      const JobConst jc = wide_const(mw);
+      const uint32_t tiles = R.tile0[j + 1] - R.tile0[j];
+      const int m = (int)min(tiles, (uint32_t)G);
+      const uint32_t me = (uint32_t)(b + G - (int)(R.tile0[j] % (uint32_t)G)) % (uint32_t)G;
+      // classification of the last pass (parameters from the totals of pass P-1)
+      gather(A, S, X.slots + (size_t)((P - 1) & 1) * X.slot_cap * kAccWords, R.slot0[j], m, 5, (seq0 + P - 1) & 0xFFFFu);
+      derive_params_warp0(S, jc, A.norm);
+      __syncthreads();
+      const PassParams pp = S.pp;
+      __syncthreads();
+      gather(A, S, X.slots + (size_t)(P & 1) * X.slot_cap * kAccWords, R.slot0[j], m, kAccWords, (seq0 + P) & 0xFFFFu);
+      if (S.tot[kAccPts] > jc.size) continue;  // only after an expired wait: never scatter out of the segment
+      const uint32_t size_old = jc.size - (uint32_t)S.tot[kAccPts];
+      uint32_t *cur = X.cursors + (size_t)(round & 1) * 2 * K + 2 * j;
+      for (uint32_t tt = me * (kWideTile / T); tt < tiles * (kWideTile / T); tt += (tt % (kWideTile / T) == kWideTile / T - 1) ? (uint32_t)(G - 1) * (kWideTile / T) + 1 : 1u) {
+        // tt enumerates T-point pieces of this CTA's tiles: tile = tt / (kWideTile/T)
+        const uint32_t off = tt * T + tid;
+        const bool valid = off < jc.size;
+        uint2 p = make_uint2(0, 0);
+        if (valid) p = ld_cg_u2(A.pts[jc.buf] + jc.begin + off);
+        const bool to_new = valid && goes_new(pp, false, p.x);
+        const unsigned m_new = __ballot_sync(0xffffffffu, to_new);
+        const unsigned m_old = __ballot_sync(0xffffffffu, valid && !to_new);
+        uint32_t base_new = 0, base_old = 0;
+        if (lane == 0) {
+          if (m_new) base_new = atomicAdd(cur + 1, (uint32_t)__popc(m_new));
+          if (m_old) base_old = atomicAdd(cur, (uint32_t)__popc(m_old));
+        }
+        base_new = __shfl_sync(0xffffffffu, base_new, 0);
+        base_old = __shfl_sync(0xffffffffu, base_old, 0);
+        if (valid) {
+          const unsigned below = (1u << lane) - 1u;
+          const uint32_t dst = to_new ? jc.begin + size_old + base_new + __popc(m_new & below)
+                                      : jc.begin + base_old + __popc(m_old & below);
+          A.pts[jc.buf ^ 1][dst] = p;
+        }
+      }
+      if (me == 0) {  // owner: the CTA holding the job's first tile
+        if (tid == 0) S.cur = load_node(A, S, R.jobnode[j]);
+        __syncthreads();
+        write_children(A, S, R.jobnode[j], child_base + 2 * j, jc);
+      }
+      __syncthreads();
+    }
+    if (n_mywide) trace2(A, kTracePartition, n_mywide);
+    DQ_PROGRESS(round * 10000 + 3000);
+
+    // ================= narrow jobs: everything inside this CTA =================
+    for (int mn = 0; mn < n_mynarrow; ++mn) {
+      const int j = R.mynarrow[mn];
+      const int node = R.jobnode[j];
+      if (tid == 0) {
+        S.cur = load_node(A, S, node);
+        S.cur_old = 0;
+        S.cur_new = 0;
+      }
+      __syncthreads();
+      const JobConst jc = job_const_of(S.cur);
+      // as few warps as possible, kNarrowPPT points per thread, held in registers for every pass
+      const uint32_t nthr = min((uint32_t)T, max(32u, ((jc.size + kNarrowPPT - 1) / kNarrowPPT + 31u) & ~31u));
+      const int nwarps = (int)(nthr >> 5);
+      uint2 p[kNarrowPPT];
+      unsigned validmask = 0;
+#pragma unroll
+      for (int k = 0; k < kNarrowPPT; ++k) {
+        const uint32_t off = (uint32_t)k * nthr + tid;
+        p[k] = make_uint2(0, 0);
+        if ((uint32_t)tid < nthr && off < jc.size) {
+          p[k] = ld_cg_u2(A.pts[jc.buf] + jc.begin + off);
+          validmask |= 1u << k;
+        }
+      }
+      set_split_params(S, jc);
+      __syncthreads();
+      unsigned newmask = 0;
+      for (int pass = 0; pass <= P; ++pass) {
+        const PassParams pp = S.pp;
+        uint64_t v[kAccWords] = {0, 0, 0, 0, 0, 0, 0, 0};
+        newmask = 0;
+#pragma unroll
+        for (int k = 0; k < kNarrowPPT; ++k) {
+          if (((validmask >> k) & 1u) && goes_new(pp, pass == 0, p[k].x)) {
+            add_point(v, p[k], pass == P);
+            newmask |= 1u << k;
+          }
+        }
+        if (pass == P) {
+          block_total<kAccWords>(S, v, nwarps);
+        } else {
+          block_total<5>(S, v, nwarps);
+          derive_params_warp0(S, jc, A.norm);
+          __syncthreads();
+        }
+      }
+      // S.tot = totals of the last pass; newmask = membership decided by it
+      const uint32_t size_old = jc.size - (uint32_t)S.tot[kAccPts];
+      if (tid < (int)nthr) {
+#pragma unroll
+        for (int k = 0; k < kNarrowPPT; ++k) {
+          const bool valid = (validmask >> k) & 1u;
+          const bool to_new = (newmask >> k) & 1u;
+          const unsigned m_new = __ballot_sync(0xffffffffu, to_new);
+          const unsigned m_old = __ballot_sync(0xffffffffu, valid && !to_new);
+          uint32_t base_new = 0, base_old = 0;
+          if (lane == 0) {
+            if (m_new) base_new = atomicAdd(&S.cur_new, (uint32_t)__popc(m_new));
+            if (m_old) base_old = atomicAdd(&S.cur_old, (uint32_t)__popc(m_old));
+          }
+          base_new = __shfl_sync(0xffffffffu, base_new, 0);
+          base_old = __shfl_sync(0xffffffffu, base_old, 0);
+          if (valid) {
+            const unsigned below = (1u << lane) - 1u;
+            const uint32_t dst = to_new ? jc.begin + size_old + base_new + __popc(m_new & below)
+                                        : jc.begin + base_old + __popc(m_old & below);
+            A.pts[jc.buf ^ 1][dst] = p[k];
+          }
+        }
+      }
+      write_children(A, S, node, child_base + 2 * j, jc);
+      __syncthreads();
+    }
+    if (n_mynarrow) trace2(A, kTracePartition, 1000 + n_mynarrow);
+    DQ_PROGRESS(round * 10000 + 4000);
+
+    grid_barrier2(A, bar_target, X.progress);
+    trace2(A, kTraceCtlBarrier, round);
+  }
+}
+
+size_t split2_smem_bytes(uint32_t K, uint32_t cap) {
+  size_t s = (sizeof(Shared2) + 15) & ~size_t(15);
+  s += (size_t)cap * (8 + 4 + 4 + 4 + 4);
+  s += (size_t)K * (8 + 4 + 4 + 4);
+  s += (size_t)(K + 1) * 4 * 3;
+  s += (size_t)K * 2 * 2;
+  return s + 64;
+}
+
+}  // namespace
+
+size_t split2_slot_capacity(uint32_t point_capacity, uint32_t num_colors, int sm_count) {
+  // every wide job needs min(tiles, CTAs) slots; wide tiles <= points / kWideTile + jobs
+  (void)sm_count;
+  return (size_t)point_capacity / kWideTile + num_colors + 64;
+}
+
+SplitLaunch split2_plan(int sm_count, uint32_t num_colors) {
+  SplitLaunch plan;
+  plan.grid = sm_count;
+  plan.smem_bytes = split2_smem_bytes(num_colors, 8 * num_colors + 16);
+  return plan;
+}
+
+void split2_launch(const SplitArgs &args_in, const Split2Extra &extra, const SplitLaunch &plan, cudaStream_t stream) {
+  SplitArgs args = args_in;
+  args.node_cap = 8 * args.num_colors + 16;
+  static size_t configured = 0;
+  if (plan.smem_bytes > configured) {
+    DQ_CUDA_CHECK(cudaFuncSetAttribute(split2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes));
+    configured = plan.smem_bytes;
+  }
+  Split2Extra x = extra;
+  void *kargs[] = {(void *)&args, (void *)&x};
+  DQ_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)split2_kernel, dim3(plan.grid), dim3(T), kargs, plan.smem_bytes, stream));
+}
+
+}  // namespace dq

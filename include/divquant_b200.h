@@ -154,6 +154,12 @@ uint32_t dq_debug_split_points(dq_context *ctx, const uint32_t *colours, const u
 uint32_t dq_debug_histogram(dq_context *ctx, const uint32_t *inPixels, uint32_t numPixels, uint32_t *colours,
                             uint32_t *counts);
 
+/* Tracing aid for the persistent split kernel: when enabled, CTA 0 records (tag<<32|arg, SM clock) pairs at
+ * its phase boundaries during the next calls.  Call again with pairs_out to fetch the last trace
+ * (returns the number of pairs).  Tags: 1 round begin, 2 children finalised, 3 replay done, 4 jobs
+ * issued, 5 barrier after controller, 6 pass done, 7 partition done, 8 root statistics done. */
+uint32_t dq_debug_split_timeline(dq_context *ctx, int enable, uint64_t *pairs_out, uint32_t capacity_pairs);
+
 /* Host-only pieces of the path (no device needed): the palette handling the shim does between the
  * kernels, exposed so that CPU-only tests can check it against the oracle.
  *   dq_host_dedup_palette       first occurrence wins, order kept (quant_util.cpp:93-118); returns the new size.
