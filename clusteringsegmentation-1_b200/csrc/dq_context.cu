@@ -225,6 +225,7 @@ uint32_t run_split(dq_context *ctx, uint32_t point_capacity, double norm, uint32
     x.cursors = ctx->d_cursors.ptr;
     ctx->d_progress.ensure(1024);
     x.progress = ctx->d_progress.ptr;
+    if (getenv("DQ_PROFILE_NARROW")) DQ_CUDA_CHECK(cudaMemsetAsync(ctx->d_progress.ptr, 0, 1024 * sizeof(uint32_t), ctx->stream));
     split2_launch(a, x, split2_plan(ctx->sm_count, K), ctx->stream);
   } else {
     split_launch(a, split_plan(ctx->sm_count, K), ctx->stream);
@@ -248,6 +249,13 @@ uint32_t run_split(dq_context *ctx, uint32_t point_capacity, double norm, uint32
       fprintf(stderr, "\n");
     }
     abort();
+  }
+  if (use_v2 && getenv("DQ_PROFILE_NARROW")) {
+    uint32_t prof[8];
+    cudaMemcpy(prof, ctx->d_progress.ptr + 256, sizeof(prof), cudaMemcpyDeviceToHost);
+    if (prof[4])
+      fprintf(stderr, "narrow profile (cycles per pass, thread 0): classify %.0f stage1+sync %.0f warp0(stage2+derive) %.0f sync %.0f ; %u passes, %u points\n",
+              (double)prof[0] / prof[4], (double)prof[1] / prof[4], (double)prof[2] / prof[4], (double)prof[3] / prof[4], prof[4], prof[5]);
   }
   const uint32_t actual = ctx->h_cb->result[0], empty = ctx->h_cb->result[1];
   memcpy(colortable_out, ctx->h_small, actual * sizeof(uint32_t));

@@ -29,7 +29,7 @@ namespace {
 constexpr int kWarps = 16;
 constexpr int T = 32 * kWarps;  // 16 warps, up to 128 registers per thread: points stay in registers without spills
 constexpr uint32_t kWideTile = 1024;  // points per wide tile
-constexpr int kWidePPT = 4;           // points per thread when a CTA classifies its share of a wide job
+constexpr int kWidePPT = 2;           // points per thread when a CTA classifies its share of a wide job
 constexpr int kNarrowPPT = 8;         // points per thread of a narrow job (kept in registers for all passes)
 constexpr uint32_t kNarrowMax = kNarrowPPT * T;
 constexpr int kWideCache = 4;         // wide jobs whose constants a CTA keeps in shared memory
@@ -48,6 +48,7 @@ struct Shared2 {
   SplitNode root;
   SplitNode cur;  // node being split by a narrow job / finalised by an owner
   JobConst wide[kWideCache];
+  PassParams wide_pp[kWideCache];  // classification of the last pass, reused by the partition
   int32_t n_nodes, n_prev, njobs, prev_njobs;
   int32_t nwide_tiles, n_mywide, n_mynarrow;
   int32_t mode;  // 0 = threshold policy, 1 = replicated sequential replay
@@ -157,35 +158,53 @@ __device__ __forceinline__ void trace2(const SplitArgs &A, int tag, int arg) {
 
 // ---- block-level helpers ----------------------------------------------------------------------------
 
-// Warp sum of values below 2^50 with the REDUX unit: three 16/16/18-bit limbs, upper limbs skipped
-// when the whole warp has none (2 cycles per REDUX per SM against 10 shuffles for a 64-bit butterfly).
-__device__ __forceinline__ uint64_t warp_sum_limbs(uint64_t v) {
-  uint64_t s = __reduce_add_sync(0xffffffffu, (unsigned)(v & 0xFFFFu));
-  if (__any_sync(0xffffffffu, (v >> 16) != 0)) {
-    s += (uint64_t)__reduce_add_sync(0xffffffffu, (unsigned)((v >> 16) & 0xFFFFu)) << 16;
-    if (__any_sync(0xffffffffu, (v >> 32) != 0)) s += (uint64_t)__reduce_add_sync(0xffffffffu, (unsigned)(v >> 32)) << 32;
-  }
-  return s;
+// Warp sum of values below 2^50 with the REDUX unit (2 cycles per REDUX per SM, against ten dependent
+// shuffles for a 64-bit butterfly): one 32-bit REDUX when every lane is below 2^27 (warp-uniform
+// branch), otherwise two 24/26-bit limbs.
+__device__ __forceinline__ uint64_t warp_sum_redux(uint64_t v) {
+  if (!__any_sync(0xffffffffu, (v >> 27) != 0)) return __reduce_add_sync(0xffffffffu, (unsigned)v);
+  const unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)(v & 0xFFFFFFu));
+  const unsigned hi = __reduce_add_sync(0xffffffffu, (unsigned)(v >> 24));
+  return (uint64_t)lo + ((uint64_t)hi << 24);
 }
 
-// Sum of v[0..WORDS) over the first `warps` warps of the CTA into S.tot (visible to all threads on
-// return).  Threads of the other warps must pass zeros or simply not matter: they are not read.
+// Stage 1 of a CTA-wide sum: the first `warps` warps reduce their WORDS values into S.red[warp][].
+// Ends with a barrier.
 template <int WORDS>
-__device__ __forceinline__ void block_total(Shared2 &S, const uint64_t (&v)[kAccWords], int warps = kWarps) {
+__device__ __forceinline__ void reduce_stage1(Shared2 &S, const uint64_t (&v)[kAccWords], int warps) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (warp < warps) {
 #pragma unroll
     for (int w = 0; w < WORDS; ++w) {
-      const uint64_t s = warp_sum_limbs(v[w]);
+      const uint64_t s = (w == kAccPts) ? (uint64_t)__reduce_add_sync(0xffffffffu, (unsigned)v[w]) : warp_sum_redux(v[w]);
       if (lane == 0) S.red[warp][w] = s;
     }
   }
   __syncthreads();
-  if (threadIdx.x < WORDS * 32) {
-    const int w = threadIdx.x >> 5;
-    const uint64_t s = warp_sum_u64(lane < warps ? S.red[lane][w] : 0ull);
-    if (lane == 0) S.tot[w] = s;
+}
+
+// Stage 2, executed by warp 0 only: sums rows 0..rows-1 (<= 32) of S.red (values below 2^54) into
+// S.tot with two 27-bit limbs per word.  Totals are visible to warp 0 on return (no CTA barrier).
+template <int WORDS>
+__device__ __forceinline__ void reduce_stage2_warp0(Shared2 &S, int rows) {
+  const int lane = threadIdx.x & 31;
+  uint64_t x[WORDS];
+#pragma unroll
+  for (int w = 0; w < WORDS; ++w) x[w] = lane < rows ? S.red[lane][w] : 0ull;
+#pragma unroll
+  for (int w = 0; w < WORDS; ++w) {
+    const unsigned a = __reduce_add_sync(0xffffffffu, (unsigned)(x[w] & 0x7FFFFFFu));
+    const unsigned c = __reduce_add_sync(0xffffffffu, (unsigned)(x[w] >> 27));
+    if (lane == 0) S.tot[w] = (uint64_t)a + ((uint64_t)c << 27);
   }
+  __syncwarp();
+}
+
+// Sum of v[0..WORDS) over the first `warps` warps of the CTA into S.tot, visible to all threads.
+template <int WORDS>
+__device__ __forceinline__ void block_total(Shared2 &S, const uint64_t (&v)[kAccWords], int warps = kWarps) {
+  reduce_stage1<WORDS>(S, v, warps);
+  if (threadIdx.x < 32) reduce_stage2_warp0<WORDS>(S, warps);
   __syncthreads();
 }
 
@@ -265,10 +284,10 @@ __device__ __forceinline__ SplitNode load_node(const SplitArgs &A, const Shared2
 // Classification parameters of the next pass from the totals in S.tot, computed by warp 0
 // (one lane per channel), left in S.pp.  Caller synchronises afterwards.
 __device__ __forceinline__ void derive_params_warp0(Shared2 &S, const JobConst &jc, double norm) {
-  if (threadIdx.x < 32) {
+  if (threadIdx.x < 32) {  // uniform per warp
     const int c = min((int)threadIdx.x, 2);
-    const double nw = fmul(__ull2double_rn(S.tot[kAccCnt]), norm);
-    const double nm = fdiv(fmul(__ull2double_rn(S.tot[kAccR + c]), norm), nw);
+    const double nw = fmul(u52_to_double(S.tot[kAccCnt]), norm);
+    const double nm = fdiv(fmul(u52_to_double(S.tot[kAccR + c]), norm), nw);
     const double ow = fsub(jc.tw, nw);
     const double om = fdiv(fsub(fmul(jc.tw, jc.tm[c]), fmul(nw, nm)), ow);
     const double a = fsq(om), b = fsq(nm);
@@ -370,12 +389,8 @@ __device__ __forceinline__ void gather(const SplitArgs &A, Shared2 &S, const uns
   sum += __shfl_xor_sync(0xffffffffu, sum, 16);
   if (lane < 8) S.red[warp][lane] = sum;
   __syncthreads();
-  if (tid < kAccWords * 32) {
-    const int ww = tid >> 5;
-    const uint64_t s = warp_sum_u64(lane < kWarps ? S.red[lane][ww] : 0ull);
-    if (lane == 0) S.tot[ww] = s;
-  }
-  __syncthreads();
+  if (tid < 32) reduce_stage2_warp0<kAccWords>(S, kWarps);
+  // no barrier here: callers let warp 0 go on (parameter derivation) and synchronise afterwards
 }
 
 // ---- final assignment of cluster indices --------------------------------------------------------------
@@ -622,6 +637,60 @@ __device__ void sequential_controller(const SplitArgs &A, Shared2 &S, const Arra
       S, 0, nc, [&](int i) { return R.cand[i] >= 0; }, [&](int pos, int i) { R.jobnode[pos] = R.cnode[R.cand[i]]; },
       &S.njobs);
   __syncthreads();
+}
+
+// One pass of a narrow job: classify the (register-resident) points, reduce, and -- except after the
+// last pass -- derive the next pass's parameters.  SPLIT: cut test of pass 0; FINAL: last LKM pass
+// (also sums count*c*c).  Returns the membership mask of this thread's points.
+template <bool SPLIT, bool FINAL>
+__device__ __forceinline__ unsigned narrow_pass(Shared2 &S, const uint2 (&p)[kNarrowPPT], unsigned validmask, int ppt,
+                                                int nwarps, const JobConst &jc, double norm) {
+  const PassParams pp = S.pp;
+  AccD acc = acc_zero();
+  unsigned newmask = 0;
+#pragma unroll
+  for (int k = 0; k < kNarrowPPT; ++k) {
+    if (k < ppt && ((validmask >> k) & 1u)) {
+      const PointD d = to_point(p[k]);
+      if (goes_new_t<SPLIT>(pp, d)) {
+        acc_add(acc, d, FINAL);
+        newmask |= 1u << k;
+      }
+    }
+  }
+  uint64_t v[kAccWords];
+  acc_words(acc, v);
+  constexpr int WORDS = FINAL ? kAccWords : 5;
+  reduce_stage1<WORDS>(S, v, nwarps);
+  if (threadIdx.x < 32) {
+    reduce_stage2_warp0<WORDS>(S, nwarps);
+    if (!FINAL) derive_params_warp0(S, jc, norm);
+  }
+  __syncthreads();
+  return newmask;
+}
+
+// This CTA's share of a wide job in one pass: partial sums into v[].
+template <bool SPLIT, bool FINAL, typename OffsetFn>
+__device__ __forceinline__ void wide_classify(const PassParams &pp, const uint2 (&pre)[kWidePPT], uint32_t n_my, uint32_t nthr,
+                                              const uint2 *seg, OffsetFn offset_of, uint64_t (&v)[kAccWords]) {
+  AccD acc = acc_zero();
+  const uint32_t tid = threadIdx.x;
+  if (tid < nthr) {
+#pragma unroll
+    for (int k = 0; k < kWidePPT; ++k) {
+      const uint32_t q = tid + (uint32_t)k * nthr;
+      if (q < n_my) {
+        const PointD d = to_point(pre[k]);
+        if (goes_new_t<SPLIT>(pp, d)) acc_add(acc, d, FINAL);
+      }
+    }
+    for (uint32_t q = tid + kWidePPT * nthr; q < n_my; q += nthr) {
+      const PointD d = to_point(ld_cg_u2(seg + offset_of(q)));
+      if (goes_new_t<SPLIT>(pp, d)) acc_add(acc, d, FINAL);
+    }
+  }
+  acc_words(acc, v);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -902,7 +971,7 @@ __global__ void __launch_bounds__(512, 1) split2_kernel(const SplitArgs A, const
         const int m = (int)min(tiles, (uint32_t)G);
         const uint32_t me = (uint32_t)(b + G - (int)(R.tile0[j] % (uint32_t)G)) % (uint32_t)G;
         const uint32_t n_my = share_points(tiles, me, jc.size);
-        const uint32_t nthr = min((uint32_t)T, ((n_my + kWidePPT - 1) / kWidePPT + 31u) & ~31u);
+        const uint32_t nthr = min((uint32_t)T, (n_my + 31u) & ~31u);  // spread over as many warps as there are points for
         // prefetch the first points of this CTA's share while the previous pass's totals arrive
         uint2 pre[kWidePPT];
 #pragma unroll
@@ -919,24 +988,27 @@ __global__ void __launch_bounds__(512, 1) split2_kernel(const SplitArgs A, const
         }
         __syncthreads();
         const PassParams pp = S.pp;
-        uint64_t v[kAccWords] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if ((uint32_t)tid < nthr) {
-#pragma unroll
-          for (int k = 0; k < kWidePPT; ++k) {
-            const uint32_t q = (uint32_t)tid + (uint32_t)k * nthr;
-            if (q < n_my && goes_new(pp, pass == 0, pre[k].x)) add_point(v, pre[k], pass == P);
-          }
-          for (uint32_t q = (uint32_t)tid + kWidePPT * nthr; q < n_my; q += nthr) {
-            const uint2 p = ld_cg_u2(A.pts[jc.buf] + jc.begin + share_offset(q, me));
-            if (goes_new(pp, pass == 0, p.x)) add_point(v, p, pass == P);
-          }
+        uint64_t v[kAccWords];
+        {
+          const uint2 *seg = A.pts[jc.buf] + jc.begin;
+          auto off = [&](uint32_t q) { return share_offset(q, me); };
+          if (pass == 0) wide_classify<true, false>(pp, pre, n_my, nthr, seg, off, v);
+          else if (pass == P) wide_classify<false, true>(pp, pre, n_my, nthr, seg, off, v);
+          else wide_classify<false, false>(pp, pre, n_my, nthr, seg, off, v);
         }
         if (pass == P) {
-          block_total<kAccWords>(S, v, (int)(nthr >> 5));
-          publish<kAccWords>(slots_w, R.slot0[j] + me, S, (seq0 + pass) & 0xFFFFu);
+          if (tid == 0 && mw < kWideCache) S.wide_pp[mw] = pp;
+          reduce_stage1<kAccWords>(S, v, (int)(nthr >> 5));
+          if (tid < 32) {
+            reduce_stage2_warp0<kAccWords>(S, (int)(nthr >> 5));
+            publish<kAccWords>(slots_w, R.slot0[j] + me, S, (seq0 + pass) & 0xFFFFu);
+          }
         } else {
-          block_total<5>(S, v, (int)(nthr >> 5));
-          publish<5>(slots_w, R.slot0[j] + me, S, (seq0 + pass) & 0xFFFFu);
+          reduce_stage1<5>(S, v, (int)(nthr >> 5));
+          if (tid < 32) {
+            reduce_stage2_warp0<5>(S, (int)(nthr >> 5));
+            publish<5>(slots_w, R.slot0[j] + me, S, (seq0 + pass) & 0xFFFFu);
+          }
         }
         __syncthreads();
       }
@@ -951,12 +1023,15 @@ __global__ void __launch_bounds__(512, 1) split2_kernel(const SplitArgs A, const
       const int m = (int)min(tiles, (uint32_t)G);
       const uint32_t me = (uint32_t)(b + G - (int)(R.tile0[j] % (uint32_t)G)) % (uint32_t)G;
       // classification of the last pass (parameters from the totals of pass P-1)
-      gather(A, S, X.slots + (size_t)((P - 1) & 1) * X.slot_cap * kAccWords, R.slot0[j], m, 5, (seq0 + P - 1) & 0xFFFFu);
-      derive_params_warp0(S, jc, A.norm);
-      __syncthreads();
-      const PassParams pp = S.pp;
+      if (mw >= kWideCache) {
+        gather(A, S, X.slots + (size_t)((P - 1) & 1) * X.slot_cap * kAccWords, R.slot0[j], m, 5, (seq0 + P - 1) & 0xFFFFu);
+        derive_params_warp0(S, jc, A.norm);
+        __syncthreads();
+      }
+      const PassParams pp = (mw < kWideCache) ? S.wide_pp[mw] : S.pp;
       __syncthreads();
       gather(A, S, X.slots + (size_t)(P & 1) * X.slot_cap * kAccWords, R.slot0[j], m, kAccWords, (seq0 + P) & 0xFFFFu);
+      __syncthreads();
       if (S.tot[kAccPts] > jc.size) continue;  // only after an expired wait: never scatter out of the segment
       const uint32_t size_old = jc.size - (uint32_t)S.tot[kAccPts];
       uint32_t *cur = X.cursors + (size_t)(round & 1) * 2 * K + 2 * j;
@@ -1004,8 +1079,8 @@ __global__ void __launch_bounds__(512, 1) split2_kernel(const SplitArgs A, const
       }
       __syncthreads();
       const JobConst jc = job_const_of(S.cur);
-      // as few warps as possible, kNarrowPPT points per thread, held in registers for every pass
-      const uint32_t nthr = min((uint32_t)T, max(32u, ((jc.size + kNarrowPPT - 1) / kNarrowPPT + 31u) & ~31u));
+      // all warps the job has points for; up to kNarrowPPT points per thread, held in registers for every pass
+      const uint32_t nthr = min((uint32_t)T, max(32u, (jc.size + 31u) & ~31u));
       const int nwarps = (int)(nthr >> 5);
       uint2 p[kNarrowPPT];
       unsigned validmask = 0;
@@ -1020,26 +1095,10 @@ __global__ void __launch_bounds__(512, 1) split2_kernel(const SplitArgs A, const
       }
       set_split_params(S, jc);
       __syncthreads();
-      unsigned newmask = 0;
-      for (int pass = 0; pass <= P; ++pass) {
-        const PassParams pp = S.pp;
-        uint64_t v[kAccWords] = {0, 0, 0, 0, 0, 0, 0, 0};
-        newmask = 0;
-#pragma unroll
-        for (int k = 0; k < kNarrowPPT; ++k) {
-          if (((validmask >> k) & 1u) && goes_new(pp, pass == 0, p[k].x)) {
-            add_point(v, p[k], pass == P);
-            newmask |= 1u << k;
-          }
-        }
-        if (pass == P) {
-          block_total<kAccWords>(S, v, nwarps);
-        } else {
-          block_total<5>(S, v, nwarps);
-          derive_params_warp0(S, jc, A.norm);
-          __syncthreads();
-        }
-      }
+      const int ppt = (int)((jc.size + nthr - 1) / nthr);
+      unsigned newmask = narrow_pass<true, false>(S, p, validmask, ppt, nwarps, jc, A.norm);
+      for (int pass = 1; pass < P; ++pass) newmask = narrow_pass<false, false>(S, p, validmask, ppt, nwarps, jc, A.norm);
+      newmask = narrow_pass<false, true>(S, p, validmask, ppt, nwarps, jc, A.norm);
       // S.tot = totals of the last pass; newmask = membership decided by it
       const uint32_t size_old = jc.size - (uint32_t)S.tot[kAccPts];
       if (tid < (int)nthr) {

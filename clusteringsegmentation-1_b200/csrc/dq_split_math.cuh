@@ -7,6 +7,20 @@
 
 namespace dq {
 
+// Exact u8 -> double without the (slow, XU-pipe) I2F.F64: 2^52 + x has x in its low mantissa bits.
+__device__ __forceinline__ double byte_to_double(uint32_t x) {
+  return __dsub_rn(__hiloint2double(0x43300000, (int)x), 4503599627370496.0);
+}
+
+// Exact integer -> double for 0 <= x < 2^52 (sums of a pass are below 2^48) and back, again without
+// the conversion pipe: one FP64 add each way.
+__device__ __forceinline__ double u52_to_double(uint64_t x) {
+  return __dsub_rn(__longlong_as_double((long long)(0x4330000000000000ull | x)), 4503599627370496.0);
+}
+__device__ __forceinline__ uint64_t double_to_u52(double x) {  // x a non-negative integer below 2^52
+  return (uint64_t)__double_as_longlong(__dadd_rn(x, 4503599627370496.0)) & 0x000FFFFFFFFFFFFFull;
+}
+
 struct Means {
   double nw, ow;
   double nm[3], om[3];
@@ -16,10 +30,10 @@ struct Means {
 // (:561-581 after the split pass, :780-810 after an LKM iteration; uniform-weight form).
 __device__ __forceinline__ void derive_means(double tw, const double *tm, double norm, uint64_t cnt, uint64_t sr,
                                              uint64_t sg, uint64_t sb, Means &m) {
-  m.nw = fmul(__ull2double_rn(cnt), norm);
-  m.nm[0] = fdiv(fmul(__ull2double_rn(sr), norm), m.nw);
-  m.nm[1] = fdiv(fmul(__ull2double_rn(sg), norm), m.nw);
-  m.nm[2] = fdiv(fmul(__ull2double_rn(sb), norm), m.nw);
+  m.nw = fmul(u52_to_double(cnt), norm);
+  m.nm[0] = fdiv(fmul(u52_to_double(sr), norm), m.nw);
+  m.nm[1] = fdiv(fmul(u52_to_double(sg), norm), m.nw);
+  m.nm[2] = fdiv(fmul(u52_to_double(sb), norm), m.nw);
   m.ow = fsub(tw, m.nw);
 #pragma unroll
   for (int c = 0; c < 3; ++c) m.om[c] = fdiv(fsub(fmul(tw, tm[c]), fmul(m.nw, m.nm[c])), m.ow);
@@ -48,13 +62,84 @@ __device__ __forceinline__ void hyperplane(const Means &m, PassParams &pp) {
   pp.r[2] = fsub(m.om[2], m.nm[2]);
 }
 
+// A point with its channels and multiplicity as exact doubles: the hyperplane test needs the channels
+// in FP64 anyway, and count*channel sums stay exact in FP64 (all values are integers below 2^53), so
+// the whole inner loop runs on the FP64 pipe: 6 operations to classify, 4 fused multiply-adds to
+// accumulate (FMA is harmless here: every product and sum is exactly representable).
+struct PointD {
+  double r, g, b, c;
+};
+__device__ __forceinline__ PointD to_point(uint2 p) {
+  PointD d;
+  d.r = byte_to_double((p.x >> 16) & 0xFFu);
+  d.g = byte_to_double((p.x >> 8) & 0xFFu);
+  d.b = byte_to_double(p.x & 0xFFu);
+  d.c = __dsub_rn(__hiloint2double(0x43300000, (int)p.y), 4503599627370496.0);
+  return d;
+}
+__device__ __forceinline__ uint2 from_point(const PointD &d) {
+  const uint32_t R = (uint32_t)double_to_u52(d.r), G = (uint32_t)double_to_u52(d.g), B = (uint32_t)double_to_u52(d.b);
+  return make_uint2((R << 16) | (G << 8) | B, (uint32_t)double_to_u52(d.c));
+}
+__device__ __forceinline__ bool goes_new(const PassParams &pp, bool split_pass, const PointD &d) {
+  if (split_pass) {
+    const double ch = (pp.axis == 0) ? d.r : ((pp.axis == 1) ? d.g : d.b);
+    return pp.a < ch;  // (:473)
+  }
+  const double dot = fadd(fadd(fmul(pp.r[0], d.r), fmul(pp.r[1], d.g)), fmul(pp.r[2], d.b));
+  return !(pp.a < dot);  // (:683)
+}
+template <bool SPLIT>
+__device__ __forceinline__ bool goes_new_t(const PassParams &pp, const PointD &d) {
+  if (SPLIT) {
+    const double ch = (pp.axis == 0) ? d.r : ((pp.axis == 1) ? d.g : d.b);
+    return pp.a < ch;  // (:473)
+  }
+  const double dot = fadd(fadd(fmul(pp.r[0], d.r), fmul(pp.r[1], d.g)), fmul(pp.r[2], d.b));
+  return !(pp.a < dot);  // (:683)
+}
+struct AccD {
+  double cnt, r, g, b, rr, gg, bb;
+  uint32_t n;
+};
+__device__ __forceinline__ AccD acc_zero() {
+  AccD a;
+  a.cnt = a.r = a.g = a.b = a.rr = a.gg = a.bb = 0.0;
+  a.n = 0;
+  return a;
+}
+__device__ __forceinline__ void acc_add(AccD &a, const PointD &d, bool with_squares) {
+  a.cnt = __dadd_rn(a.cnt, d.c);
+  const double cr = __dmul_rn(d.c, d.r), cg = __dmul_rn(d.c, d.g), cb = __dmul_rn(d.c, d.b);  // exact
+  a.r = __dadd_rn(a.r, cr);
+  a.g = __dadd_rn(a.g, cg);
+  a.b = __dadd_rn(a.b, cb);
+  a.n += 1;
+  if (with_squares) {
+    a.rr = __fma_rn(cr, d.r, a.rr);
+    a.gg = __fma_rn(cg, d.g, a.gg);
+    a.bb = __fma_rn(cb, d.b, a.bb);
+  }
+}
+__device__ __forceinline__ void acc_words(const AccD &a, uint64_t (&v)[kAccWords]) {
+  v[kAccCnt] = double_to_u52(a.cnt);
+  v[kAccR] = double_to_u52(a.r);
+  v[kAccG] = double_to_u52(a.g);
+  v[kAccB] = double_to_u52(a.b);
+  v[kAccPts] = a.n;
+  v[kAccRR] = double_to_u52(a.rr);
+  v[kAccGG] = double_to_u52(a.gg);
+  v[kAccBB] = double_to_u52(a.bb);
+}
+
 __device__ __forceinline__ bool goes_new(const PassParams &pp, bool split_pass, uint32_t colour) {
   const uint32_t R = (colour >> 16) & 0xFFu, G = (colour >> 8) & 0xFFu, B = colour & 0xFFu;
   if (split_pass) {
     const uint32_t ch = (pp.axis == 0) ? R : ((pp.axis == 1) ? G : B);
-    return pp.a < (double)ch;  // (:473)
+    return pp.a < byte_to_double(ch);  // (:473)
   }
-  const double dot = fadd(fadd(fmul(pp.r[0], (double)R), fmul(pp.r[1], (double)G)), fmul(pp.r[2], (double)B));
+  const double dot = fadd(fadd(fmul(pp.r[0], byte_to_double(R)), fmul(pp.r[1], byte_to_double(G))),
+                          fmul(pp.r[2], byte_to_double(B)));
   return !(pp.a < dot);  // (:683) -- false on NaN, exactly like the reference's else branch
 }
 
@@ -83,7 +168,7 @@ __device__ __forceinline__ void make_children(const SplitNode &parent, int paren
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     // new side: sum(w x^2)/sum(w) - mean^2 (:836-838); old side: combined variance (:844-855)
-    const double sq_sum = fmul(__ull2double_rn(sums[kAccRR + c]), norm);
+    const double sq_sum = fmul(u52_to_double(sums[kAccRR + c]), norm);
     n.tv[c] = fsub(fdiv(sq_sum, m.nw), fsq(m.nm[c]));
     o.tv[c] = fsub(fdiv(fsub(fmul(parent.tw, parent.tv[c]), fmul(m.nw, fadd(n.tv[c], fsq(fsub(m.nm[c], parent.tm[c]))))),
                         m.ow),
