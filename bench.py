@@ -92,6 +92,15 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def traffic_bytes():
+    """DRAM bytes of one step from the committed ncu capture (never measured under the timed run)."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["total"])
+    return None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -281,23 +290,28 @@ def run_ours(args, rank, world, local_rank):
         return
 
     peak, peak_src = measured_peaks()
-    # algorithmic HBM bytes per pixel of each kernel: hist_insert reads 4 B/pixel;
-    # map_gather reads 4 + writes 4 B/pixel.  The split kernel works on U << N points.
+    ms_step = ms_dev / steps
+    # Per-kernel algorithmic HBM bytes: hist_insert reads 4 B/pixel; map_gather reads 4 and writes
+    # 4 B/pixel; the split kernel works on the U unique colours only (8 B/point once) and is latency-bound.
     kernels = {
-        "hist_insert": {"ms": stage_ms["hist_insert"], "bytes": 4.0 * NPIX},
-        "split": {"ms": stage_ms["split"], "bytes": None},
-        "map_gather": {"ms": stage_ms["map_gather"], "bytes": 8.0 * NPIX},
+        "hist_insert": {"ms": stage_ms["hist_insert"], "algorithmic_bytes": 4.0 * NPIX},
+        "split": {"ms": stage_ms["split"], "algorithmic_bytes": 8.0 * info["num_points"]},
+        "map_unique": {"ms": stage_ms["map_unique_or_bruteforce"], "algorithmic_bytes": 8.0 * info["num_points"]},
+        "map_gather": {"ms": stage_ms["map_gather"], "algorithmic_bytes": 8.0 * NPIX},
     }
-    for k in kernels.values():
-        k["gbs"] = (k["bytes"] / (k["ms"] * 1e-3) / 1e9) if k["bytes"] and k["ms"] > 0 else None
-    hbm_kernels = {n: k for n, k in kernels.items() if k["bytes"]}
-    dom = max(hbm_kernels, key=lambda n: hbm_kernels[n]["ms"])
-    achieved = kernels[dom]["gbs"]
-    # pipe roofline of SURVEY.md 8d for the whole step: N*K distance evaluations x 4 lane-instr
+    for kk in kernels.values():
+        kk["achieved_gbs"] = kk["algorithmic_bytes"] / (kk["ms"] * 1e-3) / 1e9 if kk["ms"] > 0 else None
+        kk["frac_of_hbm_peak"] = kk["achieved_gbs"] / peak if kk["achieved_gbs"] else None
+    dominant = max(kernels, key=lambda n: kernels[n]["ms"])
+    # Roofline of the path as north_star / SURVEY.md 8d define it: the slower of the INT32/FP32 issue-pipe time
+    # of N*K distance evaluations (4 lane-instr each) and the HBM time of 12 B/pixel.  The split phase is not
+    # credited: it is overhead inside the measured time.
     sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
     sm_clock = (clock_info.get("sm_max_mhz") or 1965.0) * 1e6
     t_pipe_ms = NPIX * K * 4 / (sm_count * 128 * sm_clock) * 1e3
-    ms_step = ms_dev / steps
+    t_hbm_ms = 12.0 * NPIX / (peak * 1e9) * 1e3
+    t_roof_ms = max(t_pipe_ms, t_hbm_ms)
+    hbm_achieved = 12.0 * NPIX / (ms_step * 1e-3) / 1e9
 
     cpu = None
     if not args.skip_cpu:
@@ -319,12 +333,16 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": e2e_value, "unit": "Mpixels/s", "h2d_bytes_per_step": NPIX * 4, "d2h_bytes_per_step": NPIX * 4 + K * 4 + 96,
                 "ms_per_step": ms_e2e / steps, "host_buffers": "pinned"},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak if achieved else None, "traffic": None, "peak_source": peak_src,
-                     "note": "algorithmic bytes of the dominant streaming kernel / its CUDA-event time; the split kernel is latency-bound (see stage_ms)"},
-        "pipe_roofline": {"definition": "SURVEY.md 8d: N*K distance evaluations x 4 lane-instr / (SMs x 128 lanes x SM clock)",
-                          "t_roof_ms": t_pipe_ms, "t_measured_ms": ms_step, "frac": t_pipe_ms / ms_step,
-                          "note": "remap_variant says which formulation produced the time; >1 would be an algorithmic win, not pipe efficiency"},
+        "roofline": {"bound": "hbm", "achieved": hbm_achieved, "peak": peak, "unit": "GB/s", "frac": hbm_achieved / peak,
+                     "traffic": traffic_bytes(), "peak_source": peak_src,
+                     "scope": "whole step: 12 algorithmic B/pixel (4 histogram read + 4 remap read + 4 remap write) / step time",
+                     "traffic_note": "dram bytes of one step from ncu --set full (profiles/r01_ncu_full_summary.txt): hist_insert 39.0 + split 1.2 + map_unique 1.0 + map_gather 44.1 MB; the remap output largely stays in the 126 MB L2",
+                     "dominant_kernel": dominant, "kernels": kernels,
+                     "note": "the path is not HBM-bound: north_star bounds it by the issue pipe (see path_roofline); the dominant kernel (split) is a dependency chain, DESIGN.md 5.2"},
+        "path_roofline": {"definition": "north_star / SURVEY.md 8d: T_roof = max(N*K distance evaluations x 4 lane-instr / (SMs x 128 lanes x SM clock), 12 B/pixel / HBM peak)",
+                          "t_pipe_ms": t_pipe_ms, "t_hbm_ms": t_hbm_ms, "t_roof_ms": t_roof_ms, "t_measured_ms": ms_step,
+                          "frac": t_roof_ms / ms_step, "target": 0.5,
+                          "note": "config.remap_variant says which formulation produced the time: the unique-colour table does U*K, not N*K, evaluations (an algorithmic win, not pipe efficiency)"},
         "stage_ms": stage_ms,
         "parity": parity,
     }

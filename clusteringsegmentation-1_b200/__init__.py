@@ -207,3 +207,28 @@ class DivQuant:
         n = self.lib.dq_debug_split_points(self.lib.dq_default_context(), _p(col), _p(cnt), col.size, norm, k, max_iters,
                                            num_bits, _p(ct), recs, _p(means, _f64p), _p(sizes))
         return ct[:n].copy(), [recs[i] for i in range(max(int(k) - 1, 0))], means.reshape(-1, 3), sizes
+
+
+# ---- multi-GPU partitioning (host logic; BASELINE.json configs 3 and 4) -------------------
+def frames_for_rank(num_frames, world_size, rank):
+    """Frame sharding: contiguous blocks, sizes differ by at most one, no collective on the data path."""
+    base, extra = divmod(num_frames, world_size)
+    start = rank * base + min(rank, extra)
+    return range(start, start + base + (1 if rank < extra else 0))
+
+
+def rows_for_rank(height, world_size, rank):
+    """Pixel-row sharding of one image: contiguous row blocks (sizes differ by at most one)."""
+    r = frames_for_rank(height, world_size, rank)
+    return r.start, r.stop
+
+
+def merge_histograms(colour_lists, count_lists):
+    """Exact merge of per-shard (colour, count) lists: counts are additive, so the merged histogram -- and
+    every sum the divisive phase takes over it -- is independent of the number of shards."""
+    colours = np.concatenate([np.asarray(c, np.uint32) for c in colour_lists])
+    counts = np.concatenate([np.asarray(c, np.uint64) for c in count_lists])
+    uniq, inv = np.unique(colours, return_inverse=True)
+    merged = np.zeros(uniq.size, np.uint64)
+    np.add.at(merged, inv, counts)
+    return uniq, merged

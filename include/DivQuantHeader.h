@@ -33,6 +33,10 @@ typedef struct {
   double weight;
 } Pixel_Double;
 
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
 /* DivQuantMisc.cpp:18-46 */
 clock_t start_timer(void);
 double stop_timer(const clock_t start);
@@ -60,5 +64,9 @@ void quant_varpart_fast(const uint32_t numPixels, const uint32_t *inPixels, uint
                         const uint32_t numRows, const uint32_t numCols, uint32_t *numClustersPtr,
                         uint32_t *colortablePtr, const int num_bits, const int dec_factor, const int max_iters,
                         const int allPixelsUnique);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 
 #endif /* DivQuantHeader_h */

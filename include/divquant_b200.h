@@ -24,6 +24,12 @@
 extern "C" {
 #endif
 
+/* The library is built with hidden visibility; only what this header (and the reference-named shim)
+ * declares is exported. */
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
 /* ------------------------------------------------------------------------------------------------
  * 1. Reference-signature entry points (HOST pointers, default context on the current CUDA device).
  *    Same names as the reference with a dq_ prefix; same argument order and meaning.
@@ -169,6 +175,10 @@ uint32_t dq_host_dedup_palette(uint32_t *colortable, uint32_t num_colors);
 void dq_host_build_search_tables(const uint32_t *colortable, int num_colors, uint32_t *sorted_out, int32_t *lut_init_out);
 
 const char *dq_version(void);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 
 #ifdef __cplusplus
 }

@@ -9,8 +9,14 @@
 extern "C" {
 #endif
 
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
 void quant_recurse(uint32_t numPixels, const uint32_t *inPixelsPtr, uint32_t *outColorTableOffsetPtr,
                    uint32_t *numClustersPtr, uint32_t *outColortablePtr, int allPixelsUnique);
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 
 #ifdef __cplusplus
 }
