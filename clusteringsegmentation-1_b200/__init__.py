@@ -83,6 +83,13 @@ def load_library(path=LIB_PATH):
         "dq_quant_varpart_device": (None, [vp, C.c_uint32, vp, C.c_uint32, C.c_uint32, _u32p, _u32p, C.c_int,
                                            C.c_int, C.c_int, C.c_int]),
         "dq_quant_recurse_ctx": (None, [vp, C.c_uint32, _u32p, _u32p, _u32p, _u32p, C.c_int]),
+        "dq_pipeline_create": (vp, [C.c_int, C.c_uint32, C.c_int]),
+        "dq_pipeline_destroy": (None, [vp]),
+        "dq_pipeline_submit": (None, [vp, C.c_uint32, _u32p, _u32p, _u32p, _u32p, C.c_int]),
+        "dq_pipeline_flush": (None, [vp]),
+        "dq_pipeline_last_elapsed_ms": (C.c_float, [vp]),
+        "dq_pipeline_context": (vp, [vp]),
+        "dq_pipeline_kernel_launches": (C.c_uint64, [vp]),
         "dq_debug_split_points": (C.c_uint32, [vp, _u32p, _u32p, C.c_uint32, C.c_double, C.c_uint32, C.c_int, C.c_int,
                                                _u32p, C.POINTER(SplitRecord), _f64p, _u32p]),
         "dq_debug_histogram": (C.c_uint32, [vp, _u32p, C.c_uint32, _u32p, _u32p]),
@@ -102,6 +109,8 @@ EXPORTED_C_SYMBOLS = [
     "dq_get_double_scale", "dq_validate_num_bits", "dq_set_display_timings", "dq_context_create", "dq_context_destroy",
     "dq_default_context", "dq_context_stream", "dq_context_synchronize", "dq_context_last_stats", "dq_context_set_profiling",
     "dq_quant_recurse_device", "dq_map_colors_device", "dq_quant_varpart_device", "dq_quant_recurse_ctx",
+    "dq_pipeline_create", "dq_pipeline_destroy", "dq_pipeline_submit", "dq_pipeline_flush", "dq_pipeline_last_elapsed_ms",
+    "dq_pipeline_context", "dq_pipeline_kernel_launches",
     "dq_debug_split_points", "dq_debug_histogram", "dq_debug_split_timeline", "dq_host_dedup_palette", "dq_host_build_search_tables",
 ]
 
@@ -207,6 +216,31 @@ class DivQuant:
         n = self.lib.dq_debug_split_points(self.lib.dq_default_context(), _p(col), _p(cnt), col.size, norm, k, max_iters,
                                            num_bits, _p(ct), recs, _p(means, _f64p), _p(sizes))
         return ct[:n].copy(), [recs[i] for i in range(max(int(k) - 1, 0))], means.reshape(-1, 3), sizes
+
+
+class FramePipeline:
+    """dq_pipeline: quant_recurse over a stream of frames with host (preferably pinned) buffers."""
+
+    def __init__(self, lib, device, max_pixels, depth=3):
+        self.lib = lib
+        self.handle = lib.dq_pipeline_create(device, max_pixels, depth)
+        self._keep = []
+
+    def submit(self, pixels, out, k, colortable, nk, all_unique=0):
+        """pixels/out/colortable: uint32 numpy arrays (or objects exposing .ctypes) that outlive flush();
+        nk: ctypes.c_uint32 holding the requested K (updated in place)."""
+        self._keep.append((pixels, out, colortable, nk))
+        self.lib.dq_pipeline_submit(self.handle, pixels.size, _p(pixels), _p(out), C.byref(nk), _p(colortable), all_unique)
+
+    def flush(self):
+        self.lib.dq_pipeline_flush(self.handle)
+        self._keep.clear()
+        return float(self.lib.dq_pipeline_last_elapsed_ms(self.handle))
+
+    def close(self):
+        if self.handle:
+            self.lib.dq_pipeline_destroy(self.handle)
+            self.handle = None
 
 
 # ---- multi-GPU partitioning (host logic; BASELINE.json configs 3 and 4, SURVEY.md 8e) -------------------

@@ -728,6 +728,139 @@ int dq_calc_color_table(const uint32_t *inPixels, uint32_t numPixels, uint32_t *
   return 0;
 }
 
+// ---- frame pipeline ----
+
+}  // extern "C"
+
+struct dq_pipeline {
+  struct Slot {
+    uint32_t *d_in = nullptr, *d_out = nullptr;
+    cudaEvent_t h2d_done = nullptr, d2h_done = nullptr;
+    bool busy = false;  // a D2H of this slot may still be in flight
+    // the frame waiting in this slot for its compute step
+    uint32_t n = 0;
+    uint32_t *out = nullptr, *k_ptr = nullptr, *colortable = nullptr;
+    int all_unique = 0;
+  };
+  dq_context *ctx = nullptr;
+  cudaStream_t h2d = nullptr, d2h = nullptr;
+  std::vector<Slot> slots;
+  uint32_t max_pixels = 0;
+  uint64_t submitted = 0;   // frames whose H2D was enqueued
+  uint64_t computed = 0;    // frames whose kernels ran
+  uint64_t launches = 0;
+  cudaEvent_t first = nullptr, last = nullptr;
+  bool have_first = false;
+  float last_ms = 0.f;
+};
+
+namespace {
+
+// Kernels + D2H of the oldest frame that has only been uploaded so far.
+void pipeline_compute_next(dq_pipeline *p) {
+  dq_pipeline::Slot &s = p->slots[p->computed % p->slots.size()];
+  dq_context *ctx = p->ctx;
+  DQ_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, s.h2d_done, 0));
+  memset(&ctx->stats, 0, sizeof(ctx->stats));
+  ctx->stats.num_pixels = s.n;
+  quant_recurse_device_impl(ctx, s.n, s.d_in, s.d_out, s.k_ptr, s.colortable, s.all_unique, nullptr, nullptr);
+  p->launches += ctx->stats.kernel_launches;
+  // quant_recurse_device_impl returns with the compute stream drained: the D2H can start right away
+  DQ_CUDA_CHECK(cudaMemcpyAsync(s.out, s.d_out, (size_t)s.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, p->d2h));
+  DQ_CUDA_CHECK(cudaEventRecord(s.d2h_done, p->d2h));
+  s.busy = true;
+  p->computed++;
+}
+
+}  // namespace
+
+extern "C" {
+
+dq_pipeline *dq_pipeline_create(int device, uint32_t max_pixels, int depth) {
+  if (depth < 2) depth = 2;
+  if (depth > 8) depth = 8;
+  dq_pipeline *p = new dq_pipeline();
+  p->ctx = dq_context_create(device);
+  p->max_pixels = max_pixels;
+  DQ_CUDA_CHECK(cudaStreamCreateWithFlags(&p->h2d, cudaStreamNonBlocking));
+  DQ_CUDA_CHECK(cudaStreamCreateWithFlags(&p->d2h, cudaStreamNonBlocking));
+  p->slots.resize(depth);
+  for (auto &s : p->slots) {
+    DQ_CUDA_CHECK(cudaMalloc(&s.d_in, (size_t)max_pixels * sizeof(uint32_t)));
+    DQ_CUDA_CHECK(cudaMalloc(&s.d_out, (size_t)max_pixels * sizeof(uint32_t)));
+    DQ_CUDA_CHECK(cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
+    DQ_CUDA_CHECK(cudaEventCreateWithFlags(&s.d2h_done, cudaEventDisableTiming));
+  }
+  DQ_CUDA_CHECK(cudaEventCreate(&p->first));
+  DQ_CUDA_CHECK(cudaEventCreate(&p->last));
+  return p;
+}
+
+void dq_pipeline_destroy(dq_pipeline *p) {
+  if (!p) return;
+  dq_pipeline_flush(p);
+  for (auto &s : p->slots) {
+    cudaFree(s.d_in);
+    cudaFree(s.d_out);
+    cudaEventDestroy(s.h2d_done);
+    cudaEventDestroy(s.d2h_done);
+  }
+  cudaEventDestroy(p->first);
+  cudaEventDestroy(p->last);
+  cudaStreamDestroy(p->h2d);
+  cudaStreamDestroy(p->d2h);
+  dq_context_destroy(p->ctx);
+  delete p;
+}
+
+void dq_pipeline_submit(dq_pipeline *p, uint32_t numPixels, const uint32_t *inPixelsPtr, uint32_t *outPixelsPtr,
+                        uint32_t *numClustersPtr, uint32_t *outColortablePtr, int allPixelsUnique) {
+  require_device(p->ctx);
+  if (numPixels > p->max_pixels) {
+    fprintf(stderr, "divquant_b200: frame of %u pixels exceeds the pipeline's max_pixels (%u)\n", numPixels, p->max_pixels);
+    abort();
+  }
+  check_quant_args(numPixels, *numClustersPtr, 8);
+  // never more than depth-1 uploaded-but-not-computed frames: the slot we are about to fill must be free
+  while (p->submitted - p->computed >= p->slots.size() - 1 && p->computed < p->submitted) pipeline_compute_next(p);
+  dq_pipeline::Slot &s = p->slots[p->submitted % p->slots.size()];
+  if (s.busy) {  // its previous frame's D2H must have left d_out ... and d_in is reused as well
+    DQ_CUDA_CHECK(cudaEventSynchronize(s.d2h_done));
+    s.busy = false;
+  }
+  if (!p->have_first) {
+    DQ_CUDA_CHECK(cudaEventRecord(p->first, p->h2d));
+    p->have_first = true;
+  }
+  DQ_CUDA_CHECK(cudaMemcpyAsync(s.d_in, inPixelsPtr, (size_t)numPixels * sizeof(uint32_t), cudaMemcpyHostToDevice, p->h2d));
+  DQ_CUDA_CHECK(cudaEventRecord(s.h2d_done, p->h2d));
+  s.n = numPixels;
+  s.out = outPixelsPtr;
+  s.k_ptr = numClustersPtr;
+  s.colortable = outColortablePtr;
+  s.all_unique = allPixelsUnique;
+  p->submitted++;
+  // while that upload runs on the copy engine, do the kernels of the frame before it
+  if (p->submitted - p->computed >= 2) pipeline_compute_next(p);
+}
+
+void dq_pipeline_flush(dq_pipeline *p) {
+  require_device(p->ctx);
+  while (p->computed < p->submitted) pipeline_compute_next(p);
+  if (p->have_first) {
+    DQ_CUDA_CHECK(cudaEventRecord(p->last, p->d2h));
+    DQ_CUDA_CHECK(cudaStreamSynchronize(p->d2h));
+    DQ_CUDA_CHECK(cudaEventSynchronize(p->first));
+    DQ_CUDA_CHECK(cudaEventElapsedTime(&p->last_ms, p->first, p->last));
+    p->have_first = false;
+  }
+  for (auto &s : p->slots) s.busy = false;
+}
+
+float dq_pipeline_last_elapsed_ms(const dq_pipeline *p) { return p->last_ms; }
+dq_context *dq_pipeline_context(dq_pipeline *p) { return p->ctx; }
+uint64_t dq_pipeline_kernel_launches(const dq_pipeline *p) { return p->launches; }
+
 // ---- test hooks ----
 
 uint32_t dq_debug_split_timeline(dq_context *ctx, int enable, uint64_t *pairs_out, uint32_t capacity_pairs) {

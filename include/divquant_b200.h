@@ -136,6 +136,30 @@ void dq_quant_recurse_ctx(dq_context *ctx, uint32_t numPixels, const uint32_t *i
                           uint32_t *numClustersPtr, uint32_t *outColortablePtr, int allPixelsUnique);
 
 /* ------------------------------------------------------------------------------------------------
+ * 2b. Frame pipeline: quant_recurse over a stream of frames with HOST buffers (BASELINE.json config 4,
+ *     "batch of frames", and the end-to-end leg of bench.py).  Frames are independent units, so the copy
+ *     engines and the SMs work on different frames at the same time: H2D of frame f+1, kernels of frame f
+ *     and D2H of frame f-1 overlap.  Results are exactly those of dq_quant_recurse frame by frame.
+ *     Host buffers should be pinned (cudaHostAlloc / torch pin_memory) for the copies to be asynchronous;
+ *     pageable buffers work but serialise.  All host pointers of a frame must stay valid until
+ *     dq_pipeline_flush() returns (or until `depth` later submits have returned).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct dq_pipeline dq_pipeline;
+/* depth = frames in flight (2..8). max_pixels = largest frame that will be submitted. */
+dq_pipeline *dq_pipeline_create(int device, uint32_t max_pixels, int depth);
+void dq_pipeline_destroy(dq_pipeline *pipe);
+void dq_pipeline_submit(dq_pipeline *pipe, uint32_t numPixels, const uint32_t *inPixelsPtr, uint32_t *outPixelsPtr,
+                        uint32_t *numClustersPtr, uint32_t *outColortablePtr, int allPixelsUnique);
+/* Returns when every submitted frame's outPixels / colortable / numClusters are in host memory. */
+void dq_pipeline_flush(dq_pipeline *pipe);
+/* The context the pipeline computes on (for dq_context_last_stats) and its streams' first/last events are
+ * internal; elapsed device time of everything submitted since the last flush, in milliseconds: */
+float dq_pipeline_last_elapsed_ms(const dq_pipeline *pipe);
+dq_context *dq_pipeline_context(dq_pipeline *pipe);
+/* Kernels launched since creation (sum over frames). */
+uint64_t dq_pipeline_kernel_launches(const dq_pipeline *pipe);
+
+/* ------------------------------------------------------------------------------------------------
  * 3. Test hooks (used by tests/ to compare intermediate results with the oracle).
  * ---------------------------------------------------------------------------------------------- */
 

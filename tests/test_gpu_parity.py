@@ -209,3 +209,25 @@ def test_degenerate_inputs(dq, oracle):
     with muted((2,)):
         out, pal = dq.quant_recurse(np.array([0xFFABCDEF], np.uint32), 4, 0)
     assert list(pal) == [0xABCDEF] and list(out) == [0xABCDEF]
+
+
+def test_frame_pipeline_matches_single_calls(dq, pkg, oracle):
+    import ctypes as C
+    import torch
+    frames = [oracle.generate(1, 320, 200, 100 + i) for i in range(7)] + [oracle.generate(2, 64, 64, 5)]
+    npix = max(f.size for f in frames)
+    pipe = pkg.FramePipeline(dq.lib, 0, npix, depth=3)
+    ins = [torch.from_numpy(f.view(np.int32).copy()).pin_memory() for f in frames]
+    outs = [torch.zeros(f.size, dtype=torch.int32).pin_memory() for f in frames]
+    cts = [np.zeros(32, np.uint32) for _ in frames]
+    nks = [C.c_uint32(32) for _ in frames]
+    for i in range(len(frames)):
+        pipe.submit(ins[i].numpy().view(np.uint32), outs[i].numpy().view(np.uint32), 32, cts[i], nks[i], 0)
+    ms = pipe.flush()
+    assert ms > 0
+    for i, f in enumerate(frames):
+        with muted((2,)):
+            out, pal = dq.quant_recurse(f, 32, 0)
+        assert np.array_equal(cts[i][:nks[i].value], pal), i
+        assert np.array_equal(outs[i].numpy().view(np.uint32), out), i
+    pipe.close()
