@@ -15,6 +15,8 @@
 //   * de-duplicated (map_unique + map_gather): the K evaluations are done once per UNIQUE colour and
 //     the answer is parked in the 2^24-entry direct table; pixels then gather through it.  Used
 //     whenever a histogram of the same pixels is at hand (quant_recurse always has one).
+#include <algorithm>
+
 #include "dq_kernels.cuh"
 
 namespace dq {
@@ -54,6 +56,138 @@ __device__ __forceinline__ void stage_palette(const uint32_t *sorted, int num_co
   for (int i = threadIdx.x; i < (int)kLutEntries; i += blockDim.x) s_lut[i] = lut_init[i];
   __syncthreads();
 }
+
+// ---- fast formulation (palette in shared memory) --------------------------------------------------
+// dist(k) - |p|^2 = |c_k|^2 - 2 p.c_k is linear in the pixel, so with the palette pre-expanded to
+// {-2r, -2g, -2b, r^2+g^2+b^2} one evaluation is 3 FFMA + 1 FMNMX (all values are integers below 2^24 in
+// magnitude, hence exact in FP32) -- the "4 lane-instructions per evaluation" of SURVEY.md 8d.  One
+// broadcast LDS.128 per palette entry is shared by PIX pixels of the thread.  The arg-min with the
+// reference's tie-break is then found by walking the reference's own visiting order (start index, +1, -1,
+// +2, ...) until the first entry at the minimal distance: that entry is argmin (dist, rank) by definition.
+template <int PIX>
+struct PixelBlock {
+  float r[PIX], g[PIX], b[PIX], best[PIX];
+};
+
+__device__ __forceinline__ float entry_key(const float4 e, float r, float g, float b) {
+  return fmaf(r, e.x, fmaf(g, e.y, fmaf(b, e.z, e.w)));
+}
+
+template <int PIX>
+__device__ __forceinline__ void min_distance(const float4 *s_pal, int num_colors, PixelBlock<PIX> &px) {
+#pragma unroll
+  for (int i = 0; i < PIX; ++i) px.best[i] = 3.0e38f;
+#pragma unroll 8
+  for (int k = 0; k < num_colors; ++k) {
+    const float4 e = s_pal[k];
+#pragma unroll
+    for (int i = 0; i < PIX; ++i) px.best[i] = fminf(px.best[i], entry_key(e, px.r[i], px.g[i], px.b[i]));
+  }
+}
+
+// First entry, in the reference's visiting order from start index s, whose distance equals the minimum.
+__device__ __forceinline__ int first_at_minimum(const float4 *s_pal, int num_colors, int s, float r, float g, float b,
+                                                float best) {
+  if (entry_key(s_pal[s], r, g, b) == best) return s;
+  for (int d = 1; d < num_colors; ++d) {
+    const int up = s + d, down = s - d;
+    if (up < num_colors && entry_key(s_pal[up], r, g, b) == best) return up;
+    if (down >= 0 && entry_key(s_pal[down], r, g, b) == best) return down;
+  }
+  return s;  // unreachable: the minimum is attained by some entry
+}
+
+__device__ __forceinline__ void stage_palette_fast(const uint32_t *sorted, int num_colors, const int *lut_init,
+                                                   float4 *s_pal, uint32_t *s_word, int *s_lut) {
+  for (int k = threadIdx.x; k < num_colors; k += blockDim.x) {
+    const uint32_t c = sorted[k] & 0x00FFFFFFu;
+    const float r = (float)((c >> 16) & 0xFF), g = (float)((c >> 8) & 0xFF), b = (float)(c & 0xFF);
+    s_pal[k] = make_float4(-2.f * r, -2.f * g, -2.f * b, r * r + g * g + b * b);
+    s_word[k] = c;
+  }
+  for (int i = threadIdx.x; i < (int)kLutEntries; i += blockDim.x) s_lut[i] = lut_init[i];
+  __syncthreads();
+}
+
+constexpr int kFastPix = 8;  // pixels per thread per iteration: two 128-bit loads
+
+__global__ void __launch_bounds__(kMapThreads) map_pixels_fast_kernel(const uint32_t *__restrict__ in, uint32_t n,
+                                                                     uint32_t *__restrict__ out, const uint32_t *sorted,
+                                                                     int num_colors, const int *lut_init) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  float4 *s_pal = reinterpret_cast<float4 *>(smem);
+  uint32_t *s_word = reinterpret_cast<uint32_t *>(smem + (size_t)num_colors * 16);
+  int *s_lut = reinterpret_cast<int *>(smem + (size_t)num_colors * 20);
+  stage_palette_fast(sorted, num_colors, lut_init, s_pal, s_word, s_lut);
+  const uint32_t nblk = n / kFastPix;
+  const uint4 *in4 = reinterpret_cast<const uint4 *>(in);
+  uint4 *out4 = reinterpret_cast<uint4 *>(out);
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nblk; t += gridDim.x * blockDim.x) {
+    const uint4 a = __ldcs(in4 + 2 * t), c = __ldcs(in4 + 2 * t + 1);
+    const uint32_t w[kFastPix] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+    PixelBlock<kFastPix> px;
+    int start[kFastPix];
+#pragma unroll
+    for (int i = 0; i < kFastPix; ++i) {
+      const int R = (w[i] >> 16) & 0xFF, G = (w[i] >> 8) & 0xFF, B = w[i] & 0xFF;
+      px.r[i] = (float)R, px.g[i] = (float)G, px.b[i] = (float)B;
+      start[i] = s_lut[R + G + B];
+    }
+    min_distance<kFastPix>(s_pal, num_colors, px);
+    uint32_t res[kFastPix];
+#pragma unroll
+    for (int i = 0; i < kFastPix; ++i)
+      res[i] = s_word[first_at_minimum(s_pal, num_colors, start[i], px.r[i], px.g[i], px.b[i], px.best[i])];
+    __stcs(out4 + 2 * t, make_uint4(res[0], res[1], res[2], res[3]));
+    __stcs(out4 + 2 * t + 1, make_uint4(res[4], res[5], res[6], res[7]));
+  }
+  // tail: fewer than kFastPix pixels, one thread each
+  const uint32_t tail0 = nblk * kFastPix;
+  if (blockIdx.x == 0 && tail0 + threadIdx.x < n) {
+    const uint32_t wv = in[tail0 + threadIdx.x];
+    const int R = (wv >> 16) & 0xFF, G = (wv >> 8) & 0xFF, B = wv & 0xFF;
+    PixelBlock<1> px;
+    px.r[0] = (float)R, px.g[0] = (float)G, px.b[0] = (float)B;
+    min_distance<1>(s_pal, num_colors, px);
+    out[tail0 + threadIdx.x] = s_word[first_at_minimum(s_pal, num_colors, s_lut[R + G + B], px.r[0], px.g[0], px.b[0], px.best[0])];
+  }
+}
+
+constexpr int kUniqPix = 4;
+
+__global__ void __launch_bounds__(kMapThreads) map_unique_fast_kernel(const uint32_t *__restrict__ uniq, const uint32_t *ucount,
+                                                                     uint32_t *table, const uint32_t *sorted, int num_colors,
+                                                                     const int *lut_init) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  float4 *s_pal = reinterpret_cast<float4 *>(smem);
+  uint32_t *s_word = reinterpret_cast<uint32_t *>(smem + (size_t)num_colors * 16);
+  int *s_lut = reinterpret_cast<int *>(smem + (size_t)num_colors * 20);
+  stage_palette_fast(sorted, num_colors, lut_init, s_pal, s_word, s_lut);
+  const uint32_t u = *ucount;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  // every thread takes kUniqPix colours a stride apart (coalesced loads of the unique list)
+  for (uint32_t base = blockIdx.x * blockDim.x + threadIdx.x; base < u; base += kUniqPix * stride) {
+    uint32_t c[kUniqPix];
+    PixelBlock<kUniqPix> px;
+    int start[kUniqPix];
+#pragma unroll
+    for (int i = 0; i < kUniqPix; ++i) {
+      const uint32_t idx = base + (uint32_t)i * stride;
+      c[i] = idx < u ? uniq[idx] : 0u;
+      const int R = (c[i] >> 16) & 0xFF, G = (c[i] >> 8) & 0xFF, B = c[i] & 0xFF;
+      px.r[i] = (float)R, px.g[i] = (float)G, px.b[i] = (float)B;
+      start[i] = s_lut[R + G + B];
+    }
+    min_distance<kUniqPix>(s_pal, num_colors, px);
+#pragma unroll
+    for (int i = 0; i < kUniqPix; ++i) {
+      if (base + (uint32_t)i * stride < u)
+        table[c[i]] = 0x80000000u | s_word[first_at_minimum(s_pal, num_colors, start[i], px.r[i], px.g[i], px.b[i], px.best[i])];
+    }
+  }
+}
+
+inline size_t fast_smem_bytes(int num_colors) { return (size_t)num_colors * 20 + kLutEntries * 4 + 16; }
 
 // Brute force over pixels, palette staged in shared memory.
 __global__ void __launch_bounds__(kMapThreads) map_pixels_kernel(const uint32_t *__restrict__ in, uint32_t n,
@@ -136,12 +270,24 @@ inline size_t map_smem_bytes(int num_colors) { return ((kLutEntries * 4 + 15) & 
 
 }  // namespace
 
-int map_smem_palette_limit() { return 8192; }  // 128 KB of int4 entries + the LUT fit the 227 KB carve-out
+int map_smem_palette_limit() { return 8192; }  // 160 KB of expanded entries + the LUT fit the 227 KB carve-out
 
 void map_pixels(const uint32_t *d_in, uint32_t n, uint32_t *d_out, const uint32_t *d_sorted, int num_colors,
                 const int *d_lut, int4 *d_pal_scratch, int sm_count, cudaStream_t st) {
   if (n == 0) return;
-  if (num_colors <= map_smem_palette_limit()) {
+  const bool aligned = ((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_out)) & 15u) == 0;
+  if (num_colors <= map_smem_palette_limit() && aligned) {
+    const size_t smem = fast_smem_bytes(num_colors);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+      DQ_CUDA_CHECK(cudaFuncSetAttribute(map_pixels_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = smem;
+    }
+    // resident CTAs per SM are bounded by the palette's shared memory; keep the grid a multiple of the SM count
+    int per_sm = (int)std::min<size_t>(8, std::max<size_t>(1, (200 * 1024) / smem));
+    map_pixels_fast_kernel<<<blocks_for(n / kFastPix + 1, kMapThreads, sm_count, per_sm), kMapThreads, smem, st>>>(
+        d_in, n, d_out, d_sorted, num_colors, d_lut);
+  } else if (num_colors <= map_smem_palette_limit()) {
     const size_t smem = map_smem_bytes(num_colors);
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
@@ -161,14 +307,15 @@ void map_pixels(const uint32_t *d_in, uint32_t n, uint32_t *d_out, const uint32_
 
 void map_unique(const uint32_t *d_uniq, const uint32_t *d_ucount, uint32_t u_hint, uint32_t *d_table,
                 const uint32_t *d_sorted, int num_colors, const int *d_lut, int sm_count, cudaStream_t st) {
-  const size_t smem = map_smem_bytes(num_colors);
+  const size_t smem = fast_smem_bytes(num_colors);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
-    DQ_CUDA_CHECK(cudaFuncSetAttribute(map_unique_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DQ_CUDA_CHECK(cudaFuncSetAttribute(map_unique_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  map_unique_kernel<<<blocks_for(u_hint, kMapThreads, sm_count, 8), kMapThreads, smem, st>>>(d_uniq, d_ucount, d_table,
-                                                                                            d_sorted, num_colors, d_lut);
+  int per_sm = (int)std::min<size_t>(8, std::max<size_t>(1, (200 * 1024) / smem));
+  map_unique_fast_kernel<<<blocks_for(u_hint / kUniqPix + 1, kMapThreads, sm_count, per_sm), kMapThreads, smem, st>>>(
+      d_uniq, d_ucount, d_table, d_sorted, num_colors, d_lut);
   DQ_CUDA_CHECK(cudaGetLastError());
 }
 
