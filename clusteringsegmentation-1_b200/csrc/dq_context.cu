@@ -253,6 +253,11 @@ uint32_t run_split(dq_context *ctx, uint32_t point_capacity, double norm, uint32
   if (use_v2 && getenv("DQ_PROFILE_NARROW")) {
     uint32_t prof[8];
     cudaMemcpy(prof, ctx->d_progress.ptr + 256, sizeof(prof), cudaMemcpyDeviceToHost);
+    uint32_t wp[4];
+    cudaMemcpy(wp, ctx->d_progress.ptr + 264, sizeof(wp), cudaMemcpyDeviceToHost);
+    if (wp[3])
+      fprintf(stderr, "wide profile (cycles per job-pass, thread 0 of every participant): gather %.0f derive+sync %.0f classify+reduce+publish %.0f ; %u job-passes\n",
+              (double)wp[0] / wp[3], (double)wp[1] / wp[3], (double)wp[2] / wp[3], wp[3]);
     if (prof[4])
       fprintf(stderr, "narrow profile (cycles per pass, thread 0): classify %.0f stage1+sync %.0f warp0(stage2+derive) %.0f sync %.0f ; %u passes, %u points\n",
               (double)prof[0] / prof[4], (double)prof[1] / prof[4], (double)prof[2] / prof[4], (double)prof[3] / prof[4], prof[4], prof[5]);
@@ -300,9 +305,12 @@ void upload_search_tables(dq_context *ctx, const uint32_t *colortable, int k) {
   uint32_t *h_sorted = ctx->h_small;
   int *h_lut = reinterpret_cast<int *>(ctx->h_small + k);
   build_search_tables(colortable, k, h_sorted, h_lut);
-  ctx->d_sorted.ensure(k);
-  DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->d_sorted.ptr, h_sorted, (size_t)k * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-  DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->d_lut, h_lut, kLutEntries * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  // sorted palette and start-index table travel in one copy: [k palette words | 766 lut entries]
+  ctx->d_sorted.ensure((size_t)k + kLutEntries);
+  ctx->d_lut = reinterpret_cast<int *>(ctx->d_sorted.ptr + k);
+  (void)h_lut;
+  DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->d_sorted.ptr, h_sorted, ((size_t)k + kLutEntries) * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                                ctx->stream));
   // h_small is reused by later calls: the copies above must have been issued from it before then;
   // every caller synchronises the stream before returning.
 }
@@ -477,7 +485,6 @@ dq_context *dq_context_create(int device) {
   DQ_CUDA_CHECK(cudaMemsetAsync(ctx->d_table, 0, (size_t)kColourBins * sizeof(uint32_t), ctx->stream));
   DQ_CUDA_CHECK(cudaMalloc(&ctx->d_cb, sizeof(ControlBlock)));
   DQ_CUDA_CHECK(cudaMallocHost(&ctx->h_cb, sizeof(ControlBlock)));
-  DQ_CUDA_CHECK(cudaMalloc(&ctx->d_lut, kLutEntries * sizeof(int)));
   memset(&ctx->stats, 0, sizeof(ctx->stats));
   for (int i = 0; i < 8; ++i) DQ_CUDA_CHECK(cudaEventCreate(&ctx->ev[i]));
   ctx->display_timings = display_timings_default();
@@ -513,7 +520,6 @@ void dq_context_destroy(dq_context *ctx) {
   ctx->d_progress.release();
   cudaFree(ctx->d_table);
   cudaFree(ctx->d_cb);
-  cudaFree(ctx->d_lut);
   cudaFreeHost(ctx->h_cb);
   if (ctx->h_small) cudaFreeHost(ctx->h_small);
   for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->ev[i]);

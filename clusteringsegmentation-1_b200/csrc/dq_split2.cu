@@ -483,27 +483,34 @@ __device__ void fast_assignment(const SplitArgs &A, Shared2 &S, const Arrays &R)
     S.bad = 0;
     S.scan_carry = 0;  // |L|
   }
+  for (int i = tid; i < (K + 31) / 32; i += T) R.cand[i] = 0;  // bitmap of popped ranks
+  __syncthreads();
+  // rank[i] = number of known nodes with a larger TSE
+  for (int i = tid; i < n; i += T) {
+    const double t = R.tse[i];
+    int above = n;
+    if (t == t) {  // NaN is never selected (:882)
+      above = 0;
+#pragma unroll 8
+      for (int m2 = 0; m2 < n; ++m2) above += (R.tse[m2] > t);
+    }
+    R.rank[i] = above;
+  }
   __syncthreads();
   for (int i = tid; i < n; i += T) {
     const double t = R.tse[i];
-    int above = n, equal = 1;
-    if (t == t) {  // NaN is never selected (:882)
-      above = 0;
-      equal = 0;
-      for (int m2 = 0; m2 < n; ++m2) {
-        const double u = R.tse[m2];
-        above += (u > t);
-        equal += (u == t);
-      }
-    }
-    R.rank[i] = above;
+    const int above = R.rank[i];
     if (above < K - 1) {
       atomicAdd(&S.scan_carry, 1);
-      bool ok = (equal == 1) && (R.child[i] >= 0) && (t > DBL_MIN);
+      bool ok = (R.child[i] >= 0) && (t > DBL_MIN);
       if (i != 0) ok = ok && (R.tse[R.parent[i]] > t);
+      // equal keys share a rank: every popped rank 0..K-2 must be hit exactly once (checked through |L| == K-1
+      // together with the bitmap below), and nothing may tie with the first rejected key
+      if (ok) {
+        const unsigned bit = 1u << (above & 31);
+        if (atomicOr(reinterpret_cast<unsigned *>(R.cand) + (above >> 5), bit) & bit) ok = false;
+      }
       if (!ok) S.bad = 1;
-    } else if (above == K - 1 && equal != 1) {
-      S.bad = 1;  // tie right at the boundary
     }
   }
   __syncthreads();
@@ -980,13 +987,23 @@ __global__ void __launch_bounds__(512, 1) split2_kernel(const SplitArgs A, const
           pre[k] = make_uint2(0, 0);
           if ((uint32_t)tid < nthr && q < n_my) pre[k] = ld_cg_u2(A.pts[jc.buf] + jc.begin + share_offset(q, me));
         }
+#ifdef DQ_PROFILE_NARROW
+        const long long w0 = clock64();
+        long long w1 = w0;
+#endif
         if (pass == 0) {
           set_split_params(S, jc);
         } else {
           gather(A, S, slots_r, R.slot0[j], m, 5, (seq0 + pass - 1) & 0xFFFFu);
+#ifdef DQ_PROFILE_NARROW
+          w1 = clock64();
+#endif
           derive_params_warp0(S, jc, A.norm);
         }
         __syncthreads();
+#ifdef DQ_PROFILE_NARROW
+        const long long w2 = clock64();
+#endif
         const PassParams pp = S.pp;
         uint64_t v[kAccWords];
         {
@@ -1011,6 +1028,14 @@ __global__ void __launch_bounds__(512, 1) split2_kernel(const SplitArgs A, const
           }
         }
         __syncthreads();
+#ifdef DQ_PROFILE_NARROW
+        if (tid == 0 && pass > 0) {
+          atomicAdd(X.progress + 264, (uint32_t)(w1 - w0));            // gather (wait + reduce)
+          atomicAdd(X.progress + 265, (uint32_t)(w2 - w1));            // derive + sync
+          atomicAdd(X.progress + 266, (uint32_t)(clock64() - w2));     // classify + reduce + publish
+          atomicAdd(X.progress + 267, 1u);
+        }
+#endif
       }
       if (n_mywide) trace2(A, kTracePass, pass);
       DQ_PROGRESS(round * 10000 + 2000 + pass);
