@@ -83,6 +83,8 @@ def load_library(path=LIB_PATH):
         "dq_quant_varpart_device": (None, [vp, C.c_uint32, vp, C.c_uint32, C.c_uint32, _u32p, _u32p, C.c_int,
                                            C.c_int, C.c_int, C.c_int]),
         "dq_quant_recurse_ctx": (None, [vp, C.c_uint32, _u32p, _u32p, _u32p, _u32p, C.c_int]),
+        "dq_shard_histogram": (C.c_uint32, [vp, vp, C.c_uint32, vp, vp]),
+        "dq_shard_quantize_map": (None, [vp, vp, vp, C.c_uint32, C.c_uint64, vp, C.c_uint32, vp, _u32p, _u32p]),
         "dq_pipeline_create": (vp, [C.c_int, C.c_uint32, C.c_int]),
         "dq_pipeline_destroy": (None, [vp]),
         "dq_pipeline_submit": (None, [vp, C.c_uint32, _u32p, _u32p, _u32p, _u32p, C.c_int]),
@@ -109,7 +111,7 @@ EXPORTED_C_SYMBOLS = [
     "dq_get_double_scale", "dq_validate_num_bits", "dq_set_display_timings", "dq_context_create", "dq_context_destroy",
     "dq_default_context", "dq_context_stream", "dq_context_synchronize", "dq_context_last_stats", "dq_context_set_profiling",
     "dq_quant_recurse_device", "dq_map_colors_device", "dq_quant_varpart_device", "dq_quant_recurse_ctx",
-    "dq_pipeline_create", "dq_pipeline_destroy", "dq_pipeline_submit", "dq_pipeline_flush", "dq_pipeline_last_elapsed_ms",
+    "dq_shard_histogram", "dq_shard_quantize_map", "dq_pipeline_create", "dq_pipeline_destroy", "dq_pipeline_submit", "dq_pipeline_flush", "dq_pipeline_last_elapsed_ms",
     "dq_pipeline_context", "dq_pipeline_kernel_launches",
     "dq_debug_split_points", "dq_debug_histogram", "dq_debug_split_timeline", "dq_host_dedup_palette", "dq_host_build_search_tables",
 ]
@@ -266,3 +268,40 @@ def merge_histograms(colour_lists, count_lists):
     merged = np.zeros(uniq.size, np.uint64)
     np.add.at(merged, inv, counts)
     return uniq, merged
+
+
+def row_sharded_quant_recurse(lib, ctx, shard, total_pixels, k, dist=None):
+    """quant_recurse of ONE image whose pixel rows are spread over the ranks of `dist` (torch.distributed, NCCL).
+
+    shard: this rank's rows as a CUDA int32/uint32-viewed torch tensor (flat).  Returns (out_shard, palette).
+    One exchange on the data path: an all-gather of the per-shard (colour, count) lists (sizes first)."""
+    import torch
+
+    n = shard.numel()
+    dev = shard.device
+    colours = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    counts = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    u = lib.dq_shard_histogram(ctx, shard.data_ptr(), n, colours.data_ptr(), counts.data_ptr())
+    if dist is not None and dist.get_world_size() > 1:
+        world = dist.get_world_size()
+        sizes = torch.zeros(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(sizes, torch.tensor([u], dtype=torch.int64, device=dev))
+        sizes_h = sizes.cpu().tolist()
+        cap = max(max(sizes_h), 1)
+        packed = torch.zeros(2, cap, dtype=torch.int32, device=dev)  # padding has count 0 and is skipped by the merge
+        packed[0, :u] = colours[:u]
+        packed[1, :u] = counts[:u]
+        gathered = torch.empty(world, 2, cap, dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(gathered.view(-1), packed.view(-1))
+        all_colours = gathered[:, 0, :].contiguous().view(-1)
+        all_counts = gathered[:, 1, :].contiguous().view(-1)
+        entries = world * cap
+    else:
+        all_colours, all_counts, entries = colours, counts, u
+    torch.cuda.current_stream(dev).synchronize()
+    out = torch.empty_like(shard)
+    ct = np.zeros(max(int(k), 1), np.uint32)
+    nk = C.c_uint32(k)
+    lib.dq_shard_quantize_map(ctx, all_colours.data_ptr(), all_counts.data_ptr(), entries, total_pixels, shard.data_ptr(), n,
+                              out.data_ptr(), C.byref(nk), _p(ct))
+    return out, ct[:nk.value].copy()

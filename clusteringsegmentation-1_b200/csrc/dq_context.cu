@@ -734,6 +734,59 @@ int dq_calc_color_table(const uint32_t *inPixels, uint32_t numPixels, uint32_t *
   return 0;
 }
 
+// ---- pixel-row sharding of one image ----
+
+uint32_t dq_shard_histogram(dq_context *ctx, const uint32_t *d_shard, uint32_t n_shard, uint32_t *d_colours, uint32_t *d_counts) {
+  require_device(ctx);
+  memset(&ctx->stats, 0, sizeof(ctx->stats));
+  ctx->stats.num_pixels = n_shard;
+  if (n_shard == 0) return 0;
+  reset_control(ctx);
+  ctx->d_pts0.ensure(n_shard);
+  run_histogram(ctx, d_shard, n_shard, 1, n_shard, 1, 8);
+  hist_collect(ctx->d_uniq.ptr, &ctx->d_cb->ucount, n_shard, ctx->d_table, ctx->d_pts0.ptr, ctx->sm_count, ctx->stream);
+  hist_export(ctx->d_pts0.ptr, &ctx->d_cb->ucount, n_shard, d_colours, d_counts, ctx->sm_count, ctx->stream);
+  table_clear(ctx->d_uniq.ptr, &ctx->d_cb->ucount, n_shard, ctx->d_table, ctx->sm_count, ctx->stream);
+  ctx->stats.kernel_launches += 3;
+  DQ_CUDA_CHECK(cudaMemcpyAsync(&ctx->h_cb->ucount, &ctx->d_cb->ucount, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  ctx->stats.num_points = ctx->h_cb->ucount;
+  return ctx->h_cb->ucount;
+}
+
+void dq_shard_quantize_map(dq_context *ctx, const uint32_t *d_all_colours, const uint32_t *d_all_counts, uint32_t num_entries,
+                           uint64_t total_pixels, const uint32_t *d_shard, uint32_t n_shard, uint32_t *d_out_shard,
+                           uint32_t *numClustersPtr, uint32_t *outColortablePtr) {
+  require_device(ctx);
+  memset(&ctx->stats, 0, sizeof(ctx->stats));
+  ctx->stats.num_pixels = n_shard;
+  const uint32_t K = *numClustersPtr;
+  if (total_pixels == 0 || total_pixels > 0x7fffffffull || K == 0 || num_entries == 0) {
+    fprintf(stderr, "divquant_b200: row-sharded call needs 0 < total_pixels < 2^31, K > 0 and a non-empty histogram\n");
+    abort();
+  }
+  reset_control(ctx);
+  // merged histogram: at most min(num_entries, 2^24) unique colours
+  ctx->d_uniq.ensure(num_entries);
+  ctx->d_pts0.ensure(num_entries);
+  hist_merge(d_all_colours, d_all_counts, num_entries, ctx->d_table, ctx->d_uniq.ptr, &ctx->d_cb->ucount, ctx->sm_count, ctx->stream);
+  hist_collect(ctx->d_uniq.ptr, &ctx->d_cb->ucount, num_entries, ctx->d_table, ctx->d_pts0.ptr, ctx->sm_count, ctx->stream);
+  ctx->stats.kernel_launches += 2;
+  const double norm = sample_norm(1, (uint32_t)total_pixels, 1);  // 1 / N of the WHOLE image (:172)
+  uint32_t k = run_split(ctx, num_entries, norm, K, 10, 8, outColortablePtr, nullptr, nullptr, nullptr);
+  k = dedup_palette(outColortablePtr, k);
+  *numClustersPtr = k;
+  ctx->stats.actual_colors = k;
+  upload_search_tables(ctx, outColortablePtr, (int)k);
+  // every colour of this rank's rows is in the merged list, so the table path serves the shard
+  if (n_shard) remap_through_table(ctx, d_shard, n_shard, d_out_shard, (int)k, ctx->stats.num_points);
+  else {
+    table_clear(ctx->d_uniq.ptr, &ctx->d_cb->ucount, ctx->stats.num_points, ctx->d_table, ctx->sm_count, ctx->stream);
+    ctx->stats.kernel_launches++;
+  }
+  DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}
+
 // ---- frame pipeline ----
 
 }  // extern "C"

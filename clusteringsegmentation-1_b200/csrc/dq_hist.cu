@@ -143,6 +143,39 @@ __global__ void __launch_bounds__(256) order_keys_kernel(const uint2 *__restrict
   }
 }
 
+// (colour, count) points -> two plain arrays (the exchange format of the row-sharded path)
+__global__ void __launch_bounds__(256) hist_export_kernel(const uint2 *__restrict__ pts, const uint32_t *ucount,
+                                                         uint32_t *colours, uint32_t *counts) {
+  const uint32_t u = *ucount;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < u; i += gridDim.x * blockDim.x) {
+    const uint2 p = pts[i];
+    colours[i] = p.x;
+    counts[i] = p.y;
+  }
+}
+
+// Merge of gathered per-shard lists into the direct table: counts add up exactly; the entry that bumps a
+// counter from 0 appends the colour to the merged unique list.
+__global__ void __launch_bounds__(256) hist_merge_kernel(const uint32_t *__restrict__ colours, const uint32_t *__restrict__ counts,
+                                                        uint32_t n, uint32_t *table, uint32_t *uniq, uint32_t *ucount) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const uint32_t round = (n + 31u) & ~31u;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < round; i += stride) {
+    const bool ok = i < n && counts[i] != 0;
+    const uint32_t c = ok ? (colours[i] & 0x00FFFFFFu) : 0u;
+    bool fresh = false;
+    if (ok) fresh = (atomicAdd(table + c, counts[i]) == 0u);
+    const unsigned m = __ballot_sync(0xffffffffu, fresh);
+    if (m) {
+      const int lane = threadIdx.x & 31;
+      uint32_t base = 0;
+      if (lane == __ffs(m) - 1) base = atomicAdd(ucount, (uint32_t)__popc(m));
+      base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+      if (fresh) uniq[base + __popc(m & ((1u << lane) - 1u))] = c;
+    }
+  }
+}
+
 inline int blocks_for(uint64_t items, int threads, int sm_count, int per_sm) {
   uint64_t want = (items + threads - 1) / threads;
   uint64_t cap = (uint64_t)sm_count * per_sm;
@@ -181,6 +214,19 @@ void hist_collect(const uint32_t *d_uniq, const uint32_t *d_ucount, uint32_t u_h
 void table_clear(const uint32_t *d_uniq, const uint32_t *d_ucount, uint32_t u_hint, uint32_t *d_table, int sm_count,
                  cudaStream_t st) {
   table_clear_kernel<<<blocks_for(u_hint, 256, sm_count, 8), 256, 0, st>>>(d_uniq, d_ucount, d_table);
+  DQ_CUDA_CHECK(cudaGetLastError());
+}
+
+void hist_export(const uint2 *d_pts, const uint32_t *d_ucount, uint32_t u_hint, uint32_t *d_colours, uint32_t *d_counts,
+                 int sm_count, cudaStream_t st) {
+  hist_export_kernel<<<blocks_for(u_hint, 256, sm_count, 8), 256, 0, st>>>(d_pts, d_ucount, d_colours, d_counts);
+  DQ_CUDA_CHECK(cudaGetLastError());
+}
+
+void hist_merge(const uint32_t *d_colours, const uint32_t *d_counts, uint32_t num_entries, uint32_t *d_table, uint32_t *d_uniq,
+                uint32_t *d_ucount, int sm_count, cudaStream_t st) {
+  hist_merge_kernel<<<blocks_for(num_entries, 256, sm_count, 8), 256, 0, st>>>(d_colours, d_counts, num_entries, d_table, d_uniq,
+                                                                               d_ucount);
   DQ_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -18,6 +18,11 @@ void cut_bits_device(const uint32_t *d_in, uint32_t n, uint32_t *d_out, int rbit
 void order_keys(const uint32_t *d_in, uint32_t num_rows, uint32_t num_cols, uint32_t dec, int num_bits, const uint32_t *d_uniq,
                 const uint2 *d_pts, uint32_t u, uint32_t *d_table, uint64_t *d_keys, int sm_count, cudaStream_t st);
 
+void hist_export(const uint2 *d_pts, const uint32_t *d_ucount, uint32_t u_hint, uint32_t *d_colours, uint32_t *d_counts,
+                 int sm_count, cudaStream_t st);
+void hist_merge(const uint32_t *d_colours, const uint32_t *d_counts, uint32_t num_entries, uint32_t *d_table, uint32_t *d_uniq,
+                uint32_t *d_ucount, int sm_count, cudaStream_t st);
+
 // ---- dq_map.cu ----
 int map_smem_palette_limit();
 void map_pixels(const uint32_t *d_in, uint32_t n, uint32_t *d_out, const uint32_t *d_sorted, int num_colors,

@@ -136,6 +136,26 @@ void dq_quant_recurse_ctx(dq_context *ctx, uint32_t numPixels, const uint32_t *i
                           uint32_t *numClustersPtr, uint32_t *outColortablePtr, int allPixelsUnique);
 
 /* ------------------------------------------------------------------------------------------------
+ * 2a. Pixel-row sharding of ONE image over several GPUs (BASELINE.json config 3; one process per GPU).
+ *     Counts are additive over shards and every sum of the divisive phase is an exact integer, so the
+ *     palette is independent of the number of shards.  The library does the per-device work; the caller
+ *     owns the one exchange (an all-gather of the per-shard (colour, count) lists, e.g. NCCL through
+ *     torch.distributed):
+ *       1. U_r = dq_shard_histogram(ctx, d_shard, n_r, d_colours_r, d_counts_r)        on every rank r
+ *       2. all-gather the lists -> d_all_colours / d_all_counts (M = sum of U_r entries)
+ *       3. dq_shard_quantize_map(ctx, d_all_colours, d_all_counts, M, N_total, d_shard, n_r, d_out_r, &K, palette)
+ *     Step 3 merges the lists in the direct table, runs the split on the merged histogram (replicated:
+ *     every rank takes identical decisions from identical integers) and remaps the rank's own rows.
+ *     Result: exactly dq_quant_recurse of the whole image.
+ * ---------------------------------------------------------------------------------------------- */
+/* Unique colours and counts of a shard into caller-provided DEVICE arrays (capacity n_shard each). */
+uint32_t dq_shard_histogram(dq_context *ctx, const uint32_t *d_shard, uint32_t n_shard, uint32_t *d_colours,
+                            uint32_t *d_counts);
+void dq_shard_quantize_map(dq_context *ctx, const uint32_t *d_all_colours, const uint32_t *d_all_counts, uint32_t num_entries,
+                           uint64_t total_pixels, const uint32_t *d_shard, uint32_t n_shard, uint32_t *d_out_shard,
+                           uint32_t *numClustersPtr, uint32_t *outColortablePtr);
+
+/* ------------------------------------------------------------------------------------------------
  * 2b. Frame pipeline: quant_recurse over a stream of frames with HOST buffers (BASELINE.json config 4,
  *     "batch of frames", and the end-to-end leg of bench.py).  Frames are independent units, so the copy
  *     engines and the SMs work on different frames at the same time: H2D of frame f+1, kernels of frame f
