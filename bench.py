@@ -317,6 +317,30 @@ def run_ours(args, rank, world, local_rank):
     lib.dq_context_last_stats(ctx, C.byref(stats))
     info = stats.as_dict()
 
+    # -- pixel-row sharded variant of the same workload (ONE 4K frame spread over all ranks, one all-gather of
+    #    the per-shard (colour, count) lists; strong scaling of a sub-millisecond job, reported next to the main line)
+    rows_info = None
+    if dist:
+        full = o.generate(1, WIDTH, HEIGHT, 12345)
+        r0, r1 = pkg.rows_for_rank(HEIGHT, world, rank)
+        shard = torch.from_numpy(full[r0 * WIDTH:r1 * WIDTH].view(np.int32).copy()).cuda()
+        ws = {}
+        out_s, pal_s = pkg.row_sharded_quant_recurse(lib, ctx, shard, NPIX, K, dist, ws)
+        for _ in range(2):
+            pkg.row_sharded_quant_recurse(lib, ctx, shard, NPIX, K, dist, ws)
+        barrier()
+        r_e0, r_e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r_e0.record()
+        for _ in range(steps):
+            pkg.row_sharded_quant_recurse(lib, ctx, shard, NPIX, K, dist, ws)
+        r_e1.record()
+        barrier()
+        t = torch.tensor([r_e0.elapsed_time(r_e1) / steps], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        rows_info = {"ms_per_image": float(t.item()), "value": NPIX / (float(t.item()) * 1e-3) / 1e6, "unit": "Mpixels/s",
+                     "scaling": "strong", "collective": "1 x all_gather of (colour,count) lists (+ sizes) over NCCL per image",
+                     "palette_entries": int(pal_s.size)}
+
     if rank != 0:
         if dist:
             dist.destroy_process_group()
@@ -382,6 +406,8 @@ def run_ours(args, rank, world, local_rank):
         "stage_ms": stage_ms,
         "parity": parity,
     }
+    if rows_info:
+        line["row_sharded"] = rows_info
     if cpu:
         line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)

@@ -270,7 +270,7 @@ def merge_histograms(colour_lists, count_lists):
     return uniq, merged
 
 
-def row_sharded_quant_recurse(lib, ctx, shard, total_pixels, k, dist=None):
+def row_sharded_quant_recurse(lib, ctx, shard, total_pixels, k, dist=None, workspace=None):
     """quant_recurse of ONE image whose pixel rows are spread over the ranks of `dist` (torch.distributed, NCCL).
 
     shard: this rank's rows as a CUDA int32/uint32-viewed torch tensor (flat).  Returns (out_shard, palette).
@@ -279,8 +279,13 @@ def row_sharded_quant_recurse(lib, ctx, shard, total_pixels, k, dist=None):
 
     n = shard.numel()
     dev = shard.device
-    colours = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
-    counts = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    ws = workspace if workspace is not None else {}
+    if ws.get("n") != n:  # reusable scratch (pass the same dict again to avoid per-call allocations)
+        ws["n"] = n
+        ws["colours"] = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        ws["counts"] = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        ws["out"] = torch.empty_like(shard)
+    colours, counts = ws["colours"], ws["counts"]
     u = lib.dq_shard_histogram(ctx, shard.data_ptr(), n, colours.data_ptr(), counts.data_ptr())
     if dist is not None and dist.get_world_size() > 1:
         world = dist.get_world_size()
@@ -299,7 +304,7 @@ def row_sharded_quant_recurse(lib, ctx, shard, total_pixels, k, dist=None):
     else:
         all_colours, all_counts, entries = colours, counts, u
     torch.cuda.current_stream(dev).synchronize()
-    out = torch.empty_like(shard)
+    out = ws["out"]
     ct = np.zeros(max(int(k), 1), np.uint32)
     nk = C.c_uint32(k)
     lib.dq_shard_quantize_map(ctx, all_colours.data_ptr(), all_counts.data_ptr(), entries, total_pixels, shard.data_ptr(), n,
