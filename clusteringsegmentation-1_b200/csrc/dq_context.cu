@@ -69,7 +69,8 @@ struct dq_context {
   int device = 0;
   int sm_count = 0;
   cudaStream_t stream = nullptr;
-  uint32_t *d_table = nullptr;  // 2^24 counters / mapped colours, all zero between calls
+  uint32_t *d_table = nullptr;  // 2^24 counters, all zero between calls (hist_collect zeroes what it reads)
+  uint32_t *d_map = nullptr;    // 2^24 mapped colours; only entries written by the current call are ever read, never cleared
   ControlBlock *d_cb = nullptr;
   ControlBlock *h_cb = nullptr;  // pinned
   DevBuf<uint32_t> d_in, d_out, d_uniq;
@@ -329,14 +330,13 @@ void remap_bruteforce(dq_context *ctx, const uint32_t *d_in, uint32_t n, uint32_
 // Table path: requires the unique list of exactly these pixels in d_uniq / d_cb->ucount.
 void remap_through_table(dq_context *ctx, const uint32_t *d_in, uint32_t n, uint32_t *d_out, int k, uint32_t u_hint) {
   ctx->mark(4);
-  map_unique(ctx->d_uniq.ptr, &ctx->d_cb->ucount, u_hint, ctx->d_table, ctx->d_sorted.ptr, k, ctx->d_lut, ctx->sm_count,
+  map_unique(ctx->d_uniq.ptr, &ctx->d_cb->ucount, u_hint, ctx->d_map, ctx->d_sorted.ptr, k, ctx->d_lut, ctx->sm_count,
              ctx->stream);
   ctx->mark(5);
-  map_gather(d_in, n, d_out, ctx->d_table, ctx->sm_count, ctx->stream);
+  map_gather(d_in, n, d_out, ctx->d_map, ctx->sm_count, ctx->stream);
   ctx->mark(6);
-  table_clear(ctx->d_uniq.ptr, &ctx->d_cb->ucount, u_hint, ctx->d_table, ctx->sm_count, ctx->stream);
   ctx->mark(7);
-  ctx->stats.kernel_launches += 3;
+  ctx->stats.kernel_launches += 2;
   ctx->stats.remap_path = 2;
 }
 
@@ -354,7 +354,7 @@ void check_quant_args(uint32_t n, uint32_t k, int num_bits) {
 }
 
 // quant_varpart_fast on device-resident pixels; keeps the unique list (when one was built) valid for
-// a following table remap.  Returns true if the histogram table is still dirty (caller must clear).
+// a following table remap.  Returns true if such a unique list exists (d_uniq / d_cb->ucount).
 bool quantize_device(dq_context *ctx, uint32_t n, const uint32_t *d_in, uint32_t rows, uint32_t cols, uint32_t *k_inout,
                      uint32_t *colortable, int num_bits, int dec, int max_iters, int all_unique, dq_split_record *records,
                      double *mean_out, uint32_t *size_out) {
@@ -384,9 +384,9 @@ bool quantize_device(dq_context *ctx, uint32_t n, const uint32_t *d_in, uint32_t
     ctx->d_pts0.ensure(samples);
     run_histogram(ctx, d_in, n, rows, cols, (uint32_t)dec, num_bits);
     ctx->mark(1);
-    hist_collect(ctx->d_uniq.ptr, &ctx->d_cb->ucount, samples, ctx->d_table, ctx->d_pts0.ptr, ctx->sm_count, ctx->stream);
+    hist_collect(ctx->d_uniq.ptr, &ctx->d_cb->ucount, samples, ctx->d_table, ctx->d_pts0.ptr, true, ctx->sm_count, ctx->stream);
     ctx->stats.kernel_launches++;
-    table_dirty = true;
+    table_dirty = true;  // (= a unique list exists; the count table itself is clean again)
     norm = sample_norm(rows, cols, dec);
     point_cap = samples;
   }
@@ -407,10 +407,6 @@ void quant_recurse_device_impl(dq_context *ctx, uint32_t n, const uint32_t *d_in
   if (dirty && (uint64_t)U * 2 <= n) {
     remap_through_table(ctx, d_in, n, d_out, (int)k, U);
   } else {
-    if (dirty) {
-      table_clear(ctx->d_uniq.ptr, &ctx->d_cb->ucount, U, ctx->d_table, ctx->sm_count, ctx->stream);
-      ctx->stats.kernel_launches++;
-    }
     remap_bruteforce(ctx, d_in, n, d_out, (int)k);
   }
   DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
@@ -483,6 +479,7 @@ dq_context *dq_context_create(int device) {
   DQ_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   DQ_CUDA_CHECK(cudaMalloc(&ctx->d_table, (size_t)kColourBins * sizeof(uint32_t)));
   DQ_CUDA_CHECK(cudaMemsetAsync(ctx->d_table, 0, (size_t)kColourBins * sizeof(uint32_t), ctx->stream));
+  DQ_CUDA_CHECK(cudaMalloc(&ctx->d_map, (size_t)kColourBins * sizeof(uint32_t)));
   DQ_CUDA_CHECK(cudaMalloc(&ctx->d_cb, sizeof(ControlBlock)));
   DQ_CUDA_CHECK(cudaMallocHost(&ctx->h_cb, sizeof(ControlBlock)));
   memset(&ctx->stats, 0, sizeof(ctx->stats));
@@ -519,6 +516,7 @@ void dq_context_destroy(dq_context *ctx) {
   ctx->d_cursors.release();
   ctx->d_progress.release();
   cudaFree(ctx->d_table);
+  cudaFree(ctx->d_map);
   cudaFree(ctx->d_cb);
   cudaFreeHost(ctx->h_cb);
   if (ctx->h_small) cudaFreeHost(ctx->h_small);
@@ -578,11 +576,7 @@ void dq_quant_varpart_device(dq_context *ctx, uint32_t numPixels, const uint32_t
   ctx->stats.num_pixels = numPixels;
   const bool dirty = quantize_device(ctx, numPixels, d_in, numRows, numCols, numClustersPtr, colortablePtr, num_bits,
                                      dec_factor, max_iters, allPixelsUnique, nullptr, nullptr, nullptr);
-  if (dirty) {
-    table_clear(ctx->d_uniq.ptr, &ctx->d_cb->ucount, ctx->stats.num_points, ctx->d_table, ctx->sm_count, ctx->stream);
-    ctx->stats.kernel_launches++;
-    DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-  }
+  (void)dirty;
 }
 
 void dq_map_colors_device(dq_context *ctx, const uint32_t *d_in, uint32_t numPixels, uint32_t *d_out,
@@ -608,10 +602,10 @@ void dq_map_colors_device(dq_context *ctx, const uint32_t *d_in, uint32_t numPix
     if ((uint64_t)U * 4 <= numPixels) {
       remap_through_table(ctx, d_in, numPixels, d_out, colormapSize, U);
       done = true;
-    } else {
-      table_clear(ctx->d_uniq.ptr, &ctx->d_cb->ucount, U, ctx->d_table, ctx->sm_count, ctx->stream);
-      ctx->stats.kernel_launches++;
     }
+    // no hist_collect ran here, so the counters are zeroed explicitly
+    table_clear(ctx->d_uniq.ptr, &ctx->d_cb->ucount, U, ctx->d_table, ctx->sm_count, ctx->stream);
+    ctx->stats.kernel_launches++;
   }
   if (!done) remap_bruteforce(ctx, d_in, numPixels, d_out, colormapSize);
   DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
@@ -708,7 +702,7 @@ int dq_calc_color_table(const uint32_t *inPixels, uint32_t numPixels, uint32_t *
   ctx->d_uniq.ensure(samples);
   hist_insert(ctx->d_in.ptr, numPixels, numRows, numCols, dec, 8, ctx->d_table, ctx->d_uniq.ptr, &ctx->d_cb->ucount,
               ctx->sm_count, ctx->stream);
-  hist_collect(ctx->d_uniq.ptr, &ctx->d_cb->ucount, samples, ctx->d_table, ctx->d_pts0.ptr, ctx->sm_count, ctx->stream);
+  hist_collect(ctx->d_uniq.ptr, &ctx->d_cb->ucount, samples, ctx->d_table, ctx->d_pts0.ptr, true, ctx->sm_count, ctx->stream);
   DQ_CUDA_CHECK(cudaMemcpyAsync(&ctx->h_cb->ucount, &ctx->d_cb->ucount, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   const uint32_t U = ctx->h_cb->ucount;
@@ -744,10 +738,9 @@ uint32_t dq_shard_histogram(dq_context *ctx, const uint32_t *d_shard, uint32_t n
   reset_control(ctx);
   ctx->d_pts0.ensure(n_shard);
   run_histogram(ctx, d_shard, n_shard, 1, n_shard, 1, 8);
-  hist_collect(ctx->d_uniq.ptr, &ctx->d_cb->ucount, n_shard, ctx->d_table, ctx->d_pts0.ptr, ctx->sm_count, ctx->stream);
+  hist_collect(ctx->d_uniq.ptr, &ctx->d_cb->ucount, n_shard, ctx->d_table, ctx->d_pts0.ptr, true, ctx->sm_count, ctx->stream);
   hist_export(ctx->d_pts0.ptr, &ctx->d_cb->ucount, n_shard, d_colours, d_counts, ctx->sm_count, ctx->stream);
-  table_clear(ctx->d_uniq.ptr, &ctx->d_cb->ucount, n_shard, ctx->d_table, ctx->sm_count, ctx->stream);
-  ctx->stats.kernel_launches += 3;
+  ctx->stats.kernel_launches += 2;
   DQ_CUDA_CHECK(cudaMemcpyAsync(&ctx->h_cb->ucount, &ctx->d_cb->ucount, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   ctx->stats.num_points = ctx->h_cb->ucount;
@@ -770,7 +763,7 @@ void dq_shard_quantize_map(dq_context *ctx, const uint32_t *d_all_colours, const
   ctx->d_uniq.ensure(num_entries);
   ctx->d_pts0.ensure(num_entries);
   hist_merge(d_all_colours, d_all_counts, num_entries, ctx->d_table, ctx->d_uniq.ptr, &ctx->d_cb->ucount, ctx->sm_count, ctx->stream);
-  hist_collect(ctx->d_uniq.ptr, &ctx->d_cb->ucount, num_entries, ctx->d_table, ctx->d_pts0.ptr, ctx->sm_count, ctx->stream);
+  hist_collect(ctx->d_uniq.ptr, &ctx->d_cb->ucount, num_entries, ctx->d_table, ctx->d_pts0.ptr, true, ctx->sm_count, ctx->stream);
   ctx->stats.kernel_launches += 2;
   const double norm = sample_norm(1, (uint32_t)total_pixels, 1);  // 1 / N of the WHOLE image (:172)
   uint32_t k = run_split(ctx, num_entries, norm, K, 10, 8, outColortablePtr, nullptr, nullptr, nullptr);
@@ -780,10 +773,6 @@ void dq_shard_quantize_map(dq_context *ctx, const uint32_t *d_all_colours, const
   upload_search_tables(ctx, outColortablePtr, (int)k);
   // every colour of this rank's rows is in the merged list, so the table path serves the shard
   if (n_shard) remap_through_table(ctx, d_shard, n_shard, d_out_shard, (int)k, ctx->stats.num_points);
-  else {
-    table_clear(ctx->d_uniq.ptr, &ctx->d_cb->ucount, ctx->stats.num_points, ctx->d_table, ctx->sm_count, ctx->stream);
-    ctx->stats.kernel_launches++;
-  }
   DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
 }
 
@@ -960,8 +949,7 @@ uint32_t dq_debug_histogram(dq_context *ctx, const uint32_t *inPixels, uint32_t 
   DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->d_in.ptr, inPixels, (size_t)numPixels * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
   reset_control(ctx);
   run_histogram(ctx, ctx->d_in.ptr, numPixels, 1, numPixels, 1, 8);
-  hist_collect(ctx->d_uniq.ptr, &ctx->d_cb->ucount, numPixels, ctx->d_table, ctx->d_pts0.ptr, ctx->sm_count, ctx->stream);
-  table_clear(ctx->d_uniq.ptr, &ctx->d_cb->ucount, numPixels, ctx->d_table, ctx->sm_count, ctx->stream);
+  hist_collect(ctx->d_uniq.ptr, &ctx->d_cb->ucount, numPixels, ctx->d_table, ctx->d_pts0.ptr, true, ctx->sm_count, ctx->stream);
   DQ_CUDA_CHECK(cudaMemcpyAsync(&ctx->h_cb->ucount, &ctx->d_cb->ucount, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   const uint32_t U = ctx->h_cb->ucount;

@@ -80,12 +80,15 @@ __global__ void __launch_bounds__(256) hist_insert_sampled_kernel(const uint32_t
   }
 }
 
+// (colour, count) points for the divisive phase.  With `clear` the counter is zeroed on the way out, which
+// restores the count table's all-zero invariant without a separate pass.
 __global__ void __launch_bounds__(256) hist_collect_kernel(const uint32_t *__restrict__ uniq, const uint32_t *ucount,
-                                                          const uint32_t *table, uint2 *pts) {
+                                                          uint32_t *table, uint2 *pts, int clear) {
   const uint32_t u = *ucount;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < u; i += gridDim.x * blockDim.x) {
     const uint32_t c = uniq[i];
     pts[i] = make_uint2(c, table[c]);
+    if (clear) table[c] = 0u;
   }
 }
 
@@ -205,9 +208,9 @@ void hist_insert(const uint32_t *d_in, uint32_t n, uint32_t num_rows, uint32_t n
   DQ_CUDA_CHECK(cudaGetLastError());
 }
 
-void hist_collect(const uint32_t *d_uniq, const uint32_t *d_ucount, uint32_t u_hint, const uint32_t *d_table, uint2 *d_pts,
-                  int sm_count, cudaStream_t st) {
-  hist_collect_kernel<<<blocks_for(u_hint, 256, sm_count, 8), 256, 0, st>>>(d_uniq, d_ucount, d_table, d_pts);
+void hist_collect(const uint32_t *d_uniq, const uint32_t *d_ucount, uint32_t u_hint, uint32_t *d_table, uint2 *d_pts,
+                  bool clear_table, int sm_count, cudaStream_t st) {
+  hist_collect_kernel<<<blocks_for(u_hint, 256, sm_count, 8), 256, 0, st>>>(d_uniq, d_ucount, d_table, d_pts, clear_table ? 1 : 0);
   DQ_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -235,6 +235,8 @@ __global__ void __launch_bounds__(kMapThreads) expand_palette_kernel(const uint3
 __global__ void __launch_bounds__(kMapThreads) map_gather_kernel(const uint32_t *__restrict__ in, uint32_t n,
                                                                 uint32_t *__restrict__ out, const uint32_t *table,
                                                                 uint32_t word_mask, uint32_t shift) {
+  // 4 pixels per thread: one streaming 128-bit load, four table reads (the table entries of an image's colours
+  // live in L2), one streaming 128-bit store.  (8 per thread measured slower: 35 vs 28 us at 4K.)
   const uint32_t nvec = n >> 2;
   const uint4 *in4 = reinterpret_cast<const uint4 *>(in);
   uint4 *out4 = reinterpret_cast<uint4 *>(out);

@@ -14,6 +14,8 @@ from oracle import muted
 from conftest import small_case_ids
 
 pytestmark = pytest.mark.gpu
+import os as _os
+ROOT_DIR = _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))
 REL_TOL = 1e-6  # north_star: "split statistics within 1e-6 relative"
 
 
@@ -231,3 +233,26 @@ def test_frame_pipeline_matches_single_calls(dq, pkg, oracle):
         assert np.array_equal(cts[i][:nks[i].value], pal), i
         assert np.array_equal(outs[i].numpy().view(np.uint32), out), i
     pipe.close()
+
+
+def test_generic_split_kernel_large_k_and_forced(dq, oracle, pkg):
+    """K > 512 uses the generic split kernel (csrc/dq_split.cu); DIVQUANT_B200_SPLIT=1 forces it for any K."""
+    import subprocess
+    import sys
+    rng = np.random.default_rng(21)
+    px = rng.integers(0, 1 << 24, 30000, dtype=np.uint32)
+    for k in (600, 1000):
+        with muted((2,)):
+            pal, empty = dq.quant_varpart_fast(px, k, all_unique=1)   # uniform path: bit-exact vs the reference restatement
+        with muted():
+            opal, oempty = oracle.quant_varpart_fast(px, k, all_unique=1)
+        assert np.array_equal(pal, opal) and empty == oempty, k
+    code = ("import importlib, numpy as np, sys; sys.path.insert(0, %r); "
+            "pkg = importlib.import_module('clusteringsegmentation-1_b200'); from oracle import Oracle, muted; "
+            "o = Oracle(); dq = pkg.DivQuant(); px = o.generate(1, 640, 360); out, pal = dq.quant_recurse(px, 64, 0); "
+            "oo, op = o.quant_recurse(px, 64, 0); assert np.array_equal(pal, op) and np.array_equal(out, oo); print('forced v1 ok')"
+            % ROOT_DIR)
+    import os
+    env = dict(os.environ, DIVQUANT_B200_SPLIT="1")
+    res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and "forced v1 ok" in res.stdout, res.stderr[-1500:]
