@@ -658,9 +658,8 @@ __device__ __forceinline__ unsigned narrow_pass(Shared2 &S, const uint2 (&p)[kNa
 #pragma unroll
   for (int k = 0; k < kNarrowPPT; ++k) {
     if (k < ppt && ((validmask >> k) & 1u)) {
-      const PointD d = to_point(p[k]);
-      if (goes_new_t<SPLIT>(pp, d)) {
-        acc_add(acc, d, FINAL);
+      if (goes_new_t<SPLIT>(pp, to_point(p[k]))) {
+        acc_add(acc, p[k], FINAL);
         newmask |= 1u << k;
       }
     }
@@ -688,13 +687,12 @@ __device__ __forceinline__ void wide_classify(const PassParams &pp, const uint2 
     for (int k = 0; k < kWidePPT; ++k) {
       const uint32_t q = tid + (uint32_t)k * nthr;
       if (q < n_my) {
-        const PointD d = to_point(pre[k]);
-        if (goes_new_t<SPLIT>(pp, d)) acc_add(acc, d, FINAL);
+        if (goes_new_t<SPLIT>(pp, to_point(pre[k]))) acc_add(acc, pre[k], FINAL);
       }
     }
     for (uint32_t q = tid + kWidePPT * nthr; q < n_my; q += nthr) {
-      const PointD d = to_point(ld_cg_u2(seg + offset_of(q)));
-      if (goes_new_t<SPLIT>(pp, d)) acc_add(acc, d, FINAL);
+      const uint2 raw = ld_cg_u2(seg + offset_of(q));
+      if (goes_new_t<SPLIT>(pp, to_point(raw))) acc_add(acc, raw, FINAL);
     }
   }
   acc_words(acc, v);

@@ -62,24 +62,16 @@ __device__ __forceinline__ void hyperplane(const Means &m, PassParams &pp) {
   pp.r[2] = fsub(m.om[2], m.nm[2]);
 }
 
-// A point with its channels and multiplicity as exact doubles: the hyperplane test needs the channels
-// in FP64 anyway, and count*channel sums stay exact in FP64 (all values are integers below 2^53), so
-// the whole inner loop runs on the FP64 pipe: 6 operations to classify, 4 fused multiply-adds to
-// accumulate (FMA is harmless here: every product and sum is exactly representable).
+// A point's channels as exact doubles for the hyperplane test (3 conversions + 6 FP64 operations per point).
 struct PointD {
-  double r, g, b, c;
+  double r, g, b;
 };
 __device__ __forceinline__ PointD to_point(uint2 p) {
   PointD d;
   d.r = byte_to_double((p.x >> 16) & 0xFFu);
   d.g = byte_to_double((p.x >> 8) & 0xFFu);
   d.b = byte_to_double(p.x & 0xFFu);
-  d.c = __dsub_rn(__hiloint2double(0x43300000, (int)p.y), 4503599627370496.0);
   return d;
-}
-__device__ __forceinline__ uint2 from_point(const PointD &d) {
-  const uint32_t R = (uint32_t)double_to_u52(d.r), G = (uint32_t)double_to_u52(d.g), B = (uint32_t)double_to_u52(d.b);
-  return make_uint2((R << 16) | (G << 8) | B, (uint32_t)double_to_u52(d.c));
 }
 __device__ __forceinline__ bool goes_new(const PassParams &pp, bool split_pass, const PointD &d) {
   if (split_pass) {
@@ -98,38 +90,40 @@ __device__ __forceinline__ bool goes_new_t(const PassParams &pp, const PointD &d
   const double dot = fadd(fadd(fmul(pp.r[0], d.r), fmul(pp.r[1], d.g)), fmul(pp.r[2], d.b));
   return !(pp.a < dot);  // (:683)
 }
+// Accumulation stays on the integer pipe (IMAD.WIDE), which runs next to the FP64 pipe that classifies:
+// exact u64 sums of count*c and count*c*c.
 struct AccD {
-  double cnt, r, g, b, rr, gg, bb;
+  uint64_t cnt, r, g, b, rr, gg, bb;
   uint32_t n;
 };
 __device__ __forceinline__ AccD acc_zero() {
   AccD a;
-  a.cnt = a.r = a.g = a.b = a.rr = a.gg = a.bb = 0.0;
+  a.cnt = a.r = a.g = a.b = a.rr = a.gg = a.bb = 0ull;
   a.n = 0;
   return a;
 }
-__device__ __forceinline__ void acc_add(AccD &a, const PointD &d, bool with_squares) {
-  a.cnt = __dadd_rn(a.cnt, d.c);
-  const double cr = __dmul_rn(d.c, d.r), cg = __dmul_rn(d.c, d.g), cb = __dmul_rn(d.c, d.b);  // exact
-  a.r = __dadd_rn(a.r, cr);
-  a.g = __dadd_rn(a.g, cg);
-  a.b = __dadd_rn(a.b, cb);
+__device__ __forceinline__ void acc_add(AccD &a, uint2 p, bool with_squares) {
+  const uint32_t R = (p.x >> 16) & 0xFFu, G = (p.x >> 8) & 0xFFu, B = p.x & 0xFFu, c = p.y;
+  a.cnt += c;
+  a.r += (uint64_t)c * R;
+  a.g += (uint64_t)c * G;
+  a.b += (uint64_t)c * B;
   a.n += 1;
   if (with_squares) {
-    a.rr = __fma_rn(cr, d.r, a.rr);
-    a.gg = __fma_rn(cg, d.g, a.gg);
-    a.bb = __fma_rn(cb, d.b, a.bb);
+    a.rr += (uint64_t)c * (R * R);
+    a.gg += (uint64_t)c * (G * G);
+    a.bb += (uint64_t)c * (B * B);
   }
 }
 __device__ __forceinline__ void acc_words(const AccD &a, uint64_t (&v)[kAccWords]) {
-  v[kAccCnt] = double_to_u52(a.cnt);
-  v[kAccR] = double_to_u52(a.r);
-  v[kAccG] = double_to_u52(a.g);
-  v[kAccB] = double_to_u52(a.b);
+  v[kAccCnt] = a.cnt;
+  v[kAccR] = a.r;
+  v[kAccG] = a.g;
+  v[kAccB] = a.b;
   v[kAccPts] = a.n;
-  v[kAccRR] = double_to_u52(a.rr);
-  v[kAccGG] = double_to_u52(a.gg);
-  v[kAccBB] = double_to_u52(a.bb);
+  v[kAccRR] = a.rr;
+  v[kAccGG] = a.gg;
+  v[kAccBB] = a.bb;
 }
 
 __device__ __forceinline__ bool goes_new(const PassParams &pp, bool split_pass, uint32_t colour) {
