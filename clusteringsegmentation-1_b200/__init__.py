@@ -83,6 +83,8 @@ def load_library(path=LIB_PATH):
         "dq_quant_varpart_device": (None, [vp, C.c_uint32, vp, C.c_uint32, C.c_uint32, _u32p, _u32p, C.c_int,
                                            C.c_int, C.c_int, C.c_int]),
         "dq_quant_recurse_ctx": (None, [vp, C.c_uint32, _u32p, _u32p, _u32p, _u32p, C.c_int]),
+        "dq_colortable_indexes": (None, [_u32p, C.c_uint32, _u32p, C.c_int, _u32p, C.c_int]),
+        "dq_colortable_indexes_device": (None, [vp, vp, C.c_uint32, _u32p, C.c_int, vp, C.c_int]),
         "dq_shard_histogram": (C.c_uint32, [vp, vp, C.c_uint32, vp, vp]),
         "dq_shard_quantize_map": (None, [vp, vp, vp, C.c_uint32, C.c_uint64, vp, C.c_uint32, vp, _u32p, _u32p]),
         "dq_pipeline_create": (vp, [C.c_int, C.c_uint32, C.c_int]),
@@ -111,7 +113,7 @@ EXPORTED_C_SYMBOLS = [
     "dq_get_double_scale", "dq_validate_num_bits", "dq_set_display_timings", "dq_context_create", "dq_context_destroy",
     "dq_default_context", "dq_context_stream", "dq_context_synchronize", "dq_context_last_stats", "dq_context_set_profiling",
     "dq_quant_recurse_device", "dq_map_colors_device", "dq_quant_varpart_device", "dq_quant_recurse_ctx",
-    "dq_shard_histogram", "dq_shard_quantize_map", "dq_pipeline_create", "dq_pipeline_destroy", "dq_pipeline_submit", "dq_pipeline_flush", "dq_pipeline_last_elapsed_ms",
+    "dq_colortable_indexes", "dq_colortable_indexes_device", "dq_shard_histogram", "dq_shard_quantize_map", "dq_pipeline_create", "dq_pipeline_destroy", "dq_pipeline_submit", "dq_pipeline_flush", "dq_pipeline_last_elapsed_ms",
     "dq_pipeline_context", "dq_pipeline_kernel_launches",
     "dq_debug_split_points", "dq_debug_histogram", "dq_debug_split_timeline", "dq_host_dedup_palette", "dq_host_build_search_tables",
 ]
@@ -180,6 +182,14 @@ class DivQuant:
         px = _u32(pixels)
         out = np.zeros_like(px)
         self.lib.dq_cut_bits(_p(px), px.size, _p(out), rbits, gbits, bbits)
+        return out
+
+    def colortable_indexes(self, quant_pixels, colortable, greyscale=False):
+        """Label image: index of every quantized pixel in the caller's palette order (last duplicate wins)."""
+        px = _u32(quant_pixels)
+        ct = _u32(colortable).copy()
+        out = np.zeros_like(px)
+        self.lib.dq_colortable_indexes(_p(px), px.size, _p(ct), ct.size, _p(out), 1 if greyscale else 0)
         return out
 
     # -- host-only palette handling (no device) ------------------------------------------------

@@ -728,6 +728,54 @@ int dq_calc_color_table(const uint32_t *inPixels, uint32_t numPixels, uint32_t *
   return 0;
 }
 
+// ---- label image ----
+
+void dq_colortable_indexes_device(dq_context *ctx, const uint32_t *d_quantPixels, uint32_t numPixels, const uint32_t *colortable,
+                                  int colormapSize, uint32_t *d_labelsOut, int asGreyscale) {
+  require_device(ctx);
+  if (colormapSize <= 0 || colormapSize > 24000) {
+    fprintf(stderr, "divquant_b200: colortable of %d entries is not supported for label images (1..24000)\n", colormapSize);
+    abort();
+  }
+  // colour -> last index holding it (the reference fills an unordered_map in palette order, :795-799)
+  std::vector<std::pair<uint32_t, uint32_t>> pairs;
+  pairs.reserve(colormapSize);
+  for (int i = 0; i < colormapSize; ++i) pairs.emplace_back(colortable[i] & 0x00FFFFFFu, (uint32_t)i);
+  std::stable_sort(pairs.begin(), pairs.end(), [](const std::pair<uint32_t, uint32_t> &a, const std::pair<uint32_t, uint32_t> &b) { return a.first < b.first; });
+  std::vector<uint2> uniq;
+  for (size_t i = 0; i < pairs.size(); ++i) {
+    if (!uniq.empty() && uniq.back().x == pairs[i].first) uniq.back().y = pairs[i].second;  // later duplicate wins
+    else uniq.push_back(make_uint2(pairs[i].first, pairs[i].second));
+    if (asGreyscale && pairs[i].second > 255u) {
+      fprintf(stderr, "divquant_b200: greyscale label images need indexes below 256\n");
+      abort();  // assert(offset < 256) (:836)
+    }
+  }
+  ctx->d_keys.ensure(uniq.size() + 1);  // reuse the 8-byte scratch buffer for the pairs
+  reset_control(ctx);
+  DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->d_keys.ptr, uniq.data(), uniq.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
+  map_labels(d_quantPixels, numPixels, d_labelsOut, reinterpret_cast<const uint2 *>(ctx->d_keys.ptr), (int)uniq.size(), asGreyscale,
+             &ctx->d_cb->ucount, ctx->sm_count, ctx->stream);
+  DQ_CUDA_CHECK(cudaMemcpyAsync(&ctx->h_cb->ucount, &ctx->d_cb->ucount, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->h_cb->ucount != 0) {
+    fprintf(stderr, "divquant_b200: pixel %u has no matching colortable entry\n", ctx->h_cb->ucount - 1);
+    abort();  // assert(0) (:823)
+  }
+}
+
+void dq_colortable_indexes(const uint32_t *quantPixels, uint32_t numPixels, const uint32_t *colortable, int colormapSize,
+                           uint32_t *labelsOut, int asGreyscale) {
+  if (numPixels == 0) return;
+  dq_context *ctx = dq_default_context();
+  require_device(ctx);
+  ctx->d_in.ensure(numPixels);
+  ctx->d_out.ensure(numPixels);
+  DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->d_in.ptr, quantPixels, (size_t)numPixels * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  dq_colortable_indexes_device(ctx, ctx->d_in.ptr, numPixels, colortable, colormapSize, ctx->d_out.ptr, asGreyscale);
+  DQ_CUDA_CHECK(cudaMemcpy(labelsOut, ctx->d_out.ptr, (size_t)numPixels * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+}
+
 // ---- pixel-row sharding of one image ----
 
 uint32_t dq_shard_histogram(dq_context *ctx, const uint32_t *d_shard, uint32_t n_shard, uint32_t *d_colours, uint32_t *d_counts) {

@@ -261,6 +261,34 @@ __global__ void __launch_bounds__(kMapThreads) map_gather_scalar_kernel(const ui
     out[i] = table[in[i] & 0x00FFFFFFu] & 0x00FFFFFFu;
 }
 
+// Label image: binary search of every pixel in the palette sorted by colour value ((colour, last index) pairs).
+__global__ void __launch_bounds__(kMapThreads) map_labels_kernel(const uint32_t *__restrict__ in, uint32_t n,
+                                                                uint32_t *__restrict__ out, const uint2 *pairs, int num_pairs,
+                                                                int greyscale, uint32_t *error) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  uint2 *s_pairs = reinterpret_cast<uint2 *>(smem);
+  for (int i = threadIdx.x; i < num_pairs; i += blockDim.x) s_pairs[i] = pairs[i];
+  __syncthreads();
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t c = in[i] & 0x00FFFFFFu;
+    int lo = 0, hi = num_pairs - 1, found = -1;
+    while (lo <= hi) {
+      const int mid = (lo + hi) >> 1;
+      const uint32_t v = s_pairs[mid].x;
+      if (v == c) {
+        found = (int)s_pairs[mid].y;
+        break;
+      }
+      if (v < c) lo = mid + 1; else hi = mid - 1;
+    }
+    if (found < 0) {
+      atomicMax(error, i + 1u);
+      found = 0;
+    }
+    out[i] = greyscale ? ((uint32_t)found << 16) | ((uint32_t)found << 8) | (uint32_t)found : (uint32_t)found;
+  }
+}
+
 inline int blocks_for(uint64_t items, int threads, int sm_count, int per_sm) {
   uint64_t want = (items + threads - 1) / threads;
   uint64_t cap = (uint64_t)sm_count * per_sm;
@@ -318,6 +346,20 @@ void map_unique(const uint32_t *d_uniq, const uint32_t *d_ucount, uint32_t u_hin
   int per_sm = (int)std::min<size_t>(8, std::max<size_t>(1, (200 * 1024) / smem));
   map_unique_fast_kernel<<<blocks_for(u_hint / kUniqPix + 1, kMapThreads, sm_count, per_sm), kMapThreads, smem, st>>>(
       d_uniq, d_ucount, d_table, d_sorted, num_colors, d_lut);
+  DQ_CUDA_CHECK(cudaGetLastError());
+}
+
+void map_labels(const uint32_t *d_in, uint32_t n, uint32_t *d_out, const uint2 *d_pairs, int num_pairs, int greyscale,
+                uint32_t *d_error, int sm_count, cudaStream_t st) {
+  if (n == 0) return;
+  const size_t smem = (size_t)num_pairs * sizeof(uint2);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    DQ_CUDA_CHECK(cudaFuncSetAttribute(map_labels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  map_labels_kernel<<<blocks_for(n, kMapThreads, sm_count, 4), kMapThreads, smem, st>>>(d_in, n, d_out, d_pairs, num_pairs,
+                                                                                       greyscale, d_error);
   DQ_CUDA_CHECK(cudaGetLastError());
 }
 

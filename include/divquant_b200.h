@@ -135,6 +135,16 @@ void dq_quant_varpart_device(dq_context *ctx, uint32_t numPixels, const uint32_t
 void dq_quant_recurse_ctx(dq_context *ctx, uint32_t numPixels, const uint32_t *inPixelsPtr, uint32_t *outPixelsPtr,
                           uint32_t *numClustersPtr, uint32_t *outColortablePtr, int allPixelsUnique);
 
+/* Label image.  Replaces  mapQuantPixelsToColortableIndexes   superpixels/OpenCVUtil.cpp:787-849:
+ * every (already quantized) pixel -> index of its colour in the CALLER's palette order, the last duplicate
+ * winning; asGreyscale != 0 writes (i<<16 | i<<8 | i) like the reference (indexes must then be < 256).
+ * A pixel that is not in the palette is fatal (message + abort; assert(0) in the reference).  Host pointers. */
+void dq_colortable_indexes(const uint32_t *quantPixels, uint32_t numPixels, const uint32_t *colortable, int colormapSize,
+                           uint32_t *labelsOut, int asGreyscale);
+/* Same with device pixel / label buffers on an explicit context. */
+void dq_colortable_indexes_device(dq_context *ctx, const uint32_t *d_quantPixels, uint32_t numPixels,
+                                  const uint32_t *colortable, int colormapSize, uint32_t *d_labelsOut, int asGreyscale);
+
 /* ------------------------------------------------------------------------------------------------
  * 2a. Pixel-row sharding of ONE image over several GPUs (BASELINE.json config 3; one process per GPU).
  *     Counts are additive over shards and every sum of the divisive phase is an exact integer, so the

@@ -188,6 +188,15 @@ void initial_mean_and_var(const DivisiveState &s, Vec3 *mean, Vec3 *var) {
 
 }  // namespace
 
+// Diagnostics for DESIGN.md: in how many LKM iterations does a split reach its fixed point?
+static int g_converged_at[4096];
+static int g_converged_n = 0;
+extern "C" int oracle_debug_convergence(int *out, int cap) {
+  int n = g_converged_n < cap ? g_converged_n : cap;
+  for (int i = 0; i < n; ++i) out[i] = g_converged_at[i];
+  return n;
+}
+
 static int varpart_impl(uint32_t num_pixels, const uint32_t *in, uint32_t num_rows, uint32_t num_cols,
                         uint32_t *num_clusters, uint32_t *colortable, int num_bits, int dec_factor,
                         int max_iters, int all_pixels_unique, oracle_split_record *records, int *num_records,
@@ -333,6 +342,9 @@ static int varpart_impl(uint32_t num_pixels, const uint32_t *in, uint32_t num_ro
 
     // ---- local 2-means refinement (:613-811) ----
     int new_size = 0;
+    int prev_size = -1, converged_at = max_iters;
+    uint64_t prev_sig = 0;
+    if (new_index == 1) g_converged_n = 0;
     for (int it = 0; it < max_iters; ++it) {
       const double lhs =
           0.5 * (sq(om.r) - sq(nm.r) + sq(om.g) - sq(nm.g) + sq(om.b) - sq(nm.b));  // (:616-619)
@@ -378,6 +390,13 @@ static int varpart_impl(uint32_t num_pixels, const uint32_t *in, uint32_t num_ro
           new_size++;
         }
       }
+      {
+        // signature of the membership sums of this iteration (exact in the integer paths)
+        uint64_t sig = s.uniform ? (ir * 1000003ull + ig * 10007ull + ib * 101ull + cnt) : (uint64_t)new_size;
+        if (converged_at == max_iters && prev_size == new_size && sig == prev_sig) converged_at = it;
+        prev_size = new_size;
+        prev_sig = sig;
+      }
       if (s.uniform) {
         nm.r += (double)ir;
         nm.g += (double)ig;
@@ -404,6 +423,7 @@ static int varpart_impl(uint32_t num_pixels, const uint32_t *in, uint32_t num_ro
 
     size[old_index] = cur_n - new_size;
     size[new_index] = new_size;
+    if (g_converged_n < 4096) g_converged_at[g_converged_n++] = converged_at;
 
     oracle_split_record rec;
     memset(&rec, 0, sizeof(rec));

@@ -256,3 +256,15 @@ def test_generic_split_kernel_large_k_and_forced(dq, oracle, pkg):
     env = dict(os.environ, DIVQUANT_B200_SPLIT="1")
     res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert res.returncode == 0 and "forced v1 ok" in res.stdout, res.stderr[-1500:]
+
+
+def test_label_image_matches_oracle(dq, oracle, images, golden):
+    # mapQuantPixelsToColortableIndexes (OpenCVUtil.cpp:787-849), last duplicate wins
+    px = images["cookie"][:200000]
+    grid = golden["grid125"]
+    quant = dq.map_colors_mps(px, grid)
+    assert np.array_equal(dq.colortable_indexes(quant, grid), oracle.colortable_indexes(quant, grid))
+    pal = np.array([0x101010, 0x202020, 0x101010, 0x303030, 0xFF202020], np.uint32)
+    q = np.array([0x101010, 0x303030, 0x202020, 0x101010], np.uint32)
+    assert list(dq.colortable_indexes(q, pal)) == [2, 3, 4, 2]
+    assert list(dq.colortable_indexes(q, pal, greyscale=True)) == [0x020202, 0x030303, 0x040404, 0x020202]
