@@ -966,6 +966,24 @@ __global__ void __launch_bounds__(512, 1) split2_kernel(const SplitArgs A, const
       const uint32_t tail = (last == tiles - 1) ? size - last * kWideTile : kWideTile;
       return (mine - 1) * kWideTile + tail;
     };
+    // The points of a CTA's share do not change during a round: with a single wide job (the common case) they
+    // are loaded once and stay in registers for all passes.
+    uint2 pre0[kWidePPT];
+    const bool single_wide = (n_mywide == 1);
+    if (single_wide) {
+      const int j = R.mywide[0];
+      const JobConst jc = wide_const(0);
+      const uint32_t tiles = R.tile0[j + 1] - R.tile0[j];
+      const uint32_t me = (uint32_t)(b + G - (int)(R.tile0[j] % (uint32_t)G)) % (uint32_t)G;
+      const uint32_t n_my = share_points(tiles, me, jc.size);
+      const uint32_t nthr = min((uint32_t)T, (n_my + 31u) & ~31u);
+#pragma unroll
+      for (int k = 0; k < kWidePPT; ++k) {
+        const uint32_t q = (uint32_t)tid + (uint32_t)k * nthr;
+        pre0[k] = make_uint2(0, 0);
+        if ((uint32_t)tid < nthr && q < n_my) pre0[k] = ld_cg_u2(A.pts[jc.buf] + jc.begin + share_offset(q, me));
+      }
+    }
     for (int pass = 0; pass <= P; ++pass) {
       unsigned long long *slots_w = X.slots + (size_t)(pass & 1) * X.slot_cap * kAccWords;
       const unsigned long long *slots_r = X.slots + (size_t)((pass & 1) ^ 1) * X.slot_cap * kAccWords;
@@ -982,8 +1000,11 @@ __global__ void __launch_bounds__(512, 1) split2_kernel(const SplitArgs A, const
 #pragma unroll
         for (int k = 0; k < kWidePPT; ++k) {
           const uint32_t q = (uint32_t)tid + (uint32_t)k * nthr;
-          pre[k] = make_uint2(0, 0);
-          if ((uint32_t)tid < nthr && q < n_my) pre[k] = ld_cg_u2(A.pts[jc.buf] + jc.begin + share_offset(q, me));
+          pre[k] = pre0[k];
+          if (!single_wide) {
+            pre[k] = make_uint2(0, 0);
+            if ((uint32_t)tid < nthr && q < n_my) pre[k] = ld_cg_u2(A.pts[jc.buf] + jc.begin + share_offset(q, me));
+          }
         }
 #ifdef DQ_PROFILE_NARROW
         const long long w0 = clock64();
@@ -1011,6 +1032,9 @@ __global__ void __launch_bounds__(512, 1) split2_kernel(const SplitArgs A, const
           else if (pass == P) wide_classify<false, true>(pp, pre, n_my, nthr, seg, off, v);
           else wide_classify<false, false>(pp, pre, n_my, nthr, seg, off, v);
         }
+#ifdef DQ_PROFILE_NARROW
+        const long long w3 = clock64();
+#endif
         if (pass == P) {
           if (tid == 0 && mw < kWideCache) S.wide_pp[mw] = pp;
           reduce_stage1<kAccWords>(S, v, (int)(nthr >> 5));
@@ -1020,6 +1044,9 @@ __global__ void __launch_bounds__(512, 1) split2_kernel(const SplitArgs A, const
           }
         } else {
           reduce_stage1<5>(S, v, (int)(nthr >> 5));
+#ifdef DQ_PROFILE_NARROW
+          if (tid == 0 && pass > 0) atomicAdd(X.progress + 269, (uint32_t)(clock64() - w3));  // stage 1 + sync
+#endif
           if (tid < 32) {
             reduce_stage2_warp0<5>(S, (int)(nthr >> 5));
             publish<5>(slots_w, R.slot0[j] + me, S, (seq0 + pass) & 0xFFFFu);
@@ -1027,6 +1054,7 @@ __global__ void __launch_bounds__(512, 1) split2_kernel(const SplitArgs A, const
         }
         __syncthreads();
 #ifdef DQ_PROFILE_NARROW
+        if (tid == 0 && pass > 0) atomicAdd(X.progress + 268, (uint32_t)(w3 - w2));  // classification only
         if (tid == 0 && pass > 0) {
           atomicAdd(X.progress + 264, (uint32_t)(w1 - w0));            // gather (wait + reduce)
           atomicAdd(X.progress + 265, (uint32_t)(w2 - w1));            // derive + sync
