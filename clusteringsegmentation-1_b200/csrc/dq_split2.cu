@@ -169,15 +169,32 @@ __device__ __forceinline__ uint64_t warp_sum_redux(uint64_t v) {
 }
 
 // Stage 1 of a CTA-wide sum: the first `warps` warps reduce their WORDS values into S.red[warp][].
+// One vote decides for all words whether a single 32-bit REDUX per word is enough (every lane below 2^27,
+// the usual case) or two 24/26-bit limbs are needed: the REDUX unit, not latency, bounds this stage
+// (tools/microbench/classify_mb.cu: 340 cycles against 500 with a vote per word and 1000 with two limbs always).
 // Ends with a barrier.
 template <int WORDS>
 __device__ __forceinline__ void reduce_stage1(Shared2 &S, const uint64_t (&v)[kAccWords], int warps) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (warp < warps) {
+    uint64_t all = 0;
 #pragma unroll
-    for (int w = 0; w < WORDS; ++w) {
-      const uint64_t s = (w == kAccPts) ? (uint64_t)__reduce_add_sync(0xffffffffu, (unsigned)v[w]) : warp_sum_redux(v[w]);
-      if (lane == 0) S.red[warp][w] = s;
+    for (int w = 0; w < WORDS; ++w) all |= v[w];
+    uint64_t s[WORDS];
+    if (!__any_sync(0xffffffffu, (all >> 27) != 0)) {
+#pragma unroll
+      for (int w = 0; w < WORDS; ++w) s[w] = __reduce_add_sync(0xffffffffu, (unsigned)v[w]);
+    } else {
+#pragma unroll
+      for (int w = 0; w < WORDS; ++w) {
+        const unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)(v[w] & 0xFFFFFFu));
+        const unsigned hi = __reduce_add_sync(0xffffffffu, (unsigned)(v[w] >> 24));
+        s[w] = (uint64_t)lo + ((uint64_t)hi << 24);
+      }
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int w = 0; w < WORDS; ++w) S.red[warp][w] = s[w];
     }
   }
   __syncthreads();
