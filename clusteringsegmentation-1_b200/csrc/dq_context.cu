@@ -120,11 +120,26 @@ void require_device(dq_context *ctx) { DQ_CUDA_CHECK(cudaSetDevice(ctx->device))
 
 // First occurrence of each word survives, order kept (quant_util.cpp:93-118).
 uint32_t dedup_palette(uint32_t *colortable, uint32_t n) {
+  if (n <= 1) return n;
+  uint32_t cap = 16;
+  while (cap < 4 * n) cap <<= 1;
+  std::vector<uint32_t> slots(cap, 0xFFFFFFFFu);  // palette words have a zero alpha byte, so all-ones is free
   uint32_t kept = 0;
   for (uint32_t i = 0; i < n; ++i) {
+    const uint32_t w = colortable[i];
+    uint32_t h = (w * 2654435761u) & (cap - 1);
     bool seen = false;
-    for (uint32_t j = 0; j < kept && !seen; ++j) seen = (colortable[j] == colortable[i]);
-    if (!seen) colortable[kept++] = colortable[i];
+    while (slots[h] != 0xFFFFFFFFu) {
+      if (slots[h] == w) {
+        seen = true;
+        break;
+      }
+      h = (h + 1) & (cap - 1);
+    }
+    if (!seen) {
+      slots[h] = w;
+      colortable[kept++] = w;
+    }
   }
   return kept;
 }
@@ -163,7 +178,8 @@ void reset_control(dq_context *ctx) {
 // Leaves palette/result/ctl in ctx->h_cb / ctx->h_small after a stream synchronisation.
 // Returns the number of palette entries.
 uint32_t run_split(dq_context *ctx, uint32_t point_capacity, double norm, uint32_t K, int max_iters, int num_bits,
-                   uint32_t *colortable_out, dq_split_record *records_out, double *mean_out, uint32_t *size_out) {
+                   uint32_t *colortable_out, dq_split_record *records_out, double *mean_out, uint32_t *size_out,
+                   bool collect_from_hist = false) {
   if (max_iters < 1 || max_iters > kSplitMaxIters) {
     fprintf(stderr, "divquant_b200: max_iters ( %d ) must be in [1,%d] (the reference hard-wires local k-means on)\n",
             max_iters, kSplitMaxIters);
@@ -226,9 +242,15 @@ uint32_t run_split(dq_context *ctx, uint32_t point_capacity, double norm, uint32
     x.cursors = ctx->d_cursors.ptr;
     ctx->d_progress.ensure(1024);
     x.progress = ctx->d_progress.ptr;
+    x.collect_uniq = collect_from_hist ? ctx->d_uniq.ptr : nullptr;
+    x.collect_table = collect_from_hist ? ctx->d_table : nullptr;
     if (getenv("DQ_PROFILE_NARROW")) DQ_CUDA_CHECK(cudaMemsetAsync(ctx->d_progress.ptr, 0, 1024 * sizeof(uint32_t), ctx->stream));
     split2_launch(a, x, split2_plan(ctx->sm_count, K), ctx->stream);
   } else {
+    if (collect_from_hist) {  // the generic kernel has no fused collect
+      hist_collect(ctx->d_uniq.ptr, &ctx->d_cb->ucount, point_capacity, ctx->d_table, ctx->d_pts0.ptr, true, ctx->sm_count, ctx->stream);
+      ctx->stats.kernel_launches++;
+    }
     split_launch(a, split_plan(ctx->sm_count, K), ctx->stream);
   }
   ctx->mark(3);
@@ -384,13 +406,11 @@ bool quantize_device(dq_context *ctx, uint32_t n, const uint32_t *d_in, uint32_t
     ctx->d_pts0.ensure(samples);
     run_histogram(ctx, d_in, n, rows, cols, (uint32_t)dec, num_bits);
     ctx->mark(1);
-    hist_collect(ctx->d_uniq.ptr, &ctx->d_cb->ucount, samples, ctx->d_table, ctx->d_pts0.ptr, true, ctx->sm_count, ctx->stream);
-    ctx->stats.kernel_launches++;
-    table_dirty = true;  // (= a unique list exists; the count table itself is clean again)
+    table_dirty = true;  // (= a unique list exists; the split kernel's first pass turns it into points and zeroes the counters)
     norm = sample_norm(rows, cols, dec);
     point_cap = samples;
   }
-  *k_inout = run_split(ctx, point_cap, norm, K, max_iters, num_bits, colortable, records, mean_out, size_out);
+  *k_inout = run_split(ctx, point_cap, norm, K, max_iters, num_bits, colortable, records, mean_out, size_out, table_dirty);
   return table_dirty;
 }
 
@@ -811,10 +831,9 @@ void dq_shard_quantize_map(dq_context *ctx, const uint32_t *d_all_colours, const
   ctx->d_uniq.ensure(num_entries);
   ctx->d_pts0.ensure(num_entries);
   hist_merge(d_all_colours, d_all_counts, num_entries, ctx->d_table, ctx->d_uniq.ptr, &ctx->d_cb->ucount, ctx->sm_count, ctx->stream);
-  hist_collect(ctx->d_uniq.ptr, &ctx->d_cb->ucount, num_entries, ctx->d_table, ctx->d_pts0.ptr, true, ctx->sm_count, ctx->stream);
-  ctx->stats.kernel_launches += 2;
+  ctx->stats.kernel_launches += 1;
   const double norm = sample_norm(1, (uint32_t)total_pixels, 1);  // 1 / N of the WHOLE image (:172)
-  uint32_t k = run_split(ctx, num_entries, norm, K, 10, 8, outColortablePtr, nullptr, nullptr, nullptr);
+  uint32_t k = run_split(ctx, num_entries, norm, K, 10, 8, outColortablePtr, nullptr, nullptr, nullptr, true);
   k = dedup_palette(outColortablePtr, k);
   *numClustersPtr = k;
   ctx->stats.actual_colors = k;

@@ -132,6 +132,10 @@ struct Split2Extra {
   uint32_t slot_cap;
   uint32_t *cursors;          // [2][K][2] scatter cursors of wide jobs
   uint32_t *progress;         // [grid] last stage each CTA reached (diagnostics of an expired wait)
+  // when non-null the root pass also builds the points from the histogram (fused hist_collect):
+  // pts[0][i] = (uniq[i], table[uniq[i]]) and the counter is zeroed
+  const uint32_t *collect_uniq;
+  uint32_t *collect_table;
 };
 size_t split2_slot_capacity(uint32_t point_capacity, uint32_t num_colors, int sm_count);
 SplitLaunch split2_plan(int sm_count, uint32_t num_colors);

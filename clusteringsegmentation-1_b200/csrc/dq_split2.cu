@@ -763,7 +763,17 @@ __global__ void __launch_bounds__(512, 1) split2_kernel(const SplitArgs A, const
   // ---- global statistics of all points (DivQuantClusterInitMeanAndVar, :60-104) + scratch reset ----
   {
     uint64_t v[kAccWords] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (size_t i = (size_t)b * T + tid; i < U; i += (size_t)G * T) add_point(v, ld_cg_u2(A.pts[0] + i), true);
+    if (X.collect_uniq != nullptr) {
+      for (size_t i = (size_t)b * T + tid; i < U; i += (size_t)G * T) {
+        const uint32_t c = X.collect_uniq[i];
+        const uint2 p = make_uint2(c, X.collect_table[c]);
+        X.collect_table[c] = 0u;  // the count table is all-zero again when the kernel ends
+        A.pts[0][i] = p;
+        add_point(v, p, true);
+      }
+    } else {
+      for (size_t i = (size_t)b * T + tid; i < U; i += (size_t)G * T) add_point(v, ld_cg_u2(A.pts[0] + i), true);
+    }
     block_total<kAccWords>(S, v);
     if (tid < kAccWords && S.tot[tid] != 0)
       atomicAdd(reinterpret_cast<unsigned long long *>(A.root_acc + tid), (unsigned long long)S.tot[tid]);
