@@ -48,10 +48,32 @@ __global__ void __launch_bounds__(256) hist_insert_kernel(const uint32_t *__rest
     const bool ok = i < nvec;
     uint4 p = make_uint4(0, 0, 0, 0);
     if (ok) p = __ldcs(in4 + i);  // streamed once: keep L2 for the table
-    insert_colour(cut_colour(p.x, word_mask, shift), ok, table, uniq, ucount);
-    insert_colour(cut_colour(p.y, word_mask, shift), ok, table, uniq, ucount);
-    insert_colour(cut_colour(p.z, word_mask, shift), ok, table, uniq, ucount);
-    insert_colour(cut_colour(p.w, word_mask, shift), ok, table, uniq, ucount);
+    // all four atomics are issued before any of their results is looked at (4 L2 round trips in flight)
+    const uint32_t c[4] = {cut_colour(p.x, word_mask, shift), cut_colour(p.y, word_mask, shift),
+                           cut_colour(p.z, word_mask, shift), cut_colour(p.w, word_mask, shift)};
+    uint32_t old[4] = {1u, 1u, 1u, 1u};
+    if (ok) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) old[k] = atomicAdd(table + c[k], 1u);
+    }
+    // a thread's own duplicates: only the first one can have seen 0, nothing to fix up
+    unsigned m[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) m[k] = __ballot_sync(0xffffffffu, old[k] == 0u);
+    const unsigned any = m[0] | m[1] | m[2] | m[3];
+    if (any) {
+      const int lane = threadIdx.x & 31;
+      const uint32_t total = __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(ucount, total);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      const unsigned below = (1u << lane) - 1u;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (old[k] == 0u) uniq[base + __popc(m[k] & below)] = c[k];
+        base += __popc(m[k]);
+      }
+    }
   }
   // tail (< 4 pixels) handled by the first warp of the grid
   if (blockIdx.x == 0 && threadIdx.x < 32) {
