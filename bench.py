@@ -409,7 +409,7 @@ def run_ours(args, rank, world, local_rank):
         "roofline": {"bound": "hbm", "achieved": hbm_achieved, "peak": peak, "unit": "GB/s", "frac": hbm_achieved / peak,
                      "traffic": traffic_bytes(), "peak_source": peak_src,
                      "scope": "whole step: 12 algorithmic B/pixel (4 histogram read + 4 remap read + 4 remap write) / step time",
-                     "traffic_note": "dram bytes of one step from ncu --set full (profiles/r01_ncu_full_summary.txt): hist_insert 39.0 + split 1.2 + map_unique 1.0 + map_gather 44.1 MB; the remap output largely stays in the 126 MB L2",
+                     "traffic_note": "dram bytes of one step from ncu --set full (profiles/r01_ncu_full_summary.txt): hist_insert 39.0 + split 9.4 + map_unique 0.9 + map_gather 43.5 MB; the remap output largely stays in the 126 MB L2",
                      "dominant_kernel": dominant, "kernels": kernels,
                      "note": "the path is not HBM-bound: north_star bounds it by the issue pipe (see path_roofline); the dominant kernel (split) is a dependency chain, DESIGN.md 5.2"},
         "path_roofline": {"definition": "north_star / SURVEY.md 8d: T_roof = max(N*K distance evaluations x 4 lane-instr / (SMs x 128 lanes x SM clock), 12 B/pixel / HBM peak)",
