@@ -268,3 +268,40 @@ def test_label_image_matches_oracle(dq, oracle, images, golden):
     q = np.array([0x101010, 0x303030, 0x202020, 0x101010], np.uint32)
     assert list(dq.colortable_indexes(q, pal)) == [2, 3, 4, 2]
     assert list(dq.colortable_indexes(q, pal, greyscale=True)) == [0x020202, 0x030303, 0x040404, 0x020202]
+
+
+def test_ragged_sizes_and_alignment(dq, pkg, oracle):
+    """Sizes around the vector widths (4 / 8 pixels per thread), misaligned device pointers, huge palettes."""
+    import ctypes as C
+    import torch
+    rng = np.random.default_rng(33)
+    pal = rng.integers(0, 1 << 24, 200, dtype=np.uint32)
+    for n in (1, 2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 31, 33, 255, 257, 1023, 1025, 70001):
+        px = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+        assert np.array_equal(dq.map_colors_mps(px, pal), oracle.map_colors_mps(px, pal)), n
+        col, cnt = dq.histogram(px)
+        assert int(cnt.sum()) == n and col.size == np.unique(px & 0xFFFFFF).size, n
+    # device pointers that are only 4-byte aligned (row-sharded callers pass offsets into a frame)
+    lib = dq.lib
+    ctx = lib.dq_default_context()
+    base = rng.integers(0, 1 << 24, 500, dtype=np.uint32)
+    host = base[rng.integers(0, 500, 100003)]
+    dev = torch.from_numpy(host.view(np.int32)).cuda()
+    out = torch.zeros_like(dev)
+    for off in (1, 2, 3):
+        n = host.size - 8
+        ct = pal.copy()
+        lib.dq_map_colors_device(ctx, dev.data_ptr() + 4 * off, n, out.data_ptr() + 4 * off, ct.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                 ct.size, 1)
+        assert np.array_equal(out.cpu().numpy().view(np.uint32)[off:off + n], oracle.map_colors_mps(host[off:off + n], pal)), off
+        k = C.c_uint32(16)
+        ct16 = np.zeros(16, np.uint32)
+        lib.dq_quant_recurse_device(ctx, n, dev.data_ptr() + 4 * off, out.data_ptr() + 4 * off, C.byref(k),
+                                    ct16.ctypes.data_as(C.POINTER(C.c_uint32)), 0)
+        with muted():
+            oout, opal = oracle.quant_recurse(host[off:off + n], 16, 0)
+        assert np.array_equal(ct16[:k.value], opal) and np.array_equal(out.cpu().numpy().view(np.uint32)[off:off + n], oout), off
+    # palette larger than the shared-memory limit of the fast kernels (global-memory fallback)
+    big = rng.integers(0, 1 << 24, 9000, dtype=np.uint32)
+    px = rng.integers(0, 1 << 24, 3000, dtype=np.uint32)
+    assert np.array_equal(dq.map_colors_mps(px, big), oracle.map_colors_mps(px, big))
