@@ -49,6 +49,8 @@ struct Shared2 {
   SplitNode cur;  // node being split by a narrow job / finalised by an owner
   JobConst wide[kWideCache];
   PassParams wide_pp[kWideCache];  // classification of the last pass, reused by the partition
+  uint64_t prev_tot[4];            // narrow jobs: {cnt, R, G, B} sums of the previous pass (fixed-point detection)
+  int32_t converged;
   int32_t n_nodes, n_prev, njobs, prev_njobs;
   int32_t nwide_tiles, n_mywide, n_mynarrow;
   int32_t mode;  // 0 = threshold policy, 1 = replicated sequential replay
@@ -687,7 +689,21 @@ __device__ __forceinline__ unsigned narrow_pass(Shared2 &S, const uint2 (&p)[kNa
   reduce_stage1<WORDS>(S, v, nwarps);
   if (threadIdx.x < 32) {
     reduce_stage2_warp0<WORDS>(S, nwarps);
-    if (!FINAL) derive_params_warp0(S, jc, norm);
+    if (!FINAL) {
+      // Fixed point of the local 2-means: the next pass's parameters are a function of {cnt, R, G, B} only, so
+      // equal sums in two consecutive passes mean every later pass repeats this one exactly -- the remaining
+      // iterations can be skipped without changing a bit of the result (the caller goes straight to the last pass).
+      if (threadIdx.x == 0) {
+        bool same = !SPLIT;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          same = same && (S.prev_tot[w] == S.tot[w]);
+          S.prev_tot[w] = S.tot[w];
+        }
+        S.converged = same ? 1 : 0;
+      }
+      derive_params_warp0(S, jc, norm);
+    }
   }
   __syncthreads();
   return newmask;
@@ -1175,7 +1191,10 @@ __global__ void __launch_bounds__(512, 1) split2_kernel(const SplitArgs A, const
       __syncthreads();
       const int ppt = (int)((jc.size + nthr - 1) / nthr);
       unsigned newmask = narrow_pass<true, false>(S, p, validmask, ppt, nwarps, jc, A.norm);
-      for (int pass = 1; pass < P; ++pass) newmask = narrow_pass<false, false>(S, p, validmask, ppt, nwarps, jc, A.norm);
+      for (int pass = 1; pass < P; ++pass) {
+        newmask = narrow_pass<false, false>(S, p, validmask, ppt, nwarps, jc, A.norm);
+        if (S.converged) break;  // CTA-uniform: written before the barrier that ends the pass
+      }
       newmask = narrow_pass<false, true>(S, p, validmask, ppt, nwarps, jc, A.norm);
       // S.tot = totals of the last pass; newmask = membership decided by it
       const uint32_t size_old = jc.size - (uint32_t)S.tot[kAccPts];
