@@ -83,6 +83,10 @@ def load_library(path=LIB_PATH):
         "dq_quant_varpart_device": (None, [vp, C.c_uint32, vp, C.c_uint32, C.c_uint32, _u32p, _u32p, C.c_int,
                                            C.c_int, C.c_int, C.c_int]),
         "dq_quant_recurse_ctx": (None, [vp, C.c_uint32, _u32p, _u32p, _u32p, _u32p, C.c_int]),
+        "dq_pixel_histogram": (C.c_uint32, [_u32p, C.c_uint32, _u32p, _u32p, C.c_uint32]),
+        "dq_block_vote": (None, [_u32p, C.c_uint32, C.c_uint32, C.c_uint32, _u32p]),
+        "dq_block_vote_device": (None, [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp]),
+        "dq_quant_blocks": (None, [_u32p, C.c_uint32, C.c_uint32, C.c_uint32, _u32p, C.c_int, _u32p, _u32p]),
         "dq_colortable_indexes": (None, [_u32p, C.c_uint32, _u32p, C.c_int, _u32p, C.c_int]),
         "dq_colortable_indexes_device": (None, [vp, vp, C.c_uint32, _u32p, C.c_int, vp, C.c_int]),
         "dq_shard_histogram": (C.c_uint32, [vp, vp, C.c_uint32, vp, vp]),
@@ -113,7 +117,7 @@ EXPORTED_C_SYMBOLS = [
     "dq_get_double_scale", "dq_validate_num_bits", "dq_set_display_timings", "dq_context_create", "dq_context_destroy",
     "dq_default_context", "dq_context_stream", "dq_context_synchronize", "dq_context_last_stats", "dq_context_set_profiling",
     "dq_quant_recurse_device", "dq_map_colors_device", "dq_quant_varpart_device", "dq_quant_recurse_ctx",
-    "dq_colortable_indexes", "dq_colortable_indexes_device", "dq_shard_histogram", "dq_shard_quantize_map", "dq_pipeline_create", "dq_pipeline_destroy", "dq_pipeline_submit", "dq_pipeline_flush", "dq_pipeline_last_elapsed_ms",
+    "dq_pixel_histogram", "dq_block_vote", "dq_block_vote_device", "dq_quant_blocks", "dq_colortable_indexes", "dq_colortable_indexes_device", "dq_shard_histogram", "dq_shard_quantize_map", "dq_pipeline_create", "dq_pipeline_destroy", "dq_pipeline_submit", "dq_pipeline_flush", "dq_pipeline_last_elapsed_ms",
     "dq_pipeline_context", "dq_pipeline_kernel_launches",
     "dq_debug_split_points", "dq_debug_histogram", "dq_debug_split_timeline", "dq_host_dedup_palette", "dq_host_build_search_tables",
 ]
@@ -183,6 +187,31 @@ class DivQuant:
         out = np.zeros_like(px)
         self.lib.dq_cut_bits(_p(px), px.size, _p(out), rbits, gbits, bbits)
         return out
+
+    def pixel_histogram(self, pixels):
+        """generatePixelHistogram: (distinct 24-bit pixels ascending, counts)."""
+        px = _u32(pixels)
+        cap = min(px.size, 1 << 24)
+        keys, counts = np.zeros(cap, np.uint32), np.zeros(cap, np.uint32)
+        u = self.lib.dq_pixel_histogram(_p(px), px.size, _p(keys), _p(counts), cap)
+        return keys[:u].copy(), counts[:u].copy()
+
+    def block_vote(self, quant_pixels, width, height, dim=4):
+        px = _u32(quant_pixels)
+        bw, bh = -(-width // dim), -(-height // dim)
+        out = np.zeros(bw * bh, np.uint32)
+        self.lib.dq_block_vote(_p(px), width, height, dim, _p(out))
+        return out.reshape(bh, bw)
+
+    def quant_blocks(self, pixels, width, height, colortable, dim=4):
+        """genHistogramsForBlocks' numeric part: remap to `colortable`, then one representative per block."""
+        px = _u32(pixels)
+        ct = _u32(colortable).copy()
+        bw, bh = -(-width // dim), -(-height // dim)
+        quant = np.zeros_like(px)
+        blocks = np.zeros(bw * bh, np.uint32)
+        self.lib.dq_quant_blocks(_p(px), width, height, dim, _p(ct), ct.size, _p(quant), _p(blocks))
+        return quant, blocks.reshape(bh, bw)
 
     def colortable_indexes(self, quant_pixels, colortable, greyscale=False):
         """Label image: index of every quantized pixel in the caller's palette order (last duplicate wins)."""

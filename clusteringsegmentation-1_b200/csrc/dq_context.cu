@@ -748,6 +748,50 @@ int dq_calc_color_table(const uint32_t *inPixels, uint32_t numPixels, uint32_t *
   return 0;
 }
 
+// ---- block majority vote ----
+
+void dq_block_vote_device(dq_context *ctx, const uint32_t *d_quantPixels, uint32_t width, uint32_t height, uint32_t superpixelDim,
+                          uint32_t *d_blocksOut) {
+  require_device(ctx);
+  if (superpixelDim < 1 || superpixelDim > 8 || width == 0 || height == 0) {
+    fprintf(stderr, "divquant_b200: block vote needs a non-empty image and superpixelDim in 1..8\n");
+    abort();
+  }
+  block_vote(d_quantPixels, width, height, superpixelDim, d_blocksOut, ctx->sm_count, ctx->stream);
+  ctx->stats.kernel_launches++;
+}
+
+void dq_block_vote(const uint32_t *quantPixels, uint32_t width, uint32_t height, uint32_t superpixelDim, uint32_t *blocksOut) {
+  dq_context *ctx = dq_default_context();
+  require_device(ctx);
+  const uint32_t n = width * height;
+  const uint32_t nb = ((width + superpixelDim - 1) / superpixelDim) * ((height + superpixelDim - 1) / superpixelDim);
+  ctx->d_in.ensure(n);
+  ctx->d_out.ensure(n);
+  DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->d_in.ptr, quantPixels, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  dq_block_vote_device(ctx, ctx->d_in.ptr, width, height, superpixelDim, ctx->d_out.ptr);
+  DQ_CUDA_CHECK(cudaMemcpyAsync(blocksOut, ctx->d_out.ptr, (size_t)nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}
+
+void dq_quant_blocks(const uint32_t *inPixels, uint32_t width, uint32_t height, uint32_t superpixelDim, const uint32_t *colortable,
+                     int colormapSize, uint32_t *quantOut, uint32_t *blocksOut) {
+  dq_context *ctx = dq_default_context();
+  require_device(ctx);
+  const uint32_t n = width * height;
+  const uint32_t nb = ((width + superpixelDim - 1) / superpixelDim) * ((height + superpixelDim - 1) / superpixelDim);
+  ctx->d_in.ensure(n);
+  ctx->d_out.ensure(n);
+  ctx->d_keys.ensure(nb / 2 + 2);  // 8-byte scratch reused for the nb block words
+  DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->d_in.ptr, inPixels, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  dq_map_colors_device(ctx, ctx->d_in.ptr, n, ctx->d_out.ptr, colortable, colormapSize, 1);
+  uint32_t *d_blocks = reinterpret_cast<uint32_t *>(ctx->d_keys.ptr);
+  dq_block_vote_device(ctx, ctx->d_out.ptr, width, height, superpixelDim, d_blocks);
+  if (quantOut) DQ_CUDA_CHECK(cudaMemcpyAsync(quantOut, ctx->d_out.ptr, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  DQ_CUDA_CHECK(cudaMemcpyAsync(blocksOut, d_blocks, (size_t)nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}
+
 // ---- label image ----
 
 void dq_colortable_indexes_device(dq_context *ctx, const uint32_t *d_quantPixels, uint32_t numPixels, const uint32_t *colortable,
@@ -1027,6 +1071,29 @@ uint32_t dq_debug_histogram(dq_context *ctx, const uint32_t *inPixels, uint32_t 
     counts[i] = pts[i].y;
   }
   ctx->stats.num_points = U;
+  return U;
+}
+
+uint32_t dq_pixel_histogram(const uint32_t *pixels, uint32_t numPixels, uint32_t *pixelsOut, uint32_t *countsOut, uint32_t capacity) {
+  dq_context *ctx = dq_default_context();
+  require_device(ctx);
+  if (numPixels == 0) return 0;
+  ctx->d_in.ensure(numPixels);
+  ctx->d_pts0.ensure(numPixels);
+  DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->d_in.ptr, pixels, (size_t)numPixels * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  reset_control(ctx);
+  run_histogram(ctx, ctx->d_in.ptr, numPixels, 1, numPixels, 1, 8);
+  hist_collect(ctx->d_uniq.ptr, &ctx->d_cb->ucount, numPixels, ctx->d_table, ctx->d_pts0.ptr, true, ctx->sm_count, ctx->stream);
+  DQ_CUDA_CHECK(cudaMemcpyAsync(&ctx->h_cb->ucount, &ctx->d_cb->ucount, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  const uint32_t U = ctx->h_cb->ucount;
+  std::vector<uint2> pts(U);
+  DQ_CUDA_CHECK(cudaMemcpy(pts.data(), ctx->d_pts0.ptr, (size_t)U * sizeof(uint2), cudaMemcpyDeviceToHost));
+  std::sort(pts.begin(), pts.end(), [](const uint2 &a, const uint2 &b) { return a.x < b.x; });
+  for (uint32_t i = 0; i < U && i < capacity; ++i) {
+    pixelsOut[i] = pts[i].x;
+    countsOut[i] = pts[i].y;
+  }
   return U;
 }
 

@@ -29,6 +29,8 @@ void map_pixels(const uint32_t *d_in, uint32_t n, uint32_t *d_out, const uint32_
                 const int *d_lut, int4 *d_pal_scratch, int sm_count, cudaStream_t st);
 void map_unique(const uint32_t *d_uniq, const uint32_t *d_ucount, uint32_t u_hint, uint32_t *d_table,
                 const uint32_t *d_sorted, int num_colors, const int *d_lut, int sm_count, cudaStream_t st);
+void block_vote(const uint32_t *d_quant, uint32_t width, uint32_t height, uint32_t dim, uint32_t *d_blocks, int sm_count,
+                cudaStream_t st);
 void map_labels(const uint32_t *d_in, uint32_t n, uint32_t *d_out, const uint2 *d_pairs, int num_pairs, int greyscale,
                 uint32_t *d_error, int sm_count, cudaStream_t st);
 void map_gather(const uint32_t *d_in, uint32_t n, uint32_t *d_out, const uint32_t *d_table, int sm_count, cudaStream_t st);

@@ -261,6 +261,78 @@ __global__ void __launch_bounds__(kMapThreads) map_gather_scalar_kernel(const ui
     out[i] = table[in[i] & 0x00FFFFFFu] & 0x00FFFFFFu;
 }
 
+// ---- block majority vote (genHistogramsForBlocks, ClusteringSegmentation.cpp:417-563) ------------------------
+// One thread per block.  The reference counts in a std::unordered_map<uint32_t,uint32_t> and takes the first
+// maximum in ITERATION order, so that order is reproduced: libstdc++ keeps one singly linked list; a new key
+// whose bucket (key % bucket_count, identity hash) is empty goes to the front of the whole list, otherwise to the
+// front of its bucket's run; the table starts with 1 bucket, grows to the next prime >= max(n+1, 2*buckets) when
+// n+1 would exceed the bucket count, and a rehash re-inserts the nodes in list order by the same rule.
+constexpr int kVoteMaxKeys = 64;  // superpixelDim <= 8
+
+__device__ __forceinline__ uint32_t next_bucket_count(uint32_t want) {
+  // the entries of libstdc++'s prime table that matter below 2*64
+  const uint32_t primes[] = {2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37, 41, 43, 47, 53, 59, 61, 67, 71, 73, 79, 83, 89, 97, 103, 109, 113, 127, 137, 139, 149, 157, 167};
+  for (uint32_t p : primes) if (p >= want) return p;
+  return 167;
+}
+
+__device__ __forceinline__ void list_insert(const uint32_t *keys, int *ord, int n_in_list, int e, uint32_t nb) {
+  const uint32_t b = keys[e] % nb;
+  int pos = 0;  // empty bucket: front of the list
+  for (int i = 0; i < n_in_list; ++i) {
+    if (keys[ord[i]] % nb == b) {
+      pos = i;  // front of that bucket's run
+      break;
+    }
+  }
+  for (int i = n_in_list; i > pos; --i) ord[i] = ord[i - 1];
+  ord[pos] = e;
+}
+
+__global__ void __launch_bounds__(128) block_vote_kernel(const uint32_t *__restrict__ quant, uint32_t width, uint32_t height,
+                                                        uint32_t dim, uint32_t bw, uint32_t bh, uint32_t *__restrict__ blocks) {
+  const uint32_t blk = blockIdx.x * blockDim.x + threadIdx.x;
+  if (blk >= bw * bh) return;
+  const uint32_t bx = blk % bw, by = blk / bw;
+  uint32_t keys[kVoteMaxKeys], counts[kVoteMaxKeys];
+  int ord[kVoteMaxKeys], tmp[kVoteMaxKeys];
+  int n = 0;
+  uint32_t nb = 1, resize_at = 0;  // default-constructed table: 1 bucket, first insert rehashes
+  for (uint32_t y = by * dim; y < by * dim + dim && y < height; ++y) {
+    for (uint32_t x = bx * dim; x < bx * dim + dim && x < width; ++x) {
+      const uint32_t q = quant[(size_t)y * width + x];
+      int found = -1;
+      for (int i = 0; i < n; ++i) if (keys[i] == q) found = i;
+      if (found >= 0) {
+        counts[found] += 1;
+        continue;
+      }
+      if ((uint32_t)n + 1 > resize_at) {
+        nb = next_bucket_count(max((uint32_t)n + 1, nb * 2));
+        if (n == 0) nb = 13;  // _Prime_rehash_policy: the first insertion always lands on 13 buckets
+        resize_at = nb;       // max_load_factor 1.0
+        for (int i = 0; i < n; ++i) tmp[i] = ord[i];
+        for (int i = 0; i < n; ++i) list_insert(keys, ord, i, tmp[i], nb);
+      }
+      keys[n] = q;
+      counts[n] = 1;
+      list_insert(keys, ord, n, n, nb);
+      ++n;
+    }
+  }
+  // all-same blocks fall out naturally (one key); otherwise the first strict maximum in iteration order (:535-547)
+  uint32_t best = 0;
+  int max_count = 0;
+  for (int i = 0; i < n; ++i) {
+    const int e = ord[i];
+    if ((int)counts[e] > max_count) {
+      max_count = (int)counts[e];
+      best = keys[e];
+    }
+  }
+  blocks[blk] = best;
+}
+
 // Label image: binary search of every pixel in the palette sorted by colour value ((colour, last index) pairs).
 __global__ void __launch_bounds__(kMapThreads) map_labels_kernel(const uint32_t *__restrict__ in, uint32_t n,
                                                                 uint32_t *__restrict__ out, const uint2 *pairs, int num_pairs,
@@ -346,6 +418,14 @@ void map_unique(const uint32_t *d_uniq, const uint32_t *d_ucount, uint32_t u_hin
   int per_sm = (int)std::min<size_t>(8, std::max<size_t>(1, (200 * 1024) / smem));
   map_unique_fast_kernel<<<blocks_for(u_hint / kUniqPix + 1, kMapThreads, sm_count, per_sm), kMapThreads, smem, st>>>(
       d_uniq, d_ucount, d_table, d_sorted, num_colors, d_lut);
+  DQ_CUDA_CHECK(cudaGetLastError());
+}
+
+void block_vote(const uint32_t *d_quant, uint32_t width, uint32_t height, uint32_t dim, uint32_t *d_blocks, int sm_count,
+                cudaStream_t st) {
+  const uint32_t bw = (width + dim - 1) / dim, bh = (height + dim - 1) / dim;
+  (void)sm_count;
+  block_vote_kernel<<<(bw * bh + 127) / 128, 128, 0, st>>>(d_quant, width, height, dim, bw, bh, d_blocks);
   DQ_CUDA_CHECK(cudaGetLastError());
 }
 

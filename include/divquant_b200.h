@@ -135,6 +135,26 @@ void dq_quant_varpart_device(dq_context *ctx, uint32_t numPixels, const uint32_t
 void dq_quant_recurse_ctx(dq_context *ctx, uint32_t numPixels, const uint32_t *inPixelsPtr, uint32_t *outPixelsPtr,
                           uint32_t *numClustersPtr, uint32_t *outColortablePtr, int allPixelsUnique);
 
+/* Block majority vote.  Replaces the numeric part of  genHistogramsForBlocks
+ * ClusteringSegmentation/ClusteringSegmentation.cpp:417-563: every superpixelDim x superpixelDim block (clipped at
+ * the border; ceil(width/dim) x ceil(height/dim) blocks, ClusteringSegmentationMain.cpp:139-149) is represented
+ * by its most frequent quantized pixel.  Ties go to the first maximum in the iteration order of the
+ * std::unordered_map<uint32_t,uint32_t> the reference counts in (libstdc++ bucket rule, reproduced on the device).
+ * superpixelDim in 1..8.  Host pointers; blocksOut has ceil(width/dim)*ceil(height/dim) words, row-major. */
+void dq_block_vote(const uint32_t *quantPixels, uint32_t width, uint32_t height, uint32_t superpixelDim, uint32_t *blocksOut);
+void dq_block_vote_device(dq_context *ctx, const uint32_t *d_quantPixels, uint32_t width, uint32_t height,
+                          uint32_t superpixelDim, uint32_t *d_blocksOut);
+/* The whole numeric front half of genHistogramsForBlocks in one call (ClusteringSegmentation.cpp:397-563): remap the
+ * image to `colortable` and vote per block; the quantized image never leaves the GPU unless quantOut != NULL. */
+void dq_quant_blocks(const uint32_t *inPixels, uint32_t width, uint32_t height, uint32_t superpixelDim,
+                     const uint32_t *colortable, int colormapSize, uint32_t *quantOut, uint32_t *blocksOut);
+
+/* Per-image pixel histogram.  Replaces  generatePixelHistogram  superpixels/OpenCVUtil.cpp:736-781
+ * (3-channel form: pixel &= 0x00FFFFFF): the (pixel, count) pairs the reference leaves in its unordered_map, here as
+ * two arrays sorted by ascending pixel value (a map has no order to mirror).  Returns the number of distinct
+ * pixels U; writes min(U, capacity) pairs.  Host pointers. */
+uint32_t dq_pixel_histogram(const uint32_t *pixels, uint32_t numPixels, uint32_t *pixelsOut, uint32_t *countsOut, uint32_t capacity);
+
 /* Label image.  Replaces  mapQuantPixelsToColortableIndexes   superpixels/OpenCVUtil.cpp:787-849:
  * every (already quantized) pixel -> index of its colour in the CALLER's palette order, the last duplicate
  * winning; asGreyscale != 0 writes (i<<16 | i<<8 | i) like the reference (indexes must then be < 256).

@@ -95,6 +95,8 @@ class Oracle:
         L.oracle_quant_recurse.argtypes = [C.c_uint32, _u32p, _u32p, _u32p, _u32p, C.c_int]
         L.oracle_colortable_indexes.restype = C.c_int
         L.oracle_colortable_indexes.argtypes = [_u32p, C.c_uint32, _u32p, C.c_int, _u32p]
+        L.oracle_block_vote.restype = None
+        L.oracle_block_vote.argtypes = [_u32p, C.c_uint32, C.c_uint32, C.c_uint32, _u32p]
         L.oracle_hash_words.restype = C.c_uint64
         L.oracle_hash_words.argtypes = [_u32p, C.c_uint64]
         L.oracle_generate.restype = None
@@ -167,6 +169,13 @@ class Oracle:
         if rc != 0:
             raise ValueError("pixel not present in colortable")
         return out
+
+    def block_vote(self, quant_pixels, width, height, dim=4):
+        px = _u32(quant_pixels)
+        bw, bh = -(-width // dim), -(-height // dim)
+        out = np.zeros(bw * bh, np.uint32)
+        self.lib.oracle_block_vote(_ptr(px), width, height, dim, _ptr(out))
+        return out.reshape(bh, bw)
 
     # -- utilities ------------------------------------------------------------------------
     def hash_words(self, words):

@@ -22,6 +22,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <unordered_map>
 #include <vector>
 
 namespace {
@@ -694,6 +695,44 @@ extern "C" int oracle_colortable_indexes(const uint32_t *quant_pixels, uint32_t 
     labels_out[i] = (uint32_t)found;
   }
   return 0;
+}
+
+// Reference: genHistogramsForBlocks, ClusteringSegmentation/ClusteringSegmentation.cpp:417-563 (block size
+// = ceil(dim/superpixelDim) as in ClusteringSegmentationMain.cpp:139-149).  Every superpixelDim x superpixelDim
+// block (clipped at the image border) is represented by its most frequent quantized pixel; ties go to the
+// first maximum in the iteration order of the std::unordered_map the counts live in -- the same libstdc++
+// container here, filled in the same (row-major) order, hence the same order.
+extern "C" void oracle_block_vote(const uint32_t *quant_pixels, uint32_t width, uint32_t height, uint32_t dim,
+                                  uint32_t *block_out) {
+  const uint32_t bw = (width + dim - 1) / dim, bh = (height + dim - 1) / dim;
+  for (uint32_t by = 0; by < bh; ++by) {
+    for (uint32_t bx = 0; bx < bw; ++bx) {
+      std::vector<uint32_t> px;
+      bool all_same = true;
+      for (uint32_t y = by * dim; y < by * dim + dim; ++y)
+        for (uint32_t x = bx * dim; x < bx * dim + dim; ++x) {
+          if (x > width - 1 || y > height - 1) continue;
+          const uint32_t q = quant_pixels[(size_t)y * width + x];
+          if (!px.empty() && q != px[0]) all_same = false;
+          px.push_back(q);
+        }
+      uint32_t best = 0;
+      if (all_same) {
+        best = px[0];
+      } else {
+        std::unordered_map<uint32_t, uint32_t> counts;
+        for (uint32_t q : px) counts[q] += 1;
+        int max_count = 0;
+        for (auto it = counts.begin(); it != counts.end(); ++it) {
+          if ((int)it->second > max_count) {
+            max_count = (int)it->second;
+            best = it->first;
+          }
+        }
+      }
+      block_out[(size_t)by * bw + bx] = best;
+    }
+  }
 }
 
 extern "C" uint64_t oracle_hash_words(const uint32_t *words, uint64_t n) {

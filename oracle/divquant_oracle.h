@@ -77,6 +77,10 @@ void oracle_quant_recurse(uint32_t num_pixels, const uint32_t *in, uint32_t *out
 int oracle_colortable_indexes(const uint32_t *quant_pixels, uint32_t num_pixels, const uint32_t *colortable,
                               int num_colors, uint32_t *labels_out);
 
+/* Block majority vote of genHistogramsForBlocks (ClusteringSegmentation.cpp:417-563): block_out has
+ * ceil(width/dim) * ceil(height/dim) entries, row-major. */
+void oracle_block_vote(const uint32_t *quant_pixels, uint32_t width, uint32_t height, uint32_t dim, uint32_t *block_out);
+
 /* FNV-1a style fingerprint over u32 words used by SURVEY.md section 8c. */
 uint64_t oracle_hash_words(const uint32_t *words, uint64_t n);
 

@@ -305,3 +305,28 @@ def test_ragged_sizes_and_alignment(dq, pkg, oracle):
     big = rng.integers(0, 1 << 24, 9000, dtype=np.uint32)
     px = rng.integers(0, 1 << 24, 3000, dtype=np.uint32)
     assert np.array_equal(dq.map_colors_mps(px, big), oracle.map_colors_mps(px, big))
+
+
+def test_block_majority_vote(dq, oracle, golden):
+    # genHistogramsForBlocks (ClusteringSegmentation.cpp:417-563), ties by unordered_map order
+    cookie = np.load(_os.path.join(ROOT_DIR, "tests", "golden", "cookie_px.npz"))
+    px, (h, w) = cookie["px"].ravel(), cookie["shape"]
+    quant, blocks = dq.quant_blocks(px, int(w), int(h), golden["grid125"], 4)   # the live call of the reference pipeline
+    assert np.array_equal(quant, oracle.map_colors_mps(px, golden["grid125"]))
+    assert np.array_equal(blocks, oracle.block_vote(quant, int(w), int(h), 4))
+    # adversarial ties: few colours, every block mixed, ragged borders, all supported block sizes
+    rng = np.random.default_rng(9)
+    for dim, (ww, hh), ncol in ((4, (203, 101), 3), (4, (64, 64), 40), (2, (33, 17), 2), (3, (50, 31), 5), (8, (95, 70), 70), (1, (9, 5), 4)):
+        pal = rng.integers(0, 1 << 24, ncol, dtype=np.uint32)
+        q = pal[rng.integers(0, ncol, ww * hh)]
+        assert np.array_equal(dq.block_vote(q, ww, hh, dim), oracle.block_vote(q, ww, hh, dim)), (dim, ww, hh, ncol)
+
+
+def test_pixel_histogram(dq, oracle):
+    # generatePixelHistogram (OpenCVUtil.cpp:736-781) == np.unique on the 24-bit pixels
+    px = oracle.generate(1, 640, 360, 12345)
+    keys, counts = dq.pixel_histogram(px)
+    ek, ec = np.unique(px & 0xFFFFFF, return_counts=True)
+    assert np.array_equal(keys, ek) and np.array_equal(counts, ec)
+    keys, counts = dq.pixel_histogram(np.array([0xFF000005, 5, 7], np.uint32))
+    assert keys.tolist() == [5, 7] and counts.tolist() == [2, 1]
