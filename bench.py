@@ -4,15 +4,17 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
-One "step" = one whole quant_recurse (24-bit histogram -> divisive split with 10 local 2-means
-iterations -> palette dedup/sort -> remap) of one synthetic 3840x2160 frame (generator G1 of
-SURVEY.md 8d, seed 12345+frame).  N > 1: every rank owns one GPU and its own stream of frames
-(frame-sharded, no collective: weak scaling); value = all ranks' pixels / max-over-ranks device time.
+One "step" = one batch of --frames-per-step (8) synthetic 3840x2160 frames (generator G1 of SURVEY.md 8d,
+seed 12345+frame), each a whole quant_recurse (24-bit histogram -> divisive split with 10 local 2-means
+iterations -> palette dedup/sort -> remap), pushed through the frame pipeline (`lanes` frames in flight
+on the GPU).  N > 1: every rank owns one GPU and its own stream of frames (frame-sharded, no collective:
+weak scaling); value = all ranks' pixels / max-over-ranks device time.
 
 Printed JSON line (rank 0): see the task contract.  value = device-resident throughput (inputs in HBM,
-CUDA events on the library's stream); e2e = the same call through the host-pointer C ABI with pinned
-host buffers, H2D and D2H inside the timed region; roofline = dominant kernel against the measured
-HBM peak; cpu_baseline = the reference's own code (oracle/_ref) on one host core.
+CUDA events on the lanes' streams); e2e = the same stream through the host-pointer API with pinned host
+buffers, H2D and D2H of every frame inside the timed region; single_call = latency of one isolated call;
+roofline = the path against the measured HBM peak + per-kernel figures; path_roofline = north_star's
+issue-pipe bound; cpu_baseline = the reference's own code (oracle/_ref) on one host core.
 """
 import argparse
 import importlib
@@ -274,49 +276,75 @@ def run_ours(args, rank, world, local_rank):
         parity = bool(np.array_equal(ref_pal, ct[:nk.value]) and np.array_equal(ref_out, got))
         log(f"[bench] parity vs {kind}: {'bit-exact' if parity else 'MISMATCH'}")
 
-    # -- device-resident throughput --
-    clocks = ClockSampler(local_rank)
-    clocks.start()
-    ms_dev, launches = timed(step_device, steps, warmup)
-    clock_info = clocks.stop()
-    value = world * steps * NPIX / (ms_dev * 1e-3) / 1e6
+    # -- frame pipeline (the public API for a stream of frames): `lanes` frames in flight on one GPU, each lane a
+    #    context + host thread walking one frame at a time through [H2D ->] kernels [-> D2H]; split kernels of
+    #    different lanes sit on disjoint SM groups.  One step = one batch of FRAMES_PER_STEP frames. --
+    u32p = C.POINTER(C.c_uint32)
 
-    # -- end to end, single blocking calls through the host-pointer API (pinned buffers; H2D + D2H inside) --
-    ms_e2e_single, _ = timed(step_host, steps, warmup)
-
-    # -- end to end through the frame pipeline (the public API for a stream of frames): every step's input is
-    #    copied from pinned host memory and its result copied back inside the timed region; the copy engines
-    #    and the SMs work on different frames concurrently --
-    pipe = lib.dq_pipeline_create(local_rank, NPIX, 3)
-    host_outs = [torch.empty(NPIX, dtype=torch.int32).pin_memory() for _ in range(3)]
-    cts = [np.zeros(K, np.uint32) for _ in range(3)]
-    nks = [C.c_uint32(K) for _ in range(3)]
-
-    def run_pipeline(n_frames, first):
+    def run_stream(pipe, n_frames, first, outs, on_device):
+        nbuf = len(outs)
+        nks = [C.c_uint32(K) for _ in range(n_frames)]
+        cts = [np.zeros(K, np.uint32) for _ in range(n_frames)]
+        tickets = []
         for i in range(n_frames):
             f = first + i
-            nks[f % 3].value = K
-            lib.dq_pipeline_submit(pipe, NPIX, C.cast(host_frames[f % RING].data_ptr(), C.POINTER(C.c_uint32)),
-                                   C.cast(host_outs[f % 3].data_ptr(), C.POINTER(C.c_uint32)), C.byref(nks[f % 3]),
-                                   cts[f % 3].ctypes.data_as(C.POINTER(C.c_uint32)), 0)
+            if i >= nbuf:  # the output buffer about to be reused must be complete
+                lib.dq_pipeline_wait(pipe, tickets[i - nbuf])
+            if on_device:
+                t = lib.dq_pipeline_submit_device(pipe, NPIX, dev_frames[f % RING].data_ptr(), outs[i % nbuf].data_ptr(),
+                                                  C.byref(nks[i]), cts[i].ctypes.data_as(u32p), 0)
+            else:
+                t = lib.dq_pipeline_submit(pipe, NPIX, C.cast(host_frames[f % RING].data_ptr(), u32p),
+                                           C.cast(outs[i % nbuf].data_ptr(), u32p), C.byref(nks[i]), cts[i].ctypes.data_as(u32p), 0)
+            tickets.append(t)
         lib.dq_pipeline_flush(pipe)
-        return float(lib.dq_pipeline_last_elapsed_ms(pipe))
+        last = (first + n_frames - 1, outs[(n_frames - 1) % nbuf], cts[-1][:nks[-1].value].copy())
+        return float(lib.dq_pipeline_last_elapsed_ms(pipe)), last  # CUDA events: first op of first frame .. last op of last
 
-    run_pipeline(warmup, 0)
-    barrier()
-    ms_e2e = run_pipeline(steps, warmup)  # CUDA events: first H2D enqueued .. last D2H done
-    barrier()
-    if dist:
-        t = torch.tensor([ms_e2e], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = float(t.item())
-    e2e_value = world * steps * NPIX / (ms_e2e * 1e-3) / 1e6
-    e2e_parity = None
-    if parity is not None:  # last frame of the pipeline against the device-resident result of the same frame
-        step_device((warmup + steps - 1) % RING)
-        torch.cuda.synchronize()
-        e2e_parity = bool(np.array_equal(host_outs[(warmup + steps - 1) % 3].numpy(), dev_out.cpu().numpy()))
-    lib.dq_pipeline_destroy(pipe)
+    def timed_stream(lanes, on_device):
+        pipe = lib.dq_pipeline_create_lanes(local_rank, 0 if on_device else NPIX, lanes, 0)
+        outs = [torch.empty(NPIX, dtype=torch.int32, device="cuda") if on_device else torch.empty(NPIX, dtype=torch.int32).pin_memory()
+                for _ in range(lanes + 2)]
+        run_stream(pipe, warmup * FPS, 0, outs, on_device)
+        barrier()
+        l0 = lib.dq_pipeline_kernel_launches(pipe)
+        w0 = time.perf_counter()
+        ms, last = run_stream(pipe, steps * FPS, warmup * FPS, outs, on_device)
+        wall_ms = (time.perf_counter() - w0) * 1e3
+        n_launch = lib.dq_pipeline_kernel_launches(pipe) - l0
+        barrier()
+        if dist:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        ok = None
+        if parity is not None:  # last frame of the stream against a single blocking call on the same frame
+            frame, out_buf, pal = last
+            step_device(frame % RING)
+            torch.cuda.synchronize()
+            ok = bool(np.array_equal(out_buf.cpu().numpy(), dev_out.cpu().numpy()) and np.array_equal(pal, ct[:nk.value]))
+        lib.dq_pipeline_destroy(pipe)
+        log(f"[bench] pipeline lanes={lanes} {'device' if on_device else 'host'} frames: {ms / (steps * FPS):.3f} ms/frame by events, "
+            f"{wall_ms / (steps * FPS):.3f} by host clock, matches single call: {ok}")
+        return ms, n_launch, ok
+
+    FPS = args.frames_per_step
+    # every lane has a host thread that waits on its stream: leave one core per rank for the submitting thread
+    cpus = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lane_cap = max(2, cpus // world - 1)
+    args.lanes, args.e2e_lanes = min(args.lanes, lane_cap), min(args.e2e_lanes, lane_cap)
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    # -- device-resident throughput (frames already in HBM, results left in HBM) --
+    ms_dev, launches, dev_parity = timed_stream(args.lanes, True)
+    value = world * steps * FPS * NPIX / (ms_dev * 1e-3) / 1e6
+    # -- end to end: pinned host frames, H2D and D2H of every frame inside the timed region --
+    ms_e2e, _, e2e_parity = timed_stream(args.e2e_lanes, False)
+    e2e_value = world * steps * FPS * NPIX / (ms_e2e * 1e-3) / 1e6
+    # -- latency of ONE call (no concurrency between frames): device-resident and through the host-pointer API --
+    ms_single, single_launches = timed(step_device, steps, warmup)
+    ms_e2e_single, _ = timed(step_host, steps, warmup)
+    clock_info = clocks.stop()
 
     # -- per-stage device times (CUDA events inside the library) for the roofline --
     lib.dq_context_set_profiling(ctx, 1)
@@ -361,6 +389,8 @@ def run_ours(args, rank, world, local_rank):
 
     peak, peak_src = measured_peaks()
     ms_step = ms_dev / steps
+    ms_frame = ms_step / FPS
+    ms_single_frame = ms_single / steps
     # Per-kernel algorithmic HBM bytes: hist_insert reads 4 B/pixel; map_gather reads 4 and writes
     # 4 B/pixel; the split kernel works on the U unique colours only (8 B/point once) and is latency-bound.
     kernels = {
@@ -381,7 +411,7 @@ def run_ours(args, rank, world, local_rank):
     t_pipe_ms = NPIX * K * 4 / (sm_count * 128 * sm_clock) * 1e3
     t_hbm_ms = 12.0 * NPIX / (peak * 1e9) * 1e3
     t_roof_ms = max(t_pipe_ms, t_hbm_ms)
-    hbm_achieved = 12.0 * NPIX / (ms_step * 1e-3) / 1e9
+    hbm_achieved = 12.0 * NPIX / (ms_frame * 1e-3) / 1e9
 
     cpu = None
     if not args.skip_cpu:
@@ -395,29 +425,36 @@ def run_ours(args, rank, world, local_rank):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32+f64",
         "data": "synthetic",
         "config": {"workload": f"{WIDTH}x{HEIGHT} RGBA G1 natural-like, K={K}, quant_recurse (histogram + split with 10 LKM iterations + remap)",
-                   "frames_per_rank": RING, "sharding": "frames (one stream of frames per GPU, no collective)" if world > 1 else "single GPU",
+                   "frames_per_step": FPS, "lanes": args.lanes,
+                   "api": "dq_pipeline_submit_device/flush: a stream of independent frames, `lanes` in flight on one GPU (each frame is one unmodified quant_recurse; split kernels of different frames on disjoint SM groups)",
+                   "distinct_frames_per_rank": RING, "sharding": "frames (one stream of frames per GPU, no collective)" if world > 1 else "single GPU",
                    "l2": f"inputs rotate over {RING} distinct frames = {RING * NPIX * 4 / 1e6:.0f} MB > 126 MB L2",
                    "remap_variant": "unique-colour table (U*K evaluations + N gathers)" if info["remap_path"] == 2 else "brute force N*K",
                    "unique_colours": info["num_points"], "split_rounds": info["split_rounds"], "splits_computed": info["splits_computed"]},
         "clocks": clock_info,
-        "e2e": {"value": e2e_value, "unit": "Mpixels/s", "h2d_bytes_per_step": NPIX * 4, "d2h_bytes_per_step": NPIX * 4 + K * 4 + 96,
-                "ms_per_step": ms_e2e / steps, "host_buffers": "pinned",
-                "api": "dq_pipeline_submit/flush (3 frames in flight: H2D, kernels and D2H of different frames overlap)",
+        "e2e": {"value": e2e_value, "unit": "Mpixels/s", "h2d_bytes_per_step": FPS * NPIX * 4, "d2h_bytes_per_step": FPS * (NPIX * 4 + K * 4 + 4),
+                "h2d_bytes_per_frame": NPIX * 4, "d2h_bytes_per_frame": NPIX * 4 + K * 4 + 4,
+                "ms_per_step": ms_e2e / steps, "ms_per_frame": ms_e2e / steps / FPS, "host_buffers": "pinned", "lanes": args.e2e_lanes,
+                "api": "dq_pipeline_submit/flush (H2D, kernels and D2H of different frames overlap)",
                 "single_call_ms": ms_e2e_single / steps, "single_call_value": world * steps * NPIX / (ms_e2e_single * 1e-3) / 1e6,
-                "matches_device_result": e2e_parity},
+                "matches_single_call": e2e_parity},
+        "single_call": {"api": "dq_quant_recurse_device, one frame at a time (latency of one call, all SMs on one frame)",
+                        "ms": ms_single_frame, "value": world * NPIX / (ms_single_frame * 1e-3) / 1e6, "unit": "Mpixels/s",
+                        "path_roofline_frac": t_roof_ms / ms_single_frame, "gpu_launches_per_call": single_launches / steps},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": hbm_achieved, "peak": peak, "unit": "GB/s", "frac": hbm_achieved / peak,
                      "traffic": traffic_bytes(), "peak_source": peak_src,
-                     "scope": "whole step: 12 algorithmic B/pixel (4 histogram read + 4 remap read + 4 remap write) / step time",
+                     "scope": "whole path per frame: 12 algorithmic B/pixel (4 histogram read + 4 remap read + 4 remap write) / time per frame at the measured throughput; per-kernel times in `kernels` are single-call CUDA-event times (one frame alone on the GPU)",
                      "traffic_note": "dram bytes of one step from ncu --set full (profiles/r01_ncu_full_summary.txt): hist_insert 39.0 + split 9.4 + map_unique 0.9 + map_gather 43.5 MB; the remap output largely stays in the 126 MB L2",
                      "dominant_kernel": dominant, "kernels": kernels,
                      "note": "the path is not HBM-bound: north_star bounds it by the issue pipe (see path_roofline); the dominant kernel (split) is a dependency chain, DESIGN.md 5.2"},
         "path_roofline": {"definition": "north_star / SURVEY.md 8d: T_roof = max(N*K distance evaluations x 4 lane-instr / (SMs x 128 lanes x SM clock), 12 B/pixel / HBM peak)",
-                          "t_pipe_ms": t_pipe_ms, "t_hbm_ms": t_hbm_ms, "t_roof_ms": t_roof_ms, "t_measured_ms": ms_step,
-                          "frac": t_roof_ms / ms_step, "target": 0.5,
+                          "t_pipe_ms": t_pipe_ms, "t_hbm_ms": t_hbm_ms, "t_roof_ms": t_roof_ms, "t_measured_ms": ms_frame,
+                          "frac": t_roof_ms / ms_frame, "frac_single_call": t_roof_ms / ms_single_frame, "target": 0.5,
+                          "basis": "per frame at the throughput of `value` (lanes frames in flight); frac_single_call is the same bound against the latency of one isolated call",
                           "note": "config.remap_variant says which formulation produced the time: the unique-colour table does U*K, not N*K, evaluations (an algorithmic win, not pipe efficiency)"},
         "stage_ms": stage_ms,
-        "parity": parity,
+        "parity": parity, "pipeline_matches_single_call": dev_parity,
     }
     if rows_info:
         line["row_sharded"] = rows_info
@@ -435,6 +472,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-frames", type=int, default=10, help="frames of the single-thread CPU baseline sample")
+    ap.add_argument("--lanes", type=int, default=8, help="frames in flight per GPU, device-resident leg")
+    ap.add_argument("--e2e-lanes", type=int, default=6, help="frames in flight per GPU, host-buffer leg")
+    ap.add_argument("--frames-per-step", type=int, default=8, help="frames in one step (one batch)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-parity", action="store_true")
     ap.add_argument("--width", type=int, default=3840, help="frame width (default: the BASELINE.json headline config)")

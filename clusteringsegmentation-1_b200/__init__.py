@@ -83,6 +83,7 @@ def load_library(path=LIB_PATH):
         "dq_quant_varpart_device": (None, [vp, C.c_uint32, vp, C.c_uint32, C.c_uint32, _u32p, _u32p, C.c_int,
                                            C.c_int, C.c_int, C.c_int]),
         "dq_quant_recurse_ctx": (None, [vp, C.c_uint32, _u32p, _u32p, _u32p, _u32p, C.c_int]),
+        "dq_context_set_split_ctas": (None, [vp, C.c_int]),
         "dq_pixel_histogram": (C.c_uint32, [_u32p, C.c_uint32, _u32p, _u32p, C.c_uint32]),
         "dq_block_vote": (None, [_u32p, C.c_uint32, C.c_uint32, C.c_uint32, _u32p]),
         "dq_block_vote_device": (None, [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp]),
@@ -93,7 +94,11 @@ def load_library(path=LIB_PATH):
         "dq_shard_quantize_map": (None, [vp, vp, vp, C.c_uint32, C.c_uint64, vp, C.c_uint32, vp, _u32p, _u32p]),
         "dq_pipeline_create": (vp, [C.c_int, C.c_uint32, C.c_int]),
         "dq_pipeline_destroy": (None, [vp]),
-        "dq_pipeline_submit": (None, [vp, C.c_uint32, _u32p, _u32p, _u32p, _u32p, C.c_int]),
+        "dq_pipeline_create_lanes": (vp, [C.c_int, C.c_uint32, C.c_int, C.c_int]),
+        "dq_pipeline_submit": (C.c_uint64, [vp, C.c_uint32, _u32p, _u32p, _u32p, _u32p, C.c_int]),
+        "dq_pipeline_submit_device": (C.c_uint64, [vp, C.c_uint32, vp, vp, _u32p, _u32p, C.c_int]),
+        "dq_pipeline_wait": (None, [vp, C.c_uint64]),
+        "dq_pipeline_lanes": (C.c_int, [vp]),
         "dq_pipeline_flush": (None, [vp]),
         "dq_pipeline_last_elapsed_ms": (C.c_float, [vp]),
         "dq_pipeline_context": (vp, [vp]),
@@ -117,7 +122,7 @@ EXPORTED_C_SYMBOLS = [
     "dq_get_double_scale", "dq_validate_num_bits", "dq_set_display_timings", "dq_context_create", "dq_context_destroy",
     "dq_default_context", "dq_context_stream", "dq_context_synchronize", "dq_context_last_stats", "dq_context_set_profiling",
     "dq_quant_recurse_device", "dq_map_colors_device", "dq_quant_varpart_device", "dq_quant_recurse_ctx",
-    "dq_pixel_histogram", "dq_block_vote", "dq_block_vote_device", "dq_quant_blocks", "dq_colortable_indexes", "dq_colortable_indexes_device", "dq_shard_histogram", "dq_shard_quantize_map", "dq_pipeline_create", "dq_pipeline_destroy", "dq_pipeline_submit", "dq_pipeline_flush", "dq_pipeline_last_elapsed_ms",
+    "dq_context_set_split_ctas", "dq_pixel_histogram", "dq_block_vote", "dq_block_vote_device", "dq_quant_blocks", "dq_colortable_indexes", "dq_colortable_indexes_device", "dq_shard_histogram", "dq_shard_quantize_map", "dq_pipeline_create", "dq_pipeline_create_lanes", "dq_pipeline_destroy", "dq_pipeline_submit", "dq_pipeline_submit_device", "dq_pipeline_wait", "dq_pipeline_lanes", "dq_pipeline_flush", "dq_pipeline_last_elapsed_ms",
     "dq_pipeline_context", "dq_pipeline_kernel_launches",
     "dq_debug_split_points", "dq_debug_histogram", "dq_debug_split_timeline", "dq_host_dedup_palette", "dq_host_build_search_tables",
 ]
@@ -260,18 +265,26 @@ class DivQuant:
 
 
 class FramePipeline:
-    """dq_pipeline: quant_recurse over a stream of frames with host (preferably pinned) buffers."""
+    """dq_pipeline: quant_recurse over a stream of frames, `depth` frames (lanes) in flight on one GPU."""
 
-    def __init__(self, lib, device, max_pixels, depth=3):
+    def __init__(self, lib, device, max_pixels, depth=3, split_ctas=0):
         self.lib = lib
-        self.handle = lib.dq_pipeline_create(device, max_pixels, depth)
+        self.handle = lib.dq_pipeline_create_lanes(device, max_pixels, depth, split_ctas)
         self._keep = []
 
     def submit(self, pixels, out, k, colortable, nk, all_unique=0):
         """pixels/out/colortable: uint32 numpy arrays (or objects exposing .ctypes) that outlive flush();
-        nk: ctypes.c_uint32 holding the requested K (updated in place)."""
+        nk: ctypes.c_uint32 holding the requested K (updated in place).  Returns the frame's ticket."""
         self._keep.append((pixels, out, colortable, nk))
-        self.lib.dq_pipeline_submit(self.handle, pixels.size, _p(pixels), _p(out), C.byref(nk), _p(colortable), all_unique)
+        return self.lib.dq_pipeline_submit(self.handle, pixels.size, _p(pixels), _p(out), C.byref(nk), _p(colortable), all_unique)
+
+    def submit_device(self, d_in, d_out, num_pixels, colortable, nk, all_unique=0):
+        """d_in/d_out: device addresses (ints) of uint32 frames on the pipeline's GPU."""
+        self._keep.append((colortable, nk))
+        return self.lib.dq_pipeline_submit_device(self.handle, num_pixels, d_in, d_out, C.byref(nk), _p(colortable), all_unique)
+
+    def wait(self, ticket):
+        self.lib.dq_pipeline_wait(self.handle, ticket)
 
     def flush(self):
         self.lib.dq_pipeline_flush(self.handle)

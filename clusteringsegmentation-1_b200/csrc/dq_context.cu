@@ -10,10 +10,15 @@
 // The product has no CPU path for any per-pixel or per-point work; the host only handles the <= K
 // palette words exactly as the reference's scalar code does.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
+#include <condition_variable>
 #include <cstring>
+#include <deque>
 #include <mutex>
+#include <set>
+#include <thread>
 #include <vector>
 
 #include "../../include/divquant_b200.h"
@@ -68,6 +73,7 @@ constexpr int kLutEntries = 3 * 255 + 1;
 struct dq_context {
   int device = 0;
   int sm_count = 0;
+  int split_ctas = 0;  // CTAs of the persistent split kernel (<= sm_count); fewer leaves SMs to concurrent contexts
   cudaStream_t stream = nullptr;
   uint32_t *d_table = nullptr;  // 2^24 counters, all zero between calls (hist_collect zeroes what it reads)
   uint32_t *d_map = nullptr;    // 2^24 mapped colours; only entries written by the current call are ever read, never cleared
@@ -245,13 +251,13 @@ uint32_t run_split(dq_context *ctx, uint32_t point_capacity, double norm, uint32
     x.collect_uniq = collect_from_hist ? ctx->d_uniq.ptr : nullptr;
     x.collect_table = collect_from_hist ? ctx->d_table : nullptr;
     if (getenv("DQ_PROFILE_NARROW")) DQ_CUDA_CHECK(cudaMemsetAsync(ctx->d_progress.ptr, 0, 1024 * sizeof(uint32_t), ctx->stream));
-    split2_launch(a, x, split2_plan(ctx->sm_count, K), ctx->stream);
+    split2_launch(a, x, split2_plan(ctx->split_ctas, K), ctx->stream);
   } else {
     if (collect_from_hist) {  // the generic kernel has no fused collect
       hist_collect(ctx->d_uniq.ptr, &ctx->d_cb->ucount, point_capacity, ctx->d_table, ctx->d_pts0.ptr, true, ctx->sm_count, ctx->stream);
       ctx->stats.kernel_launches++;
     }
-    split_launch(a, split_plan(ctx->sm_count, K), ctx->stream);
+    split_launch(a, split_plan(ctx->split_ctas, K), ctx->stream);
   }
   ctx->mark(3);
   ctx->stats.kernel_launches++;
@@ -415,7 +421,7 @@ bool quantize_device(dq_context *ctx, uint32_t n, const uint32_t *d_in, uint32_t
 }
 
 void quant_recurse_device_impl(dq_context *ctx, uint32_t n, const uint32_t *d_in, uint32_t *d_out, uint32_t *k_inout,
-                               uint32_t *colortable, int all_unique, double *ms_quant, double *ms_map) {
+                               uint32_t *colortable, int all_unique, double *ms_quant, double *ms_map, bool final_sync = true) {
   auto t0 = std::chrono::steady_clock::now();
   const bool dirty = quantize_device(ctx, n, d_in, 1, n, k_inout, colortable, 8, 1, 10, all_unique, nullptr, nullptr, nullptr);
   auto t1 = std::chrono::steady_clock::now();
@@ -429,7 +435,7 @@ void quant_recurse_device_impl(dq_context *ctx, uint32_t n, const uint32_t *d_in
   } else {
     remap_bruteforce(ctx, d_in, n, d_out, (int)k);
   }
-  DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  if (final_sync || ctx->profiling) DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   if (ctx->profiling) {
     auto span = [&](int a, int b) {
       float ms = 0.f;
@@ -496,6 +502,11 @@ dq_context *dq_context_create(int device) {
     abort();
   }
   ctx->sm_count = prop.multiProcessorCount;
+  ctx->split_ctas = ctx->sm_count;
+  if (const char *e = getenv("DIVQUANT_B200_SPLIT_CTAS")) {
+    const int v = atoi(e);
+    if (v >= 1 && v <= ctx->sm_count) ctx->split_ctas = v;
+  }
   DQ_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   DQ_CUDA_CHECK(cudaMalloc(&ctx->d_table, (size_t)kColourBins * sizeof(uint32_t)));
   DQ_CUDA_CHECK(cudaMemsetAsync(ctx->d_table, 0, (size_t)kColourBins * sizeof(uint32_t), ctx->stream));
@@ -508,6 +519,11 @@ dq_context *dq_context_create(int device) {
   if (const char *e = getenv("DIVQUANT_B200_SPLIT")) ctx->split_version = (e[0] == '1') ? 1 : 2;
   DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   return ctx;
+}
+
+void dq_context_set_split_ctas(dq_context *ctx, int num_ctas) {
+  require_device(ctx);
+  ctx->split_ctas = (num_ctas >= 1 && num_ctas <= ctx->sm_count) ? num_ctas : ctx->sm_count;
 }
 
 void dq_context_destroy(dq_context *ctx) {
@@ -891,134 +907,205 @@ void dq_shard_quantize_map(dq_context *ctx, const uint32_t *d_all_colours, const
 
 }  // extern "C"
 
+// ---- frame pipeline: lanes ------------------------------------------------------------------------------------
+// One frame's critical path is a chain of ~100 dependent passes inside the persistent split kernel, which keeps
+// most of the GPU idle.  Frames are independent, so the pipeline runs `lanes` of them side by side: every lane
+// owns a context (stream, tables, scratch), a pair of frame buffers and a host thread that walks one frame at a
+// time through H2D -> kernels -> D2H.  Split kernels of different lanes occupy disjoint groups of SMs
+// (dq_context_set_split_ctas); histogram / remap kernels and the copy engines fill in around them.
 struct dq_pipeline {
-  struct Slot {
-    uint32_t *d_in = nullptr, *d_out = nullptr;
-    cudaEvent_t h2d_done = nullptr, d2h_done = nullptr;
-    bool busy = false;  // a D2H of this slot may still be in flight
-    // the frame waiting in this slot for its compute step
+  struct Job {
+    uint64_t ticket = 0;
     uint32_t n = 0;
+    const uint32_t *in = nullptr;
     uint32_t *out = nullptr, *k_ptr = nullptr, *colortable = nullptr;
     int all_unique = 0;
+    bool device_ptrs = false;
   };
-  dq_context *ctx = nullptr;
-  cudaStream_t h2d = nullptr, d2h = nullptr;
-  std::vector<Slot> slots;
+  struct Lane {
+    dq_context *ctx = nullptr;
+    uint32_t *d_in = nullptr, *d_out = nullptr;
+    cudaEvent_t begin = nullptr, end = nullptr;
+    bool have_begin = false;
+    std::thread worker;
+  };
+  int device = 0;
   uint32_t max_pixels = 0;
-  uint64_t submitted = 0;   // frames whose H2D was enqueued
-  uint64_t computed = 0;    // frames whose kernels ran
-  uint64_t launches = 0;
-  cudaEvent_t first = nullptr, last = nullptr;
-  bool have_first = false;
+  std::vector<Lane> lanes;
+  std::mutex mu;
+  std::condition_variable cv_work, cv_done;
+  std::deque<Job> queue;
+  std::set<uint64_t> done_above;  // completed tickets >= low_water
+  uint64_t submitted = 0, low_water = 0;  // every ticket < low_water has completed
+  bool stop = false;
+  std::atomic<uint64_t> launches{0};
   float last_ms = 0.f;
 };
 
 namespace {
 
-// Kernels + D2H of the oldest frame that has only been uploaded so far.
-void pipeline_compute_next(dq_pipeline *p) {
-  dq_pipeline::Slot &s = p->slots[p->computed % p->slots.size()];
-  dq_context *ctx = p->ctx;
-  DQ_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, s.h2d_done, 0));
-  memset(&ctx->stats, 0, sizeof(ctx->stats));
-  ctx->stats.num_pixels = s.n;
-  quant_recurse_device_impl(ctx, s.n, s.d_in, s.d_out, s.k_ptr, s.colortable, s.all_unique, nullptr, nullptr);
-  p->launches += ctx->stats.kernel_launches;
-  // quant_recurse_device_impl returns with the compute stream drained: the D2H can start right away
-  DQ_CUDA_CHECK(cudaMemcpyAsync(s.out, s.d_out, (size_t)s.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, p->d2h));
-  DQ_CUDA_CHECK(cudaEventRecord(s.d2h_done, p->d2h));
-  s.busy = true;
-  p->computed++;
+void pipeline_worker(dq_pipeline *p, int lane_index) {
+  dq_pipeline::Lane &lane = p->lanes[lane_index];
+  dq_context *ctx = lane.ctx;
+  require_device(ctx);
+  for (;;) {
+    dq_pipeline::Job job;
+    {
+      std::unique_lock<std::mutex> lock(p->mu);
+      p->cv_work.wait(lock, [&] { return p->stop || !p->queue.empty(); });
+      if (p->queue.empty()) return;  // stop requested and nothing left
+      job = p->queue.front();
+      p->queue.pop_front();
+    }
+    if (!lane.have_begin) {
+      DQ_CUDA_CHECK(cudaEventRecord(lane.begin, ctx->stream));
+      lane.have_begin = true;
+    }
+    const uint32_t *d_in = job.in;
+    uint32_t *d_out = job.out;
+    if (!job.device_ptrs) {
+      d_in = lane.d_in;
+      d_out = lane.d_out;
+      DQ_CUDA_CHECK(cudaMemcpyAsync(lane.d_in, job.in, (size_t)job.n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    memset(&ctx->stats, 0, sizeof(ctx->stats));
+    ctx->stats.num_pixels = job.n;
+    quant_recurse_device_impl(ctx, job.n, d_in, d_out, job.k_ptr, job.colortable, job.all_unique, nullptr, nullptr, false);
+    if (!job.device_ptrs)
+      DQ_CUDA_CHECK(cudaMemcpyAsync(job.out, lane.d_out, (size_t)job.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    DQ_CUDA_CHECK(cudaEventRecord(lane.end, ctx->stream));
+    DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    p->launches += ctx->stats.kernel_launches;
+    {
+      std::lock_guard<std::mutex> lock(p->mu);
+      p->done_above.insert(job.ticket);
+      while (!p->done_above.empty() && *p->done_above.begin() == p->low_water) {
+        p->done_above.erase(p->done_above.begin());
+        p->low_water++;
+      }
+    }
+    p->cv_done.notify_all();
+  }
+}
+
+uint64_t pipeline_enqueue(dq_pipeline *p, uint32_t n, const uint32_t *in, uint32_t *out, uint32_t *k_ptr, uint32_t *colortable,
+                          int all_unique, bool device_ptrs) {
+  if (!device_ptrs && n > p->max_pixels) {
+    fprintf(stderr, "divquant_b200: frame of %u pixels exceeds the pipeline's max_pixels (%u)\n", n, p->max_pixels);
+    abort();
+  }
+  check_quant_args(n, *k_ptr, 8);
+  dq_pipeline::Job job;
+  job.n = n;
+  job.in = in;
+  job.out = out;
+  job.k_ptr = k_ptr;
+  job.colortable = colortable;
+  job.all_unique = all_unique;
+  job.device_ptrs = device_ptrs;
+  {
+    std::lock_guard<std::mutex> lock(p->mu);
+    job.ticket = p->submitted++;
+    p->queue.push_back(job);
+  }
+  p->cv_work.notify_one();
+  return job.ticket;
 }
 
 }  // namespace
 
 extern "C" {
 
+dq_pipeline *dq_pipeline_create_lanes(int device, uint32_t max_pixels, int lanes, int split_ctas) {
+  if (lanes < 1) lanes = 1;
+  if (lanes > 16) lanes = 16;
+  dq_pipeline *p = new dq_pipeline();
+  p->max_pixels = max_pixels;
+  p->lanes.resize(lanes);
+  for (auto &lane : p->lanes) {
+    lane.ctx = dq_context_create(device);
+    p->device = lane.ctx->device;
+    if (split_ctas <= 0) split_ctas = std::max(lane.ctx->sm_count / lanes, std::min(lane.ctx->sm_count, 16));
+    dq_context_set_split_ctas(lane.ctx, split_ctas);
+    if (max_pixels) {
+      DQ_CUDA_CHECK(cudaMalloc(&lane.d_in, (size_t)max_pixels * sizeof(uint32_t)));
+      DQ_CUDA_CHECK(cudaMalloc(&lane.d_out, (size_t)max_pixels * sizeof(uint32_t)));
+    }
+    DQ_CUDA_CHECK(cudaEventCreate(&lane.begin));
+    DQ_CUDA_CHECK(cudaEventCreate(&lane.end));
+  }
+  for (int i = 0; i < lanes; ++i) p->lanes[i].worker = std::thread(pipeline_worker, p, i);
+  return p;
+}
+
 dq_pipeline *dq_pipeline_create(int device, uint32_t max_pixels, int depth) {
   if (depth < 2) depth = 2;
   if (depth > 8) depth = 8;
-  dq_pipeline *p = new dq_pipeline();
-  p->ctx = dq_context_create(device);
-  p->max_pixels = max_pixels;
-  DQ_CUDA_CHECK(cudaStreamCreateWithFlags(&p->h2d, cudaStreamNonBlocking));
-  DQ_CUDA_CHECK(cudaStreamCreateWithFlags(&p->d2h, cudaStreamNonBlocking));
-  p->slots.resize(depth);
-  for (auto &s : p->slots) {
-    DQ_CUDA_CHECK(cudaMalloc(&s.d_in, (size_t)max_pixels * sizeof(uint32_t)));
-    DQ_CUDA_CHECK(cudaMalloc(&s.d_out, (size_t)max_pixels * sizeof(uint32_t)));
-    DQ_CUDA_CHECK(cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
-    DQ_CUDA_CHECK(cudaEventCreateWithFlags(&s.d2h_done, cudaEventDisableTiming));
-  }
-  DQ_CUDA_CHECK(cudaEventCreate(&p->first));
-  DQ_CUDA_CHECK(cudaEventCreate(&p->last));
-  return p;
+  return dq_pipeline_create_lanes(device, max_pixels, depth, 0);
 }
 
 void dq_pipeline_destroy(dq_pipeline *p) {
   if (!p) return;
   dq_pipeline_flush(p);
-  for (auto &s : p->slots) {
-    cudaFree(s.d_in);
-    cudaFree(s.d_out);
-    cudaEventDestroy(s.h2d_done);
-    cudaEventDestroy(s.d2h_done);
+  {
+    std::lock_guard<std::mutex> lock(p->mu);
+    p->stop = true;
   }
-  cudaEventDestroy(p->first);
-  cudaEventDestroy(p->last);
-  cudaStreamDestroy(p->h2d);
-  cudaStreamDestroy(p->d2h);
-  dq_context_destroy(p->ctx);
+  p->cv_work.notify_all();
+  for (auto &lane : p->lanes) lane.worker.join();
+  for (auto &lane : p->lanes) {
+    require_device(lane.ctx);
+    cudaFree(lane.d_in);
+    cudaFree(lane.d_out);
+    cudaEventDestroy(lane.begin);
+    cudaEventDestroy(lane.end);
+    dq_context_destroy(lane.ctx);
+  }
   delete p;
 }
 
-void dq_pipeline_submit(dq_pipeline *p, uint32_t numPixels, const uint32_t *inPixelsPtr, uint32_t *outPixelsPtr,
-                        uint32_t *numClustersPtr, uint32_t *outColortablePtr, int allPixelsUnique) {
-  require_device(p->ctx);
-  if (numPixels > p->max_pixels) {
-    fprintf(stderr, "divquant_b200: frame of %u pixels exceeds the pipeline's max_pixels (%u)\n", numPixels, p->max_pixels);
-    abort();
-  }
-  check_quant_args(numPixels, *numClustersPtr, 8);
-  // never more than depth-1 uploaded-but-not-computed frames: the slot we are about to fill must be free
-  while (p->submitted - p->computed >= p->slots.size() - 1 && p->computed < p->submitted) pipeline_compute_next(p);
-  dq_pipeline::Slot &s = p->slots[p->submitted % p->slots.size()];
-  if (s.busy) {  // its previous frame's D2H must have left d_out ... and d_in is reused as well
-    DQ_CUDA_CHECK(cudaEventSynchronize(s.d2h_done));
-    s.busy = false;
-  }
-  if (!p->have_first) {
-    DQ_CUDA_CHECK(cudaEventRecord(p->first, p->h2d));
-    p->have_first = true;
-  }
-  DQ_CUDA_CHECK(cudaMemcpyAsync(s.d_in, inPixelsPtr, (size_t)numPixels * sizeof(uint32_t), cudaMemcpyHostToDevice, p->h2d));
-  DQ_CUDA_CHECK(cudaEventRecord(s.h2d_done, p->h2d));
-  s.n = numPixels;
-  s.out = outPixelsPtr;
-  s.k_ptr = numClustersPtr;
-  s.colortable = outColortablePtr;
-  s.all_unique = allPixelsUnique;
-  p->submitted++;
-  // while that upload runs on the copy engine, do the kernels of the frame before it
-  if (p->submitted - p->computed >= 2) pipeline_compute_next(p);
+uint64_t dq_pipeline_submit(dq_pipeline *p, uint32_t numPixels, const uint32_t *inPixelsPtr, uint32_t *outPixelsPtr,
+                            uint32_t *numClustersPtr, uint32_t *outColortablePtr, int allPixelsUnique) {
+  return pipeline_enqueue(p, numPixels, inPixelsPtr, outPixelsPtr, numClustersPtr, outColortablePtr, allPixelsUnique, false);
+}
+
+uint64_t dq_pipeline_submit_device(dq_pipeline *p, uint32_t numPixels, const uint32_t *d_in, uint32_t *d_out,
+                                   uint32_t *numClustersPtr, uint32_t *outColortablePtr, int allPixelsUnique) {
+  return pipeline_enqueue(p, numPixels, d_in, d_out, numClustersPtr, outColortablePtr, allPixelsUnique, true);
+}
+
+void dq_pipeline_wait(dq_pipeline *p, uint64_t ticket) {
+  std::unique_lock<std::mutex> lock(p->mu);
+  p->cv_done.wait(lock, [&] { return ticket < p->low_water || p->done_above.count(ticket) != 0; });
 }
 
 void dq_pipeline_flush(dq_pipeline *p) {
-  require_device(p->ctx);
-  while (p->computed < p->submitted) pipeline_compute_next(p);
-  if (p->have_first) {
-    DQ_CUDA_CHECK(cudaEventRecord(p->last, p->d2h));
-    DQ_CUDA_CHECK(cudaStreamSynchronize(p->d2h));
-    DQ_CUDA_CHECK(cudaEventSynchronize(p->first));
-    DQ_CUDA_CHECK(cudaEventElapsedTime(&p->last_ms, p->first, p->last));
-    p->have_first = false;
+  {
+    std::unique_lock<std::mutex> lock(p->mu);
+    p->cv_done.wait(lock, [&] { return p->low_water == p->submitted; });
   }
-  for (auto &s : p->slots) s.busy = false;
+  // device time from the first lane that started to the last that finished (workers are idle now)
+  require_device(p->lanes[0].ctx);
+  float span = 0.f;
+  bool any = false;
+  for (auto &a : p->lanes) {
+    if (!a.have_begin) continue;
+    for (auto &b : p->lanes) {
+      if (!b.have_begin) continue;
+      float ms = 0.f;
+      DQ_CUDA_CHECK(cudaEventElapsedTime(&ms, a.begin, b.end));
+      span = std::max(span, ms);
+      any = true;
+    }
+  }
+  if (any) p->last_ms = span;
+  for (auto &lane : p->lanes) lane.have_begin = false;
 }
 
 float dq_pipeline_last_elapsed_ms(const dq_pipeline *p) { return p->last_ms; }
-dq_context *dq_pipeline_context(dq_pipeline *p) { return p->ctx; }
-uint64_t dq_pipeline_kernel_launches(const dq_pipeline *p) { return p->launches; }
+dq_context *dq_pipeline_context(dq_pipeline *p) { return p->lanes[0].ctx; }
+uint64_t dq_pipeline_kernel_launches(const dq_pipeline *p) { return p->launches.load(); }
+int dq_pipeline_lanes(const dq_pipeline *p) { return (int)p->lanes.size(); }
 
 // ---- test hooks ----
 

@@ -113,6 +113,11 @@ typedef struct {
 void dq_context_last_stats(const dq_context *ctx, dq_call_stats *out);
 /* Per-stage CUDA-event timing of dq_quant_recurse_device / _ctx calls (off by default). */
 void dq_context_set_profiling(dq_context *ctx, int enabled);
+/* Number of CTAs (one per SM) the persistent split kernel of this context occupies; default = all SMs
+ * (lowest latency of one call).  Several contexts with num_ctas = SMs / contexts run their latency-bound split
+ * phases side by side on one GPU (frame pipeline with lanes, section 2b).  Results do not depend on it.
+ * Out-of-range values restore the default.  Environment: DIVQUANT_B200_SPLIT_CTAS. */
+void dq_context_set_split_ctas(dq_context *ctx, int num_ctas);
 
 /* quant_recurse with pixels already resident in HBM.  d_in / d_out are device pointers on the
  * context's device; colortable and numClustersPtr are host pointers.  Synchronous with respect to
@@ -186,28 +191,44 @@ void dq_shard_quantize_map(dq_context *ctx, const uint32_t *d_all_colours, const
                            uint32_t *numClustersPtr, uint32_t *outColortablePtr);
 
 /* ------------------------------------------------------------------------------------------------
- * 2b. Frame pipeline: quant_recurse over a stream of frames with HOST buffers (BASELINE.json config 4,
- *     "batch of frames", and the end-to-end leg of bench.py).  Frames are independent units, so the copy
- *     engines and the SMs work on different frames at the same time: H2D of frame f+1, kernels of frame f
- *     and D2H of frame f-1 overlap.  Results are exactly those of dq_quant_recurse frame by frame.
+ * 2b. Frame pipeline: quant_recurse over a stream of frames (BASELINE.json config 4, "batch of frames", and both
+ *     legs of bench.py).  Frames are independent units and one frame's critical path (the chain of dependent
+ *     passes of the split) leaves most of the GPU idle, so the pipeline runs `lanes` frames side by side: every
+ *     lane owns a context, a pair of frame buffers and a host thread that walks one frame at a time through
+ *     H2D -> kernels -> D2H.  The split kernels of different lanes occupy disjoint groups of SMs, histogram / remap
+ *     kernels and both copy engines fill in around them.  Results are exactly those of dq_quant_recurse frame by
+ *     frame (they do not depend on the lane or on split_ctas).
  *     Host buffers should be pinned (cudaHostAlloc / torch pin_memory) for the copies to be asynchronous;
- *     pageable buffers work but serialise.  All host pointers of a frame must stay valid until
- *     dq_pipeline_flush() returns (or until `depth` later submits have returned).
+ *     pageable buffers work but serialise.  All pointers of a frame (pixels, numClustersPtr, colortable) must stay
+ *     valid until dq_pipeline_wait(ticket) or dq_pipeline_flush() returns.  submit / wait / flush may be called
+ *     from one thread at a time.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct dq_pipeline dq_pipeline;
-/* depth = frames in flight (2..8). max_pixels = largest frame that will be submitted. */
+/* lanes = frames in flight (1..16); max_pixels = largest HOST frame that will be submitted (0 if only device frames
+ * are used); split_ctas = CTAs of each lane's split kernel, 0 = SMs / lanes. */
+dq_pipeline *dq_pipeline_create_lanes(int device, uint32_t max_pixels, int lanes, int split_ctas);
+/* Same with lanes = depth (2..8) and the default SM partition. */
 dq_pipeline *dq_pipeline_create(int device, uint32_t max_pixels, int depth);
 void dq_pipeline_destroy(dq_pipeline *pipe);
-void dq_pipeline_submit(dq_pipeline *pipe, uint32_t numPixels, const uint32_t *inPixelsPtr, uint32_t *outPixelsPtr,
-                        uint32_t *numClustersPtr, uint32_t *outColortablePtr, int allPixelsUnique);
-/* Returns when every submitted frame's outPixels / colortable / numClusters are in host memory. */
+/* Queue one frame with HOST pointers; returns its ticket (0, 1, 2, ... in submission order). */
+uint64_t dq_pipeline_submit(dq_pipeline *pipe, uint32_t numPixels, const uint32_t *inPixelsPtr, uint32_t *outPixelsPtr,
+                            uint32_t *numClustersPtr, uint32_t *outColortablePtr, int allPixelsUnique);
+/* Queue one frame whose pixels are DEVICE pointers on the pipeline's device (no copies; numClustersPtr and
+ * outColortablePtr stay host pointers).  d_in must be complete when this is called: lanes run on their own streams. */
+uint64_t dq_pipeline_submit_device(dq_pipeline *pipe, uint32_t numPixels, const uint32_t *d_in, uint32_t *d_out,
+                                   uint32_t *numClustersPtr, uint32_t *outColortablePtr, int allPixelsUnique);
+/* Returns when that frame's outPixels / colortable / numClusters are complete. */
+void dq_pipeline_wait(dq_pipeline *pipe, uint64_t ticket);
+/* Returns when every submitted frame is complete. */
 void dq_pipeline_flush(dq_pipeline *pipe);
-/* The context the pipeline computes on (for dq_context_last_stats) and its streams' first/last events are
- * internal; elapsed device time of everything submitted since the last flush, in milliseconds: */
+/* Device time (CUDA events on the lanes' streams) from the first operation of the first frame to the last
+ * operation of the last frame submitted between the previous two flushes, in milliseconds. */
 float dq_pipeline_last_elapsed_ms(const dq_pipeline *pipe);
+/* Lane 0's context (for dq_context_last_stats). */
 dq_context *dq_pipeline_context(dq_pipeline *pipe);
-/* Kernels launched since creation (sum over frames). */
+/* Kernels launched since creation (sum over frames and lanes). */
 uint64_t dq_pipeline_kernel_launches(const dq_pipeline *pipe);
+int dq_pipeline_lanes(const dq_pipeline *pipe);
 
 /* ------------------------------------------------------------------------------------------------
  * 3. Test hooks (used by tests/ to compare intermediate results with the oracle).

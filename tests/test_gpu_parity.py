@@ -235,6 +235,39 @@ def test_frame_pipeline_matches_single_calls(dq, pkg, oracle):
     pipe.close()
 
 
+@pytest.mark.parametrize("lanes,split_ctas", [(1, 0), (4, 0), (8, 9), (5, 148)])
+def test_frame_pipeline_lanes_device_frames(dq, pkg, oracle, lanes, split_ctas):
+    """Frames in flight on disjoint SM groups: results must not depend on the lane count or the SM partition
+    (including an oversubscribed one: 5 lanes that each ask for all SMs simply take turns)."""
+    import ctypes as C
+    import torch
+    shapes = [(320, 200, 1), (64, 64, 2), (500, 333, 1), (17, 3, 2)]
+    frames = [oracle.generate(kind, w, h, 200 + i) for i, (w, h, kind) in enumerate(shapes * 4)]
+    ks = [(16, 64, 256, 5)[i % 4] for i in range(len(frames))]
+    uniq = [1 if i % 5 == 4 else 0 for i in range(len(frames))]
+    pipe = pkg.FramePipeline(dq.lib, 0, 0, depth=lanes, split_ctas=split_ctas)
+    assert dq.lib.dq_pipeline_lanes(pipe.handle) == lanes
+    d_in = [torch.from_numpy(f.view(np.int32).copy()).cuda() for f in frames]
+    d_out = [torch.zeros(f.size, dtype=torch.int32, device="cuda") for f in frames]
+    cts = [np.zeros(k, np.uint32) for k in ks]
+    nks = [C.c_uint32(k) for k in ks]
+    torch.cuda.synchronize()
+    tickets = [pipe.submit_device(d_in[i].data_ptr(), d_out[i].data_ptr(), frames[i].size, cts[i], nks[i], uniq[i])
+               for i in range(len(frames))]
+    assert tickets == list(range(len(frames)))
+    pipe.wait(tickets[3])     # a single frame can be awaited out of order
+    got3 = d_out[3].cpu().numpy().view(np.uint32).copy()
+    pipe.flush()
+    for i, f in enumerate(frames):
+        with muted((2,)):
+            out, pal = dq.quant_recurse(f, ks[i], uniq[i])
+        assert np.array_equal(cts[i][:nks[i].value], pal), i
+        assert np.array_equal(d_out[i].cpu().numpy().view(np.uint32), out), i
+        if i == 3:
+            assert np.array_equal(got3, out)
+    pipe.close()
+
+
 def test_generic_split_kernel_large_k_and_forced(dq, oracle, pkg):
     """K > 512 uses the generic split kernel (csrc/dq_split.cu); DIVQUANT_B200_SPLIT=1 forces it for any K."""
     import subprocess
