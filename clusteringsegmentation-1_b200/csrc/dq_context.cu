@@ -251,13 +251,13 @@ uint32_t run_split(dq_context *ctx, uint32_t point_capacity, double norm, uint32
     x.collect_uniq = collect_from_hist ? ctx->d_uniq.ptr : nullptr;
     x.collect_table = collect_from_hist ? ctx->d_table : nullptr;
     if (getenv("DQ_PROFILE_NARROW")) DQ_CUDA_CHECK(cudaMemsetAsync(ctx->d_progress.ptr, 0, 1024 * sizeof(uint32_t), ctx->stream));
-    split2_launch(a, x, split2_plan(ctx->split_ctas, K), ctx->stream);
+    split2_launch(a, x, split2_plan(ctx->split_ctas, ctx->sm_count, K), ctx->stream);
   } else {
     if (collect_from_hist) {  // the generic kernel has no fused collect
       hist_collect(ctx->d_uniq.ptr, &ctx->d_cb->ucount, point_capacity, ctx->d_table, ctx->d_pts0.ptr, true, ctx->sm_count, ctx->stream);
       ctx->stats.kernel_launches++;
     }
-    split_launch(a, split_plan(ctx->split_ctas, K), ctx->stream);
+    split_launch(a, split_plan(std::min(ctx->split_ctas > 0 ? ctx->split_ctas : ctx->sm_count, ctx->sm_count), K), ctx->stream);
   }
   ctx->mark(3);
   ctx->stats.kernel_launches++;
@@ -271,7 +271,7 @@ uint32_t run_split(dq_context *ctx, uint32_t point_capacity, double norm, uint32
             ctx->h_cb->ctl[kCtlError], use_v2 ? 2 : 1, ctx->h_cb->ctl[kCtlWords - 1], ctx->h_cb->ctl[kCtlJobs],
             ctx->h_cb->ctl[kCtlTiles], ctx->h_cb->ctl[kCtlNodes]);
     if (use_v2) {
-      std::vector<uint32_t> prog(ctx->sm_count);
+      std::vector<uint32_t> prog(split2_max_ctas(ctx->sm_count, K));
       cudaMemcpy(prog.data(), ctx->d_progress.ptr, prog.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost);
       fprintf(stderr, "  last stage per CTA:");
       for (size_t i = 0; i < prog.size(); ++i) fprintf(stderr, " %u", prog[i]);
@@ -281,9 +281,9 @@ uint32_t run_split(dq_context *ctx, uint32_t point_capacity, double norm, uint32
   }
   if (use_v2 && getenv("DQ_PROFILE_NARROW")) {
     uint32_t prof[8];
-    cudaMemcpy(prof, ctx->d_progress.ptr + 256, sizeof(prof), cudaMemcpyDeviceToHost);
+    cudaMemcpy(prof, ctx->d_progress.ptr + 756, sizeof(prof), cudaMemcpyDeviceToHost);
     uint32_t wp[6];
-    cudaMemcpy(wp, ctx->d_progress.ptr + 264, sizeof(wp), cudaMemcpyDeviceToHost);
+    cudaMemcpy(wp, ctx->d_progress.ptr + 764, sizeof(wp), cudaMemcpyDeviceToHost);
     if (wp[3])
       fprintf(stderr, "wide profile (cycles per job-pass, thread 0 of every participant): gather %.0f derive+sync %.0f classify+reduce+publish %.0f (classify %.0f, stage1+sync %.0f) ; %u job-passes\n",
               (double)wp[0] / wp[3], (double)wp[1] / wp[3], (double)wp[2] / wp[3], (double)wp[4] / wp[3], (double)wp[5] / wp[3], wp[3]);
@@ -502,11 +502,8 @@ dq_context *dq_context_create(int device) {
     abort();
   }
   ctx->sm_count = prop.multiProcessorCount;
-  ctx->split_ctas = ctx->sm_count;
-  if (const char *e = getenv("DIVQUANT_B200_SPLIT_CTAS")) {
-    const int v = atoi(e);
-    if (v >= 1 && v <= ctx->sm_count) ctx->split_ctas = v;
-  }
+  ctx->split_ctas = 0;  // 0 = as many as can be co-resident
+  if (const char *e = getenv("DIVQUANT_B200_SPLIT_CTAS")) ctx->split_ctas = std::max(atoi(e), 0);
   DQ_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   DQ_CUDA_CHECK(cudaMalloc(&ctx->d_table, (size_t)kColourBins * sizeof(uint32_t)));
   DQ_CUDA_CHECK(cudaMemsetAsync(ctx->d_table, 0, (size_t)kColourBins * sizeof(uint32_t), ctx->stream));
@@ -523,7 +520,7 @@ dq_context *dq_context_create(int device) {
 
 void dq_context_set_split_ctas(dq_context *ctx, int num_ctas) {
   require_device(ctx);
-  ctx->split_ctas = (num_ctas >= 1 && num_ctas <= ctx->sm_count) ? num_ctas : ctx->sm_count;
+  ctx->split_ctas = num_ctas >= 1 ? num_ctas : 0;  // clamped to the co-residency limit at launch
 }
 
 void dq_context_destroy(dq_context *ctx) {
@@ -1025,7 +1022,7 @@ dq_pipeline *dq_pipeline_create_lanes(int device, uint32_t max_pixels, int lanes
   for (auto &lane : p->lanes) {
     lane.ctx = dq_context_create(device);
     p->device = lane.ctx->device;
-    if (split_ctas <= 0) split_ctas = std::max(lane.ctx->sm_count / lanes, std::min(lane.ctx->sm_count, 16));
+    if (split_ctas <= 0) split_ctas = std::max(split2_max_ctas(lane.ctx->sm_count, 256) / lanes, 8);
     dq_context_set_split_ctas(lane.ctx, split_ctas);
     if (max_pixels) {
       DQ_CUDA_CHECK(cudaMalloc(&lane.d_in, (size_t)max_pixels * sizeof(uint32_t)));

@@ -138,7 +138,8 @@ struct Split2Extra {
   uint32_t *collect_table;
 };
 size_t split2_slot_capacity(uint32_t point_capacity, uint32_t num_colors, int sm_count);
-SplitLaunch split2_plan(int sm_count, uint32_t num_colors);
+SplitLaunch split2_plan(int requested_ctas, int sm_count, uint32_t num_colors);
+int split2_max_ctas(int sm_count, uint32_t num_colors);
 void split2_launch(const SplitArgs &args, const Split2Extra &extra, const SplitLaunch &plan, cudaStream_t stream);
 
 }  // namespace dq

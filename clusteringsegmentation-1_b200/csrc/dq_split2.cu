@@ -20,13 +20,18 @@
 //    words that carry their own 16-bit pass tag next to the 48-bit value, so publishing is a plain
 //    store and gathering is one polling L2 read: no atomics, no fences, no barrier per pass.
 #include <cfloat>
+#include <map>
+#include <mutex>
 
 #include "dq_split_math.cuh"
 
 namespace dq {
 namespace {
 
-constexpr int kWarps = 16;
+#ifndef DQ_SPLIT_WARPS
+#define DQ_SPLIT_WARPS 16
+#endif
+constexpr int kWarps = DQ_SPLIT_WARPS;
 constexpr int T = 32 * kWarps;  // 16 warps, up to 128 registers per thread: points stay in registers without spills
 constexpr uint32_t kWideTile = 1024;  // points per wide tile
 constexpr int kWidePPT = 2;           // points per thread when a CTA classifies its share of a wide job
@@ -734,7 +739,7 @@ __device__ __forceinline__ void wide_classify(const PassParams &pp, const uint2 
 // ---------------------------------------------------------------------------------------------------------
 // The kernel
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512, 1) split2_kernel(const SplitArgs A, const Split2Extra X) {
+__global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const SplitArgs A, const Split2Extra X) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Shared2 &S = *reinterpret_cast<Shared2 *>(smem_raw);
   const int K = (int)A.num_colors, P = A.max_iters, G = (int)gridDim.x, b = (int)blockIdx.x;
@@ -1088,7 +1093,7 @@ __global__ void __launch_bounds__(512, 1) split2_kernel(const SplitArgs A, const
         } else {
           reduce_stage1<5>(S, v, (int)(nthr >> 5));
 #ifdef DQ_PROFILE_NARROW
-          if (tid == 0 && pass > 0) atomicAdd(X.progress + 269, (uint32_t)(clock64() - w3));  // stage 1 + sync
+          if (tid == 0 && pass > 0) atomicAdd(X.progress + 769, (uint32_t)(clock64() - w3));  // stage 1 + sync
 #endif
           if (tid < 32) {
             reduce_stage2_warp0<5>(S, (int)(nthr >> 5));
@@ -1097,12 +1102,12 @@ __global__ void __launch_bounds__(512, 1) split2_kernel(const SplitArgs A, const
         }
         __syncthreads();
 #ifdef DQ_PROFILE_NARROW
-        if (tid == 0 && pass > 0) atomicAdd(X.progress + 268, (uint32_t)(w3 - w2));  // classification only
+        if (tid == 0 && pass > 0) atomicAdd(X.progress + 768, (uint32_t)(w3 - w2));  // classification only
         if (tid == 0 && pass > 0) {
-          atomicAdd(X.progress + 264, (uint32_t)(w1 - w0));            // gather (wait + reduce)
-          atomicAdd(X.progress + 265, (uint32_t)(w2 - w1));            // derive + sync
-          atomicAdd(X.progress + 266, (uint32_t)(clock64() - w2));     // classify + reduce + publish
-          atomicAdd(X.progress + 267, 1u);
+          atomicAdd(X.progress + 764, (uint32_t)(w1 - w0));            // gather (wait + reduce)
+          atomicAdd(X.progress + 765, (uint32_t)(w2 - w1));            // derive + sync
+          atomicAdd(X.progress + 766, (uint32_t)(clock64() - w2));     // classify + reduce + publish
+          atomicAdd(X.progress + 767, 1u);
         }
 #endif
       }
@@ -1248,9 +1253,26 @@ size_t split2_slot_capacity(uint32_t point_capacity, uint32_t num_colors, int sm
   return (size_t)point_capacity / kWideTile + num_colors + 64;
 }
 
-SplitLaunch split2_plan(int sm_count, uint32_t num_colors) {
+// CTAs of the split kernel that can be co-resident on the device (cooperative launch limit) for this K.
+int split2_max_ctas(int sm_count, uint32_t num_colors) {
+  static std::mutex mu;
+  static std::map<size_t, int> cache;
+  const size_t smem = split2_smem_bytes(num_colors, 8 * num_colors + 16);
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(smem);
+  if (it == cache.end()) {
+    int per_sm = 0;
+    DQ_CUDA_CHECK(cudaFuncSetAttribute(split2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)(200 * 1024))));
+    DQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, split2_kernel, T, smem));
+    it = cache.emplace(smem, std::max(per_sm, 1)).first;
+  }
+  return it->second * sm_count;
+}
+
+SplitLaunch split2_plan(int requested_ctas, int sm_count, uint32_t num_colors) {
   SplitLaunch plan;
-  plan.grid = sm_count;
+  const int cap = split2_max_ctas(sm_count, num_colors);
+  plan.grid = (requested_ctas >= 1 && requested_ctas <= cap) ? requested_ctas : cap;
   plan.smem_bytes = split2_smem_bytes(num_colors, 8 * num_colors + 16);
   return plan;
 }
@@ -1258,11 +1280,7 @@ SplitLaunch split2_plan(int sm_count, uint32_t num_colors) {
 void split2_launch(const SplitArgs &args_in, const Split2Extra &extra, const SplitLaunch &plan, cudaStream_t stream) {
   SplitArgs args = args_in;
   args.node_cap = 8 * args.num_colors + 16;
-  static size_t configured = 0;
-  if (plan.smem_bytes > configured) {
-    DQ_CUDA_CHECK(cudaFuncSetAttribute(split2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes));
-    configured = plan.smem_bytes;
-  }
+  (void)split2_max_ctas(1, args.num_colors);  // raises the kernel's dynamic shared memory limit once
   Split2Extra x = extra;
   void *kargs[] = {(void *)&args, (void *)&x};
   DQ_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)split2_kernel, dim3(plan.grid), dim3(T), kargs, plan.smem_bytes, stream));

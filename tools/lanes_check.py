@@ -31,6 +31,7 @@ ref = {}
 
 def run(lanes, ctas, on_device):
     pipe = lib.dq_pipeline_create_lanes(0, 0 if on_device else N, lanes, ctas)
+    lib.dq_context_set_profiling(lib.dq_pipeline_context(pipe), 1)
     nbuf = max(lanes + 2, 4)
     outs = [torch.empty(N, dtype=torch.int32, device="cuda") if on_device else torch.empty(N, dtype=torch.int32).pin_memory()
             for _ in range(nbuf)]
@@ -60,6 +61,9 @@ def run(lanes, ctas, on_device):
         ref[tag] = (key, last)
     print(f"{tag:4s} lanes={lanes:2d} ctas={ctas:3d}: wall {dt / FR * 1e3:.3f} ms/frame, events {ms / FR:.3f} ms/frame = "
           f"{N * FR / ms / 1e6:.2f} Gpix/s  same={ref[tag] == (key, last)}", flush=True)
+    st = pkg.CallStats()
+    lib.dq_context_last_stats(lib.dq_pipeline_context(pipe), C.byref(st))
+    print("      lane 0, last frame, stage ms:", " ".join(f"{n}={v:.3f}" for n, v in zip(pkg.CallStats.STAGES, st.stage_ms)), flush=True)
     lib.dq_pipeline_destroy(pipe)
 
 
