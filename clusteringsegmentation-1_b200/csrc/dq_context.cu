@@ -96,6 +96,7 @@ struct dq_context {
   DevBuf<unsigned long long> d_slots;
   DevBuf<uint32_t> d_cursors;
   DevBuf<uint32_t> d_progress;
+  int exact_small = 1;    // small weighted inputs take the sequential-order kernel (DIVQUANT_B200_EXACT_SMALL=0 turns it off)
   int split_version = 2;  // 1 = generic kernel, 2 = latency-optimised kernel (falls back to 1 when it cannot run)
   int trace_split = 0;
   int *d_lut = nullptr;
@@ -180,12 +181,20 @@ void reset_control(dq_context *ctx) {
   DQ_CUDA_CHECK(cudaMemsetAsync(ctx->d_cb, 0, sizeof(ControlBlock), ctx->stream));
 }
 
+// The sampled pixels behind a histogram: what split_exact_kernel needs to put a small input's unique colours
+// into calc_color_table's emission order.
+struct ExactSource {
+  const uint32_t *d_in;
+  uint32_t rows, cols, dec;
+  int bits;
+};
+
 // Runs the divisive phase on ctx->d_pts0[0..U).  U is read on the device from d_cb->ucount.
 // Leaves palette/result/ctl in ctx->h_cb / ctx->h_small after a stream synchronisation.
 // Returns the number of palette entries.
 uint32_t run_split(dq_context *ctx, uint32_t point_capacity, double norm, uint32_t K, int max_iters, int num_bits,
                    uint32_t *colortable_out, dq_split_record *records_out, double *mean_out, uint32_t *size_out,
-                   bool collect_from_hist = false) {
+                   bool collect_from_hist = false, const ExactSource *exact = nullptr) {
   if (max_iters < 1 || max_iters > kSplitMaxIters) {
     fprintf(stderr, "divquant_b200: max_iters ( %d ) must be in [1,%d] (the reference hard-wires local k-means on)\n",
             max_iters, kSplitMaxIters);
@@ -236,6 +245,15 @@ uint32_t run_split(dq_context *ctx, uint32_t point_capacity, double norm, uint32
 
   const bool use_v2 = ctx->split_version == 2 && K <= kSplit2MaxColors;
   ctx->mark(2);
+  if (exact != nullptr && collect_from_hist && K <= kExactMaxColors && ctx->exact_small) {
+    // small inputs: the reference's own summation order (dq_split_exact.cu); no-op kernels for large ones
+    ctx->d_ctl_f64.ensure((size_t)8 * K + node_cap + 16);
+    a.g_cluster_tse = ctx->d_ctl_f64.ptr;
+    a.exact_small_max = kExactMaxPoints;
+    split_exact_launch(a, exact->d_in, exact->rows, exact->cols, exact->dec, exact->bits, ctx->d_uniq.ptr, ctx->d_table, ctx->d_map,
+                       ctx->d_ctl_f64.ptr, ctx->d_ctl_i32.ptr, ctx->sm_count, ctx->stream);
+    ctx->stats.kernel_launches += 3;
+  }
   if (use_v2) {
     Split2Extra x;
     const size_t slot_cap = split2_slot_capacity(point_capacity, K, ctx->sm_count);
@@ -416,7 +434,9 @@ bool quantize_device(dq_context *ctx, uint32_t n, const uint32_t *d_in, uint32_t
     norm = sample_norm(rows, cols, dec);
     point_cap = samples;
   }
-  *k_inout = run_split(ctx, point_cap, norm, K, max_iters, num_bits, colortable, records, mean_out, size_out, table_dirty);
+  const ExactSource src = {d_in, rows, cols, (uint32_t)dec, num_bits};
+  *k_inout = run_split(ctx, point_cap, norm, K, max_iters, num_bits, colortable, records, mean_out, size_out, table_dirty,
+                       table_dirty ? &src : nullptr);
   return table_dirty;
 }
 
@@ -514,6 +534,7 @@ dq_context *dq_context_create(int device) {
   for (int i = 0; i < 8; ++i) DQ_CUDA_CHECK(cudaEventCreate(&ctx->ev[i]));
   ctx->display_timings = display_timings_default();
   if (const char *e = getenv("DIVQUANT_B200_SPLIT")) ctx->split_version = (e[0] == '1') ? 1 : 2;
+  if (const char *e = getenv("DIVQUANT_B200_EXACT_SMALL")) ctx->exact_small = (e[0] != '0');
   DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   return ctx;
 }

@@ -451,6 +451,7 @@ __global__ void __launch_bounds__(kSplitThreads, 1) split_kernel(const SplitArgs
 
   const int tid = threadIdx.x;
   const uint32_t U = A.num_points_dev ? ld_cg_u32(A.num_points_dev) : A.num_points;
+  if (A.exact_small_max != 0u && U <= A.exact_small_max) return;  // split_exact_kernel has done this input
   if (tid == 0) S.num_points = U;
   unsigned int bar_target = 0;
   const size_t acc_job_stride = (size_t)(P + 1) * kAccWords;

@@ -111,7 +111,18 @@ struct SplitArgs {
   // optional trace: CTA 0 appends (tag, SM clock) pairs; [0] = number of pairs (tracing aid, see tools/)
   unsigned long long *timeline;
   uint32_t timeline_cap;
+  // inputs of at most this many points are handled by split_exact_kernel (dq_split_exact.cu): the split kernels
+  // return at once for them.  0 = off.
+  uint32_t exact_small_max;
 };
+
+// Largest input (unique colours) that takes the sequential-order path of dq_split_exact.cu.
+constexpr uint32_t kExactMaxPoints = 4096;
+constexpr uint32_t kExactMaxColors = 4096;
+// Small weighted inputs in the reference's own summation order.  g_f64: 8*K doubles, g_i32: K ints of scratch.
+void split_exact_launch(const SplitArgs &args, const uint32_t *d_in, uint32_t num_rows, uint32_t num_cols, uint32_t dec,
+                        int bits, const uint32_t *d_uniq, uint32_t *d_table, uint32_t *d_first_seen, double *g_f64,
+                        int32_t *g_i32, int sm_count, cudaStream_t st);
 
 // Launch description computed on the host.
 struct SplitLaunch {

@@ -780,6 +780,7 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
 
   const uint32_t U = A.num_points_dev ? ld_cg_u32(A.num_points_dev) : A.num_points;
   unsigned int bar_target = 0;
+  if (A.exact_small_max != 0u && U <= A.exact_small_max) return;  // split_exact_kernel has done this input
 
   // ---- global statistics of all points (DivQuantClusterInitMeanAndVar, :60-104) + scratch reset ----
   {

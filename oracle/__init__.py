@@ -123,14 +123,15 @@ class Oracle:
 
     # -- quantize -------------------------------------------------------------------------
     def quant_varpart_fast(self, pixels, k, num_bits=8, dec_factor=1, max_iters=10, all_unique=0,
-                           with_records=False, exact_counts=False):
+                           with_records=False, exact_counts=False, rows=1, cols=None):
         px = _u32(pixels)
+        cols = px.size if cols is None else cols
         ct = np.zeros(max(k, 1), np.uint32)
         nk = C.c_uint32(k)
         recs = (SplitRecord * max(k, 1))()
         nrec = C.c_int32(0)
         fn = self.lib.oracle_quant_varpart_fast_exact if exact_counts else self.lib.oracle_quant_varpart_fast
-        empty = fn(px.size, _ptr(px), 1, px.size, C.byref(nk), _ptr(ct), num_bits,
+        empty = fn(px.size, _ptr(px), rows, cols, C.byref(nk), _ptr(ct), num_bits,
                    dec_factor, max_iters, all_unique, recs, C.byref(nrec))
         pal = ct[:nk.value].copy()
         if with_records:
