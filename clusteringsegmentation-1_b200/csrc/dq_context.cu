@@ -544,6 +544,8 @@ void dq_context_set_split_ctas(dq_context *ctx, int num_ctas) {
   ctx->split_ctas = num_ctas >= 1 ? num_ctas : 0;  // clamped to the co-residency limit at launch
 }
 
+void dq_context_set_exact_small(dq_context *ctx, int enabled) { ctx->exact_small = enabled ? 1 : 0; }
+
 void dq_context_destroy(dq_context *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);

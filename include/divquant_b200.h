@@ -118,6 +118,12 @@ void dq_context_set_profiling(dq_context *ctx, int enabled);
  * phases side by side on one GPU (frame pipeline with lanes, section 2b).  Results do not depend on it.
  * Out-of-range values restore the default.  Environment: DIVQUANT_B200_SPLIT_CTAS. */
 void dq_context_set_split_ctas(dq_context *ctx, int num_ctas);
+/* Inputs of at most 4096 unique colours (and K <= 4096) are split by a kernel that adds in the reference's own
+ * order (calc_color_table emission order, one sequential double sum per accumulator), so that even decisions that
+ * sit exactly on a tie come out as in the reference; it costs up to ~3.6 ms for 4096 colours at K = 256.
+ * enabled = 0 sends small inputs through the exact-integer kernels like large ones (identical unless such a tie
+ * occurs).  Default 1; environment DIVQUANT_B200_EXACT_SMALL=0. */
+void dq_context_set_exact_small(dq_context *ctx, int enabled);
 
 /* quant_recurse with pixels already resident in HBM.  d_in / d_out are device pointers on the
  * context's device; colortable and numClustersPtr are host pointers.  Synchronous with respect to
