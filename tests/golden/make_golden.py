@@ -82,6 +82,29 @@ def small_cases(rng, n_cases=48):
     return cases
 
 
+CROP_IMAGES = ("batman", "cookie", "g1")   # g1 = oracle.generate(1, 1920, 1080, seed 99)
+CROP_DIMS = {"batman": (1000, 1778), "cookie": (1000, 1000), "g1": (1080, 1920)}
+
+
+def crop_specs(n=36, seed=4242):
+    """(image index, y, x, height, width, step, K) of seeded crops; kept when the crop is big enough to have more than
+    4096 unique colours in practice (checked by the caller through crop<i>_unique)."""
+    rng = np.random.default_rng(seed)
+    specs = []
+    while len(specs) < n:
+        im = int(rng.integers(0, 3))
+        h, w = CROP_DIMS[CROP_IMAGES[im]]
+        ch, cw = int(rng.integers(150, 700)), int(rng.integers(150, 700))
+        y, x = int(rng.integers(0, h - ch + 1)), int(rng.integers(0, w - cw + 1))
+        specs.append((im, y, x, ch, cw, int(rng.choice([1, 1, 2])), int(rng.choice([16, 64, 125, 256]))))
+    return specs
+
+
+def crop_pixels(shaped, spec):
+    im, y, x, ch, cw, step, _ = (int(v) for v in spec)
+    return np.ascontiguousarray(shaped[CROP_IMAGES[im]][y:y + ch:step, x:x + cw:step]).ravel()
+
+
 def main():
     import cv2
     o, r = Oracle(), Reference()
@@ -144,6 +167,18 @@ def main():
         uq_c, uq_w = r.calc_color_table(px)
         ref[f"small{i}_hist_colours"] = uq_c
         ref[f"small{i}_hist_weights"] = uq_w
+    # ---- seeded crops of the fixture images / G1 with more unique colours than the sequential-order kernel takes
+    #      (U > 4096): palettes of the compiled reference, for the tolerance test of the exact-integer path ----
+    crops = crop_specs()
+    ref["crop_specs"] = np.array(crops, np.int64)
+    shaped = {"batman": images["batman"].reshape(1000, 1778), "cookie": images["cookie"].reshape(1000, 1000),
+              "g1": o.generate(1, 1920, 1080, 99).reshape(1080, 1920)}
+    for i, spec in enumerate(crops):
+        px = crop_pixels(shaped, spec)
+        out, pal = r.quant_recurse(px, int(spec[6]), 0)
+        ref[f"crop{i}_palette"] = pal
+        ref[f"crop{i}_out_hash"] = np.array([o.hash_words(out)], np.uint64)
+        ref[f"crop{i}_unique"] = np.array([np.unique(px & 0xFFFFFF).size], np.uint64)
     np.savez_compressed(os.path.join(HERE, "reference_outputs.npz"), **ref)
     print("golden fixtures written:", sorted(os.listdir(HERE)))
 
