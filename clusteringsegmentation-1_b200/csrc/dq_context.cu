@@ -828,6 +828,37 @@ void dq_quant_blocks(const uint32_t *inPixels, uint32_t width, uint32_t height, 
   DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
 }
 
+// ---- SRM front half ----
+
+uint32_t dq_srm_num_pairs(uint32_t width, uint32_t height) { return srm_num_pairs(width, height); }
+
+void dq_srm_sorted_edges_device(dq_context *ctx, const uint8_t *d_in, uint32_t width, uint32_t height, uint32_t channels,
+                                uint32_t widthStep, dq_srm_pair *d_orderedPairs) {
+  require_device(ctx);
+  if (width == 0 || height == 0 || channels < 3 || widthStep < width * channels) {
+    fprintf(stderr, "divquant_b200: SRM edges need a non-empty image with >= 3 interleaved channels and widthStep >= width*channels\n");
+    abort();
+  }
+  ctx->d_keys.ensure(srm_scratch_words(width, height) / 2 + 2);
+  ctx->stats.kernel_launches += srm_sorted_edges(d_in, width, height, channels, widthStep, reinterpret_cast<uint32_t *>(d_orderedPairs),
+                                                 reinterpret_cast<uint32_t *>(ctx->d_keys.ptr), ctx->stream);
+}
+
+void dq_srm_sorted_edges(const uint8_t *in, uint32_t width, uint32_t height, uint32_t channels, uint32_t widthStep,
+                         dq_srm_pair *orderedPairs) {
+  dq_context *ctx = dq_default_context();
+  require_device(ctx);
+  const size_t bytes = (size_t)height * widthStep;
+  const uint32_t n = srm_num_pairs(width, height);
+  ctx->d_in.ensure(bytes / 4 + 1);
+  ctx->d_pts0.ensure(((size_t)n * 3 + 1) / 2 + 1);  // 8-byte elements holding the 12-byte pairs
+  DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->d_in.ptr, in, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  dq_srm_pair *d_pairs = reinterpret_cast<dq_srm_pair *>(ctx->d_pts0.ptr);
+  dq_srm_sorted_edges_device(ctx, reinterpret_cast<const uint8_t *>(ctx->d_in.ptr), width, height, channels, widthStep, d_pairs);
+  DQ_CUDA_CHECK(cudaMemcpyAsync(orderedPairs, d_pairs, (size_t)n * sizeof(dq_srm_pair), cudaMemcpyDeviceToHost, ctx->stream));
+  DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}
+
 // ---- label image ----
 
 void dq_colortable_indexes_device(dq_context *ctx, const uint32_t *d_quantPixels, uint32_t numPixels, const uint32_t *colortable,

@@ -35,4 +35,11 @@ void map_labels(const uint32_t *d_in, uint32_t n, uint32_t *d_out, const uint2 *
                 uint32_t *d_error, int sm_count, cudaStream_t st);
 void map_gather(const uint32_t *d_in, uint32_t n, uint32_t *d_out, const uint32_t *d_table, int sm_count, cudaStream_t st);
 
+// ---- dq_srm.cu ----
+uint32_t srm_num_pairs(uint32_t width, uint32_t height);
+size_t srm_scratch_words(uint32_t width, uint32_t height);
+// Returns the number of kernels launched.  d_pairs: 3 words per edge (r1, r2, diff) in merge order.
+int srm_sorted_edges(const uint8_t *d_in, uint32_t width, uint32_t height, uint32_t channels, uint32_t width_step,
+                     uint32_t *d_pairs, uint32_t *d_scratch, cudaStream_t st);
+
 }  // namespace dq

@@ -166,6 +166,21 @@ void dq_quant_blocks(const uint32_t *inPixels, uint32_t width, uint32_t height, 
  * pixels U; writes min(U, capacity) pairs.  Host pointers. */
 uint32_t dq_pixel_histogram(const uint32_t *pixels, uint32_t numPixels, uint32_t *pixelsOut, uint32_t *countsOut, uint32_t capacity);
 
+/* SRM front half.  Replaces the edge generation and bucket sort inside  segmentation()
+ * SRM/srm.c:135-177, :226-246 : the C4 edge list of an interleaved 8-bit image (colour bytes 0..2 of every pixel,
+ * `channels` bytes per pixel, `widthStep` bytes per row) in the reference's generation order, stably sorted by
+ * diff = the largest per-channel absolute difference (srm.c:103-121) -- i.e. exactly srm->ordered_pairs, the merge
+ * order of the union-find loop that stays on the host (srm.c:181-190).  dq_srm_pair is field-compatible with the
+ * reference's `struct my_pair` (SRM/srm.h:5-9).  orderedPairs holds dq_srm_num_pairs(width, height) entries. */
+typedef struct {
+  uint32_t r1, r2, diff;
+} dq_srm_pair;
+uint32_t dq_srm_num_pairs(uint32_t width, uint32_t height); /* 2(w-1)(h-1) + (h-1) + (w-1), srm.c:58 */
+void dq_srm_sorted_edges(const uint8_t *in, uint32_t width, uint32_t height, uint32_t channels, uint32_t widthStep,
+                         dq_srm_pair *orderedPairs);                                       /* host pointers   */
+void dq_srm_sorted_edges_device(dq_context *ctx, const uint8_t *d_in, uint32_t width, uint32_t height, uint32_t channels,
+                                uint32_t widthStep, dq_srm_pair *d_orderedPairs);          /* device pointers */
+
 /* Label image.  Replaces  mapQuantPixelsToColortableIndexes   superpixels/OpenCVUtil.cpp:787-849:
  * every (already quantized) pixel -> index of its colour in the CALLER's palette order, the last duplicate
  * winning; asGreyscale != 0 writes (i<<16 | i<<8 | i) like the reference (indexes must then be < 256).

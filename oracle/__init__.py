@@ -97,6 +97,8 @@ class Oracle:
         L.oracle_colortable_indexes.argtypes = [_u32p, C.c_uint32, _u32p, C.c_int, _u32p]
         L.oracle_block_vote.restype = None
         L.oracle_block_vote.argtypes = [_u32p, C.c_uint32, C.c_uint32, C.c_uint32, _u32p]
+        L.oracle_srm_sorted_edges.restype = C.c_uint32
+        L.oracle_srm_sorted_edges.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _u32p]
         L.oracle_hash_words.restype = C.c_uint64
         L.oracle_hash_words.argtypes = [_u32p, C.c_uint64]
         L.oracle_generate.restype = None
@@ -178,6 +180,15 @@ class Oracle:
         self.lib.oracle_block_vote(_ptr(px), width, height, dim, _ptr(out))
         return out.reshape(bh, bw)
 
+    def srm_sorted_edges(self, image):
+        """image: uint8 array (height, width, channels) in B,G,R[,A] order.  Returns (n_pairs, 3) uint32: r1, r2, diff."""
+        im = np.ascontiguousarray(image, np.uint8)
+        h, w, ch = im.shape
+        n = self.lib.oracle_srm_sorted_edges(im.ctypes.data, w, h, ch, w * ch, None)
+        out = np.zeros((n, 3), np.uint32)
+        self.lib.oracle_srm_sorted_edges(im.ctypes.data, w, h, ch, w * ch, _ptr(out.reshape(-1)))
+        return out
+
     # -- utilities ------------------------------------------------------------------------
     def hash_words(self, words):
         w = _u32(words)
@@ -187,6 +198,29 @@ class Oracle:
         out = np.empty(width * height, np.uint32)
         self.lib.oracle_generate(kind, width, height, seed, _ptr(out))
         return out
+
+
+SRM_REF_SO = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "libsrm_ref.so")
+
+
+class ReferenceSRM:
+    """The unmodified reference SRM (oracle/_ref/libsrm_ref.so): its sorted edge list and its segmentation."""
+
+    def __init__(self, path=SRM_REF_SO):
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.lib = C.CDLL(path)
+        self.lib.ref_srm_sorted_edges.restype = C.c_uint
+        self.lib.ref_srm_sorted_edges.argtypes = [C.c_double, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p, _u32p]
+
+    def sorted_edges(self, image, q=32.0):
+        im = np.ascontiguousarray(image, np.uint8).copy()
+        h, w, ch = im.shape
+        out_img = np.zeros_like(im)
+        n = self.lib.ref_srm_sorted_edges(q, w, h, ch, w * ch, im.ctypes.data, out_img.ctypes.data, None)
+        pairs = np.zeros((n, 3), np.uint32)
+        self.lib.ref_srm_sorted_edges(q, w, h, ch, w * ch, im.ctypes.data, out_img.ctypes.data, _ptr(pairs.reshape(-1)))
+        return pairs, out_img
 
 
 class Reference:

@@ -735,6 +735,52 @@ extern "C" void oracle_block_vote(const uint32_t *quant_pixels, uint32_t width, 
   }
 }
 
+// Reference: SRM/srm.c:103-121 (diff = largest per-channel absolute difference, channels B,G,R at offset
+// row*widthStep + channels*col), :135-177 (edge list: for every pixel of the (h-1) x (w-1) interior its right and
+// lower neighbour, then the last column's lower neighbours, then the last row's right neighbours) and :226-246
+// (stable 256-bin counting sort by diff).  pairs_out: 3 words per pair (r1, r2, diff).  Returns n_pairs.
+extern "C" uint32_t oracle_srm_sorted_edges(const uint8_t *in, uint32_t width, uint32_t height, uint32_t channels,
+                                            uint32_t width_step, uint32_t *pairs_out) {
+  const uint32_t n = 2 * (width - 1) * (height - 1) + (height - 1) + (width - 1);
+  if (!pairs_out) return n;
+  std::vector<uint32_t> pairs((size_t)n * 3);
+  auto diff = [&](uint32_t a, uint32_t b) {
+    const uint8_t *pa = in + (size_t)(a / width) * width_step + (size_t)channels * (a % width);
+    const uint8_t *pb = in + (size_t)(b / width) * width_step + (size_t)channels * (b % width);
+    uint32_t d = 0;
+    for (int c = 0; c < 3; ++c) {
+      const uint32_t x = pa[c], y = pb[c];
+      const uint32_t dc = x > y ? x - y : y - x;
+      if (dc > d) d = dc;
+    }
+    return d;
+  };
+  size_t p = 0;
+  auto emit = [&](uint32_t a, uint32_t b) {
+    pairs[3 * p] = a;
+    pairs[3 * p + 1] = b;
+    pairs[3 * p + 2] = diff(a, b);
+    ++p;
+  };
+  for (uint32_t i = 0; i + 1 < height; ++i)
+    for (uint32_t j = 0; j + 1 < width; ++j) {
+      emit(i * width + j, i * width + j + 1);
+      emit(i * width + j, i * width + j + width);
+    }
+  for (uint32_t i = 0; i + 1 < height; ++i) emit(i * width + width - 1, i * width + width - 1 + width);
+  for (uint32_t j = 0; j + 1 < width; ++j) emit((height - 1) * width + j, (height - 1) * width + j + 1);
+  uint32_t start[257] = {0};
+  for (size_t q = 0; q < n; ++q) start[pairs[3 * q + 2] + 1]++;
+  for (int b = 0; b < 256; ++b) start[b + 1] += start[b];
+  for (size_t q = 0; q < n; ++q) {
+    const uint32_t at = start[pairs[3 * q + 2]]++;
+    pairs_out[3 * at] = pairs[3 * q];
+    pairs_out[3 * at + 1] = pairs[3 * q + 1];
+    pairs_out[3 * at + 2] = pairs[3 * q + 2];
+  }
+  return n;
+}
+
 extern "C" uint64_t oracle_hash_words(const uint32_t *words, uint64_t n) {
   uint64_t h = 0xcbf29ce484222325ull;
   for (uint64_t i = 0; i < n; ++i) {

@@ -81,6 +81,11 @@ int oracle_colortable_indexes(const uint32_t *quant_pixels, uint32_t num_pixels,
  * ceil(width/dim) * ceil(height/dim) entries, row-major. */
 void oracle_block_vote(const uint32_t *quant_pixels, uint32_t width, uint32_t height, uint32_t dim, uint32_t *block_out);
 
+/* Sorted edge list of SRM's segmentation() (SRM/srm.c:135-177 + :226-246): 3 words per pair (r1, r2, diff); returns
+ * n_pairs = 2(w-1)(h-1) + (h-1) + (w-1); pairs_out may be NULL to query the count. */
+uint32_t oracle_srm_sorted_edges(const uint8_t *in, uint32_t width, uint32_t height, uint32_t channels, uint32_t width_step,
+                                 uint32_t *pairs_out);
+
 /* FNV-1a style fingerprint over u32 words used by SURVEY.md section 8c. */
 uint64_t oracle_hash_words(const uint32_t *words, uint64_t n);
 

@@ -105,6 +105,11 @@ def crop_pixels(shaped, spec):
     return np.ascontiguousarray(shaped[CROP_IMAGES[im]][y:y + ch:step, x:x + cw:step]).ravel()
 
 
+def srm_image(px2d):
+    """Packed 0x00RRGGBB words (height, width) -> the interleaved B,G,R bytes generateSRM hands to SRM()."""
+    return np.stack([px2d & 0xFF, (px2d >> 8) & 0xFF, (px2d >> 16) & 0xFF], axis=-1).astype(np.uint8)
+
+
 def main():
     import cv2
     o, r = Oracle(), Reference()
@@ -179,6 +184,15 @@ def main():
         ref[f"crop{i}_palette"] = pal
         ref[f"crop{i}_out_hash"] = np.array([o.hash_words(out)], np.uint64)
         ref[f"crop{i}_unique"] = np.array([np.unique(px & 0xFFFFFF).size], np.uint64)
+    # ---- SRM front half: the sorted edge list the unmodified reference builds (SRM/srm.c), as fingerprints ----
+    from oracle import ReferenceSRM
+    rs = ReferenceSRM()
+    for name in ("batman", "cookie"):
+        pairs, _ = rs.sorted_edges(srm_image(shaped[name]))
+        ref[f"srm_{name}_pairs_hash"] = np.array([o.hash_words(pairs.reshape(-1))], np.uint64)
+        ref[f"srm_{name}_num_pairs"] = np.array([pairs.shape[0]], np.uint64)
+    small = srm_image(shaped["cookie"][100:137, 200:251])          # full list for a small crop (ragged 37 x 51)
+    ref["srm_small_pairs"] = rs.sorted_edges(small)[0]
     np.savez_compressed(os.path.join(HERE, "reference_outputs.npz"), **ref)
     print("golden fixtures written:", sorted(os.listdir(HERE)))
 

@@ -464,3 +464,23 @@ def test_pixel_histogram(dq, oracle):
     assert np.array_equal(keys, ek) and np.array_equal(counts, ec)
     keys, counts = dq.pixel_histogram(np.array([0xFF000005, 5, 7], np.uint32))
     assert keys.tolist() == [5, 7] and counts.tolist() == [2, 1]
+
+
+def test_srm_sorted_edges(dq, oracle, golden):
+    """SRM's edge list + stable 256-bin sort (SRM/srm.c:135-177, :226-246) -- integer work, bit-exact,
+    order inside a bucket included (it is the merge order)."""
+    import sys
+    sys.path.insert(0, _os.path.join(ROOT_DIR, "tests", "golden"))
+    from make_golden import srm_image
+    z = np.load(_os.path.join(ROOT_DIR, "tests", "golden", "cookie_px.npz"))
+    img = srm_image(z["px"].reshape(int(z["shape"][0]), int(z["shape"][1])))
+    pairs = dq.srm_sorted_edges(img)
+    assert oracle.hash_words(pairs.reshape(-1)) == int(golden["srm_cookie_pairs_hash"][0])     # the reference's own list
+    assert np.array_equal(dq.srm_sorted_edges(np.ascontiguousarray(img[100:137, 200:251])), golden["srm_small_pairs"])
+    rng = np.random.default_rng(31)
+    for h, w, ch, levels in ((2, 2, 3, 256), (1, 9, 3, 256), (9, 1, 3, 256), (1, 1, 3, 4), (64, 33, 4, 256), (200, 300, 3, 4),
+                             (131, 257, 3, 2), (40, 2100, 3, 16), (300, 200, 4, 1)):
+        im = (rng.integers(0, levels, (h, w, ch)) * (256 // levels)).astype(np.uint8)
+        got, want = dq.srm_sorted_edges(im), oracle.srm_sorted_edges(im)
+        assert got.shape == want.shape and np.array_equal(got, want), (h, w, ch, levels)
+    assert np.all(np.diff(pairs[:, 2].astype(np.int64)) >= 0)    # sortedness of the full-size list

@@ -141,3 +141,22 @@ def test_live_fuzz_against_compiled_reference(oracle, reference):
         assert np.array_equal(ou[0], ru[0]) and np.array_equal(ou[1], ru[1])
         cb = tuple(int(x) for x in rng.integers(1, 9, 3))
         assert np.array_equal(oracle.cut_bits(px, *cb), reference.cut_bits(px, *cb))
+
+
+def test_srm_sorted_edges_oracle_matches_reference_fixtures(oracle, golden):
+    """the oracle's edge list + stable bucket sort against what the unmodified SRM/srm.c built
+    (fingerprints and one full list written by tests/golden/make_golden.py)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_golden import srm_image
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    for name in ("batman", "cookie"):
+        z = np.load(os.path.join(here, f"{name}_px.npz"))
+        img = srm_image(z["px"].reshape(int(z["shape"][0]), int(z["shape"][1])))
+        pairs = oracle.srm_sorted_edges(img)
+        assert pairs.shape[0] == int(golden[f"srm_{name}_num_pairs"][0])
+        assert oracle.hash_words(pairs.reshape(-1)) == int(golden[f"srm_{name}_pairs_hash"][0])
+        if name == "cookie":
+            small = np.ascontiguousarray(img[100:137, 200:251])
+            assert np.array_equal(oracle.srm_sorted_edges(small), golden["srm_small_pairs"])
