@@ -245,17 +245,19 @@ uint32_t run_split(dq_context *ctx, uint32_t point_capacity, double norm, uint32
 
   const bool use_v2 = ctx->split_version == 2 && K <= kSplit2MaxColors;
   ctx->mark(2);
-  if (exact != nullptr && collect_from_hist && K <= kExactMaxColors && ctx->exact_small) {
-    // small inputs: the reference's own summation order (dq_split_exact.cu); no-op kernels for large ones
+  const bool exact_path = exact != nullptr && collect_from_hist && K <= kExactMaxColors && ctx->exact_small;
+  ExactSampling sampling;
+  memset(&sampling, 0, sizeof(sampling));
+  if (exact_path) {
+    // small inputs: the reference's own summation order (dq_split_exact.cuh); large ones take one branch
     ctx->d_ctl_f64.ensure((size_t)8 * K + node_cap + 16);
     a.g_cluster_tse = ctx->d_ctl_f64.ptr;
     a.exact_small_max = kExactMaxPoints;
-    split_exact_launch(a, exact->d_in, exact->rows, exact->cols, exact->dec, exact->bits, ctx->d_uniq.ptr, ctx->d_table, ctx->d_map,
-                       ctx->d_ctl_f64.ptr, ctx->d_ctl_i32.ptr, ctx->sm_count, ctx->stream);
-    ctx->stats.kernel_launches += 3;
+    sampling = exact_sampling(exact->d_in, exact->rows, exact->cols, exact->dec, exact->bits);
   }
   if (use_v2) {
     Split2Extra x;
+    memset(&x, 0, sizeof(x));
     const size_t slot_cap = split2_slot_capacity(point_capacity, K, ctx->sm_count);
     ctx->d_slots.ensure(2 * slot_cap * kAccWords);
     ctx->d_cursors.ensure((size_t)4 * K);
@@ -269,8 +271,23 @@ uint32_t run_split(dq_context *ctx, uint32_t point_capacity, double norm, uint32
     x.collect_uniq = collect_from_hist ? ctx->d_uniq.ptr : nullptr;
     x.collect_table = collect_from_hist ? ctx->d_table : nullptr;
     if (getenv("DQ_PROFILE_NARROW")) DQ_CUDA_CHECK(cudaMemsetAsync(ctx->d_progress.ptr, 0, 1024 * sizeof(uint32_t), ctx->stream));
-    split2_launch(a, x, split2_plan(ctx->split_ctas, ctx->sm_count, K), ctx->stream);
+    const bool fuse = exact_path && split2_plan(0, ctx->sm_count, K, true).smem_bytes >= split_exact_smem_bytes();
+    if (fuse) {
+      x.exact_fused = 1;
+      x.exact_src = sampling;
+      x.exact_first_seen = ctx->d_map;
+      x.exact_f64 = ctx->d_ctl_f64.ptr;
+      x.exact_i32 = ctx->d_ctl_i32.ptr;
+    } else if (exact_path) {
+      split_exact_launch(a, sampling, ctx->d_uniq.ptr, ctx->d_table, ctx->d_map, ctx->d_ctl_f64.ptr, ctx->d_ctl_i32.ptr, ctx->stream);
+      ctx->stats.kernel_launches += 2;
+    }
+    split2_launch(a, x, split2_plan(ctx->split_ctas, ctx->sm_count, K, fuse), ctx->stream);
   } else {
+    if (exact_path) {
+      split_exact_launch(a, sampling, ctx->d_uniq.ptr, ctx->d_table, ctx->d_map, ctx->d_ctl_f64.ptr, ctx->d_ctl_i32.ptr, ctx->stream);
+      ctx->stats.kernel_launches += 2;
+    }
     if (collect_from_hist) {  // the generic kernel has no fused collect
       hist_collect(ctx->d_uniq.ptr, &ctx->d_cb->ucount, point_capacity, ctx->d_table, ctx->d_pts0.ptr, true, ctx->sm_count, ctx->stream);
       ctx->stats.kernel_launches++;
@@ -343,7 +360,8 @@ void check_sampling(uint32_t n, uint32_t rows, uint32_t cols, uint32_t dec) {
 void run_histogram(dq_context *ctx, const uint32_t *d_in, uint32_t n, uint32_t rows, uint32_t cols, uint32_t dec, int bits) {
   check_sampling(n, rows, cols, dec);
   ctx->d_uniq.ensure(n);
-  hist_insert(d_in, n, rows, cols, dec, bits, ctx->d_table, ctx->d_uniq.ptr, &ctx->d_cb->ucount, ctx->sm_count, ctx->stream);
+  hist_insert(d_in, n, rows, cols, dec, bits, ctx->d_table, ctx->d_uniq.ptr, &ctx->d_cb->ucount, ctx->sm_count, ctx->stream,
+              ctx->exact_small ? ctx->d_map : nullptr);
   ctx->stats.kernel_launches++;
 }
 

@@ -21,8 +21,10 @@ __device__ __forceinline__ uint32_t cut_colour(uint32_t pixel, uint32_t word_mas
   return (pixel & word_mask) >> shift;
 }
 
+// seen_init (may be null): second direct table; a colour's entry is set to 0xFFFFFFFF by its first toucher, which is
+// what the first-seen pass of the small-input path starts from (dq_split_exact.cu).
 __device__ __forceinline__ void insert_colour(uint32_t c, bool active, uint32_t *table, uint32_t *uniq,
-                                              uint32_t *ucount) {
+                                              uint32_t *ucount, uint32_t *seen_init) {
   bool fresh = false;
   if (active) fresh = (atomicAdd(table + c, 1u) == 0u);
   const unsigned m = __ballot_sync(0xffffffffu, fresh);
@@ -31,14 +33,17 @@ __device__ __forceinline__ void insert_colour(uint32_t c, bool active, uint32_t 
     uint32_t base = 0;
     if (lane == __ffs(m) - 1) base = atomicAdd(ucount, (uint32_t)__popc(m));
     base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-    if (fresh) uniq[base + __popc(m & ((1u << lane) - 1u))] = c;
+    if (fresh) {
+      uniq[base + __popc(m & ((1u << lane) - 1u))] = c;
+      if (seen_init) seen_init[c] = 0xFFFFFFFFu;
+    }
   }
 }
 
 // Contiguous sampling (dec_factor == 1, numRows == 1: every live caller, quant_util.cpp:60).
 __global__ void __launch_bounds__(256) hist_insert_kernel(const uint32_t *__restrict__ in, uint32_t n,
                                                          uint32_t word_mask, uint32_t shift, uint32_t *table,
-                                                         uint32_t *uniq, uint32_t *ucount) {
+                                                         uint32_t *uniq, uint32_t *ucount, uint32_t *seen_init) {
   const uint32_t nvec = n >> 2;
   const uint4 *in4 = reinterpret_cast<const uint4 *>(in);
   const uint32_t stride = gridDim.x * blockDim.x;
@@ -70,7 +75,10 @@ __global__ void __launch_bounds__(256) hist_insert_kernel(const uint32_t *__rest
       const unsigned below = (1u << lane) - 1u;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        if (old[k] == 0u) uniq[base + __popc(m[k] & below)] = c[k];
+        if (old[k] == 0u) {
+          uniq[base + __popc(m[k] & below)] = c[k];
+          if (seen_init) seen_init[c[k]] = 0xFFFFFFFFu;
+        }
         base += __popc(m[k]);
       }
     }
@@ -80,7 +88,7 @@ __global__ void __launch_bounds__(256) hist_insert_kernel(const uint32_t *__rest
     const uint32_t i = (nvec << 2) + threadIdx.x;
     const bool ok = i < n;
     const uint32_t p = ok ? in[i] : 0u;
-    insert_colour(cut_colour(p, word_mask, shift), ok, table, uniq, ucount);
+    insert_colour(cut_colour(p, word_mask, shift), ok, table, uniq, ucount, seen_init);
   }
 }
 
@@ -88,7 +96,7 @@ __global__ void __launch_bounds__(256) hist_insert_kernel(const uint32_t *__rest
 __global__ void __launch_bounds__(256) hist_insert_sampled_kernel(const uint32_t *__restrict__ in, uint32_t samples_per_row,
                                                                  uint32_t num_samples, uint32_t num_rows, uint32_t dec,
                                                                  uint32_t word_mask, uint32_t shift, uint32_t *table,
-                                                                 uint32_t *uniq, uint32_t *ucount) {
+                                                                 uint32_t *uniq, uint32_t *ucount, uint32_t *seen_init) {
   const uint32_t stride = gridDim.x * blockDim.x;
   const uint32_t round = (num_samples + 31u) & ~31u;
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < round; s += stride) {
@@ -98,7 +106,7 @@ __global__ void __launch_bounds__(256) hist_insert_sampled_kernel(const uint32_t
       const uint32_t ir = (s / samples_per_row) * dec, ic = (s % samples_per_row) * dec;
       p = in[ic + ir * num_rows];
     }
-    insert_colour(cut_colour(p, word_mask, shift), ok, table, uniq, ucount);
+    insert_colour(cut_colour(p, word_mask, shift), ok, table, uniq, ucount, seen_init);
   }
 }
 
@@ -211,7 +219,7 @@ inline int blocks_for(uint64_t items, int threads, int sm_count, int per_sm) {
 }  // namespace
 
 void hist_insert(const uint32_t *d_in, uint32_t n, uint32_t num_rows, uint32_t num_cols, uint32_t dec, int num_bits,
-                 uint32_t *d_table, uint32_t *d_uniq, uint32_t *d_ucount, int sm_count, cudaStream_t st) {
+                 uint32_t *d_table, uint32_t *d_uniq, uint32_t *d_ucount, int sm_count, cudaStream_t st, uint32_t *d_seen_init) {
   const uint32_t shift = 8u - (uint32_t)num_bits;
   const uint32_t byte_mask = (0xFFu >> shift) << shift;
   const uint32_t word_mask = (byte_mask << 16) | (byte_mask << 8) | byte_mask;
@@ -219,13 +227,13 @@ void hist_insert(const uint32_t *d_in, uint32_t n, uint32_t num_rows, uint32_t n
   if (dec == 1 && num_rows == 1 && aligned) {
     const uint32_t count = num_cols < n ? num_cols : n;
     hist_insert_kernel<<<blocks_for((count >> 2) + 32, 256, sm_count, 8), 256, 0, st>>>(d_in, count, word_mask, shift,
-                                                                                        d_table, d_uniq, d_ucount);
+                                                                                        d_table, d_uniq, d_ucount, d_seen_init);
   } else {
     const uint32_t nr = (num_rows + dec - 1) / dec, nc = (num_cols + dec - 1) / dec;
     const uint32_t samples = nr * nc;
     hist_insert_sampled_kernel<<<blocks_for(samples, 256, sm_count, 8), 256, 0, st>>>(d_in, nc, samples, num_rows, dec,
                                                                                      word_mask, shift, d_table, d_uniq,
-                                                                                     d_ucount);
+                                                                                     d_ucount, d_seen_init);
   }
   DQ_CUDA_CHECK(cudaGetLastError());
 }

@@ -119,10 +119,17 @@ struct SplitArgs {
 // Largest input (unique colours) that takes the sequential-order path of dq_split_exact.cu.
 constexpr uint32_t kExactMaxPoints = 4096;
 constexpr uint32_t kExactMaxColors = 4096;
-// Small weighted inputs in the reference's own summation order.  g_f64: 8*K doubles, g_i32: K ints of scratch.
-void split_exact_launch(const SplitArgs &args, const uint32_t *d_in, uint32_t num_rows, uint32_t num_cols, uint32_t dec,
-                        int bits, const uint32_t *d_uniq, uint32_t *d_table, uint32_t *d_first_seen, double *g_f64,
-                        int32_t *g_i32, int sm_count, cudaStream_t st);
+// Small weighted inputs in the reference's own summation order (dq_split_exact.cuh).
+// The sampled pixels behind the histogram: needed to put the unique colours into calc_color_table's emission order.
+struct ExactSampling {
+  const uint32_t *in;
+  uint32_t samples_per_row, num_samples, num_rows, dec, word_mask, shift;
+};
+ExactSampling exact_sampling(const uint32_t *d_in, uint32_t num_rows, uint32_t num_cols, uint32_t dec, int bits);
+size_t split_exact_smem_bytes();
+// Stand-alone form (two launches that return at once for large inputs).  g_f64: 8*K doubles, g_i32: K ints of scratch.
+void split_exact_launch(const SplitArgs &args, const ExactSampling &q, const uint32_t *d_uniq, uint32_t *d_table,
+                        uint32_t *d_first_seen, double *g_f64, int32_t *g_i32, cudaStream_t st);
 
 // Launch description computed on the host.
 struct SplitLaunch {
@@ -147,9 +154,16 @@ struct Split2Extra {
   // pts[0][i] = (uniq[i], table[uniq[i]]) and the counter is zeroed
   const uint32_t *collect_uniq;
   uint32_t *collect_table;
+  // when exact_fused != 0 (and SplitArgs::exact_small_max != 0) the kernel itself handles small inputs: every CTA
+  // takes part in the first-seen pass, then CTA 0 runs split_exact_body on the histogram above
+  uint32_t exact_fused;
+  ExactSampling exact_src;
+  uint32_t *exact_first_seen;
+  double *exact_f64;   // 8*K doubles
+  int32_t *exact_i32;  // K ints
 };
 size_t split2_slot_capacity(uint32_t point_capacity, uint32_t num_colors, int sm_count);
-SplitLaunch split2_plan(int requested_ctas, int sm_count, uint32_t num_colors);
+SplitLaunch split2_plan(int requested_ctas, int sm_count, uint32_t num_colors, bool exact_fused = false);
 int split2_max_ctas(int sm_count, uint32_t num_colors);
 void split2_launch(const SplitArgs &args, const Split2Extra &extra, const SplitLaunch &plan, cudaStream_t stream);
 

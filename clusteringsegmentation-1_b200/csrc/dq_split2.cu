@@ -23,6 +23,7 @@
 #include <map>
 #include <mutex>
 
+#include "dq_split_exact.cuh"
 #include "dq_split_math.cuh"
 
 namespace dq {
@@ -780,7 +781,19 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
 
   const uint32_t U = A.num_points_dev ? ld_cg_u32(A.num_points_dev) : A.num_points;
   unsigned int bar_target = 0;
-  if (A.exact_small_max != 0u && U <= A.exact_small_max) return;  // split_exact_kernel has done this input
+  if (A.exact_small_max != 0u && U <= A.exact_small_max) {
+    // small input: the reference's own summation order (dq_split_exact.cuh); stand-alone kernels did it unless fused
+    if (X.exact_fused && U > 0u) {
+      exact_first_seen(X.exact_src, X.exact_first_seen, (uint32_t)(b * T + tid), (uint32_t)(G * T));
+      grid_barrier2(A, bar_target, X.progress);
+      if (b == 0) {
+        const size_t Kz = (size_t)K;
+        exact::split_exact_body<T>(A, (int)U, smem_raw, X.collect_uniq, X.collect_table, X.exact_first_seen, X.exact_f64,
+                                   X.exact_f64 + Kz, X.exact_f64 + 2 * Kz, X.exact_f64 + 5 * Kz, X.exact_i32);
+      }
+    }
+    return;
+  }
 
   // ---- global statistics of all points (DivQuantClusterInitMeanAndVar, :60-104) + scratch reset ----
   {
@@ -1270,11 +1283,13 @@ int split2_max_ctas(int sm_count, uint32_t num_colors) {
   return it->second * sm_count;
 }
 
-SplitLaunch split2_plan(int requested_ctas, int sm_count, uint32_t num_colors) {
+SplitLaunch split2_plan(int requested_ctas, int sm_count, uint32_t num_colors, bool exact_fused) {
   SplitLaunch plan;
   const int cap = split2_max_ctas(sm_count, num_colors);
   plan.grid = (requested_ctas >= 1 && requested_ctas <= cap) ? requested_ctas : cap;
   plan.smem_bytes = split2_smem_bytes(num_colors, 8 * num_colors + 16);
+  // the small-input body lives in the same dynamic shared memory (one CTA per SM either way: 128 registers x 512)
+  if (exact_fused && kWarps == 16) plan.smem_bytes = std::max(plan.smem_bytes, split_exact_smem_bytes());
   return plan;
 }
 
