@@ -108,12 +108,14 @@ class ClockSampler:
 
 
 def traffic_bytes():
-    """DRAM bytes of one step from the committed ncu capture (never measured under the timed run)."""
+    """DRAM bytes of one frame from the committed ncu capture (never measured under the timed run): (total, note)."""
     path = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if os.path.exists(path):
         with open(path) as f:
-            return float(json.load(f)["total"])
-    return None
+            t = json.load(f)
+        parts = " + ".join(f"{k.replace('_kernel', '')} {v / 1e6:.1f}" for k, v in t["dram_bytes_per_step"].items())
+        return float(t["total"]), f"dram bytes of one frame, {t['source']}: {parts} MB; the remap output largely stays in the 126 MB L2"
+    return None, "no ncu capture committed"
 
 
 def measured_peaks():
@@ -303,6 +305,7 @@ def run_ours(args, rank, world, local_rank):
 
     def timed_stream(lanes, on_device):
         pipe = lib.dq_pipeline_create_lanes(local_rank, 0 if on_device else NPIX, lanes, 0)
+        lib.dq_pipeline_set_blocking_wait(pipe, blocking)
         outs = [torch.empty(NPIX, dtype=torch.int32, device="cuda") if on_device else torch.empty(NPIX, dtype=torch.int32).pin_memory()
                 for _ in range(lanes + 2)]
         run_stream(pipe, warmup * FPS, 0, outs, on_device)
@@ -331,8 +334,9 @@ def run_ours(args, rank, world, local_rank):
     FPS = args.frames_per_step
     # every lane has a host thread that waits on its stream: leave one core per rank for the submitting thread
     cpus = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    lane_cap = max(2, cpus // world - 1)
-    args.lanes, args.e2e_lanes = min(args.lanes, lane_cap), min(args.e2e_lanes, lane_cap)
+    blocking = 1 if cpus // world < max(args.lanes, args.e2e_lanes) + 1 else 0   # fewer cores than lanes: sleep, do not spin
+    if blocking:
+        args.lanes = max(args.lanes, 12)   # sleeping lane threads wake up later: more lanes hide it (tools/lanes_check.py)
     clocks = ClockSampler(local_rank)
     clocks.start()
     # -- device-resident throughput (frames already in HBM, results left in HBM) --
@@ -425,7 +429,8 @@ def run_ours(args, rank, world, local_rank):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32+f64",
         "data": "synthetic",
         "config": {"workload": f"{WIDTH}x{HEIGHT} RGBA G1 natural-like, K={K}, quant_recurse (histogram + split with 10 LKM iterations + remap)",
-                   "frames_per_step": FPS, "lanes": args.lanes,
+                   "frames_per_step": FPS, "lanes": args.lanes, "lane_threads_wait": "sleep on an event" if blocking else "spin",
+                   "host_cores_per_rank": cpus // world,
                    "api": "dq_pipeline_submit_device/flush: a stream of independent frames, `lanes` in flight on one GPU (each frame is one unmodified quant_recurse; split kernels of different frames on disjoint SM groups)",
                    "distinct_frames_per_rank": RING, "sharding": "frames (one stream of frames per GPU, no collective)" if world > 1 else "single GPU",
                    "l2": f"inputs rotate over {RING} distinct frames = {RING * NPIX * 4 / 1e6:.0f} MB > 126 MB L2",
@@ -443,9 +448,9 @@ def run_ours(args, rank, world, local_rank):
                         "path_roofline_frac": t_roof_ms / ms_single_frame, "gpu_launches_per_call": single_launches / steps},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": hbm_achieved, "peak": peak, "unit": "GB/s", "frac": hbm_achieved / peak,
-                     "traffic": traffic_bytes(), "peak_source": peak_src,
+                     "traffic": traffic_bytes()[0], "peak_source": peak_src,
                      "scope": "whole path per frame: 12 algorithmic B/pixel (4 histogram read + 4 remap read + 4 remap write) / time per frame at the measured throughput; per-kernel times in `kernels` are single-call CUDA-event times (one frame alone on the GPU)",
-                     "traffic_note": "dram bytes of one step from ncu --set full (profiles/r01_ncu_full_summary.txt): hist_insert 39.0 + split 9.4 + map_unique 0.9 + map_gather 43.5 MB; the remap output largely stays in the 126 MB L2",
+                     "traffic_note": traffic_bytes()[1],
                      "dominant_kernel": dominant, "kernels": kernels,
                      "note": "the path is not HBM-bound: north_star bounds it by the issue pipe (see path_roofline); the dominant kernel (split) is a dependency chain, DESIGN.md 5.2"},
         "path_roofline": {"definition": "north_star / SURVEY.md 8d: T_roof = max(N*K distance evaluations x 4 lane-instr / (SMs x 128 lanes x SM clock), 12 B/pixel / HBM peak)",

@@ -110,6 +110,19 @@ struct dq_context {
   void mark(int i) {
     if (profiling) DQ_CUDA_CHECK(cudaEventRecord(ev[i], stream));
   }
+  // Host waits on the hot path.  Default: spin (lowest latency).  blocking_wait: the thread sleeps on an event, which
+  // is what a frame pipeline with more lanes than free host cores wants.
+  int blocking_wait = 0;
+  cudaEvent_t wait_ev = nullptr;
+  void wait() {
+    if (!blocking_wait) {
+      DQ_CUDA_CHECK(cudaStreamSynchronize(stream));
+      return;
+    }
+    if (!wait_ev) DQ_CUDA_CHECK(cudaEventCreateWithFlags(&wait_ev, cudaEventBlockingSync | cudaEventDisableTiming));
+    DQ_CUDA_CHECK(cudaEventRecord(wait_ev, stream));
+    DQ_CUDA_CHECK(cudaEventSynchronize(wait_ev));
+  }
 
   void ensure_small(size_t words) {
     if (words <= h_small_words) return;
@@ -300,7 +313,7 @@ uint32_t run_split(dq_context *ctx, uint32_t point_capacity, double norm, uint32
   ctx->ensure_small((size_t)K + 16);
   DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->h_small, ctx->d_palette.ptr, K * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->h_cb, ctx->d_cb, sizeof(ControlBlock), cudaMemcpyDeviceToHost, ctx->stream));
-  DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  ctx->wait();
   if (ctx->h_cb->ctl[kCtlError] != 0) {
     fprintf(stderr, "divquant_b200: split controller failed (code %u, kernel v%d, detail %u/%u/%u, barrier counter %u; internal error)\n",
             ctx->h_cb->ctl[kCtlError], use_v2 ? 2 : 1, ctx->h_cb->ctl[kCtlWords - 1], ctx->h_cb->ctl[kCtlJobs],
@@ -473,7 +486,7 @@ void quant_recurse_device_impl(dq_context *ctx, uint32_t n, const uint32_t *d_in
   } else {
     remap_bruteforce(ctx, d_in, n, d_out, (int)k);
   }
-  if (final_sync || ctx->profiling) DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  if (final_sync || ctx->profiling) ctx->wait();
   if (ctx->profiling) {
     auto span = [&](int a, int b) {
       float ms = 0.f;
@@ -595,6 +608,7 @@ void dq_context_destroy(dq_context *ctx) {
   cudaFreeHost(ctx->h_cb);
   if (ctx->h_small) cudaFreeHost(ctx->h_small);
   for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->ev[i]);
+  if (ctx->wait_ev) cudaEventDestroy(ctx->wait_ev);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -1043,7 +1057,7 @@ void pipeline_worker(dq_pipeline *p, int lane_index) {
     if (!job.device_ptrs)
       DQ_CUDA_CHECK(cudaMemcpyAsync(job.out, lane.d_out, (size_t)job.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     DQ_CUDA_CHECK(cudaEventRecord(lane.end, ctx->stream));
-    DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->wait();
     p->launches += ctx->stats.kernel_launches;
     {
       std::lock_guard<std::mutex> lock(p->mu);
@@ -1105,6 +1119,11 @@ dq_pipeline *dq_pipeline_create_lanes(int device, uint32_t max_pixels, int lanes
   }
   for (int i = 0; i < lanes; ++i) p->lanes[i].worker = std::thread(pipeline_worker, p, i);
   return p;
+}
+
+void dq_pipeline_set_blocking_wait(dq_pipeline *p, int enabled) {
+  dq_pipeline_flush(p);
+  for (auto &lane : p->lanes) lane.ctx->blocking_wait = enabled ? 1 : 0;
 }
 
 dq_pipeline *dq_pipeline_create(int device, uint32_t max_pixels, int depth) {

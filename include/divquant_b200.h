@@ -250,6 +250,9 @@ dq_context *dq_pipeline_context(dq_pipeline *pipe);
 /* Kernels launched since creation (sum over frames and lanes). */
 uint64_t dq_pipeline_kernel_launches(const dq_pipeline *pipe);
 int dq_pipeline_lanes(const dq_pipeline *pipe);
+/* Lane threads spin while they wait for the GPU (lowest latency; default) or, with enabled = 1, sleep on an event:
+ * use it when the pipeline has more lanes than the process has free host cores (several ranks on one host). */
+void dq_pipeline_set_blocking_wait(dq_pipeline *pipe, int enabled);
 
 /* ------------------------------------------------------------------------------------------------
  * 3. Test hooks (used by tests/ to compare intermediate results with the oracle).

@@ -31,7 +31,9 @@ ref = {}
 
 def run(lanes, ctas, on_device):
     pipe = lib.dq_pipeline_create_lanes(0, 0 if on_device else N, lanes, ctas)
-    lib.dq_context_set_profiling(lib.dq_pipeline_context(pipe), 1)
+    lib.dq_pipeline_set_blocking_wait(pipe, int(os.environ.get("LANES_BLOCKING", "0")))
+    if os.environ.get("LANES_PROFILE"):
+        lib.dq_context_set_profiling(lib.dq_pipeline_context(pipe), 1)
     nbuf = max(lanes + 2, 4)
     outs = [torch.empty(N, dtype=torch.int32, device="cuda") if on_device else torch.empty(N, dtype=torch.int32).pin_memory()
             for _ in range(nbuf)]
