@@ -97,6 +97,8 @@ struct dq_context {
   DevBuf<uint32_t> d_cursors;
   DevBuf<uint32_t> d_progress;
   int exact_small = 1;    // small weighted inputs take the sequential-order kernel (DIVQUANT_B200_EXACT_SMALL=0 turns it off)
+  uint32_t exact_max_points = kExactMaxPoints;  // ... up to this many unique colours (DIVQUANT_B200_EXACT_MAX)
+  DevBuf<uint64_t> d_exact;
   int split_version = 2;  // 1 = generic kernel, 2 = latency-optimised kernel (falls back to 1 when it cannot run)
   int trace_split = 0;
   int *d_lut = nullptr;
@@ -258,14 +260,15 @@ uint32_t run_split(dq_context *ctx, uint32_t point_capacity, double norm, uint32
 
   const bool use_v2 = ctx->split_version == 2 && K <= kSplit2MaxColors;
   ctx->mark(2);
-  const bool exact_path = exact != nullptr && collect_from_hist && K <= kExactMaxColors && ctx->exact_small;
+  const bool exact_path = exact != nullptr && collect_from_hist && K <= kExactMaxColors && ctx->exact_small && ctx->exact_max_points > 0;
   ExactSampling sampling;
   memset(&sampling, 0, sizeof(sampling));
   if (exact_path) {
     // small inputs: the reference's own summation order (dq_split_exact.cuh); large ones take one branch
     ctx->d_ctl_f64.ensure((size_t)8 * K + node_cap + 16);
     a.g_cluster_tse = ctx->d_ctl_f64.ptr;
-    a.exact_small_max = kExactMaxPoints;
+    a.exact_small_max = std::min<uint32_t>(ctx->exact_max_points, kExactMaxPoints);
+    ctx->d_exact.ensure(split_exact_scratch_bytes() / 8 + 1);
     sampling = exact_sampling(exact->d_in, exact->rows, exact->cols, exact->dec, exact->bits);
   }
   if (use_v2) {
@@ -289,16 +292,17 @@ uint32_t run_split(dq_context *ctx, uint32_t point_capacity, double norm, uint32
       x.exact_fused = 1;
       x.exact_src = sampling;
       x.exact_first_seen = ctx->d_map;
+      x.exact_scratch = reinterpret_cast<unsigned char *>(ctx->d_exact.ptr);
       x.exact_f64 = ctx->d_ctl_f64.ptr;
       x.exact_i32 = ctx->d_ctl_i32.ptr;
     } else if (exact_path) {
-      split_exact_launch(a, sampling, ctx->d_uniq.ptr, ctx->d_table, ctx->d_map, ctx->d_ctl_f64.ptr, ctx->d_ctl_i32.ptr, ctx->stream);
+      split_exact_launch(a, sampling, reinterpret_cast<unsigned char *>(ctx->d_exact.ptr), ctx->d_uniq.ptr, ctx->d_table, ctx->d_map, ctx->d_ctl_f64.ptr, ctx->d_ctl_i32.ptr, ctx->stream);
       ctx->stats.kernel_launches += 2;
     }
     split2_launch(a, x, split2_plan(ctx->split_ctas, ctx->sm_count, K, fuse), ctx->stream);
   } else {
     if (exact_path) {
-      split_exact_launch(a, sampling, ctx->d_uniq.ptr, ctx->d_table, ctx->d_map, ctx->d_ctl_f64.ptr, ctx->d_ctl_i32.ptr, ctx->stream);
+      split_exact_launch(a, sampling, reinterpret_cast<unsigned char *>(ctx->d_exact.ptr), ctx->d_uniq.ptr, ctx->d_table, ctx->d_map, ctx->d_ctl_f64.ptr, ctx->d_ctl_i32.ptr, ctx->stream);
       ctx->stats.kernel_launches += 2;
     }
     if (collect_from_hist) {  // the generic kernel has no fused collect
@@ -566,6 +570,7 @@ dq_context *dq_context_create(int device) {
   ctx->display_timings = display_timings_default();
   if (const char *e = getenv("DIVQUANT_B200_SPLIT")) ctx->split_version = (e[0] == '1') ? 1 : 2;
   if (const char *e = getenv("DIVQUANT_B200_EXACT_SMALL")) ctx->exact_small = (e[0] != '0');
+  if (const char *e = getenv("DIVQUANT_B200_EXACT_MAX")) ctx->exact_max_points = (uint32_t)std::min<long>(std::max<long>(atol(e), 0), kExactMaxPoints);
   DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   return ctx;
 }
@@ -576,6 +581,9 @@ void dq_context_set_split_ctas(dq_context *ctx, int num_ctas) {
 }
 
 void dq_context_set_exact_small(dq_context *ctx, int enabled) { ctx->exact_small = enabled ? 1 : 0; }
+void dq_context_set_exact_max_points(dq_context *ctx, uint32_t max_points) {
+  ctx->exact_max_points = std::min<uint32_t>(max_points, kExactMaxPoints);
+}
 
 void dq_context_destroy(dq_context *ctx) {
   if (!ctx) return;
@@ -602,6 +610,7 @@ void dq_context_destroy(dq_context *ctx) {
   ctx->d_slots.release();
   ctx->d_cursors.release();
   ctx->d_progress.release();
+  ctx->d_exact.release();
   cudaFree(ctx->d_table);
   cudaFree(ctx->d_map);
   cudaFree(ctx->d_cb);

@@ -117,7 +117,7 @@ struct SplitArgs {
 };
 
 // Largest input (unique colours) that takes the sequential-order path of dq_split_exact.cu.
-constexpr uint32_t kExactMaxPoints = 4096;
+constexpr uint32_t kExactMaxPoints = 65536;  // compile-time ceiling; the run-time limit is SplitArgs::exact_small_max
 constexpr uint32_t kExactMaxColors = 4096;
 // Small weighted inputs in the reference's own summation order (dq_split_exact.cuh).
 // The sampled pixels behind the histogram: needed to put the unique colours into calc_color_table's emission order.
@@ -127,9 +127,10 @@ struct ExactSampling {
 };
 ExactSampling exact_sampling(const uint32_t *d_in, uint32_t num_rows, uint32_t num_cols, uint32_t dec, int bits);
 size_t split_exact_smem_bytes();
+size_t split_exact_scratch_bytes();  // global scratch for the point arrays of inputs above 4096 colours
 // Stand-alone form (two launches that return at once for large inputs).  g_f64: 8*K doubles, g_i32: K ints of scratch.
-void split_exact_launch(const SplitArgs &args, const ExactSampling &q, const uint32_t *d_uniq, uint32_t *d_table,
-                        uint32_t *d_first_seen, double *g_f64, int32_t *g_i32, cudaStream_t st);
+void split_exact_launch(const SplitArgs &args, const ExactSampling &q, unsigned char *d_scratch, const uint32_t *d_uniq,
+                        uint32_t *d_table, uint32_t *d_first_seen, double *g_f64, int32_t *g_i32, cudaStream_t st);
 
 // Launch description computed on the host.
 struct SplitLaunch {
@@ -159,6 +160,7 @@ struct Split2Extra {
   uint32_t exact_fused;
   ExactSampling exact_src;
   uint32_t *exact_first_seen;
+  unsigned char *exact_scratch;  // split_exact_scratch_bytes()
   double *exact_f64;   // 8*K doubles
   int32_t *exact_i32;  // K ints
 };

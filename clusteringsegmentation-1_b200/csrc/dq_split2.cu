@@ -788,7 +788,7 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
       grid_barrier2(A, bar_target, X.progress);
       if (b == 0) {
         const size_t Kz = (size_t)K;
-        exact::split_exact_body<T>(A, (int)U, smem_raw, X.collect_uniq, X.collect_table, X.exact_first_seen, X.exact_f64,
+        exact::split_exact_body<T>(A, (int)U, smem_raw, X.exact_scratch, X.collect_uniq, X.collect_table, X.exact_first_seen, X.exact_f64,
                                    X.exact_f64 + Kz, X.exact_f64 + 2 * Kz, X.exact_f64 + 5 * Kz, X.exact_i32);
       }
     }

@@ -10,24 +10,27 @@ namespace {
 
 constexpr int kExactThreads = 256;
 
-__global__ void __launch_bounds__(256) exact_first_seen_kernel(const ExactSampling q, const uint32_t *ucount, uint32_t *first_seen) {
-  if (*ucount > kExactMaxPoints) return;
+__global__ void __launch_bounds__(256) exact_first_seen_kernel(const ExactSampling q, const uint32_t *ucount, uint32_t max_points,
+                                                              uint32_t *first_seen) {
+  if (*ucount > max_points) return;
   exact_first_seen(q, first_seen, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 
-__global__ void __launch_bounds__(kExactThreads) split_exact_kernel(const SplitArgs A, const uint32_t *uniq, uint32_t *table,
-                                                                    const uint32_t *first_seen, double *g_weight,
-                                                                    double *g_tse, double *g_mean, double *g_var,
-                                                                    int32_t *g_size) {
+__global__ void __launch_bounds__(kExactThreads) split_exact_kernel(const SplitArgs A, unsigned char *scratch, const uint32_t *uniq,
+                                                                    uint32_t *table, const uint32_t *first_seen,
+                                                                    double *g_weight, double *g_tse, double *g_mean,
+                                                                    double *g_var, int32_t *g_size) {
   extern __shared__ __align__(16) unsigned char exact_smem[];
-  const int U = (int)*A.num_points_dev;
-  if (U > (int)kExactMaxPoints || U == 0) return;
-  exact::split_exact_body<kExactThreads>(A, U, exact_smem, uniq, table, first_seen, g_weight, g_tse, g_mean, g_var, g_size);
+  const uint32_t U = *A.num_points_dev;
+  if (U > A.exact_small_max || U == 0) return;
+  exact::split_exact_body<kExactThreads>(A, (int)U, exact_smem, scratch, uniq, table, first_seen, g_weight, g_tse, g_mean, g_var,
+                                         g_size);
 }
 
 }  // namespace
 
-size_t split_exact_smem_bytes() { return sizeof(exact::ExactShared); }
+size_t split_exact_smem_bytes() { return sizeof(exact::Shared); }
+size_t split_exact_scratch_bytes() { return exact::kScratchBytes; }
 
 ExactSampling exact_sampling(const uint32_t *d_in, uint32_t num_rows, uint32_t num_cols, uint32_t dec, int bits) {
   ExactSampling q;
@@ -44,17 +47,17 @@ ExactSampling exact_sampling(const uint32_t *d_in, uint32_t num_rows, uint32_t n
   return q;
 }
 
-void split_exact_launch(const SplitArgs &args, const ExactSampling &q, const uint32_t *d_uniq, uint32_t *d_table,
-                        uint32_t *d_first_seen, double *g_f64, int32_t *g_i32, cudaStream_t st) {
+void split_exact_launch(const SplitArgs &args, const ExactSampling &q, unsigned char *d_scratch, const uint32_t *d_uniq,
+                        uint32_t *d_table, uint32_t *d_first_seen, double *g_f64, int32_t *g_i32, cudaStream_t st) {
   const unsigned blocks = (unsigned)std::min<uint64_t>(((uint64_t)q.num_samples + 255) / 256, 64u);
-  exact_first_seen_kernel<<<std::max(blocks, 1u), 256, 0, st>>>(q, args.num_points_dev, d_first_seen);
+  exact_first_seen_kernel<<<std::max(blocks, 1u), 256, 0, st>>>(q, args.num_points_dev, args.exact_small_max, d_first_seen);
   static bool configured = false;
   if (!configured) {
-    DQ_CUDA_CHECK(cudaFuncSetAttribute(split_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(exact::ExactShared)));
+    DQ_CUDA_CHECK(cudaFuncSetAttribute(split_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(exact::Shared)));
     configured = true;
   }
   const size_t K = args.num_colors;
-  split_exact_kernel<<<1, kExactThreads, sizeof(exact::ExactShared), st>>>(args, d_uniq, d_table, d_first_seen, g_f64, g_f64 + K,
+  split_exact_kernel<<<1, kExactThreads, sizeof(exact::Shared), st>>>(args, d_scratch, d_uniq, d_table, d_first_seen, g_f64, g_f64 + K,
                                                                            g_f64 + 2 * K, g_f64 + 5 * K, g_i32);
   DQ_CUDA_CHECK(cudaGetLastError());
 }

@@ -10,8 +10,10 @@
 // never matters unless a decision sits exactly on a tie -- a mean on an integer, two equal variances or TSEs --
 // which is what small or synthetic inputs (few colours, equal counts, tiny clusters) produce.  There the
 // reference decides by its own rounding noise, so to return its palette bit for bit the noise has to be
-// reproduced: for U <= kExactMaxPoints this kernel walks the reference's loop with the same sequential double
-// accumulations (one lane per accumulator chain, non-contracted IEEE operations in the reference's order).
+// reproduced: up to SplitArgs::exact_small_max (<= kExactMaxPoints) unique colours this code walks the reference's
+// loop with the same sequential double accumulations (one lane per accumulator chain, non-contracted IEEE
+// operations in the reference's order).  Up to 4096 points everything lives in shared memory; above, the point
+// arrays live in a global scratch (L2) and only the staged terms and the per-cluster arrays stay on chip.
 //
 // One CTA.  Launched for every weighted call; returns at once when U is larger (the split kernels return at
 // once when it is not), so no host round trip is needed to choose.
@@ -31,27 +33,29 @@
 namespace dq {
 namespace exact {
 
-constexpr int kExactSortCap = 4096;  // power of two >= kExactMaxPoints
-constexpr int kExactIndexBits = 12;
-constexpr int kExactTile = 1024;     // new-side points whose terms are staged at a time
-constexpr int kExactSolo = 512;      // clusters up to this size are split by warp 0 alone
-constexpr int kExactSmemColors = 1024;
-static_assert(kExactSortCap >= (int)kExactMaxPoints, "sort capacity");
-static_assert(kExactSolo <= 16 * 32 && kExactSolo <= kExactTile, "a solo pass fits one tile and 16 points per lane");
-static_assert(kExactMaxPoints <= 16 * 256, "a block pass has at most 16 points per thread");
+constexpr int kSmemPoints = 4096;  // inputs up to this size keep their point arrays in shared memory
+constexpr int kIndexBits = 16;     // sort key = bucket << 48 | (0xFFFFFFFF - first seen) << 16 | arrival index
+constexpr int kTile = 1024;        // new-side points whose terms are staged at a time
+constexpr int kSolo = 512;         // clusters up to this size are split by warp 0 alone
+constexpr int kPiece = 16;         // consecutive points a thread classifies per chunk (bits of its mask)
+constexpr int kSmemColors = 1024;
+constexpr int kMaxChunks = 16;     // kExactMaxPoints / (256 threads * kPiece)
+static_assert(kExactMaxPoints <= (1u << kIndexBits), "indices are 16-bit");
+static_assert(kSolo <= kPiece * 32 && kSolo <= kTile, "a solo pass is one chunk and one tile");
+static_assert(kExactMaxPoints <= 256u * kPiece * kMaxChunks, "chunk count");
 
-struct ExactShared {
+struct Shared {
   union {
-    unsigned long long keys[kExactSortCap];  // only while the points are put in order
-    double terms[7][kExactTile];
+    unsigned long long keys[kSmemPoints];  // only while the points are put in order
+    double terms[7][kTile];
   };
-  double w[kExactMaxPoints];         // weights[] of calc_color_table (:172,185)
-  uint32_t colour[kExactMaxPoints];
-  uint16_t member[kExactMaxPoints];  // K <= kExactMaxColors <= 65535
-  uint16_t cur[kExactMaxPoints];     // points of the cluster being split, ascending original order (:929-1019)
+  double w[kSmemPoints];
+  uint32_t colour[kSmemPoints];
+  uint16_t member[kSmemPoints];
+  uint16_t cur[kSmemPoints];
   // per-cluster arrays of the reference (:296-324) when K fits, else the global scratch is used
-  double k_weight[kExactSmemColors], k_tse[kExactSmemColors], k_mean[3 * kExactSmemColors], k_var[3 * kExactSmemColors];
-  int32_t k_size[kExactSmemColors];
+  double k_weight[kSmemColors], k_tse[kSmemColors], k_mean[3 * kSmemColors], k_var[3 * kSmemColors];
+  int32_t k_size[kSmemColors];
   double chain[8];
   int32_t warp_tmp[32];
   double red_val[32];
@@ -62,6 +66,16 @@ struct ExactShared {
   double lhs, rr[3], cut;
   int32_t axis;
 };
+
+// The per-point arrays: shared memory (U <= kSmemPoints) or the global scratch.
+struct Points {
+  unsigned long long *keys;
+  double *w;         // weights[] of calc_color_table (:172,185)
+  uint32_t *colour;
+  uint16_t *member;  // K <= kExactMaxColors <= 65535
+  uint16_t *cur;     // points of the cluster being split, ascending original order (:929-1019)
+};
+constexpr size_t kScratchBytes = (size_t)kExactMaxPoints * (8 + 8 + 4 + 2 + 2);
 
 __device__ __forceinline__ double chan(uint32_t p, int c) { return byte_to_double((p >> (16 - 8 * c)) & 0xFFu); }
 __device__ __forceinline__ double chan_sq(uint32_t p, int c) {
@@ -75,9 +89,9 @@ __device__ __forceinline__ void group_sync() {
   else __syncthreads();
 }
 
-__device__ __forceinline__ void store_terms(ExactShared &S, int slot, int idx, int nchains) {
-  const double wt = S.w[idx];
-  const uint32_t p = S.colour[idx];
+__device__ __forceinline__ void store_terms(Shared &S, const Points &P, int slot, int idx, int nchains) {
+  const double wt = P.w[idx];
+  const uint32_t p = P.colour[idx];
   S.terms[0][slot] = fmul(wt, chan(p, 0));
   S.terms[1][slot] = fmul(wt, chan(p, 1));
   S.terms[2][slot] = fmul(wt, chan(p, 2));
@@ -90,7 +104,7 @@ __device__ __forceinline__ void store_terms(ExactShared &S, int slot, int idx, i
 }
 
 // lane l < nchains of warp 0 continues chain l over the n staged terms, in order
-__device__ __forceinline__ void add_terms(ExactShared &S, int n, int nchains, double &acc) {
+__device__ __forceinline__ void add_terms(Shared &S, int n, int nchains, double &acc) {
   const int t = threadIdx.x;
   if (t < nchains) {
     const double *src = S.terms[t];
@@ -111,68 +125,87 @@ __device__ __forceinline__ void add_terms(ExactShared &S, int n, int nchains, do
   }
 }
 
-// One pass: classify cur[0..cur_n) with pred (true = new side; `each` sees every point), then sum the new side's
-// terms in order.  Leaves chain[0..nchains) and new_size in S.  SOLO: executed by warp 0 only.
-// Returns true when the new side is the same set of points as in the previous pass (prev_mask, updated).
-template <int THREADS, bool SOLO, typename Pred, typename Each>
-__device__ __forceinline__ bool pass_sums(ExactShared &S, int cur_n, int nchains, unsigned &prev_mask, Pred pred, Each each) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int gsize = SOLO ? 32 : THREADS;
-  const int per = (cur_n + gsize - 1) / gsize;  // <= 16
-  const int lo = min(tid * per, cur_n), hi = min(lo + per, cur_n);
-  unsigned mask = 0;
-  for (int j = lo; j < hi; ++j) {
-    const int idx = S.cur[j];
-    const bool is_new = pred(S.colour[idx]);
-    each(idx, is_new);
-    mask |= (unsigned)is_new << (j - lo);
-  }
-  const int mine = __popc(mask);
-  const bool changed = (mask != prev_mask);
-  prev_mask = mask;
+// Exclusive rank of this thread's `mine` items among the group's and the group's total.
+template <int THREADS, bool SOLO>
+__device__ __forceinline__ void group_ranks(Shared &S, int mine, bool flag, int &first, int &total, bool &any_flag) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int incl = mine;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     const int t = __shfl_up_sync(0xffffffffu, incl, o);
     if (lane >= o) incl += t;
   }
-  int first = incl - mine, total;
-  bool any_changed;
+  first = incl - mine;
   if (SOLO) {
     total = __shfl_sync(0xffffffffu, incl, 31);
-    any_changed = __any_sync(0xffffffffu, changed);
+    any_flag = __any_sync(0xffffffffu, flag);
   } else {
+    __syncthreads();  // the previous reader of warp_tmp is done
     if (lane == 31) S.warp_tmp[warp] = incl;
-    any_changed = __syncthreads_or(changed) != 0;
+    any_flag = __syncthreads_or(flag) != 0;
     total = 0;
     for (int q = 0; q < THREADS / 32; ++q) {
       if (q < warp) first += S.warp_tmp[q];
       total += S.warp_tmp[q];
     }
   }
+}
+
+// One pass: classify cur[0..cur_n) with pred (true = new side; `each` sees every point), then sum the new side's
+// terms in order.  Leaves chain[0..nchains) and new_size in S.  SOLO: executed by warp 0 only.
+// Chunks of (group size * kPiece) points: a thread owns a contiguous piece of each chunk so that the order survives.
+// Returns true when the new side is the same set of points as in the previous pass (prev_masks, updated).
+template <int THREADS, bool SOLO, typename Pred, typename Each>
+__device__ __forceinline__ bool pass_sums(Shared &S, const Points &P, int cur_n, int nchains, unsigned *prev_masks, Pred pred,
+                                          Each each) {
+  const int tid = threadIdx.x;
+  const int gsize = SOLO ? 32 : THREADS;
+  const int chunk = gsize * kPiece;
   double acc = 0.0;
-  for (int tile = 0; tile < total; tile += kExactTile) {
-    // my new-side points have ranks [first, first + mine): stage those that fall into this tile
-    int rank = first;
+  int new_total = 0;
+  bool same = true;
+  int ci = 0;
+  for (int base = 0; base < cur_n; base += chunk, ++ci) {
+    const int n_here = min(chunk, cur_n - base);
+    const int per = (n_here + gsize - 1) / gsize;  // <= kPiece
+    const int lo = base + min(tid * per, n_here), hi = base + min(tid * per + per, n_here);
+    unsigned mask = 0;
     for (int j = lo; j < hi; ++j) {
-      if ((mask >> (j - lo)) & 1u) {
-        if (rank >= tile && rank < tile + kExactTile) store_terms(S, rank - tile, S.cur[j], nchains);
-        ++rank;
-      }
+      const int idx = P.cur[j];
+      const bool is_new = pred(P.colour[idx]);
+      each(idx, is_new);
+      mask |= (unsigned)is_new << (j - lo);
     }
-    group_sync<SOLO>();
-    add_terms(S, min(total - tile, kExactTile), nchains, acc);
-    group_sync<SOLO>();
+    const bool changed = (mask != prev_masks[ci]);
+    prev_masks[ci] = mask;
+    int first, total;
+    bool any_changed;
+    group_ranks<THREADS, SOLO>(S, __popc(mask), changed, first, total, any_changed);
+    same = same && !any_changed;
+    for (int tile = 0; tile < total; tile += kTile) {
+      // my new-side points have ranks [first, first + mine): stage those that fall into this tile
+      int rank = first;
+      for (int j = lo; j < hi; ++j) {
+        if ((mask >> (j - lo)) & 1u) {
+          if (rank >= tile && rank < tile + kTile) store_terms(S, P, rank - tile, P.cur[j], nchains);
+          ++rank;
+        }
+      }
+      group_sync<SOLO>();
+      add_terms(S, min(total - tile, kTile), nchains, acc);
+      group_sync<SOLO>();
+    }
+    new_total += total;
   }
   if (tid < nchains) S.chain[tid] = acc;
-  if (tid == 0) S.new_size = total;
+  if (tid == 0) S.new_size = new_total;
   group_sync<SOLO>();
-  return !any_changed;
+  return same;
 }
 
 // new centre from the chains, old centre by the 'combined mean' (:561-581, :780-810); lanes 0..2 = channels
 template <bool SOLO>
-__device__ __forceinline__ void derive_centres(ExactShared &S, bool with_squares) {
+__device__ __forceinline__ void derive_centres(Shared &S, bool with_squares) {
   const int t = threadIdx.x;
   if (t < 3) {
     const double nw = S.chain[3], ow = fsub(S.tw, nw);
@@ -187,7 +220,7 @@ __device__ __forceinline__ void derive_centres(ExactShared &S, bool with_squares
 
 // lhs / rhs of the hyperplane test (:616-623)
 template <bool SOLO>
-__device__ __forceinline__ void derive_hyperplane(ExactShared &S) {
+__device__ __forceinline__ void derive_hyperplane(Shared &S) {
   if (threadIdx.x == 0) {
     double l = fsub(fsq(S.om[0]), fsq(S.nm[0]));
     l = fadd(l, fsq(S.om[1]));
@@ -202,12 +235,14 @@ __device__ __forceinline__ void derive_hyperplane(ExactShared &S) {
 
 // split pass + max_iters LKM passes of one split (:438-811)
 template <int THREADS, bool SOLO>
-__device__ __forceinline__ void split_passes(ExactShared &S, int cur_n, int max_iters, int new_index, int old_index) {
-  unsigned prev_mask = 0xFFFFFFFFu;  // a piece has at most 16 points: never a real mask
+__device__ __forceinline__ void split_passes(Shared &S, const Points &P, int cur_n, int max_iters, int new_index, int old_index) {
+  unsigned prev_masks[kMaxChunks];
+#pragma unroll
+  for (int i = 0; i < kMaxChunks; ++i) prev_masks[i] = 0xFFFFFFFFu;  // a piece has at most 16 points: never a real mask
   {
     const int axis = S.axis;
     const double cut = S.cut;
-    pass_sums<THREADS, SOLO>(S, cur_n, 4, prev_mask, [&](uint32_t p) { return cut < chan(p, axis); }, [](int, bool) {});
+    pass_sums<THREADS, SOLO>(S, P, cur_n, 4, prev_masks, [&](uint32_t p) { return cut < chan(p, axis); }, [](int, bool) {});
   }
   derive_centres<SOLO>(S, false);
   for (int it = 0; it < max_iters; ++it) {
@@ -215,13 +250,13 @@ __device__ __forceinline__ void split_passes(ExactShared &S, int cur_n, int max_
     const double lhs = S.lhs, r0 = S.rr[0], r1 = S.rr[1], r2 = S.rr[2];
     const bool last = (it == max_iters - 1);
     const bool fixed_point = pass_sums<THREADS, SOLO>(
-        S, cur_n, last ? 7 : 4, prev_mask,
+        S, P, cur_n, last ? 7 : 4, prev_masks,
         [&](uint32_t p) {
           const double dot = fadd(fadd(fmul(r0, chan(p, 0)), fmul(r1, chan(p, 1))), fmul(r2, chan(p, 2)));
           return !(lhs < dot);  // (:683)
         },
         [&](int idx, bool is_new) {
-          if (last) S.member[idx] = (uint16_t)(is_new ? new_index : old_index);
+          if (last) P.member[idx] = (uint16_t)(is_new ? new_index : old_index);
         });
     derive_centres<SOLO>(S, last);
     // Same new side as in the previous pass: the same sums, hence the same centres and the same side again, until
@@ -230,23 +265,33 @@ __device__ __forceinline__ void split_passes(ExactShared &S, int cur_n, int max_
   }
 }
 
-
-// The whole divisive phase of one small input by one CTA of THREADS threads.  smem: sizeof(ExactShared) bytes.
+// The whole divisive phase of one input by one CTA of THREADS threads.  smem: sizeof(Shared) bytes; scratch:
+// kScratchBytes of global memory (used when U > kSmemPoints).
 // uniq / table: the histogram (unique colours in arrival order, counts; the counts are zeroed on the way);
 // first_seen[c]: smallest sample index of colour c; g_*: per-cluster scratch in global memory, used when K > 1024.
 template <int THREADS>
-__device__ void split_exact_body(const SplitArgs &A, int U, unsigned char *smem, const uint32_t *uniq, uint32_t *table,
-                                 const uint32_t *first_seen, double *g_weight, double *g_tse, double *g_mean, double *g_var,
-                                 int32_t *g_size) {
-  ExactShared &S = *reinterpret_cast<ExactShared *>(smem);
+__device__ void split_exact_body(const SplitArgs &A, int U, unsigned char *smem, unsigned char *scratch, const uint32_t *uniq,
+                                 uint32_t *table, const uint32_t *first_seen, double *g_weight, double *g_tse, double *g_mean,
+                                 double *g_var, int32_t *g_size) {
+  Shared &S = *reinterpret_cast<Shared *>(smem);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int K = (int)A.num_colors;
-  const bool in_smem = K <= kExactSmemColors;
+  const bool in_smem = K <= kSmemColors;
   double *const weight = in_smem ? S.k_weight : g_weight;
   double *const tse = in_smem ? S.k_tse : g_tse;
   double *const mean = in_smem ? S.k_mean : g_mean;
   double *const var = in_smem ? S.k_var : g_var;
   int32_t *const size = in_smem ? S.k_size : g_size;
+  Points P;
+  if (U <= kSmemPoints) {
+    P.keys = S.keys, P.w = S.w, P.colour = S.colour, P.member = S.member, P.cur = S.cur;
+  } else {
+    P.keys = reinterpret_cast<unsigned long long *>(scratch);
+    P.w = reinterpret_cast<double *>(scratch + (size_t)kExactMaxPoints * 8);
+    P.colour = reinterpret_cast<uint32_t *>(scratch + (size_t)kExactMaxPoints * 16);
+    P.member = reinterpret_cast<uint16_t *>(scratch + (size_t)kExactMaxPoints * 20);
+    P.cur = reinterpret_cast<uint16_t *>(scratch + (size_t)kExactMaxPoints * 22);
+  }
 
   // ---- points in calc_color_table's emission order: (bucket asc, first seen desc) ----
   int sort_n = 32;
@@ -257,10 +302,10 @@ __device__ void split_exact_body(const SplitArgs &A, int U, unsigned char *smem,
       const uint32_t c = uniq[i];
       const long R = (c >> 16) & 0xFF, G = (c >> 8) & 0xFF, B = c & 0xFF;
       const unsigned long long bucket = (unsigned long long)(((R * 33023 + G * 30013 + B * 27011) & 0x7fffffff) % 20023);
-      key = (bucket << (32 + kExactIndexBits)) | ((unsigned long long)(0xFFFFFFFFu - ld_cg_u32(first_seen + c)) << kExactIndexBits) |
+      key = (bucket << (32 + kIndexBits)) | ((unsigned long long)(0xFFFFFFFFu - ld_cg_u32(first_seen + c)) << kIndexBits) |
             (unsigned long long)i;
     }
-    S.keys[i] = key;
+    P.keys[i] = key;
   }
   __syncthreads();
   for (int k = 2; k <= sort_n; k <<= 1) {
@@ -268,11 +313,11 @@ __device__ void split_exact_body(const SplitArgs &A, int U, unsigned char *smem,
       for (int i = tid; i < sort_n; i += THREADS) {
         const int partner = i ^ j;
         if (partner > i) {
-          const unsigned long long a = S.keys[i], b = S.keys[partner];
+          const unsigned long long a = P.keys[i], b = P.keys[partner];
           const bool up = (i & k) == 0;
           if ((a > b) == up) {
-            S.keys[i] = b;
-            S.keys[partner] = a;
+            P.keys[i] = b;
+            P.keys[partner] = a;
           }
         }
       }
@@ -280,13 +325,13 @@ __device__ void split_exact_body(const SplitArgs &A, int U, unsigned char *smem,
     }
   }
   for (int i = tid; i < U; i += THREADS) {
-    const uint32_t c = uniq[(int)(S.keys[i] & ((1ull << kExactIndexBits) - 1ull))];
+    const uint32_t c = uniq[(int)(P.keys[i] & ((1ull << kIndexBits) - 1ull))];
     const uint32_t count = table[c];
     table[c] = 0u;  // the count table is all-zero again when the call ends
-    S.colour[i] = c;
-    S.w[i] = fmul(A.norm, (double)(int)count);  // weights[i] = weight * count (:185)
-    S.member[i] = 0;
-    S.cur[i] = (uint16_t)i;
+    P.colour[i] = c;
+    P.w[i] = fmul(A.norm, (double)(int)count);  // weights[i] = weight * count (:185)
+    P.member[i] = 0;
+    P.cur[i] = (uint16_t)i;
     A.pts[0][i] = make_uint2(c, count);
   }
   for (int i = tid; i < K; i += THREADS) {  // `new T[n]()` of the reference (:296-324)
@@ -298,8 +343,12 @@ __device__ void split_exact_body(const SplitArgs &A, int U, unsigned char *smem,
   __syncthreads();  // keys are dead from here on: the union now holds terms
 
   // ---- DivQuantClusterInitMeanAndVar (:60-104): chains 0..2 mean, 4..6 second moments ----
-  unsigned no_prev = 0xFFFFFFFFu;
-  pass_sums<THREADS, false>(S, U, 7, no_prev, [](uint32_t) { return true; }, [](int, bool) {});
+  {
+    unsigned no_prev[kMaxChunks];
+#pragma unroll
+    for (int i = 0; i < kMaxChunks; ++i) no_prev[i] = 0xFFFFFFFFu;
+    pass_sums<THREADS, false>(S, P, U, 7, no_prev, [](uint32_t) { return true; }, [](int, bool) {});
+  }
   if (tid == 0) {
     for (int c = 0; c < 3; ++c) {
       S.tm[c] = S.chain[c];
@@ -326,10 +375,10 @@ __device__ void split_exact_body(const SplitArgs &A, int U, unsigned char *smem,
       S.cut = cut;
     }
     __syncthreads();
-    if (cur_n <= kExactSolo) {
-      if (warp == 0) split_passes<THREADS, true>(S, cur_n, A.max_iters, new_index, old_index);
+    if (cur_n <= kSolo) {
+      if (warp == 0) split_passes<THREADS, true>(S, P, cur_n, A.max_iters, new_index, old_index);
     } else {
-      split_passes<THREADS, false>(S, cur_n, A.max_iters, new_index, old_index);
+      split_passes<THREADS, false>(S, P, cur_n, A.max_iters, new_index, old_index);
     }
     __syncthreads();
 
@@ -407,29 +456,25 @@ __device__ void split_exact_body(const SplitArgs &A, int U, unsigned char *smem,
     // ---- gather its points in ascending original order (:929-1019): contiguous pieces + exclusive scan ----
     {
       const uint16_t want = (uint16_t)S.old_index;
-      const int per = (U + THREADS - 1) / THREADS;  // <= 16
-      const int lo = min(tid * per, U), hi = min(lo + per, U);
-      unsigned mask = 0;
-      for (int i = lo; i < hi; ++i) mask |= (unsigned)(S.member[i] == want) << (i - lo);
-      const int mine = __popc(mask);
-      int incl = mine;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
+      const int chunk = THREADS * kPiece;
+      int written = 0;
+      for (int base = 0; base < U; base += chunk) {
+        const int n_here = min(chunk, U - base);
+        const int per = (n_here + THREADS - 1) / THREADS;
+        const int lo = base + min(tid * per, n_here), hi = base + min(tid * per + per, n_here);
+        unsigned mask = 0;
+        for (int i = lo; i < hi; ++i) mask |= (unsigned)(P.member[i] == want) << (i - lo);
+        int first, total;
+        bool unused;
+        group_ranks<THREADS, false>(S, __popc(mask), false, first, total, unused);
+        int pos = written + first;
+        for (int i = lo; i < hi; ++i)
+          if ((mask >> (i - lo)) & 1u) P.cur[pos++] = (uint16_t)i;
+        written += total;
       }
-      if (lane == 31) S.warp_tmp[warp] = incl;
-      __syncthreads();
-      int pos = incl - mine, total = 0;
-      for (int q = 0; q < THREADS / 32; ++q) {
-        if (q < warp) pos += S.warp_tmp[q];
-        total += S.warp_tmp[q];
-      }
-      for (int i = lo; i < hi; ++i)
-        if ((mask >> (i - lo)) & 1u) S.cur[pos++] = (uint16_t)i;
       if (tid == 0) {
-        S.cur_n = total;
-        if (total != size[S.old_index]) A.ctl[kCtlError] = 7;  // "Cluster to be split is expected to be of size ..." (:1013)
+        S.cur_n = written;
+        if (written != size[S.old_index]) A.ctl[kCtlError] = 7;  // "Cluster to be split is expected to be of size ..." (:1013)
       }
       __syncthreads();
     }
@@ -455,18 +500,12 @@ __device__ void split_exact_body(const SplitArgs &A, int U, unsigned char *smem,
       A.cluster_size[ic] = (uint32_t)sz;
       for (int c = 0; c < 3; ++c) A.cluster_mean[3 * ic + c] = m[c];
     }
-    const unsigned ballot = __ballot_sync(0xffffffffu, sz > 0);
-    if (lane == 0) S.warp_tmp[warp] = __popc(ballot);
+    int first, total;
+    bool unused;
+    group_ranks<THREADS, false>(S, sz > 0 ? 1 : 0, false, first, total, unused);
+    if (sz > 0) A.palette[S.emitted + first] = colour;
     __syncthreads();
-    int before = S.emitted;
-    for (int q = 0; q < warp; ++q) before += S.warp_tmp[q];
-    if (sz > 0) A.palette[before + __popc(ballot & ((1u << lane) - 1u))] = colour;
-    __syncthreads();
-    if (tid == 0) {
-      int tot = 0;
-      for (int q = 0; q < THREADS / 32; ++q) tot += S.warp_tmp[q];
-      S.emitted += tot;
-    }
+    if (tid == 0) S.emitted += total;
     __syncthreads();
   }
   if (tid == 0) {

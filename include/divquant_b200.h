@@ -118,11 +118,14 @@ void dq_context_set_profiling(dq_context *ctx, int enabled);
  * phases side by side on one GPU (frame pipeline with lanes, section 2b).  Results do not depend on it.
  * Out-of-range values restore the default.  Environment: DIVQUANT_B200_SPLIT_CTAS. */
 void dq_context_set_split_ctas(dq_context *ctx, int num_ctas);
-/* Inputs of at most 4096 unique colours (and K <= 4096) are split by a kernel that adds in the reference's own
- * order (calc_color_table emission order, one sequential double sum per accumulator), so that even decisions that
- * sit exactly on a tie come out as in the reference; it costs up to ~3.6 ms for 4096 colours at K = 256.
- * enabled = 0 sends small inputs through the exact-integer kernels like large ones (identical unless such a tie
- * occurs).  Default 1; environment DIVQUANT_B200_EXACT_SMALL=0. */
+/* Weighted inputs (allPixelsUnique = 0) of at most `max_points` unique colours (and K <= 4096) are split by code that
+ * adds in the reference's own order (calc_color_table emission order, one sequential double sum per accumulator), so
+ * that even decisions that sit exactly on a tie come out as in the reference: bit-exact palettes.  Larger inputs use
+ * exact integer sums: identical unless such a tie occurs (DESIGN.md 5.2 has the measured rates).  The ordered path is
+ * one CTA walking sequential chains: ~0.2 ms for 100 colours, ~3.5 ms for 4096, ~10 ms for 65536 (K = 256).
+ * max_points: 0..65536, default 65536 (environment DIVQUANT_B200_EXACT_MAX); dq_context_set_exact_small(ctx, 0)
+ * (environment DIVQUANT_B200_EXACT_SMALL=0) turns the ordered path off altogether. */
+void dq_context_set_exact_max_points(dq_context *ctx, uint32_t max_points);
 void dq_context_set_exact_small(dq_context *ctx, int enabled);
 
 /* quant_recurse with pixels already resident in HBM.  d_in / d_out are device pointers on the

@@ -74,7 +74,7 @@ def test_small_cases_uniform_path_bit_exact_vs_reference(dq, golden):
         assert np.array_equal(out, golden[f"small{i}_u1_out"]), i
 
 
-EXACT_MAX_POINTS = 4096  # kExactMaxPoints (csrc/dq_split.cuh): inputs up to this many unique colours are summed in the reference's order
+EXACT_MAX_POINTS = 65536  # kExactMaxPoints (csrc/dq_split.cuh): inputs up to this many unique colours are summed in the reference's order
 
 
 def test_small_cases_weighted_path(dq, oracle, golden):

@@ -41,7 +41,7 @@ for t in range(trials):
     with muted((2,)):
         out, pal = dq.quant_recurse(px, k, 0)
     ok = np.array_equal(pal, r_pal) and np.array_equal(out, r_out)
-    large += u > 4096
+    large += u > 65536
     if not ok:
         bad += 1
         if pal.size == r_pal.size:
@@ -55,4 +55,4 @@ for t in range(trials):
         else:
             worst = 999
             print(f"trial {t}: MISMATCH {name} n={px.size} U={u} k={k}: palette sizes {pal.size} vs {r_pal.size}", flush=True)
-print(f"{trials} natural crops against the {kind}: {bad} mismatches ({large} inputs with U > 4096), worst palette difference {worst} LSB")
+print(f"{trials} natural crops against the {kind}: {bad} mismatches ({large} inputs with U > 65536), worst palette difference {worst} LSB")

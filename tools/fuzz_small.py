@@ -45,18 +45,20 @@ for t in range(trials):
     with muted((2,)):
         out, pal = dq.quant_recurse(px, k, uniq)
     ok = np.array_equal(pal, r_pal) and np.array_equal(out, r_out)
-    small += u <= 4096
+    small += u <= 65536
     if not ok:
         bad += 1
         print(f"trial {t}: MISMATCH mode={mode} n={n} U={u} k={k} uniq={uniq} palettes_equal={np.array_equal(pal, r_pal)}", flush=True)
-print(f"{trials} trials against the {kind}: {bad} mismatches ({small} inputs with U <= 4096)")
+print(f"{trials} trials against the {kind}: {bad} mismatches ({small} inputs with U <= 65536)")
 import time
-for n, k in ((4096, 256), (4000, 16), (1000, 256), (100, 16)):
-    px = rng.integers(0, 1 << 24, n, dtype=np.uint32)
+g1 = o.generate(1, 1920, 1080, 7).reshape(1080, 1920)
+cases = [("random", rng.integers(0, 1 << 24, n, dtype=np.uint32), k) for n, k in ((65536, 256), (16384, 256), (4096, 256), (4000, 16), (1000, 256), (100, 16))]
+cases += [(f"g1 crop {s}x{s}", np.ascontiguousarray(g1[100:100 + s, 200:200 + s]).ravel(), 256) for s in (120, 200, 300, 420)]
+for name, px, k in cases:
     for _ in range(2):
         t0 = time.perf_counter()
         with muted((2,)):
             dq.quant_recurse(px, k, 0)
         dt = time.perf_counter() - t0
     st = dq.last_stats()
-    print(f"timing n={n} k={k}: {dt * 1e3:.3f} ms per call (host clock), launches {st['kernel_launches']}")
+    print(f"timing {name} n={px.size} U={st['num_points']} k={k}: {dt * 1e3:.3f} ms per call (host clock), launches {st['kernel_launches']}")
