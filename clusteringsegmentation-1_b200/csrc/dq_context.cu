@@ -116,6 +116,10 @@ struct dq_context {
   // is what a frame pipeline with more lanes than free host cores wants.
   int blocking_wait = 0;
   cudaEvent_t wait_ev = nullptr;
+  // host mailbox of the split kernel (mapped pinned memory, SplitArgs::mailbox)
+  volatile uint32_t *mailbox = nullptr;
+  uint32_t mailbox_seq = 0;
+  int use_mailbox = 1;  // DIVQUANT_B200_MAILBOX=0: always wait for the stream and copy
   void wait() {
     if (!blocking_wait) {
       DQ_CUDA_CHECK(cudaStreamSynchronize(stream));
@@ -287,6 +291,15 @@ uint32_t run_split(dq_context *ctx, uint32_t point_capacity, double norm, uint32
     x.collect_uniq = collect_from_hist ? ctx->d_uniq.ptr : nullptr;
     x.collect_table = collect_from_hist ? ctx->d_table : nullptr;
     if (getenv("DQ_PROFILE_NARROW")) DQ_CUDA_CHECK(cudaMemsetAsync(ctx->d_progress.ptr, 0, 1024 * sizeof(uint32_t), ctx->stream));
+    const bool mail = ctx->use_mailbox && !ctx->blocking_wait && !ctx->trace_split && records_out == nullptr &&
+                      mean_out == nullptr && size_out == nullptr;
+    if (mail) {
+      void *dev = nullptr;
+      DQ_CUDA_CHECK(cudaHostGetDevicePointer(&dev, const_cast<uint32_t *>(ctx->mailbox), 0));
+      a.mailbox = static_cast<uint32_t *>(dev);
+      a.mailbox_seq = ++ctx->mailbox_seq;
+      if (a.mailbox_seq == 0) a.mailbox_seq = ++ctx->mailbox_seq;  // 0 is the idle value
+    }
     const bool fuse = exact_path && split2_plan(0, ctx->sm_count, K, true).smem_bytes >= split_exact_smem_bytes();
     if (fuse) {
       x.exact_fused = 1;
@@ -315,9 +328,35 @@ uint32_t run_split(dq_context *ctx, uint32_t point_capacity, double norm, uint32
   ctx->stats.kernel_launches++;
 
   ctx->ensure_small((size_t)K + 16);
-  DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->h_small, ctx->d_palette.ptr, K * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-  DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->h_cb, ctx->d_cb, sizeof(ControlBlock), cudaMemcpyDeviceToHost, ctx->stream));
-  ctx->wait();
+  bool mailed = false;
+  if (a.mailbox != nullptr) {
+    // The kernel's last act is to store palette, result and diagnostics into mapped host memory and then the sequence
+    // number: poll for it instead of waiting for the stream to drain and two copies to come back.  If the stream is
+    // found idle without the number (an error exit), fall through to the copies below.
+    const uint32_t want = a.mailbox_seq;
+    for (unsigned spins = 0;; ++spins) {
+      if (ctx->mailbox[0] == want) {
+        mailed = true;
+        break;
+      }
+      if ((spins & 0xFFFu) == 0xFFFu && cudaStreamQuery(ctx->stream) != cudaErrorNotReady) {
+        mailed = (ctx->mailbox[0] == want);
+        break;
+      }
+    }
+    if (mailed) {
+      std::atomic_thread_fence(std::memory_order_acquire);
+      ctx->h_cb->ucount = ctx->mailbox[1];
+      for (int i = 0; i < 4; ++i) ctx->h_cb->result[i] = ctx->mailbox[2 + i];
+      for (int i = 0; i < (int)kCtlWords; ++i) ctx->h_cb->ctl[i] = ctx->mailbox[6 + i];
+      for (uint32_t i = 0; i < K; ++i) ctx->h_small[i] = ctx->mailbox[kMailboxPalette + i];
+    }
+  }
+  if (!mailed) {
+    DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->h_small, ctx->d_palette.ptr, K * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->h_cb, ctx->d_cb, sizeof(ControlBlock), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->wait();
+  }
   if (ctx->h_cb->ctl[kCtlError] != 0) {
     fprintf(stderr, "divquant_b200: split controller failed (code %u, kernel v%d, detail %u/%u/%u, barrier counter %u; internal error)\n",
             ctx->h_cb->ctl[kCtlError], use_v2 ? 2 : 1, ctx->h_cb->ctl[kCtlWords - 1], ctx->h_cb->ctl[kCtlJobs],
@@ -483,11 +522,27 @@ void quant_recurse_device_impl(dq_context *ctx, uint32_t n, const uint32_t *d_in
   uint32_t k = dedup_palette(colortable, *k_inout);
   *k_inout = k;
   ctx->stats.actual_colors = k;
-  upload_search_tables(ctx, colortable, (int)k);
   const uint32_t U = ctx->stats.num_points;
-  if (dirty && (uint64_t)U * 2 <= n) {
+  const bool through_table = dirty && (uint64_t)U * 2 <= n;
+  if (through_table && k <= 256) {
+    // the tables ride in the kernel's parameter block: no upload
+    MapTablesParam tables;
+    int lut[kLutEntries];
+    build_search_tables(colortable, (int)k, tables.sorted, lut);
+    for (int i = 0; i < kLutEntries; ++i) tables.lut[i] = (uint16_t)lut[i];
+    ctx->mark(4);
+    map_unique_params(tables, ctx->d_uniq.ptr, &ctx->d_cb->ucount, U, ctx->d_map, (int)k, ctx->sm_count, ctx->stream);
+    ctx->mark(5);
+    map_gather(d_in, n, d_out, ctx->d_map, ctx->sm_count, ctx->stream);
+    ctx->mark(6);
+    ctx->mark(7);
+    ctx->stats.kernel_launches += 2;
+    ctx->stats.remap_path = 2;
+  } else if (through_table) {
+    upload_search_tables(ctx, colortable, (int)k);
     remap_through_table(ctx, d_in, n, d_out, (int)k, U);
   } else {
+    upload_search_tables(ctx, colortable, (int)k);
     remap_bruteforce(ctx, d_in, n, d_out, (int)k);
   }
   if (final_sync || ctx->profiling) ctx->wait();
@@ -565,6 +620,13 @@ dq_context *dq_context_create(int device) {
   DQ_CUDA_CHECK(cudaMalloc(&ctx->d_map, (size_t)kColourBins * sizeof(uint32_t)));
   DQ_CUDA_CHECK(cudaMalloc(&ctx->d_cb, sizeof(ControlBlock)));
   DQ_CUDA_CHECK(cudaMallocHost(&ctx->h_cb, sizeof(ControlBlock)));
+  {
+    void *mb = nullptr;
+    DQ_CUDA_CHECK(cudaHostAlloc(&mb, kMailboxWords * sizeof(uint32_t), cudaHostAllocMapped));
+    memset(mb, 0, kMailboxWords * sizeof(uint32_t));
+    ctx->mailbox = static_cast<volatile uint32_t *>(mb);
+  }
+  if (const char *e = getenv("DIVQUANT_B200_MAILBOX")) ctx->use_mailbox = (e[0] != '0');
   memset(&ctx->stats, 0, sizeof(ctx->stats));
   for (int i = 0; i < 8; ++i) DQ_CUDA_CHECK(cudaEventCreate(&ctx->ev[i]));
   ctx->display_timings = display_timings_default();
@@ -616,6 +678,7 @@ void dq_context_destroy(dq_context *ctx) {
   cudaFree(ctx->d_cb);
   cudaFreeHost(ctx->h_cb);
   if (ctx->h_small) cudaFreeHost(ctx->h_small);
+  if (ctx->mailbox) cudaFreeHost(const_cast<uint32_t *>(ctx->mailbox));
   for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->ev[i]);
   if (ctx->wait_ev) cudaEventDestroy(ctx->wait_ev);
   cudaStreamDestroy(ctx->stream);

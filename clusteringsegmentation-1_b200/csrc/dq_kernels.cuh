@@ -30,6 +30,14 @@ void map_pixels(const uint32_t *d_in, uint32_t n, uint32_t *d_out, const uint32_
                 const int *d_lut, int4 *d_pal_scratch, int sm_count, cudaStream_t st);
 void map_unique(const uint32_t *d_uniq, const uint32_t *d_ucount, uint32_t u_hint, uint32_t *d_table,
                 const uint32_t *d_sorted, int num_colors, const int *d_lut, int sm_count, cudaStream_t st);
+// Sorted palette and start-index table small enough (K <= 256) to travel inside the kernel's parameter block: no
+// upload, no extra dependency between the host's table building and the launch.
+struct MapTablesParam {
+  uint32_t sorted[256];
+  uint16_t lut[768];  // lut_init[0..765], values < K
+};
+void map_unique_params(const MapTablesParam &tables, const uint32_t *d_uniq, const uint32_t *d_ucount, uint32_t u_hint,
+                       uint32_t *d_table, int num_colors, int sm_count, cudaStream_t st);
 void block_vote(const uint32_t *d_quant, uint32_t width, uint32_t height, uint32_t dim, uint32_t *d_blocks, int sm_count,
                 cudaStream_t st);
 void map_labels(const uint32_t *d_in, uint32_t n, uint32_t *d_out, const uint2 *d_pairs, int num_pairs, int greyscale,

@@ -97,7 +97,8 @@ __device__ __forceinline__ int first_at_minimum(const float4 *s_pal, int num_col
   return s;  // unreachable: the minimum is attained by some entry
 }
 
-__device__ __forceinline__ void stage_palette_fast(const uint32_t *sorted, int num_colors, const int *lut_init,
+template <typename LutT>
+__device__ __forceinline__ void stage_palette_fast(const uint32_t *sorted, int num_colors, const LutT *lut_init,
                                                    float4 *s_pal, uint32_t *s_word, int *s_lut) {
   for (int k = threadIdx.x; k < num_colors; k += blockDim.x) {
     const uint32_t c = sorted[k] & 0x00FFFFFFu;
@@ -105,7 +106,7 @@ __device__ __forceinline__ void stage_palette_fast(const uint32_t *sorted, int n
     s_pal[k] = make_float4(-2.f * r, -2.f * g, -2.f * b, r * r + g * g + b * b);
     s_word[k] = c;
   }
-  for (int i = threadIdx.x; i < (int)kLutEntries; i += blockDim.x) s_lut[i] = lut_init[i];
+  for (int i = threadIdx.x; i < (int)kLutEntries; i += blockDim.x) s_lut[i] = (int)lut_init[i];
   __syncthreads();
 }
 
@@ -155,9 +156,10 @@ __global__ void __launch_bounds__(kMapThreads) map_pixels_fast_kernel(const uint
 
 constexpr int kUniqPix = 4;
 
-__global__ void __launch_bounds__(kMapThreads) map_unique_fast_kernel(const uint32_t *__restrict__ uniq, const uint32_t *ucount,
-                                                                     uint32_t *table, const uint32_t *sorted, int num_colors,
-                                                                     const int *lut_init) {
+// One evaluation per unique colour: body shared by the two ways the tables arrive.
+template <typename LutT>
+__device__ __forceinline__ void map_unique_fast_body(const uint32_t *__restrict__ uniq, const uint32_t *ucount, uint32_t *table,
+                                                     const uint32_t *sorted, int num_colors, const LutT *lut_init) {
   extern __shared__ __align__(16) unsigned char smem[];
   float4 *s_pal = reinterpret_cast<float4 *>(smem);
   uint32_t *s_word = reinterpret_cast<uint32_t *>(smem + (size_t)num_colors * 16);
@@ -185,6 +187,20 @@ __global__ void __launch_bounds__(kMapThreads) map_unique_fast_kernel(const uint
         table[c[i]] = 0x80000000u | s_word[first_at_minimum(s_pal, num_colors, start[i], px.r[i], px.g[i], px.b[i], px.best[i])];
     }
   }
+}
+
+__global__ void __launch_bounds__(kMapThreads) map_unique_fast_kernel(const uint32_t *__restrict__ uniq, const uint32_t *ucount,
+                                                                     uint32_t *table, const uint32_t *sorted, int num_colors,
+                                                                     const int *lut_init) {
+  map_unique_fast_body(uniq, ucount, table, sorted, num_colors, lut_init);
+}
+
+// Tables inside the parameter block (constant bank): K <= 256.
+__global__ void __launch_bounds__(kMapThreads) map_unique_fast_param_kernel(const __grid_constant__ MapTablesParam tables,
+                                                                           const uint32_t *__restrict__ uniq,
+                                                                           const uint32_t *ucount, uint32_t *table,
+                                                                           int num_colors) {
+  map_unique_fast_body(uniq, ucount, table, tables.sorted, num_colors, tables.lut);
 }
 
 inline size_t fast_smem_bytes(int num_colors) { return (size_t)num_colors * 20 + kLutEntries * 4 + 16; }
@@ -418,6 +434,15 @@ void map_unique(const uint32_t *d_uniq, const uint32_t *d_ucount, uint32_t u_hin
   int per_sm = (int)std::min<size_t>(8, std::max<size_t>(1, (200 * 1024) / smem));
   map_unique_fast_kernel<<<blocks_for(u_hint / kUniqPix + 1, kMapThreads, sm_count, per_sm), kMapThreads, smem, st>>>(
       d_uniq, d_ucount, d_table, d_sorted, num_colors, d_lut);
+  DQ_CUDA_CHECK(cudaGetLastError());
+}
+
+void map_unique_params(const MapTablesParam &tables, const uint32_t *d_uniq, const uint32_t *d_ucount, uint32_t u_hint,
+                       uint32_t *d_table, int num_colors, int sm_count, cudaStream_t st) {
+  const size_t smem = fast_smem_bytes(num_colors);  // <= 256 colours: below 48 KB
+  int per_sm = (int)std::min<size_t>(8, std::max<size_t>(1, (200 * 1024) / smem));
+  map_unique_fast_param_kernel<<<blocks_for(u_hint / kUniqPix + 1, kMapThreads, sm_count, per_sm), kMapThreads, smem, st>>>(
+      tables, d_uniq, d_ucount, d_table, num_colors);
   DQ_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -111,6 +111,11 @@ struct SplitArgs {
   // optional trace: CTA 0 appends (tag, SM clock) pairs; [0] = number of pairs (tracing aid, see tools/)
   unsigned long long *timeline;
   uint32_t timeline_cap;
+  // Optional host mailbox (mapped pinned memory): when the kernel has finished, CTA 0 stores
+  //   [1] U  [2..5] result  [6..13] ctl  [16..16+K) palette, a system fence, then [0] = mailbox_seq,
+  // so the host can poll for the palette instead of waiting for the stream and copying it (dq_split2.cu only).
+  uint32_t *mailbox;
+  uint32_t mailbox_seq;
   // inputs of at most this many points are handled by split_exact_kernel (dq_split_exact.cu): the split kernels
   // return at once for them.  0 = off.
   uint32_t exact_small_max;
@@ -131,6 +136,9 @@ size_t split_exact_scratch_bytes();  // global scratch for the point arrays of i
 // Stand-alone form (two launches that return at once for large inputs).  g_f64: 8*K doubles, g_i32: K ints of scratch.
 void split_exact_launch(const SplitArgs &args, const ExactSampling &q, unsigned char *d_scratch, const uint32_t *d_uniq,
                         uint32_t *d_table, uint32_t *d_first_seen, double *g_f64, int32_t *g_i32, cudaStream_t st);
+
+constexpr int kMailboxPalette = 16;                      // word offset of the palette inside the mailbox
+constexpr int kMailboxWords = kMailboxPalette + 512;     // K <= kSplit2MaxColors
 
 // Launch description computed on the host.
 struct SplitLaunch {

@@ -418,6 +418,21 @@ __device__ __forceinline__ void gather(const SplitArgs &A, Shared2 &S, const uns
   // no barrier here: callers let warp 0 go on (parameter derivation) and synchronise afterwards
 }
 
+// Results to the host mailbox (see SplitArgs::mailbox).  Called by every thread of CTA 0 after the palette is in place.
+__device__ __forceinline__ void publish_mailbox(const SplitArgs &A, uint32_t U) {
+  if (A.mailbox == nullptr) return;
+  __syncthreads();  // palette / result / ctl written by this CTA are visible to it
+  volatile uint32_t *mb = A.mailbox;
+  const int tid = threadIdx.x, K = (int)A.num_colors;
+  for (int i = tid; i < K; i += T) mb[kMailboxPalette + i] = A.palette[i];
+  if (tid < 4) mb[2 + tid] = A.result[tid];
+  if (tid < (int)kCtlWords) mb[6 + tid] = A.ctl[tid];
+  if (tid == 0) mb[1] = U;
+  __threadfence_system();
+  __syncthreads();
+  if (tid == 0) mb[0] = A.mailbox_seq;
+}
+
 // ---- final assignment of cluster indices --------------------------------------------------------------
 
 // Palette = rounded means of the non-empty clusters in index order (:1030-1065). cnode[ic] = node of cluster ic.
@@ -790,6 +805,7 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
         const size_t Kz = (size_t)K;
         exact::split_exact_body<T>(A, (int)U, smem_raw, X.exact_scratch, X.collect_uniq, X.collect_table, X.exact_first_seen, X.exact_f64,
                                    X.exact_f64 + Kz, X.exact_f64 + 2 * Kz, X.exact_f64 + 5 * Kz, X.exact_i32);
+        publish_mailbox(A, U);
       }
     }
     return;
@@ -929,6 +945,7 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
           A.ctl[kCtlNodes] = (uint32_t)S.n_nodes;
           A.ctl[kCtlRounds] = (uint32_t)round;
         }
+        publish_mailbox(A, U);
       }
       break;
     }
