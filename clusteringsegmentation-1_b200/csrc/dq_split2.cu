@@ -55,6 +55,8 @@ struct Shared2 {
   SplitNode cur;  // node being split by a narrow job / finalised by an owner
   JobConst wide[kWideCache];
   PassParams wide_pp[kWideCache];  // classification of the last pass, reused by the partition
+  uint32_t part_new[kWarps], part_old[kWarps], base_new, base_old;  // partition of wide jobs: offsets without atomics
+  uint32_t piece_new[2][kWarps], piece_old[2][kWarps];
   uint64_t prev_tot[4];            // narrow jobs: {cnt, R, G, B} sums of the previous pass (fixed-point detection)
   int32_t converged;
   int32_t n_nodes, n_prev, njobs, prev_njobs;
@@ -796,6 +798,7 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
 
   const uint32_t U = A.num_points_dev ? ld_cg_u32(A.num_points_dev) : A.num_points;
   unsigned int bar_target = 0;
+  trace2(A, kTraceBegin, 0);
   if (A.exact_small_max != 0u && U <= A.exact_small_max) {
     // small input: the reference's own summation order (dq_split_exact.cuh); stand-alone kernels did it unless fused
     if (X.exact_fused && U > 0u) {
@@ -815,16 +818,30 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
   {
     uint64_t v[kAccWords] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (X.collect_uniq != nullptr) {
-      for (size_t i = (size_t)b * T + tid; i < U; i += (size_t)G * T) {
-        const uint32_t c = X.collect_uniq[i];
-        const uint2 p = make_uint2(c, X.collect_table[c]);
-        X.collect_table[c] = 0u;  // the count table is all-zero again when the kernel ends
-        A.pts[0][i] = p;
-        add_point(v, p, true);
+      // four colours per thread and trip, a grid stride apart: all loads of a trip are issued before the first store
+      // (the colours are distinct, which the compiler cannot know), so a trip costs one dependent pair of round trips
+      constexpr int kCollect = 4;
+      const size_t stride = (size_t)G * T;
+      for (size_t base = (size_t)b * T + tid; base < U; base += kCollect * stride) {
+        uint32_t c[kCollect], cnt[kCollect];
+#pragma unroll
+        for (int q = 0; q < kCollect; ++q) c[q] = (base + q * stride < U) ? __ldcs(X.collect_uniq + base + q * stride) : 0u;
+#pragma unroll
+        for (int q = 0; q < kCollect; ++q) cnt[q] = (base + q * stride < U) ? __ldcg(X.collect_table + c[q]) : 0u;
+#pragma unroll
+        for (int q = 0; q < kCollect; ++q) {
+          if (base + q * stride < U) {
+            X.collect_table[c[q]] = 0u;  // the count table is all-zero again when the kernel ends
+            const uint2 p = make_uint2(c[q], cnt[q]);
+            A.pts[0][base + q * stride] = p;
+            add_point(v, p, true);
+          }
+        }
       }
     } else {
       for (size_t i = (size_t)b * T + tid; i < U; i += (size_t)G * T) add_point(v, ld_cg_u2(A.pts[0] + i), true);
     }
+    trace2(A, kTraceCollected, 0);
     block_total<kAccWords>(S, v);
     if (tid < kAccWords && S.tot[tid] != 0)
       atomicAdd(reinterpret_cast<unsigned long long *>(A.root_acc + tid), (unsigned long long)S.tot[tid]);
@@ -832,7 +849,9 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
     for (size_t i = (size_t)b * T + tid; i < slot_words; i += (size_t)G * T) X.slots[i] = 0ull;
     for (size_t i = (size_t)b * T + tid; i < (size_t)4 * K; i += (size_t)G * T) X.cursors[i] = 0u;
   }
+  trace2(A, kTraceReduced, 0);
   grid_barrier2(A, bar_target);
+  trace2(A, kTraceRootBarrier, 0);
   trace2(A, kTraceRoot, 0);
 
   if (tid == 0) {
@@ -1164,7 +1183,33 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
       __syncthreads();
       if (S.tot[kAccPts] > jc.size) continue;  // only after an expired wait: never scatter out of the segment
       const uint32_t size_old = jc.size - (uint32_t)S.tot[kAccPts];
-      uint32_t *cur = X.cursors + (size_t)(round & 1) * 2 * K + 2 * j;
+      // Destinations without atomics: the participants' new-side counts of the last pass are in the slots just
+      // gathered, so the CTAs ranked before this one fix where its points start in both halves
+      // (deterministic, CTA-major order); inside the CTA a per-piece prefix over the warps does the rest.
+      {
+        uint32_t before_new = 0, before_all = 0;
+        const unsigned long long *slots_p = X.slots + (size_t)(P & 1) * X.slot_cap * kAccWords;
+        for (uint32_t i = (uint32_t)tid; i < me; i += T) {
+          before_new += (uint32_t)(ld_relaxed_u64(slots_p + (size_t)(R.slot0[j] + i) * kAccWords + kAccPts) & kValueMask);
+          before_all += share_points(tiles, i, jc.size);
+        }
+        before_new = __reduce_add_sync(0xffffffffu, before_new);
+        before_all = __reduce_add_sync(0xffffffffu, before_all);
+        if (lane == 0) {
+          S.part_new[tid >> 5] = before_new;
+          S.part_old[tid >> 5] = before_all;
+        }
+        __syncthreads();
+        if (tid == 0) {
+          uint32_t bn = 0, ba = 0;
+          for (int w = 0; w < kWarps; ++w) bn += S.part_new[w], ba += S.part_old[w];
+          S.base_new = bn;
+          S.base_old = ba - bn;
+        }
+        __syncthreads();
+      }
+      uint32_t run_new = S.base_new, run_old = S.base_old;
+      int flip = 0;
       for (uint32_t tt = me * (kWideTile / T); tt < tiles * (kWideTile / T); tt += (tt % (kWideTile / T) == kWideTile / T - 1) ? (uint32_t)(G - 1) * (kWideTile / T) + 1 : 1u) {
         // tt enumerates T-point pieces of this CTA's tiles: tile = tt / (kWideTile/T)
         const uint32_t off = tt * T + tid;
@@ -1174,13 +1219,22 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
         const bool to_new = valid && goes_new(pp, false, p.x);
         const unsigned m_new = __ballot_sync(0xffffffffu, to_new);
         const unsigned m_old = __ballot_sync(0xffffffffu, valid && !to_new);
-        uint32_t base_new = 0, base_old = 0;
+        uint32_t *wn = S.piece_new[flip], *wo = S.piece_old[flip];  // double-buffered: one barrier per piece
         if (lane == 0) {
-          if (m_new) base_new = atomicAdd(cur + 1, (uint32_t)__popc(m_new));
-          if (m_old) base_old = atomicAdd(cur, (uint32_t)__popc(m_old));
+          wn[tid >> 5] = (uint32_t)__popc(m_new);
+          wo[tid >> 5] = (uint32_t)__popc(m_old);
         }
-        base_new = __shfl_sync(0xffffffffu, base_new, 0);
-        base_old = __shfl_sync(0xffffffffu, base_old, 0);
+        __syncthreads();
+        uint32_t base_new = run_new, base_old = run_old, tot_new = 0, tot_old = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+          const uint32_t cn = wn[w], co = wo[w];
+          if (w < (tid >> 5)) base_new += cn, base_old += co;
+          tot_new += cn, tot_old += co;
+        }
+        run_new += tot_new;
+        run_old += tot_old;
+        flip ^= 1;
         if (valid) {
           const unsigned below = (1u << lane) - 1u;
           const uint32_t dst = to_new ? jc.begin + size_old + base_new + __popc(m_new & below)

@@ -285,7 +285,8 @@ uint32_t dq_debug_histogram(dq_context *ctx, const uint32_t *inPixels, uint32_t 
 /* Tracing aid for the persistent split kernel: when enabled, CTA 0 records (tag<<32|arg, SM clock) pairs at
  * its phase boundaries during the next calls.  Call again with pairs_out to fetch the last trace
  * (returns the number of pairs).  Tags: 1 round begin, 2 children finalised, 3 replay done, 4 jobs
- * issued, 5 barrier after controller, 6 pass done, 7 partition done, 8 root statistics done. */
+ * issued, 5 barrier after controller, 6 pass done, 7 partition done, 8 root statistics done, 9 kernel entered,
+ * 10 histogram collected, 11 root sums reduced, 12 root barrier passed. */
 uint32_t dq_debug_split_timeline(dq_context *ctx, int enable, uint64_t *pairs_out, uint32_t capacity_pairs);
 
 /* Host-only pieces of the path (no device needed): the palette handling the shim does between the

@@ -36,7 +36,7 @@ if os.environ.get("DQ_TRACE"):
     lib.dq_quant_recurse_device(ctx, px.numel(), px.data_ptr(), out.data_ptr(), C.byref(nk), ct.ctypes.data_as(C.POINTER(C.c_uint32)), 0)
     buf = (C.c_uint64 * (2 * 4096))()
     n = lib.dq_debug_split_timeline(ctx, 0, buf, 4096)
-    names = {1: "round", 2: "phaseA", 3: "phaseB", 4: "phaseC", 5: "ctlbar", 6: "pass", 7: "part", 8: "root"}
+    names = {1: "round", 2: "phaseA", 3: "phaseB", 4: "phaseC", 5: "ctlbar", 6: "pass", 7: "part", 8: "root", 9: "begin", 10: "collected", 11: "reduced", 12: "rootbar"}
     prev = None
     agg = {}
     for i in range(n):
