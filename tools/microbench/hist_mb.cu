@@ -32,6 +32,28 @@ __global__ void __launch_bounds__(256) k_red(const uint4 *in, uint32_t nvec, uin
     for (int k = 0; k < 4; ++k) { atomicAdd(table + c[k], 1u); if (flags) flags[c[k] >> 8] = 1; }
   }
 }
+// RED for the count + a 2 MB bitmap for "seen": a plain (cacheable) read filters the pixels whose colour is known
+// already, only the others pay an atomicOr with return; the thread that flips the bit appends the colour.
+__global__ void __launch_bounds__(256) k_red_bitmap(const uint4 *in, uint32_t nvec, uint32_t *table, uint32_t *bitmap, uint32_t *uniq, uint32_t *ucount) {
+  const uint32_t nround = (nvec + 31u) & ~31u;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += gridDim.x * blockDim.x) {
+    const bool ok = i < nvec;
+    uint4 p = ok ? __ldcs(in + i) : make_uint4(0, 0, 0, 0);
+    uint32_t c[4] = {p.x & 0xFFFFFF, p.y & 0xFFFFFF, p.z & 0xFFFFFF, p.w & 0xFFFFFF};
+    uint32_t seen[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { if (ok) atomicAdd(table + c[k], 1u); seen[k] = ok ? bitmap[c[k] >> 5] : 0xFFFFFFFFu; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t bit = 1u << (c[k] & 31);
+      bool fresh = false;
+      if (ok && !(seen[k] & bit)) fresh = !(atomicOr(bitmap + (c[k] >> 5), bit) & bit);
+      unsigned m = __ballot_sync(0xffffffffu, fresh);
+      if (m) { int lane = threadIdx.x & 31; uint32_t base = 0; if (lane == __ffs(m) - 1) base = atomicAdd(ucount, __popc(m)); base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1); if (fresh) uniq[base + __popc(m & ((1u << lane) - 1))] = c[k]; }
+    }
+  }
+}
+__global__ void clear_uniq_bitmap(uint32_t *table, uint32_t *bitmap, const uint32_t *uniq, const uint32_t *ucount) { for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < *ucount; i += gridDim.x * blockDim.x) { table[uniq[i]] = 0; bitmap[uniq[i] >> 5] = 0; } }
 // neighbour-merged: equal colours among the 4 pixels of a thread are counted once
 __global__ void __launch_bounds__(256) k_red_merge(const uint4 *in, uint32_t nvec, uint32_t *table) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += gridDim.x * blockDim.x) {
@@ -75,6 +97,19 @@ int main() {
       uint32_t u; CK(cudaMemcpy(&u, ucount, 4, cudaMemcpyDeviceToHost));
       if (rep == 2) printf("atom+append  grid %5d: %.1f us  U=%u\n", grid, ms * 1e3, u);
       clear_uniq<<<592, 256>>>(table, uniq, ucount); CK(cudaDeviceSynchronize());
+    }
+  }
+  {
+    uint32_t *bitmap; CK(cudaMalloc(&bitmap, 2 << 20)); CK(cudaMemset(bitmap, 0, 2 << 20));
+    for (int grid : {1184, 2368, 4736}) {
+      for (int rep = 0; rep < 3; ++rep) {
+        CK(cudaMemset(ucount, 0, 4)); cudaEventRecord(e0);
+        k_red_bitmap<<<grid, 256>>>((uint4 *)px, N / 4, table, bitmap, uniq, ucount);
+        cudaEventRecord(e1); CK(cudaDeviceSynchronize()); cudaEventElapsedTime(&ms, e0, e1);
+        uint32_t u; CK(cudaMemcpy(&u, ucount, 4, cudaMemcpyDeviceToHost));
+        if (rep == 2) printf("RED+bitmap   grid %5d: %.1f us  U=%u\n", grid, ms * 1e3, u);
+        clear_uniq_bitmap<<<592, 256>>>(table, bitmap, uniq, ucount); CK(cudaDeviceSynchronize());
+      }
     }
   }
   for (int withflags = 0; withflags < 2; ++withflags) {
