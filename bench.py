@@ -334,9 +334,12 @@ def run_ours(args, rank, world, local_rank):
     FPS = args.frames_per_step
     # every lane has a host thread that waits on its stream: leave one core per rank for the submitting thread
     cpus = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    blocking = 1 if cpus // world < max(args.lanes, args.e2e_lanes) + 1 else 0   # fewer cores than lanes: sleep, do not spin
-    if blocking:
-        args.lanes = max(args.lanes, 12)   # sleeping lane threads wake up later: more lanes hide it (tools/lanes_check.py)
+    # lane threads spin on their stream (lowest latency) when every one of them can have a core, with one left for the
+    # submitting thread; otherwise they sleep on an event and a few more lanes hide the later wake-up (tools/lanes_check.py)
+    spin_lanes = min(args.lanes, cpus // world - 1)
+    blocking = 0 if spin_lanes >= 8 else 1
+    args.lanes = spin_lanes if not blocking else max(args.lanes, 12)
+    args.e2e_lanes = min(args.e2e_lanes, max(spin_lanes, 2)) if not blocking else args.e2e_lanes
     clocks = ClockSampler(local_rank)
     clocks.start()
     # -- device-resident throughput (frames already in HBM, results left in HBM) --
@@ -477,7 +480,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-frames", type=int, default=10, help="frames of the single-thread CPU baseline sample")
-    ap.add_argument("--lanes", type=int, default=8, help="frames in flight per GPU, device-resident leg")
+    ap.add_argument("--lanes", type=int, default=12, help="frames in flight per GPU, device-resident leg")
     ap.add_argument("--e2e-lanes", type=int, default=6, help="frames in flight per GPU, host-buffer leg")
     ap.add_argument("--frames-per-step", type=int, default=8, help="frames in one step (one batch)")
     ap.add_argument("--skip-cpu", action="store_true")
