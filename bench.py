@@ -348,6 +348,31 @@ def run_ours(args, rank, world, local_rank):
     # -- end to end: pinned host frames, H2D and D2H of every frame inside the timed region --
     ms_e2e, _, e2e_parity = timed_stream(args.e2e_lanes, False)
     e2e_value = world * steps * FPS * NPIX / (ms_e2e * 1e-3) / 1e6
+    # -- what the copy engines alone can do: H2D and D2H of one frame each, concurrently, nothing else on the GPU --
+    s_up, s_down = torch.cuda.Stream(), torch.cuda.Stream()
+    pin_out = torch.empty(NPIX, dtype=torch.int32).pin_memory()
+    dev_tmp = torch.empty(NPIX, dtype=torch.int32, device="cuda")
+
+    def copies(n_frames):
+        for f in range(n_frames):
+            with torch.cuda.stream(s_up):
+                dev_tmp.copy_(host_frames[f % RING], non_blocking=True)
+            with torch.cuda.stream(s_down):
+                pin_out.copy_(dev_out, non_blocking=True)
+
+    copies(4)
+    barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    s_up.wait_event(c0)
+    s_down.wait_event(c0)
+    copies(32)
+    torch.cuda.current_stream().wait_stream(s_up)
+    torch.cuda.current_stream().wait_stream(s_down)
+    c1.record()
+    barrier()
+    ms_copy_floor = c0.elapsed_time(c1) / 32
+
     # -- latency of ONE call (no concurrency between frames): device-resident and through the host-pointer API --
     ms_single, single_launches = timed(step_device, steps, warmup)
     ms_e2e_single, _ = timed(step_host, steps, warmup)
@@ -443,6 +468,8 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": e2e_value, "unit": "Mpixels/s", "h2d_bytes_per_step": FPS * NPIX * 4, "d2h_bytes_per_step": FPS * (NPIX * 4 + K * 4 + 4),
                 "h2d_bytes_per_frame": NPIX * 4, "d2h_bytes_per_frame": NPIX * 4 + K * 4 + 4,
                 "ms_per_step": ms_e2e / steps, "ms_per_frame": ms_e2e / steps / FPS, "host_buffers": "pinned", "lanes": args.e2e_lanes,
+                "copy_floor_ms_per_frame": ms_copy_floor,
+                "copy_floor_note": "H2D + D2H of one frame each, concurrently on two streams, no kernels: what PCIe alone allows on this rank",
                 "api": "dq_pipeline_submit/flush (H2D, kernels and D2H of different frames overlap)",
                 "single_call_ms": ms_e2e_single / steps, "single_call_value": world * steps * NPIX / (ms_e2e_single * 1e-3) / 1e6,
                 "matches_single_call": e2e_parity},
