@@ -217,22 +217,6 @@ __global__ void __launch_bounds__(kMapThreads) map_pixels_kernel(const uint32_t 
     out[i] = nearest_entry(in[i], s_pal, num_colors, s_lut);
 }
 
-// One evaluation per unique colour; the answer goes to table[colour] with bit 31 set (so that a
-// mapped colour of 0x000000 is distinguishable from an untouched entry while debugging).
-__global__ void __launch_bounds__(kMapThreads) map_unique_kernel(const uint32_t *__restrict__ uniq, const uint32_t *ucount,
-                                                                uint32_t *table, const uint32_t *sorted, int num_colors,
-                                                                const int *lut_init) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  int *s_lut = reinterpret_cast<int *>(smem);
-  int4 *s_pal = reinterpret_cast<int4 *>(smem + ((kLutEntries * 4 + 15) & ~15u));
-  stage_palette(sorted, num_colors, lut_init, s_pal, s_lut);
-  const uint32_t u = *ucount;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < u; i += gridDim.x * blockDim.x) {
-    const uint32_t c = uniq[i];
-    table[c] = 0x80000000u | nearest_entry(c, s_pal, num_colors, s_lut);
-  }
-}
-
 // Same, palette read from global memory (palettes too large for shared memory).
 __global__ void __launch_bounds__(kMapThreads) map_pixels_big_kernel(const uint32_t *__restrict__ in, uint32_t n,
                                                                     uint32_t *__restrict__ out, const int4 *pal,
