@@ -97,6 +97,7 @@ struct dq_context {
   DevBuf<uint32_t> d_cursors;
   DevBuf<uint32_t> d_progress;
   int exact_small = 1;    // small weighted inputs take the sequential-order kernel (DIVQUANT_B200_EXACT_SMALL=0 turns it off)
+  int exact_parallel = 1;  // the ordered path runs on all CTAs of the split kernel (DIVQUANT_B200_EXACT_PARALLEL=0: CTA 0 only)
   uint32_t exact_max_points = kExactMaxPoints;  // ... up to this many unique colours (DIVQUANT_B200_EXACT_MAX)
   DevBuf<uint64_t> d_exact;
   int split_version = 2;  // 1 = generic kernel, 2 = latency-optimised kernel (falls back to 1 when it cannot run)
@@ -208,6 +209,8 @@ struct ExactSource {
   int bits;
 };
 
+int plan_ctas_hint(const dq_context *ctx, uint32_t K) { return split2_plan(ctx->split_ctas, ctx->sm_count, K, true).grid; }
+
 // Runs the divisive phase on ctx->d_pts0[0..U).  U is read on the device from d_cb->ucount.
 // Leaves palette/result/ctl in ctx->h_cb / ctx->h_small after a stream synchronisation.
 // Returns the number of palette entries.
@@ -272,7 +275,7 @@ uint32_t run_split(dq_context *ctx, uint32_t point_capacity, double norm, uint32
     ctx->d_ctl_f64.ensure((size_t)8 * K + node_cap + 16);
     a.g_cluster_tse = ctx->d_ctl_f64.ptr;
     a.exact_small_max = std::min<uint32_t>(ctx->exact_max_points, kExactMaxPoints);
-    ctx->d_exact.ensure(split_exact_scratch_bytes() / 8 + 1);
+    ctx->d_exact.ensure((split_exact_scratch_bytes() + ((size_t)8 * K + 16 + 64) * sizeof(uint32_t)) / 8 + 2);
     sampling = exact_sampling(exact->d_in, exact->rows, exact->cols, exact->dec, exact->bits);
   }
   if (use_v2) {
@@ -302,7 +305,7 @@ uint32_t run_split(dq_context *ctx, uint32_t point_capacity, double norm, uint32
     }
     const bool fuse = exact_path && split2_plan(0, ctx->sm_count, K, true).smem_bytes >= split_exact_smem_bytes();
     if (fuse) {
-      x.exact_fused = 1;
+      x.exact_fused = (ctx->exact_parallel && plan_ctas_hint(ctx, K) > 1) ? 2 : 1;
       x.exact_src = sampling;
       x.exact_first_seen = ctx->d_map;
       x.exact_scratch = reinterpret_cast<unsigned char *>(ctx->d_exact.ptr);
@@ -632,6 +635,7 @@ dq_context *dq_context_create(int device) {
   ctx->display_timings = display_timings_default();
   if (const char *e = getenv("DIVQUANT_B200_SPLIT")) ctx->split_version = (e[0] == '1') ? 1 : 2;
   if (const char *e = getenv("DIVQUANT_B200_EXACT_SMALL")) ctx->exact_small = (e[0] != '0');
+  if (const char *e = getenv("DIVQUANT_B200_EXACT_PARALLEL")) ctx->exact_parallel = (e[0] != '0');
   if (const char *e = getenv("DIVQUANT_B200_EXACT_MAX")) ctx->exact_max_points = (uint32_t)std::min<long>(std::max<long>(atol(e), 0), kExactMaxPoints);
   DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   return ctx;

@@ -155,6 +155,8 @@ __device__ __forceinline__ void grid_barrier2(const SplitArgs &A, unsigned int &
   __syncthreads();
 }
 
+#include "dq_split_ordered.cuh"
+
 __device__ __forceinline__ void trace2(const SplitArgs &A, int tag, int arg) {
   if (A.timeline != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
     const unsigned long long n = A.timeline[0];
@@ -803,6 +805,17 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
     // small input: the reference's own summation order (dq_split_exact.cuh); stand-alone kernels did it unless fused
     if (X.exact_fused && U > 0u) {
       exact_first_seen(X.exact_src, X.exact_first_seen, (uint32_t)(b * T + tid), (uint32_t)(G * T));
+      if (X.exact_fused == 2u && (U > (uint32_t)exact::kSmemPoints || K >= 32)) {
+        // (few splits of a small input: CTA 0 alone, with everything in shared memory, is quicker)
+        // all CTAs: controller on CTA 0, the others split leaves ahead of it (dq_split_ordered.cuh)
+        const ordered::Scratch og = ordered::carve(X.exact_scratch, A.node_cap);
+        for (uint32_t i = (uint32_t)(b * T + tid); i < A.node_cap; i += (uint32_t)(G * T)) og.state[i] = ordered::kInvalid;
+        if (b == 0 && tid < 4) og.counters[tid] = 0u;
+        grid_barrier2(A, bar_target, X.progress);
+        ordered::run(A, X, (int)U, smem_raw, b);
+        if (b == 0) publish_mailbox(A, U);
+        return;
+      }
       grid_barrier2(A, bar_target, X.progress);
       if (b == 0) {
         const size_t Kz = (size_t)K;

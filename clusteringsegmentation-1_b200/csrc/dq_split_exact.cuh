@@ -74,7 +74,11 @@ struct Points {
   uint32_t *colour;
   uint16_t *member;  // K <= kExactMaxColors <= 65535
   uint16_t *cur;     // points of the cluster being split, ascending original order (:929-1019)
+  bool cur_shared_across_ctas;  // index lists written by other CTAs: read them past the (incoherent) L1
 };
+__device__ __forceinline__ int load_cur(const Points &P, int j) {
+  return P.cur_shared_across_ctas ? (int)__ldcg(P.cur + j) : (int)P.cur[j];
+}
 constexpr size_t kScratchBytes = (size_t)kExactMaxPoints * (8 + 8 + 4 + 2 + 2);
 
 __device__ __forceinline__ double chan(uint32_t p, int c) { return byte_to_double((p >> (16 - 8 * c)) & 0xFFu); }
@@ -171,7 +175,7 @@ __device__ __forceinline__ bool pass_sums(Shared &S, const Points &P, int cur_n,
     const int lo = base + min(tid * per, n_here), hi = base + min(tid * per + per, n_here);
     unsigned mask = 0;
     for (int j = lo; j < hi; ++j) {
-      const int idx = P.cur[j];
+      const int idx = load_cur(P, j);
       const bool is_new = pred(P.colour[idx]);
       each(idx, is_new);
       mask |= (unsigned)is_new << (j - lo);
@@ -187,7 +191,7 @@ __device__ __forceinline__ bool pass_sums(Shared &S, const Points &P, int cur_n,
       int rank = first;
       for (int j = lo; j < hi; ++j) {
         if ((mask >> (j - lo)) & 1u) {
-          if (rank >= tile && rank < tile + kTile) store_terms(S, P, rank - tile, P.cur[j], nchains);
+          if (rank >= tile && rank < tile + kTile) store_terms(S, P, rank - tile, load_cur(P, j), nchains);
           ++rank;
         }
       }
@@ -234,9 +238,11 @@ __device__ __forceinline__ void derive_hyperplane(Shared &S) {
 }
 
 // split pass + max_iters LKM passes of one split (:438-811)
+// prev_masks[kMaxChunks] is the caller's: on return it holds the membership masks of the last pass (bit q of chunk ci
+// = this thread's q-th point of that chunk is on the new side).  mark_members: also write P.member (single-CTA form).
 template <int THREADS, bool SOLO>
-__device__ __forceinline__ void split_passes(Shared &S, const Points &P, int cur_n, int max_iters, int new_index, int old_index) {
-  unsigned prev_masks[kMaxChunks];
+__device__ __forceinline__ void split_passes(Shared &S, const Points &P, int cur_n, int max_iters, int new_index, int old_index,
+                                             unsigned *prev_masks, bool mark_members) {
 #pragma unroll
   for (int i = 0; i < kMaxChunks; ++i) prev_masks[i] = 0xFFFFFFFFu;  // a piece has at most 16 points: never a real mask
   {
@@ -256,7 +262,7 @@ __device__ __forceinline__ void split_passes(Shared &S, const Points &P, int cur
           return !(lhs < dot);  // (:683)
         },
         [&](int idx, bool is_new) {
-          if (last) P.member[idx] = (uint16_t)(is_new ? new_index : old_index);
+          if (last && mark_members) P.member[idx] = (uint16_t)(is_new ? new_index : old_index);
         });
     derive_centres<SOLO>(S, last);
     // Same new side as in the previous pass: the same sums, hence the same centres and the same side again, until
@@ -285,12 +291,14 @@ __device__ void split_exact_body(const SplitArgs &A, int U, unsigned char *smem,
   Points P;
   if (U <= kSmemPoints) {
     P.keys = S.keys, P.w = S.w, P.colour = S.colour, P.member = S.member, P.cur = S.cur;
+    P.cur_shared_across_ctas = false;
   } else {
     P.keys = reinterpret_cast<unsigned long long *>(scratch);
     P.w = reinterpret_cast<double *>(scratch + (size_t)kExactMaxPoints * 8);
     P.colour = reinterpret_cast<uint32_t *>(scratch + (size_t)kExactMaxPoints * 16);
     P.member = reinterpret_cast<uint16_t *>(scratch + (size_t)kExactMaxPoints * 20);
     P.cur = reinterpret_cast<uint16_t *>(scratch + (size_t)kExactMaxPoints * 22);
+    P.cur_shared_across_ctas = false;
   }
 
   // ---- points in calc_color_table's emission order: (bucket asc, first seen desc) ----
@@ -375,10 +383,13 @@ __device__ void split_exact_body(const SplitArgs &A, int U, unsigned char *smem,
       S.cut = cut;
     }
     __syncthreads();
-    if (cur_n <= kSolo) {
-      if (warp == 0) split_passes<THREADS, true>(S, P, cur_n, A.max_iters, new_index, old_index);
-    } else {
-      split_passes<THREADS, false>(S, P, cur_n, A.max_iters, new_index, old_index);
+    {
+      unsigned masks[kMaxChunks];
+      if (cur_n <= kSolo) {
+        if (warp == 0) split_passes<THREADS, true>(S, P, cur_n, A.max_iters, new_index, old_index, masks, true);
+      } else {
+        split_passes<THREADS, false>(S, P, cur_n, A.max_iters, new_index, old_index, masks, true);
+      }
     }
     __syncthreads();
 
