@@ -812,7 +812,7 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
         for (uint32_t i = (uint32_t)(b * T + tid); i < A.node_cap; i += (uint32_t)(G * T)) og.state[i] = ordered::kInvalid;
         if (b == 0 && tid < 4) og.counters[tid] = 0u;
         grid_barrier2(A, bar_target, X.progress);
-        ordered::run(A, X, (int)U, smem_raw, b);
+        ordered::run(A, X, (int)U, smem_raw, b, G, bar_target);
         if (b == 0) publish_mailbox(A, U);
         return;
       }

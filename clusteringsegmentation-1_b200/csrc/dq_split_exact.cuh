@@ -93,9 +93,7 @@ __device__ __forceinline__ void group_sync() {
   else __syncthreads();
 }
 
-__device__ __forceinline__ void store_terms(Shared &S, const Points &P, int slot, int idx, int nchains) {
-  const double wt = P.w[idx];
-  const uint32_t p = P.colour[idx];
+__device__ __forceinline__ void store_terms(Shared &S, int slot, double wt, uint32_t p, int nchains) {
   S.terms[0][slot] = fmul(wt, chan(p, 0));
   S.terms[1][slot] = fmul(wt, chan(p, 1));
   S.terms[2][slot] = fmul(wt, chan(p, 2));
@@ -173,12 +171,23 @@ __device__ __forceinline__ bool pass_sums(Shared &S, const Points &P, int cur_n,
     const int n_here = min(chunk, cur_n - base);
     const int per = (n_here + gsize - 1) / gsize;  // <= kPiece
     const int lo = base + min(tid * per, n_here), hi = base + min(tid * per + per, n_here);
+    // four points at a time: their index and colour loads are issued together (L2 round trips in the global mode)
     unsigned mask = 0;
-    for (int j = lo; j < hi; ++j) {
-      const int idx = load_cur(P, j);
-      const bool is_new = pred(P.colour[idx]);
-      each(idx, is_new);
-      mask |= (unsigned)is_new << (j - lo);
+    for (int j0 = lo; j0 < hi; j0 += 4) {
+      int idx[4];
+      uint32_t col[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) idx[q] = (j0 + q < hi) ? load_cur(P, j0 + q) : 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) col[q] = (j0 + q < hi) ? P.colour[idx[q]] : 0u;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (j0 + q < hi) {
+          const bool is_new = pred(col[q]);
+          each(idx[q], is_new);
+          mask |= (unsigned)is_new << (j0 + q - lo);
+        }
+      }
     }
     const bool changed = (mask != prev_masks[ci]);
     prev_masks[ci] = mask;
@@ -189,10 +198,27 @@ __device__ __forceinline__ bool pass_sums(Shared &S, const Points &P, int cur_n,
     for (int tile = 0; tile < total; tile += kTile) {
       // my new-side points have ranks [first, first + mine): stage those that fall into this tile
       int rank = first;
-      for (int j = lo; j < hi; ++j) {
-        if ((mask >> (j - lo)) & 1u) {
-          if (rank >= tile && rank < tile + kTile) store_terms(S, P, rank - tile, load_cur(P, j), nchains);
-          ++rank;
+      for (int j0 = lo; j0 < hi; j0 += 4) {
+        int idx[4];
+        double wt[4];
+        uint32_t col[4];
+        bool take[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          take[q] = (j0 + q < hi) && ((mask >> (j0 + q - lo)) & 1u);
+          idx[q] = take[q] ? load_cur(P, j0 + q) : 0;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          wt[q] = take[q] ? P.w[idx[q]] : 0.0;
+          col[q] = take[q] ? P.colour[idx[q]] : 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (take[q]) {
+            if (rank >= tile && rank < tile + kTile) store_terms(S, rank - tile, wt[q], col[q], nchains);
+            ++rank;
+          }
         }
       }
       group_sync<SOLO>();

@@ -233,12 +233,70 @@ __device__ int pick_leaf(const SplitArgs &A, const Scratch &G, int K) {
 
 // The whole divisive phase of one input on all CTAs.  Called by every thread of every CTA after the first-seen pass and
 // the grid barrier that follows it; state[] = kInvalid and counters[] = 0 were set before that barrier.
-__device__ void run(const SplitArgs &A, const Split2Extra &X, int U, unsigned char *smem, int b) {
+__device__ void run(const SplitArgs &A, const Split2Extra &X, int U, unsigned char *smem, int b, int nctas, unsigned int &bar_target) {
   Shared &S = *reinterpret_cast<Shared *>(smem);
   const Scratch G = carve(X.exact_scratch, A.node_cap);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int K = (int)A.num_colors;
   __shared__ uint32_t s_flag;
+
+  // ---- points in calc_color_table's emission order: (bucket asc, first seen desc) -- bitonic sort of the keys by the
+  //      whole grid (one barrier per step; every thread loads its pairs before it stores any of them) ----
+  {
+    int sort_n = 32;
+    while (sort_n < U) sort_n <<= 1;
+    const int gthreads = nctas * T, gtid = b * T + tid;
+    for (int i = gtid; i < sort_n; i += gthreads) {
+      unsigned long long key = ~0ull;
+      if (i < U) {
+        const uint32_t c = X.collect_uniq[i];
+        const long R = (c >> 16) & 0xFF, Gc = (c >> 8) & 0xFF, B = c & 0xFF;
+        const unsigned long long bucket = (unsigned long long)(((R * 33023 + Gc * 30013 + B * 27011) & 0x7fffffff) % 20023);
+        key = (bucket << (32 + exact::kIndexBits)) |
+              ((unsigned long long)(0xFFFFFFFFu - ld_cg_u32(X.exact_first_seen + c)) << exact::kIndexBits) | (unsigned long long)i;
+      }
+      G.keys[i] = key;
+    }
+    grid_barrier2(A, bar_target, X.progress);
+    const int half = sort_n >> 1;
+    for (int k = 2; k <= sort_n; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int p0 = gtid; p0 < half; p0 += 2 * gthreads) {  // two compare-exchanges per trip
+          int i[2];
+          unsigned long long x[2], y[2];
+          bool live[2];
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int pr = p0 + q * gthreads;
+            live[q] = pr < half;
+            i[q] = ((pr & ~(j - 1)) << 1) | (pr & (j - 1));  // the pr-th index whose bit j is clear
+            x[q] = live[q] ? __ldcg(G.keys + i[q]) : 0ull;
+            y[q] = live[q] ? __ldcg(G.keys + (i[q] | j)) : 0ull;
+          }
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const bool up = (i[q] & k) == 0;
+            if (live[q] && (x[q] > y[q]) == up) {
+              __stcg(G.keys + i[q], y[q]);
+              __stcg(G.keys + (i[q] | j), x[q]);
+            }
+          }
+        }
+        grid_barrier2(A, bar_target, X.progress);
+      }
+    }
+    // the points in that order: colour, weight, identity index list; the count table is zeroed on the way
+    for (int i = gtid; i < U; i += gthreads) {
+      const uint32_t c = X.collect_uniq[(int)(__ldcg(G.keys + i) & ((1ull << exact::kIndexBits) - 1ull))];
+      const uint32_t count = X.collect_table[c];
+      X.collect_table[c] = 0u;  // the count table is all-zero again when the call ends
+      G.colour[i] = c;
+      G.w[i] = fmul(A.norm, (double)(int)count);  // weights[i] = weight * count (:185)
+      G.idx[0][i] = (uint16_t)i;
+      A.pts[0][i] = make_uint2(c, count);
+    }
+    grid_barrier2(A, bar_target, X.progress);
+  }
 
   if (b != 0) {
     // ================= worker =================
@@ -289,43 +347,6 @@ __device__ void run(const SplitArgs &A, const Split2Extra &X, int U, unsigned ch
   Points P;
   P.keys = G.keys, P.w = G.w, P.colour = G.colour, P.member = nullptr, P.cur = G.idx[0];
   P.cur_shared_across_ctas = true;
-  // ---- points in calc_color_table's emission order: (bucket asc, first seen desc) ----
-  int sort_n = 32;
-  while (sort_n < U) sort_n <<= 1;
-  for (int i = tid; i < sort_n; i += T) {
-    unsigned long long key = ~0ull;
-    if (i < U) {
-      const uint32_t c = X.collect_uniq[i];
-      const long R = (c >> 16) & 0xFF, Gc = (c >> 8) & 0xFF, B = c & 0xFF;
-      const unsigned long long bucket = (unsigned long long)(((R * 33023 + Gc * 30013 + B * 27011) & 0x7fffffff) % 20023);
-      key = (bucket << (32 + exact::kIndexBits)) |
-            ((unsigned long long)(0xFFFFFFFFu - ld_cg_u32(X.exact_first_seen + c)) << exact::kIndexBits) | (unsigned long long)i;
-    }
-    P.keys[i] = key;
-  }
-  __syncthreads();
-  for (int k = 2; k <= sort_n; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = tid; i < sort_n; i += T) {
-        const int partner = i ^ j;
-        if (partner > i) {
-          const unsigned long long x = P.keys[i], y = P.keys[partner];
-          const bool up = (i & k) == 0;
-          if ((x > y) == up) P.keys[i] = y, P.keys[partner] = x;
-        }
-      }
-      __syncthreads();
-    }
-  }
-  for (int i = tid; i < U; i += T) {
-    const uint32_t c = X.collect_uniq[(int)(P.keys[i] & ((1ull << exact::kIndexBits) - 1ull))];
-    const uint32_t count = X.collect_table[c];
-    X.collect_table[c] = 0u;  // the count table is all-zero again when the call ends
-    P.colour[i] = c;
-    P.w[i] = fmul(A.norm, (double)(int)count);  // weights[i] = weight * count (:185)
-    G.idx[0][i] = (uint16_t)i;
-    A.pts[0][i] = make_uint2(c, count);
-  }
   // cluster arrays of the reference (:296-324): cluster -> node and tse[]
   double *ctse = (K <= exact::kSmemColors) ? S.k_tse : X.exact_f64;
   int32_t *cnode = (K <= exact::kSmemColors) ? S.k_size : X.exact_i32;
