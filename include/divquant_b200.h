@@ -121,8 +121,9 @@ void dq_context_set_split_ctas(dq_context *ctx, int num_ctas);
 /* Weighted inputs (allPixelsUnique = 0) of at most `max_points` unique colours (and K <= 4096) are split by code that
  * adds in the reference's own order (calc_color_table emission order, one sequential double sum per accumulator), so
  * that even decisions that sit exactly on a tie come out as in the reference: bit-exact palettes.  Larger inputs use
- * exact integer sums: identical unless such a tie occurs (DESIGN.md 5.2 has the measured rates).  The ordered path is
- * one CTA walking sequential chains: ~0.2 ms for 100 colours, ~3.5 ms for 4096, ~10 ms for 65536 (K = 256).
+ * exact integer sums: identical unless such a tie occurs (DESIGN.md 5.2 has the measured rates).  The ordered path
+ * adds sequential chains, one CTA per cluster: ~0.2 ms for 100 colours, ~1.2 ms for 4096, ~3 ms for 16384, 6-10 ms
+ * for 65536 (K = 256).
  * max_points: 0..65536, default 65536 (environment DIVQUANT_B200_EXACT_MAX); dq_context_set_exact_small(ctx, 0)
  * (environment DIVQUANT_B200_EXACT_SMALL=0) turns the ordered path off altogether. */
 void dq_context_set_exact_max_points(dq_context *ctx, uint32_t max_points);
