@@ -32,6 +32,28 @@ __global__ void __launch_bounds__(256) k_red(const uint4 *in, uint32_t nvec, uin
     for (int k = 0; k < 4; ++k) { atomicAdd(table + c[k], 1u); if (flags) flags[c[k] >> 8] = 1; }
   }
 }
+// warp-merged: equal colours among the 32 lanes (pixel k of each thread) are counted by one lane
+__global__ void __launch_bounds__(256) k_atom_match(const uint4 *in, uint32_t nvec, uint32_t *table, uint32_t *uniq, uint32_t *ucount) {
+  const uint32_t nround = (nvec + 31u) & ~31u;
+  const int lane = threadIdx.x & 31;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += gridDim.x * blockDim.x) {
+    const bool ok = i < nvec;
+    uint4 p = ok ? __ldcs(in + i) : make_uint4(0, 0, 0, 0);
+    uint32_t c[4] = {p.x & 0xFFFFFF, p.y & 0xFFFFFF, p.z & 0xFFFFFF, p.w & 0xFFFFFF};
+    uint32_t old[4] = {1u, 1u, 1u, 1u};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const unsigned m = __match_any_sync(0xffffffffu, ok ? c[k] : 0xFFFFFFFFu);
+      if (ok && lane == __ffs(m) - 1) old[k] = atomicAdd(table + c[k], (uint32_t)__popc(m));
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      bool fresh = old[k] == 0u;
+      unsigned m = __ballot_sync(0xffffffffu, fresh);
+      if (m) { uint32_t base = 0; if (lane == __ffs(m) - 1) base = atomicAdd(ucount, __popc(m)); base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1); if (fresh) uniq[base + __popc(m & ((1u << lane) - 1))] = c[k]; }
+    }
+  }
+}
 // RED for the count + a 2 MB bitmap for "seen": a plain (cacheable) read filters the pixels whose colour is known
 // already, only the others pay an atomicOr with return; the thread that flips the bit appends the colour.
 __global__ void __launch_bounds__(256) k_red_bitmap(const uint4 *in, uint32_t nvec, uint32_t *table, uint32_t *bitmap, uint32_t *uniq, uint32_t *ucount) {
@@ -96,6 +118,16 @@ int main() {
       cudaEventRecord(e1); CK(cudaDeviceSynchronize()); cudaEventElapsedTime(&ms, e0, e1);
       uint32_t u; CK(cudaMemcpy(&u, ucount, 4, cudaMemcpyDeviceToHost));
       if (rep == 2) printf("atom+append  grid %5d: %.1f us  U=%u\n", grid, ms * 1e3, u);
+      clear_uniq<<<592, 256>>>(table, uniq, ucount); CK(cudaDeviceSynchronize());
+    }
+  }
+  for (int grid : {1184, 2368}) {
+    for (int rep = 0; rep < 3; ++rep) {
+      CK(cudaMemset(ucount, 0, 4)); cudaEventRecord(e0);
+      k_atom_match<<<grid, 256>>>((uint4 *)px, N / 4, table, uniq, ucount);
+      cudaEventRecord(e1); CK(cudaDeviceSynchronize()); cudaEventElapsedTime(&ms, e0, e1);
+      uint32_t u; CK(cudaMemcpy(&u, ucount, 4, cudaMemcpyDeviceToHost));
+      if (rep == 2) printf("atom+match   grid %5d: %.1f us  U=%u\n", grid, ms * 1e3, u);
       clear_uniq<<<592, 256>>>(table, uniq, ucount); CK(cudaDeviceSynchronize());
     }
   }
