@@ -993,7 +993,6 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
       const bool wide = sz > kNarrowMax;
       const uint32_t tiles = wide ? (sz + kWideTile - 1) / kWideTile : 0u;
       R.tile0[j] = tiles;
-      R.slot0[j] = min(tiles, (uint32_t)G);
       R.nidx[j] = wide ? 0u : 1u;
     }
     __syncthreads();
@@ -1002,6 +1001,20 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
       R.tile0[njobs] = (uint32_t)S.scan_carry;
       S.nwide_tiles = S.scan_carry;
     }
+    __syncthreads();
+    // Wide tiles are dealt to the CTAs in contiguous blocks of the round's tile sequence (sizes differ by at most one),
+    // so a job spans as few CTAs as possible: with few CTAs per frame (frame pipeline) a CTA then takes part in two
+    // or three jobs per pass instead of all of them, and a CTA's share of a job is one contiguous range of points.
+    const uint32_t tq = (uint32_t)S.nwide_tiles / (uint32_t)G, tr = (uint32_t)S.nwide_tiles % (uint32_t)G;
+    auto cta_start = [&](uint32_t c) -> uint32_t { return c * tq + min(c, tr); };  // first tile of CTA c
+    auto tile_owner = [&](uint32_t g) -> uint32_t {
+      return (g < tr * (tq + 1u)) ? g / (tq + 1u) : tr + (g - tr * (tq + 1u)) / max(tq, 1u);
+    };
+    for (int j = tid; j < njobs; j += T) {
+      const uint32_t g0 = R.tile0[j], g1 = R.tile0[j + 1];
+      R.slot0[j] = (g1 > g0) ? tile_owner(g1 - 1u) - tile_owner(g0) + 1u : 0u;  // participants of the job
+    }
+    __syncthreads();
     block_scan(S, R.slot0, njobs);
     if (tid == 0) R.slot0[njobs] = (uint32_t)S.scan_carry;
     block_scan(S, R.nidx, njobs);
@@ -1020,10 +1033,9 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
     ordered_compact(
         S, 0, njobs,
         [&](int j) {
-          const uint32_t tiles = R.tile0[j + 1] - R.tile0[j];
-          if (tiles == 0) return false;
-          const uint32_t i = (uint32_t)(b + G - (int)(R.tile0[j] % (uint32_t)G)) % (uint32_t)G;
-          return i < min(tiles, (uint32_t)G);
+          const uint32_t g0 = R.tile0[j], g1 = R.tile0[j + 1];
+          if (g1 == g0) return false;
+          return tile_owner(g0) <= (uint32_t)b && (uint32_t)b <= tile_owner(g1 - 1u);
         },
         [&](int pos, int j) { R.mywide[pos] = (uint16_t)j; }, &S.n_mywide);
     ordered_compact(
@@ -1066,16 +1078,20 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
       if (mw < kWideCache) return S.wide[mw];
       return job_const_of(load_node(A, S, R.jobnode[R.mywide[mw]]));
     };
-    // q-th point of this CTA's share -> offset inside the job's segment
-    auto share_offset = [&](uint32_t q, uint32_t me) -> uint32_t {
-      return ((q / kWideTile) * (uint32_t)G + me) * kWideTile + (q % kWideTile);
+    // This CTA's share of wide job j: participants, my rank among them, my first point and how many.
+    struct Share {
+      uint32_t m, me, first_point, n_my;
     };
-    auto share_points = [&](uint32_t tiles, uint32_t me, uint32_t size) -> uint32_t {
-      if (me >= tiles) return 0u;
-      const uint32_t mine = (tiles - me + (uint32_t)G - 1) / (uint32_t)G;  // my tiles
-      const uint32_t last = me + (mine - 1) * (uint32_t)G;                 // my last tile
-      const uint32_t tail = (last == tiles - 1) ? size - last * kWideTile : kWideTile;
-      return (mine - 1) * kWideTile + tail;
+    auto share_of = [&](int j, uint32_t size) -> Share {
+      const uint32_t g0 = R.tile0[j], g1 = R.tile0[j + 1];
+      const uint32_t first = tile_owner(g0), last = tile_owner(g1 - 1u);
+      Share sh;
+      sh.m = last - first + 1u;
+      sh.me = (uint32_t)b - first;
+      const uint32_t lo = max(g0, cta_start((uint32_t)b)) - g0, hi = min(g1, cta_start((uint32_t)b + 1u)) - g0;  // my tiles of it
+      sh.first_point = lo * kWideTile;
+      sh.n_my = min(hi * kWideTile, size) - sh.first_point;
+      return sh;
     };
     // The points of a CTA's share do not change during a round: with a single wide job (the common case) they
     // are loaded once and stay in registers for all passes.
@@ -1084,15 +1100,14 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
     if (single_wide) {
       const int j = R.mywide[0];
       const JobConst jc = wide_const(0);
-      const uint32_t tiles = R.tile0[j + 1] - R.tile0[j];
-      const uint32_t me = (uint32_t)(b + G - (int)(R.tile0[j] % (uint32_t)G)) % (uint32_t)G;
-      const uint32_t n_my = share_points(tiles, me, jc.size);
+      const Share sh = share_of(j, jc.size);
+      const uint32_t n_my = sh.n_my;
       const uint32_t nthr = min((uint32_t)T, (n_my + 31u) & ~31u);
 #pragma unroll
       for (int k = 0; k < kWidePPT; ++k) {
         const uint32_t q = (uint32_t)tid + (uint32_t)k * nthr;
         pre0[k] = make_uint2(0, 0);
-        if ((uint32_t)tid < nthr && q < n_my) pre0[k] = ld_cg_u2(A.pts[jc.buf] + jc.begin + share_offset(q, me));
+        if ((uint32_t)tid < nthr && q < n_my) pre0[k] = ld_cg_u2(A.pts[jc.buf] + jc.begin + sh.first_point + q);
       }
     }
     for (int pass = 0; pass <= P; ++pass) {
@@ -1101,10 +1116,10 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
       for (int mw = 0; mw < n_mywide; ++mw) {
         const int j = R.mywide[mw];
         const JobConst jc = wide_const(mw);
-        const uint32_t tiles = R.tile0[j + 1] - R.tile0[j];
-        const int m = (int)min(tiles, (uint32_t)G);
-        const uint32_t me = (uint32_t)(b + G - (int)(R.tile0[j] % (uint32_t)G)) % (uint32_t)G;
-        const uint32_t n_my = share_points(tiles, me, jc.size);
+        const Share sh = share_of(j, jc.size);
+        const int m = (int)sh.m;
+        const uint32_t me = sh.me;
+        const uint32_t n_my = sh.n_my;
         const uint32_t nthr = min((uint32_t)T, (n_my + 31u) & ~31u);  // spread over as many warps as there are points for
         // prefetch the first points of this CTA's share while the previous pass's totals arrive
         uint2 pre[kWidePPT];
@@ -1114,7 +1129,7 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
           pre[k] = pre0[k];
           if (!single_wide) {
             pre[k] = make_uint2(0, 0);
-            if ((uint32_t)tid < nthr && q < n_my) pre[k] = ld_cg_u2(A.pts[jc.buf] + jc.begin + share_offset(q, me));
+            if ((uint32_t)tid < nthr && q < n_my) pre[k] = ld_cg_u2(A.pts[jc.buf] + jc.begin + sh.first_point + q);
           }
         }
 #ifdef DQ_PROFILE_NARROW
@@ -1138,7 +1153,7 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
         uint64_t v[kAccWords];
         {
           const uint2 *seg = A.pts[jc.buf] + jc.begin;
-          auto off = [&](uint32_t q) { return share_offset(q, me); };
+          auto off = [&](uint32_t q) { return sh.first_point + q; };
           if (pass == 0) wide_classify<true, false>(pp, pre, n_my, nthr, seg, off, v);
           else if (pass == P) wide_classify<false, true>(pp, pre, n_my, nthr, seg, off, v);
           else wide_classify<false, false>(pp, pre, n_my, nthr, seg, off, v);
@@ -1181,9 +1196,9 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
     for (int mw = 0; mw < n_mywide; ++mw) {
       const int j = R.mywide[mw];
       const JobConst jc = wide_const(mw);
-      const uint32_t tiles = R.tile0[j + 1] - R.tile0[j];
-      const int m = (int)min(tiles, (uint32_t)G);
-      const uint32_t me = (uint32_t)(b + G - (int)(R.tile0[j] % (uint32_t)G)) % (uint32_t)G;
+      const Share sh = share_of(j, jc.size);
+      const int m = (int)sh.m;
+      const uint32_t me = sh.me;
       // classification of the last pass (parameters from the totals of pass P-1)
       if (mw >= kWideCache) {
         gather(A, S, X.slots + (size_t)((P - 1) & 1) * X.slot_cap * kAccWords, R.slot0[j], m, 5, (seq0 + P - 1) & 0xFFFFu);
@@ -1200,33 +1215,28 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
       // gathered, so the CTAs ranked before this one fix where its points start in both halves
       // (deterministic, CTA-major order); inside the CTA a per-piece prefix over the warps does the rest.
       {
-        uint32_t before_new = 0, before_all = 0;
+        // (shares are contiguous and in CTA order: the points before mine are simply those of the tiles before mine)
+        uint32_t before_new = 0;
         const unsigned long long *slots_p = X.slots + (size_t)(P & 1) * X.slot_cap * kAccWords;
-        for (uint32_t i = (uint32_t)tid; i < me; i += T) {
+        for (uint32_t i = (uint32_t)tid; i < me; i += T)
           before_new += (uint32_t)(ld_relaxed_u64(slots_p + (size_t)(R.slot0[j] + i) * kAccWords + kAccPts) & kValueMask);
-          before_all += share_points(tiles, i, jc.size);
-        }
         before_new = __reduce_add_sync(0xffffffffu, before_new);
-        before_all = __reduce_add_sync(0xffffffffu, before_all);
-        if (lane == 0) {
-          S.part_new[tid >> 5] = before_new;
-          S.part_old[tid >> 5] = before_all;
-        }
+        if (lane == 0) S.part_new[tid >> 5] = before_new;
         __syncthreads();
         if (tid == 0) {
-          uint32_t bn = 0, ba = 0;
-          for (int w = 0; w < kWarps; ++w) bn += S.part_new[w], ba += S.part_old[w];
+          uint32_t bn = 0;
+          for (int w = 0; w < kWarps; ++w) bn += S.part_new[w];
           S.base_new = bn;
-          S.base_old = ba - bn;
+          S.base_old = sh.first_point - bn;
         }
         __syncthreads();
       }
       uint32_t run_new = S.base_new, run_old = S.base_old;
       int flip = 0;
-      for (uint32_t tt = me * (kWideTile / T); tt < tiles * (kWideTile / T); tt += (tt % (kWideTile / T) == kWideTile / T - 1) ? (uint32_t)(G - 1) * (kWideTile / T) + 1 : 1u) {
-        // tt enumerates T-point pieces of this CTA's tiles: tile = tt / (kWideTile/T)
-        const uint32_t off = tt * T + tid;
-        const bool valid = off < jc.size;
+      for (uint32_t piece = 0; piece < sh.n_my; piece += T) {
+        // T-point pieces of this CTA's (contiguous) share, in order
+        const uint32_t off = sh.first_point + piece + tid;
+        const bool valid = piece + tid < sh.n_my;
         uint2 p = make_uint2(0, 0);
         if (valid) p = ld_cg_u2(A.pts[jc.buf] + jc.begin + off);
         const bool to_new = valid && goes_new(pp, false, p.x);
