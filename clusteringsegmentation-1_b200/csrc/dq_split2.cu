@@ -748,9 +748,18 @@ __device__ __forceinline__ void wide_classify(const PassParams &pp, const uint2 
         if (goes_new_t<SPLIT>(pp, to_point(pre[k]))) acc_add(acc, pre[k], FINAL);
       }
     }
-    for (uint32_t q = tid + kWidePPT * nthr; q < n_my; q += nthr) {
-      const uint2 raw = ld_cg_u2(seg + offset_of(q));
-      if (goes_new_t<SPLIT>(pp, to_point(raw))) acc_add(acc, raw, FINAL);
+    // beyond the register-resident points (few CTAs per frame): four loads in flight per trip
+    for (uint32_t q = tid + kWidePPT * nthr; q < n_my; q += 4u * nthr) {
+      uint2 raw[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t qq = q + (uint32_t)u * nthr;
+        raw[u] = (qq < n_my) ? ld_cg_u2(seg + offset_of(qq)) : make_uint2(0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (q + (uint32_t)u * nthr < n_my && goes_new_t<SPLIT>(pp, to_point(raw[u]))) acc_add(acc, raw[u], FINAL);
+      }
     }
   }
   acc_words(acc, v);
@@ -1233,12 +1242,13 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
       }
       uint32_t run_new = S.base_new, run_old = S.base_old;
       int flip = 0;
+      uint2 p_next = make_uint2(0, 0);
+      if ((uint32_t)tid < sh.n_my) p_next = ld_cg_u2(A.pts[jc.buf] + jc.begin + sh.first_point + tid);
       for (uint32_t piece = 0; piece < sh.n_my; piece += T) {
-        // T-point pieces of this CTA's (contiguous) share, in order
-        const uint32_t off = sh.first_point + piece + tid;
+        // T-point pieces of this CTA's (contiguous) share, in order; the next piece's points are already on their way
         const bool valid = piece + tid < sh.n_my;
-        uint2 p = make_uint2(0, 0);
-        if (valid) p = ld_cg_u2(A.pts[jc.buf] + jc.begin + off);
+        const uint2 p = p_next;
+        if (piece + T + tid < sh.n_my) p_next = ld_cg_u2(A.pts[jc.buf] + jc.begin + sh.first_point + piece + T + tid);
         const bool to_new = valid && goes_new(pp, false, p.x);
         const unsigned m_new = __ballot_sync(0xffffffffu, to_new);
         const unsigned m_old = __ballot_sync(0xffffffffu, valid && !to_new);
