@@ -18,7 +18,11 @@
 //    1 + max_iters passes, reductions are warp shuffles + shared memory, no global traffic.
 //  * Wide jobs span many CTAs.  Partial sums are exchanged through per-(job, CTA) slots of 8-byte
 //    words that carry their own 16-bit pass tag next to the 48-bit value, so publishing is a plain
-//    store and gathering is one polling L2 read: no atomics, no fences, no barrier per pass.
+//    store and gathering is one polling L2 read: no atomics, no fences, no barrier per pass.  The round's wide
+//    tiles are dealt to the CTAs in contiguous blocks, so a job spans as few CTAs as possible and the partition --
+//    whose destinations come from the participants' counts in those slots, not from atomics -- keeps tile order.
+//  * Inputs small enough for the reference's own summation order leave at the top of the kernel into
+//    dq_split_exact.cuh / dq_split_ordered.cuh (same launch, no host decision).
 #include <cfloat>
 #include <map>
 #include <mutex>
@@ -1079,7 +1083,7 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
     DQ_PROGRESS(round * 10000 + 1000 + n_mywide * 10 + n_mynarrow);
 
     // ================= wide jobs: all passes, partial sums exchanged through tagged slots =================
-    // A CTA's share of a wide job = tiles me, me+G, ... of kWideTile points.  It is classified by as few
+    // A CTA's share of a wide job = a contiguous run of its kWideTile-point tiles.  It is classified by as few
     // warps as possible (kWidePPT points per thread): the warp reductions, not the arithmetic, are what a
     // pass costs, so fewer, busier warps are faster.
     const unsigned seq0 = 1u + (unsigned)round * (unsigned)(P + 1);
