@@ -510,3 +510,32 @@ def test_srm_sorted_edges(dq, oracle, golden):
         got, want = dq.srm_sorted_edges(im), oracle.srm_sorted_edges(im)
         assert got.shape == want.shape and np.array_equal(got, want), (h, w, ch, levels)
     assert np.all(np.diff(pairs[:, 2].astype(np.int64)) >= 0)    # sortedness of the full-size list
+
+
+def test_ordered_path_limits_and_large_k(dq, oracle):
+    """K between 1024 and 4096 (per-cluster arrays of the ordered path in global memory, generic split kernel) and the
+    run-time limit of the ordered path: below it the reference's result, above it the exact-count model's."""
+    rng = np.random.default_rng(41)
+    px = rng.integers(0, 1 << 24, 2500, dtype=np.uint32)
+    for k in (1025, 1500, 3000):
+        with muted():
+            ref_out, ref_pal = oracle.quant_recurse(px, k, 0)
+        with muted((2,)):
+            out, pal = dq.quant_recurse(px, k, 0)
+        assert np.array_equal(pal, ref_pal) and np.array_equal(out, ref_out), k
+    ctx = dq.lib.dq_default_context()
+    px = rng.integers(0, 1 << 24, 6000, dtype=np.uint32)
+    with muted():
+        ref_pal, ref_empty = oracle.quant_varpart_fast(px, 64)
+        model, mempty = oracle.quant_varpart_fast(px, 64, exact_counts=True)
+    try:
+        dq.lib.dq_context_set_exact_max_points(ctx, 10000)   # 6000 colours <= limit: ordered
+        with muted((2,)):
+            pal, empty = dq.quant_varpart_fast(px, 64)
+        assert np.array_equal(pal, ref_pal) and empty == ref_empty
+        dq.lib.dq_context_set_exact_max_points(ctx, 5000)    # above the limit: exact-integer kernels
+        with muted((2,)):
+            pal, empty = dq.quant_varpart_fast(px, 64)
+        assert np.array_equal(pal, model) and empty == mempty
+    finally:
+        dq.lib.dq_context_set_exact_max_points(ctx, 65536)
