@@ -122,7 +122,8 @@ struct SplitArgs {
 };
 
 // Largest input (unique colours) that takes the sequential-order path of dq_split_exact.cu.
-constexpr uint32_t kExactMaxPoints = 65536;  // compile-time ceiling; the run-time limit is SplitArgs::exact_small_max
+constexpr uint32_t kExactMaxPoints = 262144;       // compile-time ceiling; the run-time limit is SplitArgs::exact_small_max
+constexpr uint32_t kExactDefaultPoints = 65536;    // its default
 constexpr uint32_t kExactMaxColors = 4096;
 // Small weighted inputs in the reference's own summation order (dq_split_exact.cuh).
 // The sampled pixels behind the histogram: needed to put the unique colours into calc_color_table's emission order.

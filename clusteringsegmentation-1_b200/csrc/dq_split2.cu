@@ -1384,7 +1384,7 @@ int split2_max_ctas(int sm_count, uint32_t num_colors) {
   auto it = cache.find(smem);
   if (it == cache.end()) {
     int per_sm = 0;
-    DQ_CUDA_CHECK(cudaFuncSetAttribute(split2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)(200 * 1024))));
+    DQ_CUDA_CHECK(cudaFuncSetAttribute(split2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)(216 * 1024))));
     DQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, split2_kernel, T, smem));
     it = cache.emplace(smem, std::max(per_sm, 1)).first;
   }

@@ -34,13 +34,13 @@ namespace dq {
 namespace exact {
 
 constexpr int kSmemPoints = 4096;  // inputs up to this size keep their point arrays in shared memory
-constexpr int kIndexBits = 16;     // sort key = bucket << 48 | (0xFFFFFFFF - first seen) << 16 | arrival index
+constexpr int kIndexBits = 18;     // sort key = bucket << 49 | (0x7FFFFFFF - first seen) << 18 | arrival index
 constexpr int kTile = 1024;        // new-side points whose terms are staged at a time
 constexpr int kSolo = 512;         // clusters up to this size are split by warp 0 alone
 constexpr int kPiece = 16;         // consecutive points a thread classifies per chunk (bits of its mask)
 constexpr int kSmemColors = 1024;
-constexpr int kMaxChunks = 16;     // kExactMaxPoints / (256 threads * kPiece)
-static_assert(kExactMaxPoints <= (1u << kIndexBits), "indices are 16-bit");
+constexpr int kMaxChunks = 64;     // kExactMaxPoints / (256 threads * kPiece)
+static_assert(kExactMaxPoints <= (1u << kIndexBits), "index bits of the sort key");
 static_assert(kSolo <= kPiece * 32 && kSolo <= kTile, "a solo pass is one chunk and one tile");
 static_assert(kExactMaxPoints <= 256u * kPiece * kMaxChunks, "chunk count");
 
@@ -52,7 +52,7 @@ struct Shared {
   double w[kSmemPoints];
   uint32_t colour[kSmemPoints];
   uint16_t member[kSmemPoints];
-  uint16_t cur[kSmemPoints];
+  uint32_t cur[kSmemPoints];
   // per-cluster arrays of the reference (:296-324) when K fits, else the global scratch is used
   double k_weight[kSmemColors], k_tse[kSmemColors], k_mean[3 * kSmemColors], k_var[3 * kSmemColors];
   int32_t k_size[kSmemColors];
@@ -73,13 +73,14 @@ struct Points {
   double *w;         // weights[] of calc_color_table (:172,185)
   uint32_t *colour;
   uint16_t *member;  // K <= kExactMaxColors <= 65535
-  uint16_t *cur;     // points of the cluster being split, ascending original order (:929-1019)
+  uint32_t *cur;     // points of the cluster being split, ascending original order (:929-1019)
   bool cur_shared_across_ctas;  // index lists written by other CTAs: read them past the (incoherent) L1
 };
 __device__ __forceinline__ int load_cur(const Points &P, int j) {
   return P.cur_shared_across_ctas ? (int)__ldcg(P.cur + j) : (int)P.cur[j];
 }
-constexpr size_t kScratchBytes = (size_t)kExactMaxPoints * (8 + 8 + 4 + 2 + 2);
+// global scratch, shared layout of both forms: keys 8 | w 8 | colour 4 | index list 4 | second index list 4 | member 2 (+2)
+constexpr size_t kScratchBytes = (size_t)kExactMaxPoints * 32;
 
 __device__ __forceinline__ double chan(uint32_t p, int c) { return byte_to_double((p >> (16 - 8 * c)) & 0xFFu); }
 __device__ __forceinline__ double chan_sq(uint32_t p, int c) {
@@ -322,8 +323,8 @@ __device__ void split_exact_body(const SplitArgs &A, int U, unsigned char *smem,
     P.keys = reinterpret_cast<unsigned long long *>(scratch);
     P.w = reinterpret_cast<double *>(scratch + (size_t)kExactMaxPoints * 8);
     P.colour = reinterpret_cast<uint32_t *>(scratch + (size_t)kExactMaxPoints * 16);
-    P.member = reinterpret_cast<uint16_t *>(scratch + (size_t)kExactMaxPoints * 20);
-    P.cur = reinterpret_cast<uint16_t *>(scratch + (size_t)kExactMaxPoints * 22);
+    P.cur = reinterpret_cast<uint32_t *>(scratch + (size_t)kExactMaxPoints * 20);
+    P.member = reinterpret_cast<uint16_t *>(scratch + (size_t)kExactMaxPoints * 28);
     P.cur_shared_across_ctas = false;
   }
 
@@ -336,7 +337,7 @@ __device__ void split_exact_body(const SplitArgs &A, int U, unsigned char *smem,
       const uint32_t c = uniq[i];
       const long R = (c >> 16) & 0xFF, G = (c >> 8) & 0xFF, B = c & 0xFF;
       const unsigned long long bucket = (unsigned long long)(((R * 33023 + G * 30013 + B * 27011) & 0x7fffffff) % 20023);
-      key = (bucket << (32 + kIndexBits)) | ((unsigned long long)(0xFFFFFFFFu - ld_cg_u32(first_seen + c)) << kIndexBits) |
+      key = (bucket << (31 + kIndexBits)) | ((unsigned long long)(0x7FFFFFFFu - ld_cg_u32(first_seen + c)) << kIndexBits) |
             (unsigned long long)i;
     }
     P.keys[i] = key;
@@ -365,7 +366,7 @@ __device__ void split_exact_body(const SplitArgs &A, int U, unsigned char *smem,
     P.colour[i] = c;
     P.w[i] = fmul(A.norm, (double)(int)count);  // weights[i] = weight * count (:185)
     P.member[i] = 0;
-    P.cur[i] = (uint16_t)i;
+    P.cur[i] = (uint32_t)i;
     A.pts[0][i] = make_uint2(c, count);
   }
   for (int i = tid; i < K; i += THREADS) {  // `new T[n]()` of the reference (:296-324)
@@ -506,7 +507,7 @@ __device__ void split_exact_body(const SplitArgs &A, int U, unsigned char *smem,
         group_ranks<THREADS, false>(S, __popc(mask), false, first, total, unused);
         int pos = written + first;
         for (int i = lo; i < hi; ++i)
-          if ((mask >> (i - lo)) & 1u) P.cur[pos++] = (uint16_t)i;
+          if ((mask >> (i - lo)) & 1u) P.cur[pos++] = (uint32_t)i;
         written += total;
       }
       if (tid == 0) {

@@ -9,7 +9,7 @@
 //   * every other CTA is a worker: it claims the not-yet-split leaf of largest TSE that can still be among the
 //     K-1 splits the reference makes (fewer than K-1 known nodes have a larger TSE) and splits it with the same
 //     ordered passes (exact::split_passes), ahead of the controller.
-// A split's points are a segment of a 16-bit index list in calc_color_table order; a split partitions its segment
+// A split's points are a segment of an index list in calc_color_table order; a split partitions its segment
 // stably into [old | new] in the other buffer, so every child sees its points in that order again.
 // Node states: 3 not valid yet, 0 leaf, 1 being split, 2 split (children valid).  All waits are bounded.
 #pragma once
@@ -29,19 +29,19 @@ struct Scratch {
   unsigned long long *keys;  // [kExactMaxPoints]
   double *w;                 // [kExactMaxPoints]
   uint32_t *colour;          // [kExactMaxPoints]
-  uint16_t *idx[2];          // [kExactMaxPoints] each: index lists, double-buffered per node
+  uint32_t *idx[2];          // [kExactMaxPoints] each: index lists, double-buffered per node
   uint32_t *state;           // [node_cap]
   uint32_t *counters;        // [0] nodes allocated  [1] ready  [2] done
 };
-constexpr size_t kScratchFixed = (size_t)kExactMaxPoints * (8 + 8 + 4 + 2 + 2);
+constexpr size_t kScratchFixed = exact::kScratchBytes;
 
 __device__ __forceinline__ Scratch carve(unsigned char *base, uint32_t node_cap) {
   Scratch s;
   s.keys = reinterpret_cast<unsigned long long *>(base);
   s.w = reinterpret_cast<double *>(base + (size_t)kExactMaxPoints * 8);
   s.colour = reinterpret_cast<uint32_t *>(base + (size_t)kExactMaxPoints * 16);
-  s.idx[0] = reinterpret_cast<uint16_t *>(base + (size_t)kExactMaxPoints * 20);
-  s.idx[1] = reinterpret_cast<uint16_t *>(base + (size_t)kExactMaxPoints * 22);
+  s.idx[0] = reinterpret_cast<uint32_t *>(base + (size_t)kExactMaxPoints * 20);
+  s.idx[1] = reinterpret_cast<uint32_t *>(base + (size_t)kExactMaxPoints * 24);
   s.state = reinterpret_cast<uint32_t *>(base + kScratchFixed);
   s.counters = s.state + node_cap;
   return s;
@@ -129,7 +129,7 @@ __device__ bool split_node(const SplitArgs &A, Shared &S, const Scratch &G, int 
   }
   // ---- stable partition of the index segment into [old | new] of the other buffer ----
   {
-    uint16_t *dst = G.idx[s_nd.buf ^ 1] + s_nd.begin;
+    uint32_t *dst = G.idx[s_nd.buf ^ 1] + s_nd.begin;
     const int gsize = solo ? 32 : T;
     const int chunk = gsize * kPiece;
     int done_new = 0, done_old = 0, ci = 0;
@@ -151,7 +151,7 @@ __device__ bool split_node(const SplitArgs &A, Shared &S, const Scratch &G, int 
         }
         int pn = old_size + done_new + first_new, po = done_old + first_old;
         for (int j = lo; j < hi; ++j) {
-          const uint16_t v = (uint16_t)exact::load_cur(P, j);
+          const uint32_t v = (uint32_t)exact::load_cur(P, j);
           if ((mask >> (j - lo)) & 1u) dst[pn++] = v;
           else dst[po++] = v;
         }
@@ -252,8 +252,8 @@ __device__ void run(const SplitArgs &A, const Split2Extra &X, int U, unsigned ch
         const uint32_t c = X.collect_uniq[i];
         const long R = (c >> 16) & 0xFF, Gc = (c >> 8) & 0xFF, B = c & 0xFF;
         const unsigned long long bucket = (unsigned long long)(((R * 33023 + Gc * 30013 + B * 27011) & 0x7fffffff) % 20023);
-        key = (bucket << (32 + exact::kIndexBits)) |
-              ((unsigned long long)(0xFFFFFFFFu - ld_cg_u32(X.exact_first_seen + c)) << exact::kIndexBits) | (unsigned long long)i;
+        key = (bucket << (31 + exact::kIndexBits)) |
+              ((unsigned long long)(0x7FFFFFFFu - ld_cg_u32(X.exact_first_seen + c)) << exact::kIndexBits) | (unsigned long long)i;
       }
       G.keys[i] = key;
     }
@@ -292,7 +292,7 @@ __device__ void run(const SplitArgs &A, const Split2Extra &X, int U, unsigned ch
       X.collect_table[c] = 0u;  // the count table is all-zero again when the call ends
       G.colour[i] = c;
       G.w[i] = fmul(A.norm, (double)(int)count);  // weights[i] = weight * count (:185)
-      G.idx[0][i] = (uint16_t)i;
+      G.idx[0][i] = (uint32_t)i;
       A.pts[0][i] = make_uint2(c, count);
     }
     grid_barrier2(A, bar_target, X.progress);

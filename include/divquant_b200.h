@@ -124,7 +124,9 @@ void dq_context_set_split_ctas(dq_context *ctx, int num_ctas);
  * exact integer sums: identical unless such a tie occurs (DESIGN.md 5.2 has the measured rates).  The ordered path
  * adds sequential chains, one CTA per cluster: ~0.2 ms for 100 colours, ~1.2 ms for 4096, ~3 ms for 16384, 6-10 ms
  * for 65536 (K = 256).
- * max_points: 0..65536, default 65536 (environment DIVQUANT_B200_EXACT_MAX); dq_context_set_exact_small(ctx, 0)
+ * max_points: 0..262144, default 65536 (environment DIVQUANT_B200_EXACT_MAX) -- every BASELINE performance config has more
+ * colours than the default (G1 1080p 118 773, 4K 125 712) and stays on the exact-integer kernels; raising the limit puts them
+ * on the ordered path too (~8 ms per 4K frame instead of 0.47); dq_context_set_exact_small(ctx, 0)
  * (environment DIVQUANT_B200_EXACT_SMALL=0) turns the ordered path off altogether. */
 void dq_context_set_exact_max_points(dq_context *ctx, uint32_t max_points);
 void dq_context_set_exact_small(dq_context *ctx, int enabled);

@@ -539,3 +539,24 @@ def test_ordered_path_limits_and_large_k(dq, oracle):
         assert np.array_equal(pal, model) and empty == mempty
     finally:
         dq.lib.dq_context_set_exact_max_points(ctx, 65536)
+
+
+def test_ordered_path_above_the_default_limit(dq, oracle, golden):
+    """The ordered path goes up to 262 144 colours when asked to: a G1 frame with 68 296 colours on which the exact-integer
+    kernels differ from the reference in one palette entry (an exact tie), and the 1080p K=64 BASELINE frame (118 773)."""
+    ctx = dq.lib.dq_default_context()
+    g1 = oracle.generate(1, 400, 300, 3)
+    with muted():
+        ref_out, ref_pal = oracle.quant_recurse(g1, 64, 0)
+    try:
+        dq.lib.dq_context_set_exact_max_points(ctx, 262144)
+        with muted((2,)):
+            out, pal = dq.quant_recurse(g1, 64, 0)
+        assert np.array_equal(pal, ref_pal) and np.array_equal(out, ref_out)
+        px = oracle.generate(1, 1920, 1080)
+        with muted((2,)):
+            out, pal = dq.quant_recurse(px, 64, 0)
+        assert np.array_equal(pal, golden["g1_1080_k64_palette"])
+        assert oracle.hash_words(out) == int(golden["g1_1080_k64_out_hash"][0])
+    finally:
+        dq.lib.dq_context_set_exact_max_points(ctx, 65536)
