@@ -38,7 +38,7 @@ constexpr int kIndexBits = 18;     // sort key = bucket << 49 | (0x7FFFFFFF - fi
 constexpr int kTile = 1024;        // new-side points whose terms are staged at a time
 constexpr int kSolo = 512;         // clusters up to this size are split by warp 0 alone
 constexpr int kPiece = 16;         // consecutive points a thread classifies per chunk (bits of its mask)
-constexpr int kSmemColors = 1024;
+constexpr int kSmemColors = 896;   // (keeps sizeof(Shared) below the 196 KB shared-memory carve-out step)
 constexpr int kMaxChunks = 64;     // kExactMaxPoints / (256 threads * kPiece)
 static_assert(kExactMaxPoints <= (1u << kIndexBits), "index bits of the sort key");
 static_assert(kSolo <= kPiece * 32 && kSolo <= kTile, "a solo pass is one chunk and one tile");
@@ -66,6 +66,10 @@ struct Shared {
   double lhs, rr[3], cut;
   int32_t axis;
 };
+
+// One CTA of the split kernel per SM holds this much dynamic shared memory; above the 196 KB carve-out step the SM falls
+// back to the 228 KB configuration, which cost the frame pipeline 10-40 % (measured), so stay below it.
+static_assert(sizeof(Shared) <= 196 * 1024 - 4096, "keep the fused ordered path under the 196 KB shared-memory carve-out");
 
 // The per-point arrays: shared memory (U <= kSmemPoints) or the global scratch.
 struct Points {
