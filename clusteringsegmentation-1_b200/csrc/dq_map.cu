@@ -16,6 +16,7 @@
 //     the answer is parked in the 2^24-entry direct table; pixels then gather through it.  Used
 //     whenever a histogram of the same pixels is at hand (quant_recurse always has one).
 #include <algorithm>
+#include <atomic>
 
 #include "dq_kernels.cuh"
 
@@ -380,7 +381,7 @@ void map_pixels(const uint32_t *d_in, uint32_t n, uint32_t *d_out, const uint32_
   const bool aligned = ((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_out)) & 15u) == 0;
   if (num_colors <= map_smem_palette_limit() && aligned) {
     const size_t smem = fast_smem_bytes(num_colors);
-    static size_t configured = 0;
+    static std::atomic<size_t> configured{0};  // lanes call this from several host threads
     if (smem > 48 * 1024 && smem > configured) {
       DQ_CUDA_CHECK(cudaFuncSetAttribute(map_pixels_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       configured = smem;
@@ -391,7 +392,7 @@ void map_pixels(const uint32_t *d_in, uint32_t n, uint32_t *d_out, const uint32_
         d_in, n, d_out, d_sorted, num_colors, d_lut);
   } else if (num_colors <= map_smem_palette_limit()) {
     const size_t smem = map_smem_bytes(num_colors);
-    static size_t configured = 0;
+    static std::atomic<size_t> configured{0};  // lanes call this from several host threads
     if (smem > 48 * 1024 && smem > configured) {
       DQ_CUDA_CHECK(cudaFuncSetAttribute(map_pixels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       configured = smem;
@@ -410,7 +411,7 @@ void map_pixels(const uint32_t *d_in, uint32_t n, uint32_t *d_out, const uint32_
 void map_unique(const uint32_t *d_uniq, const uint32_t *d_ucount, uint32_t u_hint, uint32_t *d_table,
                 const uint32_t *d_sorted, int num_colors, const int *d_lut, int sm_count, cudaStream_t st) {
   const size_t smem = fast_smem_bytes(num_colors);
-  static size_t configured = 0;
+  static std::atomic<size_t> configured{0};  // lanes call this from several host threads
   if (smem > 48 * 1024 && smem > configured) {
     DQ_CUDA_CHECK(cudaFuncSetAttribute(map_unique_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
@@ -442,7 +443,7 @@ void map_labels(const uint32_t *d_in, uint32_t n, uint32_t *d_out, const uint2 *
                 uint32_t *d_error, int sm_count, cudaStream_t st) {
   if (n == 0) return;
   const size_t smem = (size_t)num_pairs * sizeof(uint2);
-  static size_t configured = 0;
+  static std::atomic<size_t> configured{0};  // lanes call this from several host threads
   if (smem > 48 * 1024 && smem > configured) {
     DQ_CUDA_CHECK(cudaFuncSetAttribute(map_labels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;

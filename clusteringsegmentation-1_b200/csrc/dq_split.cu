@@ -13,6 +13,7 @@
 // parameters of the next pass are re-derived from those sums by every CTA that needs them, so a
 // pass costs exactly one grid barrier.
 #include "dq_split_math.cuh"
+#include <atomic>
 
 #include <cfloat>
 
@@ -625,7 +626,7 @@ void split_launch(const SplitArgs &args_in, const SplitLaunch &plan, cudaStream_
   const uint32_t K = args.num_colors;
   size_t base = ((sizeof(CtaShared) + 15) & ~size_t(15)) + (((size_t)(K + 1) * 4 + 15) & ~size_t(15));
   args.use_smem_ctl = plan.smem_bytes > base ? 1 : 0;
-  static size_t configured = 0;
+  static std::atomic<size_t> configured{0};  // lanes call this from several host threads
   if (plan.smem_bytes > configured) {
     DQ_CUDA_CHECK(cudaFuncSetAttribute(split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes));
     configured = plan.smem_bytes;

@@ -2,6 +2,7 @@
 // kernel does not carry it (K > 512: the generic kernel of dq_split.cu).  The latency-optimised kernel (dq_split2.cu)
 // runs the same body itself, without extra launches.
 #include "dq_split_exact.cuh"
+#include <atomic>
 
 #include <algorithm>
 
@@ -51,7 +52,7 @@ void split_exact_launch(const SplitArgs &args, const ExactSampling &q, unsigned 
                         uint32_t *d_table, uint32_t *d_first_seen, double *g_f64, int32_t *g_i32, cudaStream_t st) {
   const unsigned blocks = (unsigned)std::min<uint64_t>(((uint64_t)q.num_samples + 255) / 256, 64u);
   exact_first_seen_kernel<<<std::max(blocks, 1u), 256, 0, st>>>(q, args.num_points_dev, args.exact_small_max, d_first_seen);
-  static bool configured = false;
+  static std::atomic<bool> configured{false};  // lanes call this from several host threads
   if (!configured) {
     DQ_CUDA_CHECK(cudaFuncSetAttribute(split_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(exact::Shared)));
     configured = true;
