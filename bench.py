@@ -4,7 +4,7 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
-One "step" = one batch of --frames-per-step (8) synthetic 3840x2160 frames (generator G1 of SURVEY.md 8d,
+One "step" = one batch of --frames-per-step (12) synthetic 3840x2160 frames (generator G1 of SURVEY.md 8d,
 seed 12345+frame), each a whole quant_recurse (24-bit histogram -> divisive split with 10 local 2-means
 iterations -> palette dedup/sort -> remap), pushed through the frame pipeline (`lanes` frames in flight
 on the GPU).  N > 1: every rank owns one GPU and its own stream of frames (frame-sharded, no collective:
@@ -509,7 +509,7 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=10, help="frames of the single-thread CPU baseline sample")
     ap.add_argument("--lanes", type=int, default=12, help="frames in flight per GPU, device-resident leg")
     ap.add_argument("--e2e-lanes", type=int, default=6, help="frames in flight per GPU, host-buffer leg")
-    ap.add_argument("--frames-per-step", type=int, default=8, help="frames in one step (one batch)")
+    ap.add_argument("--frames-per-step", type=int, default=12, help="frames in one step (one batch; a multiple of the lanes keeps them evenly loaded)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-parity", action="store_true")
     ap.add_argument("--width", type=int, default=3840, help="frame width (default: the BASELINE.json headline config)")
