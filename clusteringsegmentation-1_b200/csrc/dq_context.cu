@@ -2,11 +2,14 @@
 // that strings the kernels together, and the extern "C" layer of include/divquant_b200.h.
 //
 // Pipeline of quant_recurse (reference: DivQuant/quant_util.cpp:20-158):
-//   H2D pixels -> hist_insert/hist_collect (or points_from_pixels when allPixelsUnique)
-//              -> split_kernel (persistent, cooperative)           = quant_varpart_fast
-//              -> D2H palette; host: drop empty/duplicate entries, std::sort by r+g+b, lut_init
-//              -> map_unique + map_gather (unique-colour table) or map_pixels (brute force)
+//   H2D pixels -> hist_insert (or points_from_pixels when allPixelsUnique)
+//              -> split kernel (persistent, cooperative; collects the histogram in its first pass; small inputs
+//                 leave into the ordered path)                                   = quant_varpart_fast
+//              -> palette to the host (mapped mailbox the kernel writes last; else two small copies);
+//                 host: drop empty/duplicate entries, std::sort by r+g+b, lut_init
+//              -> map_unique (tables in its parameter block for K <= 256) + map_gather, or map_pixels (brute force)
 //              -> D2H pixels
+// Streams of frames go through dq_pipeline: several such chains side by side, one lane (context + host thread) each.
 // The product has no CPU path for any per-pixel or per-point work; the host only handles the <= K
 // palette words exactly as the reference's scalar code does.
 #include <algorithm>
