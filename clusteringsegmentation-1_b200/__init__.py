@@ -38,7 +38,7 @@ class CallStats(C.Structure):
     _fields_ = [("num_pixels", C.c_uint32), ("num_points", C.c_uint32), ("requested_colors", C.c_uint32),
                 ("actual_colors", C.c_uint32), ("empty_clusters", C.c_uint32), ("split_rounds", C.c_uint32),
                 ("splits_computed", C.c_uint32), ("remap_path", C.c_uint32), ("kernel_launches", C.c_uint32),
-                ("stage_ms", C.c_float * 7)]
+                ("stage_ms", C.c_float * 7), ("tie_flags", C.c_uint32), ("ordered_rerun", C.c_uint32)]
 
     STAGES = ("hist_insert", "hist_collect", "split", "map_unique_or_bruteforce", "map_gather", "table_clear", "total")
 
@@ -86,6 +86,7 @@ def load_library(path=LIB_PATH):
         "dq_context_set_split_ctas": (None, [vp, C.c_int]),
         "dq_context_set_exact_small": (None, [vp, C.c_int]),
         "dq_context_set_exact_max_points": (None, [vp, C.c_uint32]),
+        "dq_context_set_tie_policy": (None, [vp, C.c_int]),
         "dq_srm_num_pairs": (C.c_uint32, [C.c_uint32, C.c_uint32]),
         "dq_srm_sorted_edges": (None, [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp]),
         "dq_srm_sorted_edges_device": (None, [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp]),
@@ -128,7 +129,7 @@ EXPORTED_C_SYMBOLS = [
     "dq_get_double_scale", "dq_validate_num_bits", "dq_set_display_timings", "dq_context_create", "dq_context_destroy",
     "dq_default_context", "dq_context_stream", "dq_context_synchronize", "dq_context_last_stats", "dq_context_set_profiling",
     "dq_quant_recurse_device", "dq_map_colors_device", "dq_quant_varpart_device", "dq_quant_recurse_ctx",
-    "dq_srm_num_pairs", "dq_srm_sorted_edges", "dq_srm_sorted_edges_device", "dq_context_set_split_ctas", "dq_context_set_exact_small", "dq_context_set_exact_max_points", "dq_pixel_histogram", "dq_block_vote", "dq_block_vote_device", "dq_quant_blocks", "dq_colortable_indexes", "dq_colortable_indexes_device", "dq_shard_histogram", "dq_shard_quantize_map", "dq_pipeline_create", "dq_pipeline_create_lanes", "dq_pipeline_destroy", "dq_pipeline_submit", "dq_pipeline_submit_device", "dq_pipeline_wait", "dq_pipeline_lanes", "dq_pipeline_set_blocking_wait", "dq_pipeline_flush", "dq_pipeline_last_elapsed_ms",
+    "dq_srm_num_pairs", "dq_srm_sorted_edges", "dq_srm_sorted_edges_device", "dq_context_set_split_ctas", "dq_context_set_exact_small", "dq_context_set_exact_max_points", "dq_context_set_tie_policy", "dq_pixel_histogram", "dq_block_vote", "dq_block_vote_device", "dq_quant_blocks", "dq_colortable_indexes", "dq_colortable_indexes_device", "dq_shard_histogram", "dq_shard_quantize_map", "dq_pipeline_create", "dq_pipeline_create_lanes", "dq_pipeline_destroy", "dq_pipeline_submit", "dq_pipeline_submit_device", "dq_pipeline_wait", "dq_pipeline_lanes", "dq_pipeline_set_blocking_wait", "dq_pipeline_flush", "dq_pipeline_last_elapsed_ms",
     "dq_pipeline_context", "dq_pipeline_kernel_launches",
     "dq_debug_split_points", "dq_debug_histogram", "dq_debug_split_timeline", "dq_host_dedup_palette", "dq_host_build_search_tables",
 ]

@@ -103,6 +103,9 @@ struct dq_context {
   int exact_parallel = 1;  // the ordered path runs on all CTAs of the split kernel (DIVQUANT_B200_EXACT_PARALLEL=0: CTA 0 only)
   uint32_t exact_max_points = kExactDefaultPoints;  // ... up to this many unique colours (DIVQUANT_B200_EXACT_MAX)
   DevBuf<uint64_t> d_exact;
+  // Tie audit of the exact-integer split (dq_tie.cuh): 0 = off, 1 = report in dq_call_stats::tie_flags only,
+  // 2 (default) = a flagged frame is computed again in the reference's summation order (DIVQUANT_B200_TIE)
+  int tie_policy = 2;
   int split_version = 2;  // 1 = generic kernel, 2 = latency-optimised kernel (falls back to 1 when it cannot run)
   int trace_split = 0;
   int *d_lut = nullptr;
@@ -219,7 +222,7 @@ int plan_ctas_hint(const dq_context *ctx, uint32_t K) { return split2_plan(ctx->
 // Returns the number of palette entries.
 uint32_t run_split(dq_context *ctx, uint32_t point_capacity, double norm, uint32_t K, int max_iters, int num_bits,
                    uint32_t *colortable_out, dq_split_record *records_out, double *mean_out, uint32_t *size_out,
-                   bool collect_from_hist = false, const ExactSource *exact = nullptr) {
+                   bool collect_from_hist = false, const ExactSource *exact = nullptr, bool weighted = false) {
   if (max_iters < 1 || max_iters > kSplitMaxIters) {
     fprintf(stderr, "divquant_b200: max_iters ( %d ) must be in [1,%d] (the reference hard-wires local k-means on)\n",
             max_iters, kSplitMaxIters);
@@ -269,6 +272,8 @@ uint32_t run_split(dq_context *ctx, uint32_t point_capacity, double norm, uint32
   }
 
   const bool use_v2 = ctx->split_version == 2 && K <= kSplit2MaxColors;
+  // weighted points on exact-integer sums: audit the decisions against the reference's rounding noise (dq_tie.cuh)
+  a.tie_audit = (weighted && use_v2 && ctx->tie_policy != 0) ? 1u : 0u;
   ctx->mark(2);
   const bool exact_path = exact != nullptr && collect_from_hist && K <= kExactMaxColors && ctx->exact_small && ctx->exact_max_points > 0;
   ExactSampling sampling;
@@ -397,6 +402,7 @@ uint32_t run_split(dq_context *ctx, uint32_t point_capacity, double norm, uint32
   ctx->stats.empty_clusters = empty;
   ctx->stats.split_rounds = ctx->h_cb->ctl[kCtlRounds];
   ctx->stats.splits_computed = ctx->h_cb->ctl[kCtlSplits];
+  ctx->stats.tie_flags = a.tie_audit ? ctx->h_cb->ctl[kCtlTie] : 0u;
   if (records_out && K > 1)
     DQ_CUDA_CHECK(cudaMemcpy(records_out, ctx->d_records.ptr, (size_t)(K - 1) * sizeof(SplitRecord), cudaMemcpyDeviceToHost));
   if (mean_out) DQ_CUDA_CHECK(cudaMemcpy(mean_out, ctx->d_cluster_mean.ptr, (size_t)3 * K * sizeof(double), cudaMemcpyDeviceToHost));
@@ -516,7 +522,22 @@ bool quantize_device(dq_context *ctx, uint32_t n, const uint32_t *d_in, uint32_t
   }
   const ExactSource src = {d_in, rows, cols, (uint32_t)dec, num_bits};
   *k_inout = run_split(ctx, point_cap, norm, K, max_iters, num_bits, colortable, records, mean_out, size_out, table_dirty,
-                       table_dirty ? &src : nullptr);
+                       table_dirty ? &src : nullptr, table_dirty);
+  const uint32_t flags = ctx->stats.tie_flags;
+  if (flags != 0u && ctx->tie_policy == 2 && table_dirty && ctx->exact_small && ctx->stats.num_points <= kExactMaxPoints &&
+      K <= kExactMaxColors && K <= kSplit2MaxColors && ctx->split_version == 2) {
+    // Some decision of the exact-integer split sits inside the rounding noise of the reference's sequential sums:
+    // the reference's own summation order decides.  The count table is all-zero again (the split kernel zeroed what
+    // it collected), so the frame simply goes through the histogram and the split once more, on the ordered path.
+    const uint32_t keep = ctx->exact_max_points;
+    ctx->exact_max_points = kExactMaxPoints;
+    reset_control(ctx);
+    run_histogram(ctx, d_in, n, rows, cols, (uint32_t)dec, num_bits);
+    *k_inout = run_split(ctx, point_cap, norm, K, max_iters, num_bits, colortable, records, mean_out, size_out, true, &src, true);
+    ctx->exact_max_points = keep;
+    ctx->stats.tie_flags = flags;
+    ctx->stats.ordered_rerun = 1;
+  }
   return table_dirty;
 }
 
@@ -637,6 +658,7 @@ dq_context *dq_context_create(int device) {
   for (int i = 0; i < 8; ++i) DQ_CUDA_CHECK(cudaEventCreate(&ctx->ev[i]));
   ctx->display_timings = display_timings_default();
   if (const char *e = getenv("DIVQUANT_B200_SPLIT")) ctx->split_version = (e[0] == '1') ? 1 : 2;
+  if (const char *e = getenv("DIVQUANT_B200_TIE")) ctx->tie_policy = std::min(std::max(atoi(e), 0), 2);
   if (const char *e = getenv("DIVQUANT_B200_EXACT_SMALL")) ctx->exact_small = (e[0] != '0');
   if (const char *e = getenv("DIVQUANT_B200_EXACT_PARALLEL")) ctx->exact_parallel = (e[0] != '0');
   if (const char *e = getenv("DIVQUANT_B200_EXACT_MAX")) ctx->exact_max_points = (uint32_t)std::min<long>(std::max<long>(atol(e), 0), kExactMaxPoints);
@@ -650,6 +672,7 @@ void dq_context_set_split_ctas(dq_context *ctx, int num_ctas) {
 }
 
 void dq_context_set_exact_small(dq_context *ctx, int enabled) { ctx->exact_small = enabled ? 1 : 0; }
+void dq_context_set_tie_policy(dq_context *ctx, int policy) { ctx->tie_policy = std::min(std::max(policy, 0), 2); }
 void dq_context_set_exact_max_points(dq_context *ctx, uint32_t max_points) {
   ctx->exact_max_points = std::min<uint32_t>(max_points, kExactMaxPoints);
 }
@@ -1055,7 +1078,7 @@ void dq_shard_quantize_map(dq_context *ctx, const uint32_t *d_all_colours, const
   hist_merge(d_all_colours, d_all_counts, num_entries, ctx->d_table, ctx->d_uniq.ptr, &ctx->d_cb->ucount, ctx->sm_count, ctx->stream);
   ctx->stats.kernel_launches += 1;
   const double norm = sample_norm(1, (uint32_t)total_pixels, 1);  // 1 / N of the WHOLE image (:172)
-  uint32_t k = run_split(ctx, num_entries, norm, K, 10, 8, outColortablePtr, nullptr, nullptr, nullptr, true);
+  uint32_t k = run_split(ctx, num_entries, norm, K, 10, 8, outColortablePtr, nullptr, nullptr, nullptr, true, nullptr, true);
   k = dedup_palette(outColortablePtr, k);
   *numClustersPtr = k;
   ctx->stats.actual_colors = k;

@@ -40,6 +40,11 @@ struct SplitNode {
   int32_t child;  // node id of the "old" child (the "new" child is child+1); -1 = not split yet
   int32_t axis;   // cutting axis chosen when scheduled
   int32_t parent; // node this one was split from (-1 for the root)
+  // Tie audit of the exact-integer path (dq_tie.cuh): first-order bounds on |this kernel's value - the reference's value|
+  // of tw, tm[], tv[] and tse, and the decisions of this node's own split that fell inside such a bound (TieBit mask).
+  double eW, eM, eV, eT;
+  uint32_t tie;
+  uint32_t pad;
 };
 
 // A split being computed in the current round.
@@ -80,7 +85,19 @@ enum CtlSlot {
   kCtlRounds = 4,  // rounds executed (diagnostics)
   kCtlSplits = 5,  // splits computed, including speculative ones (diagnostics)
   kCtlError = 6,   // non-zero = internal inconsistency
-  kCtlWords = 8
+  kCtlTie = 8,     // tie audit: TieBit mask of the decisions that sit inside the reference's rounding noise (dq_tie.cuh)
+  kCtlWords = 12   // [kCtlWords - 1] = detail of an expired wait
+};
+
+// Decisions of the divisive phase that the exact-integer sums may take differently from the reference's sequential
+// double sums: bit d-1 = decision kind d was found inside the noise bound somewhere in the frame.
+enum TieBit {
+  kTieAxis = 1u,        // D1: two channel variances of a split cluster (:388-403)
+  kTieCut = 2u,         // D2: cut_pos < proj_val (:473)
+  kTieHyperplane = 4u,  // D3: lhs < rhs . x (:683)
+  kTieTse = 8u,         // D4: arg-max of the TSEs (:876-887), incl. the DBL_MIN seed
+  kTieRound = 16u,      // D5: (uint8)(mean + 0.5) (:1050-1052)
+  kTieReplay = 32u      // the sequential replay of the selection ran (degenerate TSE order): not audited, always flagged
 };
 
 struct SplitArgs {
@@ -119,6 +136,8 @@ struct SplitArgs {
   // inputs of at most this many points are handled by split_exact_kernel (dq_split_exact.cu): the split kernels
   // return at once for them.  0 = off.
   uint32_t exact_small_max;
+  // 1 = weighted path on exact-integer sums: audit every decision against the reference's rounding noise (dq_tie.cuh)
+  uint32_t tie_audit;
 };
 
 // Largest input (unique colours) that takes the sequential-order path of dq_split_exact.cu.
@@ -138,7 +157,7 @@ size_t split_exact_scratch_bytes();  // global scratch for the point arrays of i
 void split_exact_launch(const SplitArgs &args, const ExactSampling &q, unsigned char *d_scratch, const uint32_t *d_uniq,
                         uint32_t *d_table, uint32_t *d_first_seen, double *g_f64, int32_t *g_i32, cudaStream_t st);
 
-constexpr int kMailboxPalette = 16;                      // word offset of the palette inside the mailbox
+constexpr int kMailboxPalette = 32;                      // word offset of the palette inside the mailbox
 constexpr int kMailboxWords = kMailboxPalette + 512;     // K <= kSplit2MaxColors
 
 // Launch description computed on the host.

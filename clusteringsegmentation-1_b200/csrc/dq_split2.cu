@@ -47,8 +47,10 @@ constexpr unsigned long long kValueMask = (1ull << 48) - 1ull;
 
 struct JobConst {
   double tw, tm[3], cut;
+  double eW, eM;  // tie audit: the node's bounds (dq_tie.cuh); eM < 0 = audit off
   int32_t axis, buf;
   uint32_t begin, size;
+  uint32_t tie0, pad;  // kTieAxis when the axis choice itself is inside the noise
 };
 
 struct Shared2 {
@@ -72,6 +74,10 @@ struct Shared2 {
   int32_t warp_tmp[32];
   uint32_t cur_old, cur_new;
   uint32_t num_points;
+  tie::PassExt ext;   // tie audit: centres and bounds behind S.pp (written with it)
+  uint32_t near;      // tie audit: points of the pass just reduced / gathered that sit inside the noise bound
+  uint32_t job_tie;   // TieBit mask of the narrow job in flight
+  uint32_t tie_total; // TieBit mask of the frame (CTA 0, final assignment + palette)
 };
 
 struct Arrays {
@@ -89,6 +95,8 @@ struct Arrays {
   double *ctse;        // [K]
   int32_t *cand;       // [K]
   int32_t *rank;       // [cap]  number of known nodes with a larger TSE (final assignment)
+  double *terr;        // [cap]  tie audit: bound of the node's TSE
+  uint8_t *jobtie;     // [K]    tie audit: TieBit mask of this round's wide jobs (owner CTA)
 };
 
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
@@ -233,6 +241,17 @@ __device__ __forceinline__ void reduce_stage2_warp0(Shared2 &S, int rows) {
   __syncwarp();
 }
 
+// Tie audit: the classification adds (near ? 1 : 0) << 32 per thread to the point counter (kAccPts), so the number of
+// threads that saw a point inside the noise bound rides through every reduction and exchange for free.  Warp 0 calls
+// this once the totals are in S.tot: S.near = that number, S.tot[kAccPts] = the plain point count again.
+__device__ __forceinline__ void split_near_warp0(Shared2 &S) {
+  if (threadIdx.x == 0) {
+    S.near = (uint32_t)(S.tot[kAccPts] >> 32);
+    S.tot[kAccPts] &= 0xFFFFFFFFull;
+  }
+  __syncwarp();
+}
+
 // Sum of v[0..WORDS) over the first `warps` warps of the CTA into S.tot, visible to all threads.
 template <int WORDS>
 __device__ __forceinline__ void block_total(Shared2 &S, const uint64_t (&v)[kAccWords], int warps = kWarps) {
@@ -326,8 +345,20 @@ __device__ __forceinline__ void derive_params_warp0(Shared2 &S, const JobConst &
     const double a = fsq(om), b = fsq(nm);
     const double a1 = __shfl_sync(0xffffffffu, a, 1), b1 = __shfl_sync(0xffffffffu, b, 1);
     const double a2 = __shfl_sync(0xffffffffu, a, 2), b2 = __shfl_sync(0xffffffffu, b, 2);
-    if (threadIdx.x < 3) S.pp.r[c] = fsub(om, nm);
+    if (threadIdx.x < 3) {
+      S.pp.r[c] = fsub(om, nm);
+      S.ext.om[c] = om;
+      S.ext.nm[c] = nm;
+    }
     if (threadIdx.x == 0) {
+      // tie audit: tolerance of the hyperplane test for centres derived from a new side of tot[kAccPts] points
+      S.pp.tol = -1.0;
+      if (jc.eM >= 0.0) {
+        const tie::PassErr q = tie::pass_err(jc.eW, jc.eM, jc.tw, nw, ow, (double)(uint32_t)S.tot[kAccPts]);
+        S.pp.tol = tie::hyperplane_tol(q);
+        S.ext.e_om = q.e_om;
+        S.ext.e_nm = q.e_nm;
+      }
       double l = fsub(a, b);  // (:616-619), left to right
       l = fadd(l, a1);
       l = fsub(l, b1);
@@ -345,6 +376,7 @@ __device__ __forceinline__ void derive_params_warp0(Shared2 &S, const JobConst &
 __device__ __forceinline__ void set_split_params(Shared2 &S, const JobConst &jc) {
   if (threadIdx.x == 0) {
     S.pp.a = jc.cut;
+    S.pp.tol = jc.eM;  // tie audit of the cut test (:473): the cut is the node's mean
     S.pp.r[0] = S.pp.r[1] = S.pp.r[2] = 0.0;
     S.pp.axis = jc.axis;
     S.pp.buf = jc.buf;
@@ -353,11 +385,15 @@ __device__ __forceinline__ void set_split_params(Shared2 &S, const JobConst &jc)
   }
 }
 
-__device__ __forceinline__ JobConst job_const_of(const SplitNode &nd) {
+__device__ __forceinline__ JobConst job_const_of(const SplitNode &nd, bool audit) {
   JobConst jc;
   jc.tw = nd.tw;
   jc.tm[0] = nd.tm[0], jc.tm[1] = nd.tm[1], jc.tm[2] = nd.tm[2];
   choose_cut(nd.tv, nd.tm, jc.axis, jc.cut);
+  jc.eW = nd.eW;
+  jc.eM = audit ? nd.eM : -1.0;
+  jc.tie0 = (audit && tie::axis_tie(nd.tv, nd.eV)) ? (uint32_t)kTieAxis : 0u;
+  jc.pad = 0u;
   jc.buf = nd.buf;
   jc.begin = nd.begin;
   jc.size = nd.size;
@@ -379,16 +415,18 @@ __device__ __forceinline__ void add_point(uint64_t (&v)[kAccWords], uint2 p, boo
 }
 
 // Owner of a finished split writes its two children (totals of the last pass in S.tot, parent in S.cur).
-__device__ __forceinline__ void write_children(const SplitArgs &A, Shared2 &S, int node_id, int child0, const JobConst &jc) {
+__device__ __forceinline__ void write_children(const SplitArgs &A, Shared2 &S, int node_id, int child0, const JobConst &jc,
+                                               uint32_t tie_bits) {
   if (threadIdx.x == 0) {
     SplitNode o, n;
-    make_children(S.cur, node_id, child0, A.norm, S.tot, o, n);
+    make_children(S.cur, node_id, child0, A.norm, S.tot, o, n, A.tie_audit != 0u);
     A.nodes[child0] = o;
     A.nodes[child0 + 1] = n;
     SplitNode *p = A.nodes + node_id;
     p->child = child0;
     p->axis = jc.axis;
     p->cut = jc.cut;
+    p->tie = tie_bits | jc.tie0;  // decisions of this split inside the reference's noise (counted if the split is consumed)
   }
 }
 
@@ -422,7 +460,10 @@ __device__ __forceinline__ void gather(const SplitArgs &A, Shared2 &S, const uns
   sum += __shfl_xor_sync(0xffffffffu, sum, 16);
   if (lane < 8) S.red[warp][lane] = sum;
   __syncthreads();
-  if (tid < 32) reduce_stage2_warp0<kAccWords>(S, kWarps);
+  if (tid < 32) {
+    reduce_stage2_warp0<kAccWords>(S, kWarps);
+    split_near_warp0(S);
+  }
   // no barrier here: callers let warp 0 go on (parameter derivation) and synchronise afterwards
 }
 
@@ -457,6 +498,9 @@ __device__ void emit_palette(const SplitArgs &A, Shared2 &S, const Arrays &R) {
         const SplitNode nd = load_node(A, S, R.cnode[ic]);
         size = nd.size;
         mean[0] = nd.tm[0], mean[1] = nd.tm[1], mean[2] = nd.tm[2];
+        if (A.tie_audit != 0u && size > 0 &&
+            (tie::round_tie(mean[0], nd.eM) || tie::round_tie(mean[1], nd.eM) || tie::round_tie(mean[2], nd.eM)))
+          atomicOr(&S.tie_total, (uint32_t)kTieRound);  // D5 (:1050-1052)
       } else {
         size = S.num_points;
       }
@@ -565,6 +609,25 @@ __device__ void fast_assignment(const SplitArgs &A, Shared2 &S, const Arrays &R)
   if (S.scan_carry != K - 1 && tid == 0) S.bad = 1;
   __syncthreads();
   if (S.bad) return;
+  if (A.tie_audit != 0u) {
+    // D4 (:876-887): the reference pops the same nodes in the same order if every popped node's TSE is separated from the
+    // DBL_MIN seed and from the TSE of every other node of the reference's sequence (popped nodes and their children) by
+    // more than the two bounds.  Also collects the decisions flagged inside the consumed splits themselves.
+    uint32_t bits = 0u;
+    for (int i = tid; i < n; i += T) {
+      if (R.rank[i] >= K - 1) continue;
+      bits |= __ldcg(&A.nodes[i].tie);
+      if (i == 0) continue;  // the root is split first, unconditionally
+      const double t = R.tse[i], e = R.terr[i];
+      if (!(t - e > DBL_MIN)) bits |= (uint32_t)kTieTse;
+      for (int m2 = 1; m2 < n; ++m2) {
+        if (m2 == i) continue;
+        const bool relevant = R.rank[m2] < K - 1 || R.rank[R.parent[m2]] < K - 1;
+        if (relevant && fabs(R.tse[m2] - t) <= e + R.terr[m2]) bits |= (uint32_t)kTieTse;
+      }
+    }
+    if (bits) atomicOr(&S.tie_total, bits);
+  }
   for (int i = tid; i < n; i += T) {
     const bool popped = R.rank[i] < K - 1;
     const bool final_cluster = !popped && i != 0 && R.rank[R.parent[i]] < K - 1;
@@ -703,10 +766,11 @@ __device__ __forceinline__ unsigned narrow_pass(Shared2 &S, const uint2 (&p)[kNa
   const PassParams pp = S.pp;
   AccD acc = acc_zero();
   unsigned newmask = 0;
+  bool near = false;
 #pragma unroll
   for (int k = 0; k < kNarrowPPT; ++k) {
     if (k < ppt && ((validmask >> k) & 1u)) {
-      if (goes_new_t<SPLIT>(pp, to_point(p[k]))) {
+      if (goes_new_audit<SPLIT>(pp, &S.ext, to_point(p[k]), near)) {
         acc_add(acc, p[k], FINAL);
         newmask |= 1u << k;
       }
@@ -714,10 +778,13 @@ __device__ __forceinline__ unsigned narrow_pass(Shared2 &S, const uint2 (&p)[kNa
   }
   uint64_t v[kAccWords];
   acc_words(acc, v);
+  v[kAccPts] += (uint64_t)near << 32;  // tie audit (split_near_warp0)
   constexpr int WORDS = FINAL ? kAccWords : 5;
   reduce_stage1<WORDS>(S, v, nwarps);
   if (threadIdx.x < 32) {
     reduce_stage2_warp0<WORDS>(S, nwarps);
+    split_near_warp0(S);
+    if (threadIdx.x == 0 && S.near) S.job_tie |= SPLIT ? (uint32_t)kTieCut : (uint32_t)kTieHyperplane;
     if (!FINAL) {
       // Fixed point of the local 2-means: the next pass's parameters are a function of {cnt, R, G, B} only, so
       // equal sums in two consecutive passes mean every later pass repeats this one exactly -- the remaining
@@ -740,16 +807,17 @@ __device__ __forceinline__ unsigned narrow_pass(Shared2 &S, const uint2 (&p)[kNa
 
 // This CTA's share of a wide job in one pass: partial sums into v[].
 template <bool SPLIT, bool FINAL, typename OffsetFn>
-__device__ __forceinline__ void wide_classify(const PassParams &pp, const uint2 (&pre)[kWidePPT], uint32_t n_my, uint32_t nthr,
+__device__ __forceinline__ void wide_classify(const PassParams &pp, const tie::PassExt *ext, const uint2 (&pre)[kWidePPT], uint32_t n_my, uint32_t nthr,
                                               const uint2 *seg, OffsetFn offset_of, uint64_t (&v)[kAccWords]) {
   AccD acc = acc_zero();
+  bool near = false;
   const uint32_t tid = threadIdx.x;
   if (tid < nthr) {
 #pragma unroll
     for (int k = 0; k < kWidePPT; ++k) {
       const uint32_t q = tid + (uint32_t)k * nthr;
       if (q < n_my) {
-        if (goes_new_t<SPLIT>(pp, to_point(pre[k]))) acc_add(acc, pre[k], FINAL);
+        if (goes_new_audit<SPLIT>(pp, ext, to_point(pre[k]), near)) acc_add(acc, pre[k], FINAL);
       }
     }
     // beyond the register-resident points (few CTAs per frame): four loads in flight per trip
@@ -762,11 +830,12 @@ __device__ __forceinline__ void wide_classify(const PassParams &pp, const uint2 
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        if (q + (uint32_t)u * nthr < n_my && goes_new_t<SPLIT>(pp, to_point(raw[u]))) acc_add(acc, raw[u], FINAL);
+        if (q + (uint32_t)u * nthr < n_my && goes_new_audit<SPLIT>(pp, ext, to_point(raw[u]), near)) acc_add(acc, raw[u], FINAL);
       }
     }
   }
   acc_words(acc, v);
+  v[kAccPts] += (uint64_t)near << 32;  // tie audit (split_near_warp0)
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -809,7 +878,13 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
     R.mywide = reinterpret_cast<uint16_t *>(cur);
     cur += (size_t)K * 2;
     R.mynarrow = reinterpret_cast<uint16_t *>(cur);
+    cur += (size_t)K * 2;
+    R.jobtie = reinterpret_cast<uint8_t *>(cur);
+    cur += (size_t)K;
+    cur = smem_raw + (((size_t)(cur - smem_raw) + 15) & ~size_t(15));
+    R.terr = reinterpret_cast<double *>(cur);
   }
+  const bool audit = A.tie_audit != 0u;
 
   const uint32_t U = A.num_points_dev ? ld_cg_u32(A.num_points_dev) : A.num_points;
   unsigned int bar_target = 0;
@@ -895,8 +970,13 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
     root.child = -1;
     root.axis = 0;
     root.parent = -1;
+    root.eW = root.eM = root.eV = root.eT = 0.0;
+    root.tie = root.pad = 0u;
+    if (audit) tie::root_bounds((double)U, root.eW, root.eM, root.eV);
     S.root = root;
     if (b == 0) A.nodes[0] = root;
+    S.tie_total = 0u;
+    R.terr[0] = 0.0;
     R.tse[0] = __longlong_as_double(0x7ff0000000000000ll);  // +inf: the first split is unconditional
     R.child[0] = -1;
     R.size[0] = U;
@@ -923,6 +1003,7 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
       for (int i = n_prev + tid; i < n_now; i += T) {
         const SplitNode *nd = A.nodes + i;
         R.tse[i] = __ldcg(&nd->tse);
+        R.terr[i] = __ldcg(&nd->eT);
         R.size[i] = __ldcg(&nd->size);
         R.child[i] = -1;
         R.parent[i] = R.jobnode[(i - n_prev) >> 1];
@@ -960,6 +1041,7 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
       // (many equal TSEs could also request more than K leaves at once: let the exact scan decide then)
       if (S.njobs > K || (S.njobs > 0 && (uint32_t)(S.n_nodes + 2 * S.njobs) > cap / 2)) {
         if (tid == 0) {
+          if (audit) S.tie_total |= (uint32_t)kTieReplay;
           S.mode = 1;
           R.cnode[0] = 0;
           R.ctse[0] = 0.0;
@@ -969,6 +1051,7 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
         fast_assignment(A, S, R);
         if (S.bad) {
           if (tid == 0) {
+            if (audit) S.tie_total |= (uint32_t)kTieReplay;
             S.mode = 1;
             R.cnode[0] = 0;
             R.ctse[0] = 0.0;
@@ -986,6 +1069,7 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
       if (b == 0) {
         emit_palette(A, S, R);
         if (tid == 0) {
+          A.ctl[kCtlTie] = S.tie_total;
           A.ctl[kCtlDone] = 1;
           A.ctl[kCtlNodes] = (uint32_t)S.n_nodes;
           A.ctl[kCtlRounds] = (uint32_t)round;
@@ -1007,6 +1091,7 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
       const uint32_t tiles = wide ? (sz + kWideTile - 1) / kWideTile : 0u;
       R.tile0[j] = tiles;
       R.nidx[j] = wide ? 0u : 1u;
+      R.jobtie[j] = 0;
     }
     __syncthreads();
     block_scan(S, R.tile0, njobs);
@@ -1076,7 +1161,7 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
     const int n_mywide = S.n_mywide, n_mynarrow = S.n_mynarrow;
     for (int mw = tid; mw < min(n_mywide, kWideCache); mw += T) {
       // (executed by <= kWideCache threads) constants of the first few wide jobs stay in shared memory
-      S.wide[mw] = job_const_of(load_node(A, S, R.jobnode[R.mywide[mw]]));
+      S.wide[mw] = job_const_of(load_node(A, S, R.jobnode[R.mywide[mw]]), audit);
     }
     __syncthreads();
     trace2(A, kTracePhaseC, njobs);
@@ -1089,7 +1174,7 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
     const unsigned seq0 = 1u + (unsigned)round * (unsigned)(P + 1);
     auto wide_const = [&](int mw) -> JobConst {
       if (mw < kWideCache) return S.wide[mw];
-      return job_const_of(load_node(A, S, R.jobnode[R.mywide[mw]]));
+      return job_const_of(load_node(A, S, R.jobnode[R.mywide[mw]]), audit);
     };
     // This CTA's share of wide job j: participants, my rank among them, my first point and how many.
     struct Share {
@@ -1153,6 +1238,7 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
           set_split_params(S, jc);
         } else {
           gather(A, S, slots_r, R.slot0[j], m, 5, (seq0 + pass - 1) & 0xFFFFu);
+          if (tid == 0 && S.near) R.jobtie[j] |= (pass == 1) ? (uint8_t)kTieCut : (uint8_t)kTieHyperplane;
 #ifdef DQ_PROFILE_NARROW
           w1 = clock64();
 #endif
@@ -1167,9 +1253,9 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
         {
           const uint2 *seg = A.pts[jc.buf] + jc.begin;
           auto off = [&](uint32_t q) { return sh.first_point + q; };
-          if (pass == 0) wide_classify<true, false>(pp, pre, n_my, nthr, seg, off, v);
-          else if (pass == P) wide_classify<false, true>(pp, pre, n_my, nthr, seg, off, v);
-          else wide_classify<false, false>(pp, pre, n_my, nthr, seg, off, v);
+          if (pass == 0) wide_classify<true, false>(pp, &S.ext, pre, n_my, nthr, seg, off, v);
+          else if (pass == P) wide_classify<false, true>(pp, &S.ext, pre, n_my, nthr, seg, off, v);
+          else wide_classify<false, false>(pp, &S.ext, pre, n_my, nthr, seg, off, v);
         }
 #ifdef DQ_PROFILE_NARROW
         const long long w3 = clock64();
@@ -1221,6 +1307,7 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
       const PassParams pp = (mw < kWideCache) ? S.wide_pp[mw] : S.pp;
       __syncthreads();
       gather(A, S, X.slots + (size_t)(P & 1) * X.slot_cap * kAccWords, R.slot0[j], m, kAccWords, (seq0 + P) & 0xFFFFu);
+      if (tid == 0 && S.near) R.jobtie[j] |= (uint8_t)kTieHyperplane;
       __syncthreads();
       if (S.tot[kAccPts] > jc.size) continue;  // only after an expired wait: never scatter out of the segment
       const uint32_t size_old = jc.size - (uint32_t)S.tot[kAccPts];
@@ -1282,7 +1369,7 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
       if (me == 0) {  // owner: the CTA holding the job's first tile
         if (tid == 0) S.cur = load_node(A, S, R.jobnode[j]);
         __syncthreads();
-        write_children(A, S, R.jobnode[j], child_base + 2 * j, jc);
+        write_children(A, S, R.jobnode[j], child_base + 2 * j, jc, R.jobtie[j]);
       }
       __syncthreads();
     }
@@ -1297,9 +1384,10 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
         S.cur = load_node(A, S, node);
         S.cur_old = 0;
         S.cur_new = 0;
+        S.job_tie = 0u;
       }
       __syncthreads();
-      const JobConst jc = job_const_of(S.cur);
+      const JobConst jc = job_const_of(S.cur, audit);
       // all warps the job has points for; up to kNarrowPPT points per thread, held in registers for every pass
       const uint32_t nthr = min((uint32_t)T, max(32u, (jc.size + 31u) & ~31u));
       const int nwarps = (int)(nthr >> 5);
@@ -1347,7 +1435,7 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
           }
         }
       }
-      write_children(A, S, node, child_base + 2 * j, jc);
+      write_children(A, S, node, child_base + 2 * j, jc, S.job_tie);
       __syncthreads();
     }
     if (n_mynarrow) trace2(A, kTracePartition, 1000 + n_mynarrow);
@@ -1364,6 +1452,7 @@ size_t split2_smem_bytes(uint32_t K, uint32_t cap) {
   s += (size_t)K * (8 + 4 + 4 + 4);
   s += (size_t)(K + 1) * 4 * 3;
   s += (size_t)K * 2 * 2;
+  s += (size_t)K + 16 + (size_t)cap * 8;  // tie audit: jobtie, terr
   return s + 64;
 }
 

@@ -4,6 +4,7 @@
 #pragma once
 
 #include "dq_split.cuh"
+#include "dq_tie.cuh"
 
 namespace dq {
 
@@ -42,6 +43,7 @@ __device__ __forceinline__ void derive_means(double tw, const double *tm, double
 // What every thread needs to classify a point in the current pass.
 struct PassParams {
   double a;     // pass 0: cut position; later: lhs (:616-619)
+  double tol;   // tie audit: a point whose test value is within tol of `a` is inside the reference's rounding noise (< 0: off)
   double r[3];  // rhs = old_mean - new_mean (:621-623)
   int32_t axis;
   int32_t buf;
@@ -89,6 +91,24 @@ __device__ __forceinline__ bool goes_new_t(const PassParams &pp, const PointD &d
   }
   const double dot = fadd(fadd(fmul(pp.r[0], d.r), fmul(pp.r[1], d.g)), fmul(pp.r[2], d.b));
   return !(pp.a < dot);  // (:683)
+}
+// Same decision, plus the tie audit: `near` is raised when the test value lies within pp.tol of the threshold.
+// x - a has the sign of the comparison (a difference of doubles is zero only for equal operands), so one subtraction
+// serves both; a NaN on either side compares false everywhere, like the reference's else branch.
+template <bool SPLIT>
+__device__ __forceinline__ bool goes_new_audit(const PassParams &pp, const tie::PassExt *ext, const PointD &d, bool &near) {
+  double x;
+  if (SPLIT) {
+    x = (pp.axis == 0) ? d.r : ((pp.axis == 1) ? d.g : d.b);
+  } else {
+    x = fadd(fadd(fmul(pp.r[0], d.r), fmul(pp.r[1], d.g)), fmul(pp.r[2], d.b));
+  }
+  const double m = fsub(x, pp.a);
+  if (fabs(m) <= pp.tol) {  // inside the filter (a handful of points per frame): the bound for this very point decides
+    if (SPLIT) near = true;
+    else near = near || (fabs(m) <= tie::point_tol(*ext, d.r, d.g, d.b));
+  }
+  return SPLIT ? (m > 0.0) : !(m > 0.0);
 }
 // Accumulation stays on the integer pipe (IMAD.WIDE), which runs next to the FP64 pipe that classifies:
 // exact u64 sums of count*c and count*c*c.
@@ -156,7 +176,7 @@ __device__ __forceinline__ void choose_cut(const double *tv, const double *tm, i
 // The two children of a split from the final sums of its last pass (:800-871).
 // sums = {cnt, R, G, B, npts, RR, GG, BB}.
 __device__ __forceinline__ void make_children(const SplitNode &parent, int parent_id, int child0, double norm,
-                                              const uint64_t *sums, SplitNode &o, SplitNode &n) {
+                                              const uint64_t *sums, SplitNode &o, SplitNode &n, bool audit = false) {
   Means m;
   derive_means(parent.tw, parent.tm, norm, sums[kAccCnt], sums[kAccR], sums[kAccG], sums[kAccB], m);
 #pragma unroll
@@ -184,6 +204,15 @@ __device__ __forceinline__ void make_children(const SplitNode &parent, int paren
   o.size = parent.size - size_new;  // size[old] = tmp_num_points - new_size (:819)
   n.begin = parent.begin + o.size;
   n.size = size_new;
+  o.eW = o.eM = o.eV = o.eT = n.eW = n.eM = n.eV = n.eT = 0.0;
+  o.tie = n.tie = 0u;
+  o.pad = n.pad = 0u;
+  if (audit) {
+    const tie::PassErr fe = tie::pass_err(parent.eW, parent.eM, parent.tw, m.nw, m.ow, (double)size_new);
+    n.eW = fe.e_nw, n.eM = fe.e_nm, o.eW = fe.e_ow, o.eM = fe.e_om;
+    tie::child_var_bounds(fe, parent.eW, parent.eM, parent.eV, parent.tw, parent.tm, parent.tv, m.nw, m.ow, m.nm, m.om, n.tv,
+                          o.tv, (double)size_new, n.tse, o.tse, n.eV, o.eV, n.eT, o.eT);
+  }
   (void)child0;
 }
 

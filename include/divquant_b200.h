@@ -109,6 +109,13 @@ typedef struct {
    * [0] hist_insert  [1] hist_collect / points_from_pixels  [2] split kernel
    * [3] map_unique or brute-force map  [4] map_gather  [5] table_clear  [6] whole call */
   float stage_ms[7];
+  /* Tie audit of the exact-integer split (inputs above the ordered path's limit): bit d-1 set = a decision of kind d
+   * sat inside the rounding noise of the reference's sequential sums (1 axis :388-403, 2 cut :473, 4 hyperplane :683,
+   * 8 TSE arg-max :876-887, 16 palette rounding :1050-1052, 32 degenerate TSE order).  0 = the result is the
+   * reference's bit for bit.  ordered_rerun = 1: the frame was flagged and computed again in the reference's
+   * summation order (so the result is the reference's as well). */
+  uint32_t tie_flags;
+  uint32_t ordered_rerun;
 } dq_call_stats;
 void dq_context_last_stats(const dq_context *ctx, dq_call_stats *out);
 /* Per-stage CUDA-event timing of dq_quant_recurse_device / _ctx calls (off by default). */
@@ -130,6 +137,12 @@ void dq_context_set_split_ctas(dq_context *ctx, int num_ctas);
  * (environment DIVQUANT_B200_EXACT_SMALL=0) turns the ordered path off altogether. */
 void dq_context_set_exact_max_points(dq_context *ctx, uint32_t max_points);
 void dq_context_set_exact_small(dq_context *ctx, int enabled);
+/* Inputs above that limit run on exact integer sums, which equal the reference's sequential double sums up to the
+ * reference's own rounding noise.  The split kernel audits every decision it takes (axis, cut, hyperplane, TSE
+ * arg-max, palette rounding) against first-order bounds of that noise (csrc/dq_tie.cuh).  policy 2 (default): a frame
+ * with a decision inside its bound is computed again on the ordered path (up to 262144 colours), so the palette is
+ * the reference's either way; 1: only report (dq_call_stats::tie_flags); 0: no audit.  Environment: DIVQUANT_B200_TIE. */
+void dq_context_set_tie_policy(dq_context *ctx, int policy);
 
 /* quant_recurse with pixels already resident in HBM.  d_in / d_out are device pointers on the
  * context's device; colortable and numClustersPtr are host pointers.  Synchronous with respect to

@@ -198,10 +198,55 @@ extern "C" int oracle_debug_convergence(int *out, int cap) {
   return n;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tie audit of the device-arithmetic model (exact_counts): a CPU model of csrc/dq_tie.cuh.
+//
+// The exact-integer path computes every sum over points exactly and the reference sums doubles
+// sequentially, so the two agree on a decision unless the compared values are closer than the
+// rounding noise of the reference's sums.  For every cluster the audit carries first-order bounds on
+// |model - reference| of (weight, mean, variance, TSE) and flags a decision whose margin is inside the
+// bound: D1 axis choice, D2 cut test, D3 hyperplane test, D4 TSE arg-max, D5 final .5 rounding.
+// A frame with no flag is guaranteed (to first order, with a safety factor) to equal the reference.
+// ---------------------------------------------------------------------------------------------
+namespace {
+const double kU = 1.1102230246251565e-16;  // 2^-53
+const double kSafety = 1.0;
+// Rounding errors of a sequential sum of n terms: n*u is the worst case, but the errors are not aligned; the
+// probabilistic bound lambda*sqrt(n)*u (Higham & Mary 2019) fails with probability ~2 exp(-lambda^2/2) (3e-14 at 8).
+const double kLambda = 8.0;
+inline double gamma_n(double n) {
+  const double a = n + 4.0, b = kLambda * std::sqrt(n + 4.0);
+  return (a < b ? a : b) * kU;
+}
+struct ClusterErr {
+  double eW, eM, eV, eT;
+};
+struct TieAudit {
+  uint32_t flags[6];  // [1..5] = D1..D5 counts, [0] = total
+  void hit(int d) {
+    flags[d]++;
+    flags[0]++;
+  }
+};
+// bounds after a pass: the new side has n_new points, the parent's bounds are pe
+struct PassErr {
+  double e_nw, e_nm, e_ow, e_om;
+};
+inline PassErr pass_err(const ClusterErr &pe, double tw, double nw, double ow, int n_new) {
+  PassErr r;
+  r.e_nw = gamma_n(n_new) * nw;
+  r.e_nm = (2.0 * gamma_n(n_new) + 4.0 * kU) * 256.0;
+  r.e_ow = pe.eW + r.e_nw + kU * std::fabs(ow);
+  const double e_num = pe.eW * 256.0 + tw * pe.eM + r.e_nw * 256.0 + nw * r.e_nm + 4.0 * kU * (tw + nw) * 256.0;
+  r.e_om = (e_num + 256.0 * r.e_ow) / std::fabs(ow) + 2.0 * kU * 256.0;
+  return r;
+}
+}  // namespace
+
 static int varpart_impl(uint32_t num_pixels, const uint32_t *in, uint32_t num_rows, uint32_t num_cols,
                         uint32_t *num_clusters, uint32_t *colortable, int num_bits, int dec_factor,
                         int max_iters, int all_pixels_unique, oracle_split_record *records, int *num_records,
-                        bool exact_counts) {
+                        bool exact_counts, TieAudit *audit = nullptr) {
   assert(0 < num_bits && num_bits <= 8);  // (:1115-1118)
   assert(max_iters >= 1);                 // KM is hard-wired true; 0 iterations is degenerate
   if (num_records) *num_records = 0;
@@ -255,6 +300,8 @@ static int varpart_impl(uint32_t num_pixels, const uint32_t *in, uint32_t num_ro
   std::vector<int> size(K, 0);
   std::vector<Vec3> mean(K, Vec3{0, 0, 0}), var(K, Vec3{0, 0, 0});
   std::vector<uint32_t> member(U, 0u);
+  std::vector<ClusterErr> cerr(K, ClusterErr{0, 0, 0, 0});
+  if (audit) memset(audit, 0, sizeof(*audit));
 
   // The cluster being split: `cur` lists original point indices in ascending order (the reference
   // keeps tmp_data/point_index, :929-1019; before the first gather it is the identity).
@@ -272,6 +319,10 @@ static int varpart_impl(uint32_t num_pixels, const uint32_t *in, uint32_t num_ro
     Vec3 tm, tv;
     if (new_index == 1) {
       initial_mean_and_var(s, &tm, &tv);
+      // reference: U sequential adds of rounded products per sum
+      cerr[0].eW = 0.0;
+      cerr[0].eM = gamma_n(U) * 256.0;
+      cerr[0].eV = (3.0 * gamma_n(U) + 8.0 * kU) * 65536.0;
     } else {
       tm = mean[old_index];
       tv = var[old_index];
@@ -282,11 +333,14 @@ static int varpart_impl(uint32_t num_pixels, const uint32_t *in, uint32_t num_ro
     double best = tv.r;
     int axis = 0;
     double cut = tm.r;
+    const ClusterErr pe = cerr[old_index];
+    if (audit && std::fabs(best - tv.g) <= kSafety * 2.0 * pe.eV) audit->hit(1);
     if (best < tv.g) {
       best = tv.g;
       axis = 1;
       cut = tm.g;
     }
+    if (audit && std::fabs(best - tv.b) <= kSafety * 2.0 * pe.eV) audit->hit(1);
     if (best < tv.b) {
       axis = 2;
       cut = tm.b;
@@ -299,6 +353,7 @@ static int varpart_impl(uint32_t num_pixels, const uint32_t *in, uint32_t num_ro
 
     // ---- split pass (:438-559): points strictly above the cut seed the new cluster ----
     double nw = 0.0;
+    int cut_new = 0;
     {
       uint64_t ir = 0, ig = 0, ib = 0, cnt = 0;
       for (int j = 0; j < cur_n; ++j) {
@@ -306,7 +361,9 @@ static int varpart_impl(uint32_t num_pixels, const uint32_t *in, uint32_t num_ro
         uint32_t p = s.data[idx];
         uint32_t R = chan_r(p), G = chan_g(p), B = chan_b(p);
         double proj = (axis == 0) ? R : ((axis == 1) ? G : B);
+        if (audit && std::fabs(proj - cut) <= kSafety * pe.eM) audit->hit(2);
         if (cut < proj) {
+          ++cut_new;
           if (s.uniform) {
             uint64_t c = s.counts ? s.counts[idx] : 1u;
             ir += c * R;
@@ -342,7 +399,7 @@ static int varpart_impl(uint32_t num_pixels, const uint32_t *in, uint32_t num_ro
     om.b = (tw * tm.b - nw * nm.b) / ow;
 
     // ---- local 2-means refinement (:613-811) ----
-    int new_size = 0;
+    int new_size = cut_new;
     int prev_size = -1, converged_at = max_iters;
     uint64_t prev_sig = 0;
     if (new_index == 1) g_converged_n = 0;
@@ -350,6 +407,13 @@ static int varpart_impl(uint32_t num_pixels, const uint32_t *in, uint32_t num_ro
       const double lhs =
           0.5 * (sq(om.r) - sq(nm.r) + sq(om.g) - sq(nm.g) + sq(om.b) - sq(nm.b));  // (:616-619)
       const double rr = om.r - nm.r, rg = om.g - nm.g, rb = om.b - nm.b;
+      double eH = 0.0;
+      PassErr q = {0, 0, 0, 0};
+      const Vec3 om_pass = om, nm_pass = nm;  // the centres this pass classifies with
+      if (audit) {
+        q = pass_err(pe, tw, nw, ow, new_size);
+        eH = kSafety * (1536.0 * (q.e_om + q.e_nm) + 8388608.0 * kU);  // filter: holds for any point
+      }
       nw = 0.0;
       new_size = 0;
       nm = Vec3{0, 0, 0};
@@ -360,6 +424,13 @@ static int varpart_impl(uint32_t num_pixels, const uint32_t *in, uint32_t num_ro
         uint32_t p = s.data[idx];
         uint32_t R = chan_r(p), G = chan_g(p), B = chan_b(p);
         double red = R, green = G, blue = B;
+        if (audit && std::fabs(((rr * red) + (rg * green) + (rb * blue)) - lhs) <= eH) {
+          // inside the filter: the bound for this very point, sum_c |om_c - x_c| e_om + |nm_c - x_c| e_nm (dq_tie.cuh)
+          const double d_o = std::fabs(om_pass.r - red) + std::fabs(om_pass.g - green) + std::fabs(om_pass.b - blue);
+          const double d_n = std::fabs(nm_pass.r - red) + std::fabs(nm_pass.g - green) + std::fabs(nm_pass.b - blue);
+          if (std::fabs(((rr * red) + (rg * green) + (rb * blue)) - lhs) <= d_o * q.e_om + d_n * q.e_nm + 8388608.0 * kU)
+            audit->hit(3);
+        }
         if (lhs < ((rr * red) + (rg * green) + (rb * blue))) {
           // closer to the old centre (:683)
           if (it == last_it) member[idx] = (uint32_t)old_index;
@@ -425,6 +496,14 @@ static int varpart_impl(uint32_t num_pixels, const uint32_t *in, uint32_t num_ro
     size[old_index] = cur_n - new_size;
     size[new_index] = new_size;
     if (g_converged_n < 4096) g_converged_at[g_converged_n++] = converged_at;
+    PassErr fe = {0, 0, 0, 0};
+    if (audit) {
+      fe = pass_err(pe, tw, nw, ow, new_size);
+      cerr[new_index].eW = fe.e_nw;
+      cerr[new_index].eM = fe.e_nm;
+      cerr[old_index].eW = fe.e_ow;
+      cerr[old_index].eM = fe.e_om;
+    }
 
     oracle_split_record rec;
     memset(&rec, 0, sizeof(rec));
@@ -461,6 +540,28 @@ static int varpart_impl(uint32_t num_pixels, const uint32_t *in, uint32_t num_ro
     tse[old_index] = ow * (ov.r + ov.g + ov.b);
     tse[new_index] = nw * (nv.r + nv.g + nv.b);
 
+    if (audit) {
+      // new side: sum(w c^2)/nw - nm^2 ; old side: combined variance (:836-855)
+      const double eVn = (2.0 * gamma_n(new_size) + 8.0 * kU) * 65536.0 + 512.0 * fe.e_nm;
+      double eVo = 0.0;
+      const double nvv[3] = {nv.r, nv.g, nv.b}, nmm[3] = {nm.r, nm.g, nm.b}, tmm[3] = {tm.r, tm.g, tm.b},
+                   tvv[3] = {tv.r, tv.g, tv.b}, omm[3] = {om.r, om.g, om.b};
+      for (int c = 0; c < 3; ++c) {
+        const double dn = std::fabs(nmm[c] - tmm[c]), dmo = std::fabs(omm[c] - tmm[c]);
+        const double inner = std::fabs(nvv[c]) + dn * dn;
+        const double e_inner = eVn + 2.0 * dn * (fe.e_nm + pe.eM) + 3.0 * kU * inner;
+        const double e_num = pe.eW * std::fabs(tvv[c]) + tw * pe.eV + fe.e_nw * inner + nw * e_inner +
+                             3.0 * kU * (tw * std::fabs(tvv[c]) + nw * inner);
+        const double q = (tw * std::fabs(tvv[c]) + nw * inner) / std::fabs(ow);
+        const double e_q = (e_num + q * fe.e_ow) / std::fabs(ow) + kU * q;
+        const double e = e_q + 2.0 * dmo * (fe.e_om + pe.eM) + 3.0 * kU * (q + dmo * dmo);
+        if (!(e <= eVo)) eVo = e;  // NaN propagates
+      }
+      cerr[new_index].eV = eVn;
+      cerr[old_index].eV = eVo;
+      cerr[new_index].eT = fe.e_nw * std::fabs(nv.r + nv.g + nv.b) + nw * 3.0 * eVn + 4.0 * kU * std::fabs(tse[new_index]);
+      cerr[old_index].eT = fe.e_ow * std::fabs(ov.r + ov.g + ov.b) + std::fabs(ow) * 3.0 * eVo + 4.0 * kU * std::fabs(tse[old_index]);
+    }
     rec.new_var[0] = nv.r, rec.new_var[1] = nv.g, rec.new_var[2] = nv.b;
     rec.old_var[0] = ov.r, rec.old_var[1] = ov.g, rec.old_var[2] = ov.b;
     rec.new_tse = tse[new_index];
@@ -476,6 +577,18 @@ static int varpart_impl(uint32_t num_pixels, const uint32_t *in, uint32_t num_ro
         top = tse[ic];
         old_index = ic;
       }
+    }
+    if (audit) {
+      // D4: the winner must beat every other cluster (and DBL_MIN) by more than the bounds
+      bool tie = !(top - kSafety * cerr[old_index].eT > DBL_MIN);
+      for (int ic = 0; ic <= new_index && !tie; ++ic)
+        if (ic != old_index && !(top - tse[ic] > kSafety * (cerr[old_index].eT + cerr[ic].eT))) {
+          tie = true;
+          if (getenv("ORACLE_AUDIT_VERBOSE"))
+            fprintf(stderr, "D4 step %d: top %.17g (cluster %d, eT %.3e size %d) vs %.17g (cluster %d, eT %.3e size %d) diff %.3e\n", new_index, top,
+                    old_index, cerr[old_index].eT, size[old_index], tse[ic], ic, cerr[ic].eT, size[ic], top - tse[ic]);
+        }
+      if (tie) audit->hit(4);
     }
 
     // Gather its points in ascending original order (:929-1019).
@@ -498,6 +611,13 @@ static int varpart_impl(uint32_t num_pixels, const uint32_t *in, uint32_t num_ro
       uint32_t G = ((uint8_t)(mean[ic].g + 0.5)) << shift;
       uint32_t B = ((uint8_t)(mean[ic].b + 0.5)) << shift;
       colortable[emitted++] = (R << 16) | (G << 8) | B;
+      if (audit) {
+        const double mm[3] = {mean[ic].r, mean[ic].g, mean[ic].b};
+        for (int c = 0; c < 3; ++c) {
+          const double v = mm[c] + 0.5;
+          if (std::fabs(v - std::rint(v)) <= kSafety * (cerr[ic].eM + 512.0 * kU)) audit->hit(5);
+        }
+      }
     } else {
       ++empty;
     }
@@ -512,6 +632,18 @@ extern "C" int oracle_quant_varpart_fast(uint32_t num_pixels, const uint32_t *in
                                          oracle_split_record *records, int *num_records) {
   return varpart_impl(num_pixels, in, num_rows, num_cols, num_clusters, colortable, num_bits, dec_factor,
                       max_iters, all_pixels_unique, records, num_records, false);
+}
+
+// The device-arithmetic model with its tie audit: flags_out[0] = total, [1..5] = D1..D5 (see TieAudit).
+extern "C" int oracle_quant_varpart_fast_exact_audit(uint32_t num_pixels, const uint32_t *in, uint32_t num_rows,
+                                                     uint32_t num_cols, uint32_t *num_clusters, uint32_t *colortable,
+                                                     int num_bits, int dec_factor, int max_iters, int all_pixels_unique,
+                                                     uint32_t *flags_out) {
+  TieAudit audit;
+  int rc = varpart_impl(num_pixels, in, num_rows, num_cols, num_clusters, colortable, num_bits, dec_factor, max_iters,
+                        all_pixels_unique, nullptr, nullptr, true, &audit);
+  for (int i = 0; i < 6; ++i) flags_out[i] = audit.flags[i];
+  return rc;
 }
 
 extern "C" int oracle_quant_varpart_fast_exact(uint32_t num_pixels, const uint32_t *in, uint32_t num_rows,

@@ -1,0 +1,74 @@
+"""GPU parity over EVERY frame of BASELINE config 4 (1024 x 1080p G1, K=64) and every frame bench.py times (4K G1, K=256),
+against fingerprints of the compiled reference (tests/golden/frames.npz, written by tests/golden/make_golden_frames.py
+from oracle/_ref).  All of them have more colours than the ordered path's default limit, so they run on the exact-integer
+kernels with the tie audit: frames whose decisions sit inside the reference's rounding noise (11 of the 1024, three of
+which the integer sums alone would get wrong by one LSB: seeds 12410, 12830, 13124) must come back flagged AND equal to
+the reference, through the ordered re-run."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def frames():
+    return np.load(os.path.join(GOLDEN, "frames.npz"))
+
+
+def _check(dq, oracle, frames, tag, kind, w, h, k, count):
+    flagged, rerun, bad = 0, 0, []
+    for i in range(count):
+        seed = int(frames[f"{tag}_seeds"][i])
+        px = oracle.generate(kind, w, h, seed)
+        out, pal = dq.quant_recurse(px, k, 0)
+        st = dq.last_stats()
+        ok = (pal.size == int(frames[f"{tag}_pal_size"][i]) and oracle.hash_words(pal) == int(frames[f"{tag}_pal_hash"][i])
+              and oracle.hash_words(out) == int(frames[f"{tag}_out_hash"][i]))
+        if not ok:
+            bad.append((seed, st["tie_flags"], st["ordered_rerun"]))
+        model = int(frames[f"{tag}_tie_mask"][i])
+        # the device audits a superset of the model's comparisons (TSE pairs that never coexist in the reference)
+        assert (st["tie_flags"] & model) == model, (seed, st["tie_flags"], model)
+        if st["tie_flags"]:
+            flagged += 1
+            assert st["ordered_rerun"] == 1, seed
+            rerun += 1
+    assert not bad, bad
+    return flagged, rerun
+
+
+def test_config4_all_1024_frames_bit_exact(dq, oracle, frames):
+    flagged, rerun = _check(dq, oracle, frames, "c4", 1, 1920, 1080, 64, 1024)
+    assert flagged >= int((frames["c4_tie_mask"] != 0).sum()) == 11
+    assert flagged <= 40, flagged  # the audit must stay sharp: a few percent of the frames at most
+
+
+def test_bench_frames_bit_exact(dq, oracle, frames):
+    _check(dq, oracle, frames, "bench", 1, 3840, 2160, 256, len(frames["bench_seeds"]))
+
+
+def test_g2_1080p_bit_exact(dq, oracle, frames):
+    # SURVEY.md 8c/8d stress input: 1.95 M unique colours (brute-force remap, U > N/2)
+    _check(dq, oracle, frames, "g2", 2, 1920, 1080, 256, 1)
+
+
+def test_audit_off_reproduces_the_known_mismatch(dq, oracle, frames):
+    """With the audit off, seed 12410 is one LSB off in one palette entry: the reason the audit exists."""
+    lib = dq.lib
+    ctx = lib.dq_default_context()
+    lib.dq_context_set_tie_policy(ctx, 0)
+    try:
+        i = 12410 - 12345
+        px = oracle.generate(1, 1920, 1080, 12410)
+        out, pal = dq.quant_recurse(px, 64, 0)
+        assert oracle.hash_words(pal) != int(frames["c4_pal_hash"][i])
+        lib.dq_context_set_tie_policy(ctx, 1)  # report only
+        out, pal = dq.quant_recurse(px, 64, 0)
+        st = dq.last_stats()
+        assert st["tie_flags"] & 16 and st["ordered_rerun"] == 0
+    finally:
+        lib.dq_context_set_tie_policy(ctx, 2)

@@ -190,6 +190,8 @@ def test_natural_crops_ordered_and_integer_paths(dq, oracle, golden):
                     assert oracle.hash_words(out) == int(golden[f"crop{i}_out_hash"][0]), i   # integer work: bit-exact
                     continue
                 assert not (ordered and int(golden[f"crop{i}_unique"][0]) <= EXACT_MAX_POINTS), (i, "ordered path must be identical")
+                # the tie audit's contract: a frame the exact-integer kernels get wrong is a frame they flagged
+                assert dq.last_stats()["tie_flags"] != 0, (i, "integer path differs from the reference without a tie flag")
                 assert np.array_equal(out, oracle.map_colors_mps(px, pal)), i                 # remap of OUR palette: bit-exact
                 if pal.size == ref_pal.size:
                     sh = np.array([16, 8, 0])
@@ -533,12 +535,20 @@ def test_ordered_path_limits_and_large_k(dq, oracle):
         with muted((2,)):
             pal, empty = dq.quant_varpart_fast(px, 64)
         assert np.array_equal(pal, ref_pal) and empty == ref_empty
-        dq.lib.dq_context_set_exact_max_points(ctx, 5000)    # above the limit: exact-integer kernels
+        dq.lib.dq_context_set_exact_max_points(ctx, 5000)    # above the limit: exact-integer kernels ...
+        dq.lib.dq_context_set_tie_policy(ctx, 0)             # ... taken at their word (no tie audit)
         with muted((2,)):
             pal, empty = dq.quant_varpart_fast(px, 64)
         assert np.array_equal(pal, model) and empty == mempty
+        dq.lib.dq_context_set_tie_policy(ctx, 2)             # default: audited, flagged frames re-run in reference order
+        with muted((2,)):
+            pal, empty = dq.quant_varpart_fast(px, 64)
+        st = dq.last_stats()
+        assert np.array_equal(pal, ref_pal) and empty == ref_empty
+        assert st["tie_flags"] == 0 or st["ordered_rerun"] == 1
     finally:
         dq.lib.dq_context_set_exact_max_points(ctx, 65536)
+        dq.lib.dq_context_set_tie_policy(ctx, 2)
 
 
 def test_ordered_path_above_the_default_limit(dq, oracle, golden):
