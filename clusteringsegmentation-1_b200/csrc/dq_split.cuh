@@ -41,8 +41,9 @@ struct SplitNode {
   int32_t axis;   // cutting axis chosen when scheduled
   int32_t parent; // node this one was split from (-1 for the root)
   // Tie audit of the exact-integer path (dq_tie.cuh): first-order bounds on |this kernel's value - the reference's value|
-  // of tw, tm[], tv[] and tse, and the decisions of this node's own split that fell inside such a bound (TieBit mask).
-  double eW, eM, eV, eT;
+  // of the three sums behind the statistics (W, S = W*mean, Q = W*(var + mean^2)) and, derived from them, of tm[], tv[]
+  // and tse; and the decisions of this node's own split that fell inside such a bound (TieBit mask).
+  double eW, eS, eQ, eM, eV, eT;
   uint32_t tie;
   uint32_t pad;
 };

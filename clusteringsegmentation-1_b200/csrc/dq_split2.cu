@@ -47,11 +47,15 @@ constexpr unsigned long long kValueMask = (1ull << 48) - 1ull;
 
 struct JobConst {
   double tw, tm[3], cut;
-  double eW, eM;  // tie audit: the node's bounds (dq_tie.cuh); eM < 0 = audit off
   int32_t axis, buf;
   uint32_t begin, size;
-  uint32_t tie0, pad;  // kTieAxis when the axis choice itself is inside the noise
 };
+// Tie audit: what the bounds of a job's passes need from its node (dq_tie.cuh).  Lives in shared memory only; warp 1 and
+// thread 0 read it, nobody keeps it in registers.  eM < 0 = audit off.
+struct JobAudit {
+  double eW, eS, eM, m1;  // m1 = max |tm_c|
+};
+constexpr int kAudCache = 32;  // wide jobs of a CTA whose audit constants are kept (more than that: flagged wholesale)
 
 struct Shared2 {
   uint64_t red[32][kAccWords];
@@ -75,6 +79,8 @@ struct Shared2 {
   uint32_t cur_old, cur_new;
   uint32_t num_points;
   tie::PassExt ext;   // tie audit: centres and bounds behind S.pp (written with it)
+  JobAudit aud;       // tie audit: constants of the narrow job in flight
+  JobAudit wide_aud[kAudCache];
   uint32_t near;      // tie audit: points of the pass just reduced / gathered that sit inside the noise bound
   uint32_t job_tie;   // TieBit mask of the narrow job in flight
   uint32_t tie_total; // TieBit mask of the frame (CTA 0, final assignment + palette)
@@ -345,20 +351,8 @@ __device__ __forceinline__ void derive_params_warp0(Shared2 &S, const JobConst &
     const double a = fsq(om), b = fsq(nm);
     const double a1 = __shfl_sync(0xffffffffu, a, 1), b1 = __shfl_sync(0xffffffffu, b, 1);
     const double a2 = __shfl_sync(0xffffffffu, a, 2), b2 = __shfl_sync(0xffffffffu, b, 2);
-    if (threadIdx.x < 3) {
-      S.pp.r[c] = fsub(om, nm);
-      S.ext.om[c] = om;
-      S.ext.nm[c] = nm;
-    }
+    if (threadIdx.x < 3) S.pp.r[c] = fsub(om, nm);
     if (threadIdx.x == 0) {
-      // tie audit: tolerance of the hyperplane test for centres derived from a new side of tot[kAccPts] points
-      S.pp.tol = -1.0;
-      if (jc.eM >= 0.0) {
-        const tie::PassErr q = tie::pass_err(jc.eW, jc.eM, jc.tw, nw, ow, (double)(uint32_t)S.tot[kAccPts]);
-        S.pp.tol = tie::hyperplane_tol(q);
-        S.ext.e_om = q.e_om;
-        S.ext.e_nm = q.e_nm;
-      }
       double l = fsub(a, b);  // (:616-619), left to right
       l = fadd(l, a1);
       l = fsub(l, b1);
@@ -373,10 +367,64 @@ __device__ __forceinline__ void derive_params_warp0(Shared2 &S, const JobConst &
   }
 }
 
-__device__ __forceinline__ void set_split_params(Shared2 &S, const JobConst &jc) {
+// Tie audit, next to derive_params_warp0 and at the same time: WARP 1 sums the rows of S.red itself (the totals warp 0
+// is reducing into S.tot), derives the same centres and from them the tolerance of the next pass's hyperplane test
+// (dq_tie.cuh), so that the bound costs the split's critical path nothing.  Writes S.pp.tol_hi and S.ext only.
+__device__ __forceinline__ uint64_t warp_total_row(const Shared2 &S, int lane, int rows, int w) {
+  const uint64_t x = lane < rows ? S.red[lane][w] : 0ull;
+  const unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)(x & 0x7FFFFFFu));
+  const unsigned hi = __reduce_add_sync(0xffffffffu, (unsigned)(x >> 27));
+  return (uint64_t)lo + ((uint64_t)hi << 27);
+}
+__device__ __forceinline__ void derive_audit_warp1(Shared2 &S, const JobConst &jc, const JobAudit *aud, double norm, int rows) {
+  if (threadIdx.x >= 32 && threadIdx.x < 64) {  // uniform per warp
+    const int lane = threadIdx.x & 31;
+    const double eM = aud ? aud->eM : 0.0;
+    if (eM < 0.0) {  // audit off
+      if (lane == 0) S.pp.tol_hi = -1;
+      return;
+    }
+    if (aud == nullptr) {  // beyond the cache: every point counts as inside the noise (never seen in practice)
+      if (lane == 0) {
+        S.ext.tol = __longlong_as_double(0x7ff0000000000000ll);
+        S.ext.e_om = S.ext.e_nm = S.ext.tol;
+        S.pp.tol_hi = 0x7ff00001;
+      }
+      return;
+    }
+    const int c = min(lane, 2);
+    const uint64_t t_cnt = warp_total_row(S, lane, rows, kAccCnt), t_pts = warp_total_row(S, lane, rows, kAccPts);
+    const uint64_t t_r = warp_total_row(S, lane, rows, kAccR), t_g = warp_total_row(S, lane, rows, kAccG),
+                   t_b = warp_total_row(S, lane, rows, kAccB);
+    const uint64_t t_c = (c == 0) ? t_r : ((c == 1) ? t_g : t_b);
+    const double nw = fmul(u52_to_double(t_cnt), norm);
+    const double nm = fdiv(fmul(u52_to_double(t_c), norm), nw);
+    const double ow = fsub(jc.tw, nw);
+    const double om = fdiv(fsub(fmul(jc.tw, jc.tm[c]), fmul(nw, nm)), ow);
+    const double om1 = __shfl_sync(0xffffffffu, om, 1), nm1 = __shfl_sync(0xffffffffu, nm, 1);
+    const double om2 = __shfl_sync(0xffffffffu, om, 2), nm2 = __shfl_sync(0xffffffffu, nm, 2);
+    if (lane < 3) {
+      S.ext.om[c] = om;
+      S.ext.nm[c] = nm;
+    }
+    if (lane == 0) {
+      const tie::PassErr q = tie::pass_err_fast(aud->eW, aud->eS, jc.tw, aud->m1, nw, fmax(fabs(nm), fmax(fabs(nm1), fabs(nm2))), ow,
+                                                fmax(fabs(om), fmax(fabs(om1), fabs(om2))), (double)(uint32_t)t_pts);
+      const double tol = tie::hyperplane_tol(q);
+      S.ext.e_om = q.e_om;
+      S.ext.e_nm = q.e_nm;
+      S.ext.tol = tol;
+      S.pp.tol_hi = __double2hiint(tol) + (tol >= 0.0 ? 1 : 0);
+    }
+  }
+}
+
+__device__ __forceinline__ void set_split_params(Shared2 &S, const JobConst &jc, const JobAudit *aud) {
   if (threadIdx.x == 0) {
     S.pp.a = jc.cut;
-    S.pp.tol = jc.eM;  // tie audit of the cut test (:473): the cut is the node's mean
+    const double eM = aud ? aud->eM : __longlong_as_double(0x7ff0000000000000ll);
+    S.ext.tol = eM;  // tie audit of the cut test (:473): the cut is the node's mean
+    S.pp.tol_hi = __double2hiint(eM) + (eM >= 0.0 ? 1 : 0);
     S.pp.r[0] = S.pp.r[1] = S.pp.r[2] = 0.0;
     S.pp.axis = jc.axis;
     S.pp.buf = jc.buf;
@@ -385,15 +433,19 @@ __device__ __forceinline__ void set_split_params(Shared2 &S, const JobConst &jc)
   }
 }
 
-__device__ __forceinline__ JobConst job_const_of(const SplitNode &nd, bool audit) {
+__device__ __forceinline__ JobAudit job_audit_of(const SplitNode &nd, bool audit) {
+  JobAudit a;
+  a.eW = nd.eW;
+  a.eS = nd.eS;
+  a.m1 = tie::max3abs(nd.tm);
+  a.eM = audit ? nd.eM : -1.0;
+  return a;
+}
+__device__ __forceinline__ JobConst job_const_of(const SplitNode &nd) {
   JobConst jc;
   jc.tw = nd.tw;
   jc.tm[0] = nd.tm[0], jc.tm[1] = nd.tm[1], jc.tm[2] = nd.tm[2];
   choose_cut(nd.tv, nd.tm, jc.axis, jc.cut);
-  jc.eW = nd.eW;
-  jc.eM = audit ? nd.eM : -1.0;
-  jc.tie0 = (audit && tie::axis_tie(nd.tv, nd.eV)) ? (uint32_t)kTieAxis : 0u;
-  jc.pad = 0u;
   jc.buf = nd.buf;
   jc.begin = nd.begin;
   jc.size = nd.size;
@@ -426,7 +478,7 @@ __device__ __forceinline__ void write_children(const SplitArgs &A, Shared2 &S, i
     p->child = child0;
     p->axis = jc.axis;
     p->cut = jc.cut;
-    p->tie = tie_bits | jc.tie0;  // decisions of this split inside the reference's noise (counted if the split is consumed)
+    p->tie = tie_bits;  // decisions of this split inside the reference's noise (counted if the split is consumed)
   }
 }
 
@@ -578,17 +630,42 @@ __device__ void fast_assignment(const SplitArgs &A, Shared2 &S, const Arrays &R)
   for (int i = tid; i < (K + 31) / 32; i += T) R.cand[i] = 0;  // bitmap of popped ranks
   __syncthreads();
   // rank[i] = number of known nodes with a larger TSE
+  const bool audit = A.tie_audit != 0u;
   for (int i = tid; i < n; i += T) {
     const double t = R.tse[i];
     int above = n;
     if (t == t) {  // NaN is never selected (:882)
       above = 0;
+      if (!audit) {
 #pragma unroll 8
-      for (int m2 = 0; m2 < n; ++m2) above += (R.tse[m2] > t);
+        for (int m2 = 0; m2 < n; ++m2) above += (R.tse[m2] > t);
+      } else {
+        // tie audit, D4: does any other node's TSE come within the two bounds of this one?  (bit 30 of the rank word;
+        // whether that node matters to the reference's sequence is sorted out below, for the few nodes marked here)
+        const double e = R.terr[i];
+        int near = -1;  // the node itself always matches
+#pragma unroll 4
+        for (int m2 = 0; m2 < n; ++m2) {
+          const double o = R.tse[m2];
+          above += (o > t);
+          near += (fabs(o - t) <= e + R.terr[m2]);
+        }
+        if (near > 0) above |= 1 << 30;
+      }
     }
     R.rank[i] = above;
   }
   __syncthreads();
+  uint32_t near_mask = 0u;  // per thread: bit q = its q-th node was marked
+  if (audit) {
+    int q = 0;
+    for (int i = tid; i < n; i += T, ++q) {
+      if (R.rank[i] & (1 << 30)) near_mask |= 1u << (q & 31);
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += T) R.rank[i] &= ~(1 << 30);
+    __syncthreads();
+  }
   for (int i = tid; i < n; i += T) {
     const double t = R.tse[i];
     const int above = R.rank[i];
@@ -614,12 +691,14 @@ __device__ void fast_assignment(const SplitArgs &A, Shared2 &S, const Arrays &R)
     // DBL_MIN seed and from the TSE of every other node of the reference's sequence (popped nodes and their children) by
     // more than the two bounds.  Also collects the decisions flagged inside the consumed splits themselves.
     uint32_t bits = 0u;
-    for (int i = tid; i < n; i += T) {
+    int q = 0;
+    for (int i = tid; i < n; i += T, ++q) {
       if (R.rank[i] >= K - 1) continue;
       bits |= __ldcg(&A.nodes[i].tie);
       if (i == 0) continue;  // the root is split first, unconditionally
       const double t = R.tse[i], e = R.terr[i];
       if (!(t - e > DBL_MIN)) bits |= (uint32_t)kTieTse;
+      if (!((near_mask >> (q & 31)) & 1u) && q < 32) continue;
       for (int m2 = 1; m2 < n; ++m2) {
         if (m2 == i) continue;
         const bool relevant = R.rank[m2] < K - 1 || R.rank[R.parent[m2]] < K - 1;
@@ -763,6 +842,7 @@ __device__ void sequential_controller(const SplitArgs &A, Shared2 &S, const Arra
 template <bool SPLIT, bool FINAL>
 __device__ __forceinline__ unsigned narrow_pass(Shared2 &S, const uint2 (&p)[kNarrowPPT], unsigned validmask, int ppt,
                                                 int nwarps, const JobConst &jc, double norm) {
+  // (tie audit constants of the narrow job in flight: S.aud)
   const PassParams pp = S.pp;
   AccD acc = acc_zero();
   unsigned newmask = 0;
@@ -800,6 +880,8 @@ __device__ __forceinline__ unsigned narrow_pass(Shared2 &S, const uint2 (&p)[kNa
       }
       derive_params_warp0(S, jc, norm);
     }
+  } else if (!FINAL) {
+    derive_audit_warp1(S, jc, &S.aud, norm, nwarps);
   }
   __syncthreads();
   return newmask;
@@ -892,6 +974,13 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
   if (A.exact_small_max != 0u && U <= A.exact_small_max) {
     // small input: the reference's own summation order (dq_split_exact.cuh); stand-alone kernels did it unless fused
     if (X.exact_fused && U > 0u) {
+      __shared__ SplitArgs s_args;
+      __shared__ Split2Extra s_extra;
+      if (tid == 0) {
+        s_args = A;
+        s_extra = X;
+      }
+      __syncthreads();
       exact_first_seen(X.exact_src, X.exact_first_seen, (uint32_t)(b * T + tid), (uint32_t)(G * T));
       if (X.exact_fused == 2u && (U > (uint32_t)exact::kSmemPoints || K >= 32)) {
         // (few splits of a small input: CTA 0 alone, with everything in shared memory, is quicker)
@@ -900,14 +989,16 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
         for (uint32_t i = (uint32_t)(b * T + tid); i < A.node_cap; i += (uint32_t)(G * T)) og.state[i] = ordered::kInvalid;
         if (b == 0 && tid < 4) og.counters[tid] = 0u;
         grid_barrier2(A, bar_target, X.progress);
-        ordered::run(A, X, (int)U, smem_raw, b, G, bar_target);
+        // (the bodies of the ordered path are not inlined: they get the argument blocks through shared memory, so that the
+        // kernel parameters never have to be spilled to a local copy that the exact-integer path would then read too)
+        ordered::run(s_args, s_extra, (int)U, smem_raw, b, G, bar_target);
         if (b == 0) publish_mailbox(A, U);
         return;
       }
       grid_barrier2(A, bar_target, X.progress);
       if (b == 0) {
         const size_t Kz = (size_t)K;
-        exact::split_exact_body<T>(A, (int)U, smem_raw, X.exact_scratch, X.collect_uniq, X.collect_table, X.exact_first_seen, X.exact_f64,
+        exact::split_exact_body<T>(s_args, (int)U, smem_raw, X.exact_scratch, X.collect_uniq, X.collect_table, X.exact_first_seen, X.exact_f64,
                                    X.exact_f64 + Kz, X.exact_f64 + 2 * Kz, X.exact_f64 + 5 * Kz, X.exact_i32);
         publish_mailbox(A, U);
       }
@@ -970,9 +1061,12 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
     root.child = -1;
     root.axis = 0;
     root.parent = -1;
-    root.eW = root.eM = root.eV = root.eT = 0.0;
+    root.eW = root.eS = root.eQ = root.eM = root.eV = root.eT = 0.0;
     root.tie = root.pad = 0u;
-    if (audit) tie::root_bounds((double)U, root.eW, root.eM, root.eV);
+    if (audit) {
+      const tie::Bounds rb = tie::root_bounds((double)U, root.tm, root.tv);
+      root.eW = rb.eW, root.eS = rb.eS, root.eQ = rb.eQ, root.eM = rb.eM, root.eV = rb.eV, root.eT = rb.eT;
+    }
     S.root = root;
     if (b == 0) A.nodes[0] = root;
     S.tie_total = 0u;
@@ -1159,9 +1253,12 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
       for (int i = b * T + tid; i < 2 * K; i += G * T) other[i] = 0u;
     }
     const int n_mywide = S.n_mywide, n_mynarrow = S.n_mynarrow;
-    for (int mw = tid; mw < min(n_mywide, kWideCache); mw += T) {
-      // (executed by <= kWideCache threads) constants of the first few wide jobs stay in shared memory
-      S.wide[mw] = job_const_of(load_node(A, S, R.jobnode[R.mywide[mw]]), audit);
+    for (int mw = tid; mw < min(n_mywide, kAudCache); mw += T) {
+      // (executed by a few threads) constants of the first few wide jobs stay in shared memory
+      const SplitNode nd = load_node(A, S, R.jobnode[R.mywide[mw]]);
+      if (mw < kWideCache) S.wide[mw] = job_const_of(nd);
+      S.wide_aud[mw] = job_audit_of(nd, audit);
+      if (audit && tie::axis_tie(nd.tv, nd.eV)) R.jobtie[R.mywide[mw]] |= (uint8_t)kTieAxis;  // D1 (:388-403)
     }
     __syncthreads();
     trace2(A, kTracePhaseC, njobs);
@@ -1174,7 +1271,7 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
     const unsigned seq0 = 1u + (unsigned)round * (unsigned)(P + 1);
     auto wide_const = [&](int mw) -> JobConst {
       if (mw < kWideCache) return S.wide[mw];
-      return job_const_of(load_node(A, S, R.jobnode[R.mywide[mw]]), audit);
+      return job_const_of(load_node(A, S, R.jobnode[R.mywide[mw]]));
     };
     // This CTA's share of wide job j: participants, my rank among them, my first point and how many.
     struct Share {
@@ -1234,8 +1331,9 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
         const long long w0 = clock64();
         long long w1 = w0;
 #endif
+        const JobAudit *aud = (mw < kAudCache) ? &S.wide_aud[mw] : nullptr;
         if (pass == 0) {
-          set_split_params(S, jc);
+          set_split_params(S, jc, aud);
         } else {
           gather(A, S, slots_r, R.slot0[j], m, 5, (seq0 + pass - 1) & 0xFFFFu);
           if (tid == 0 && S.near) R.jobtie[j] |= (pass == 1) ? (uint8_t)kTieCut : (uint8_t)kTieHyperplane;
@@ -1243,6 +1341,7 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
           w1 = clock64();
 #endif
           derive_params_warp0(S, jc, A.norm);
+          derive_audit_warp1(S, jc, aud, A.norm, kWarps);
         }
         __syncthreads();
 #ifdef DQ_PROFILE_NARROW
@@ -1301,7 +1400,7 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
       // classification of the last pass (parameters from the totals of pass P-1)
       if (mw >= kWideCache) {
         gather(A, S, X.slots + (size_t)((P - 1) & 1) * X.slot_cap * kAccWords, R.slot0[j], m, 5, (seq0 + P - 1) & 0xFFFFu);
-        derive_params_warp0(S, jc, A.norm);
+        derive_params_warp0(S, jc, A.norm);  // (only the partition's re-classification follows: no audit)
         __syncthreads();
       }
       const PassParams pp = (mw < kWideCache) ? S.wide_pp[mw] : S.pp;
@@ -1384,10 +1483,11 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
         S.cur = load_node(A, S, node);
         S.cur_old = 0;
         S.cur_new = 0;
-        S.job_tie = 0u;
+        S.aud = job_audit_of(S.cur, audit);
+        S.job_tie = (audit && tie::axis_tie(S.cur.tv, S.cur.eV)) ? (uint32_t)kTieAxis : 0u;  // D1 (:388-403)
       }
       __syncthreads();
-      const JobConst jc = job_const_of(S.cur, audit);
+      const JobConst jc = job_const_of(S.cur);
       // all warps the job has points for; up to kNarrowPPT points per thread, held in registers for every pass
       const uint32_t nthr = min((uint32_t)T, max(32u, (jc.size + 31u) & ~31u));
       const int nwarps = (int)(nthr >> 5);
@@ -1402,7 +1502,7 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
           validmask |= 1u << k;
         }
       }
-      set_split_params(S, jc);
+      set_split_params(S, jc, &S.aud);
       __syncthreads();
       const int ppt = (int)((jc.size + nthr - 1) / nthr);
       unsigned newmask = narrow_pass<true, false>(S, p, validmask, ppt, nwarps, jc, A.norm);

@@ -79,6 +79,7 @@ struct Points {
   uint16_t *member;  // K <= kExactMaxColors <= 65535
   uint32_t *cur;     // points of the cluster being split, ascending original order (:929-1019)
   bool cur_shared_across_ctas;  // index lists written by other CTAs: read them past the (incoherent) L1
+  bool in_global;    // the point arrays live in the global scratch: Shared::w/colour/member/cur are free (chunk_sums_parallel)
 };
 __device__ __forceinline__ int load_cur(const Points &P, int j) {
   return P.cur_shared_across_ctas ? (int)__ldcg(P.cur + j) : (int)P.cur[j];
@@ -158,6 +159,215 @@ __device__ __forceinline__ void group_ranks(Shared &S, int mine, bool flag, int 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The reference's sequential double sums, evaluated in parallel.
+//
+// s <- RN(s + t) over the new-side terms of one chunk, for each of the `nchains` accumulator chains, starting from the
+// chain's accumulator and giving exactly the value the one-term-after-the-other loop of add_terms gives.  Why that is
+// possible: while the accumulator stays inside one binade [2^e, 2^(e+1)) every addition rounds to a multiple of
+// q = 2^(e-52), and s (a multiple of q) + t rounds to s + RN_q(t) unless t's remainder is exactly q/2 (round-half-even
+// looks at s then).  So inside a binade the sum of a run of terms is s + sum RN_q(t_i): an order-free exact sum.
+//   phase A  every thread adds its piece's terms (plain doubles) and a block scan of those gives the approximate
+//            accumulator at every piece: the binade e each piece runs in, or "unsafe" when the piece may cross into the
+//            next binade (judged with a 2^-20 margin) or starts from zero
+//   phase B  every thread adds RN_q(t) of its terms (C = 2^e: RN(C + t) - C, the residual t - that tells an exact half);
+//            the terms of unsafe pieces (crossings, exact halves: a few per chunk) are staged instead
+//   walk     thread c < nchains carries chain c's exact accumulator through the pieces: warps whose 32 pieces are safe
+//            in one binade in one step, safe pieces in one step each, staged terms one by one.  Every step is checked
+//            on the exact accumulator (it is in binade e before and after): a failed check abandons the chunk,
+//            and the caller falls back to the staged sequential loop.  The result is therefore the sequential sum
+//            unconditionally; the predictions only decide how fast it is reached.
+// Uses Shared::terms (piece table) and Shared::w (staged terms): only when the point arrays live in global memory.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kParSlots = 36;     // staged (unsafe) pieces per chain and chunk
+constexpr int kParMinTerms = 768; // chunks with fewer new-side terms take the sequential loop
+constexpr uint32_t kMetaEmpty = 0u, kMetaMixed = 0xFFFFFFFFu, kMetaUnsafe = 0x80000000u;
+
+__device__ __forceinline__ int exp_of(double x) { return (__double2hiint(x) >> 20) & 0x7FF; }  // biased; 0 for 0.0
+__device__ __forceinline__ double pow2_biased(int e) { return __hiloint2double(e << 20, 0); }
+
+template <int THREADS>
+struct ParScratch {
+  double pieceD[7][THREADS];
+  uint32_t meta[7][THREADS];  // 0 nothing to add | biased exponent (safe) | kMetaUnsafe | slot << 8 | terms
+  double warpD[7][THREADS / 32];
+  uint32_t warpmeta[7][THREADS / 32];  // kMetaEmpty | exponent (every piece safe, one binade) | kMetaMixed
+  double scan[7][THREADS / 32];
+  uint32_t slots[8];  // [c] staged pieces of chain c, [7] failure flag
+};
+static_assert(sizeof(ParScratch<512>) <= sizeof(double) * 7 * kTile, "piece table must fit into Shared::terms");
+static_assert(7 * kParSlots * kPiece <= kSmemPoints, "staged terms must fit into Shared::w");
+
+template <int THREADS>
+__device__ __noinline__ bool chunk_sums_parallel(Shared &S, const Points &P, int lo, int hi, unsigned mask, int nchains, double &acc) {
+  ParScratch<THREADS> &Q = *reinterpret_cast<ParScratch<THREADS> *>(&S.terms[0][0]);
+  double *const staged = S.w;  // [7][kParSlots * kPiece]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < nchains) S.chain[tid] = acc;
+  if (tid < 8) Q.slots[tid] = 0u;
+  // ---- phase A: plain sums of my piece ----
+  double p[7];
+#pragma unroll
+  for (int c = 0; c < 7; ++c) p[c] = 0.0;
+  for (int j = lo; j < hi; ++j) {
+    if (!((mask >> (j - lo)) & 1u)) continue;
+    const int idx = load_cur(P, j);
+    const double wt = P.w[idx];
+    const uint32_t col = P.colour[idx];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) p[c] = fadd(p[c], fmul(wt, chan(col, c)));
+    p[3] = fadd(p[3], wt);
+    if (nchains > 4) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) p[4 + c] = fadd(p[4 + c], fmul(wt, chan_sq(col, c)));
+    }
+  }
+  // ---- exclusive block scan of p[] ----
+  double before[7];
+#pragma unroll
+  for (int c = 0; c < 7; ++c) {
+    before[c] = 0.0;
+    if (c < nchains) {
+      double incl = p[c];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (lane == 31) Q.scan[c][warp] = incl;
+      before[c] = incl - p[c];
+    }
+  }
+  __syncthreads();
+  // ---- binade of every piece, RN_q sums (phase B) ----
+  int e[7];
+  unsigned unsafe = 0, staged_done = 0;
+  double D[7];
+#pragma unroll
+  for (int c = 0; c < 7; ++c) {
+    D[c] = 0.0;
+    e[c] = 0;
+    if (c < nchains) {
+      double a = S.chain[c] + before[c];
+      for (int w = 0; w < warp; ++w) a += Q.scan[c][w];
+      const double b = a + p[c];
+      if (p[c] > 0.0) {
+        const int ea = exp_of(a * (1.0 - 9.5367431640625e-07)), eb = exp_of(b * (1.0 + 9.5367431640625e-07));
+        e[c] = ea;
+        if (!(a > 0.0) || ea != eb || ea == 0) unsafe |= 1u << c;
+      }
+    }
+  }
+  for (int round = 0; round < 2; ++round) {
+    // round 0: RN_q sums of the safe chains, terms of the chains known to be unsafe are staged
+    // round 1: only if an exact half turned up in round 0 -- those chains are staged now
+    const unsigned to_stage = unsafe & ~staged_done;
+    int slot[7];
+#pragma unroll
+    for (int c = 0; c < 7; ++c) {
+      slot[c] = 0;
+      if (c < nchains && ((to_stage >> c) & 1u)) slot[c] = (int)atomicAdd(&Q.slots[c], 1u);
+    }
+    if (round == 1 && to_stage == 0u) break;
+    int k = 0;
+    unsigned halves = 0;
+    for (int j = lo; j < hi; ++j) {
+      if (!((mask >> (j - lo)) & 1u)) continue;
+      const int idx = load_cur(P, j);
+      const double wt = P.w[idx];
+      const uint32_t col = P.colour[idx];
+#pragma unroll
+      for (int c = 0; c < 7; ++c) {
+        if (c >= nchains) continue;
+        const bool mine_staged = (to_stage >> c) & 1u;
+        const bool mine_sum = round == 0 && p[c] > 0.0 && !((unsafe >> c) & 1u);
+        if (!mine_staged && !mine_sum) continue;
+        const double t = (c == 3) ? wt : ((c < 3) ? fmul(wt, chan(col, c)) : fmul(wt, chan_sq(col, c - 4)));
+        if (mine_staged) {
+          if (slot[c] < kParSlots) staged[(c * kParSlots + slot[c]) * kPiece + k] = t;
+        } else {
+          const double C = pow2_biased(e[c]);
+          const double y = fsub(fadd(C, t), C);  // RN_q(t), q = ulp of binade e
+          const double r = fsub(t, y);           // exact
+          if (fabs(r) == pow2_biased(e[c] - 53)) halves |= 1u << c;  // exactly q/2: the accumulator's parity decides
+          D[c] = fadd(D[c], y);
+        }
+      }
+      ++k;
+    }
+    staged_done |= to_stage;
+#pragma unroll
+    for (int c = 0; c < 7; ++c) {
+      if (c < nchains && ((to_stage >> c) & 1u)) {
+        if (slot[c] >= kParSlots) Q.slots[7] = 1u;  // no room: abandon the chunk
+        Q.meta[c][tid] = kMetaUnsafe | ((uint32_t)slot[c] << 8) | (uint32_t)k;
+      }
+    }
+    unsafe |= halves;
+    if (halves == 0u) break;
+  }
+  // ---- piece table + warp aggregates ----
+#pragma unroll
+  for (int c = 0; c < 7; ++c) {
+    if (c < nchains) {
+      const bool is_unsafe = (unsafe >> c) & 1u, empty = !(p[c] > 0.0);
+      if (!is_unsafe) {
+        Q.pieceD[c][tid] = D[c];
+        Q.meta[c][tid] = empty ? kMetaEmpty : (uint32_t)e[c];
+      }
+      const int e_max = __reduce_max_sync(0xffffffffu, (empty || is_unsafe) ? 0 : e[c]);
+      const bool uniform = __all_sync(0xffffffffu, !is_unsafe && (empty || e[c] == e_max));
+      double dw = (empty || is_unsafe) ? 0.0 : D[c];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) dw = fadd(dw, __shfl_xor_sync(0xffffffffu, dw, o));
+      if (lane == 0) {
+        Q.warpD[c][warp] = dw;
+        Q.warpmeta[c][warp] = !uniform ? kMetaMixed : (e_max == 0 ? kMetaEmpty : (uint32_t)e_max);
+      }
+    }
+  }
+  __syncthreads();
+  // ---- walk: thread c carries chain c ----
+  double s = acc;
+  if (tid < nchains && Q.slots[7] == 0u) {
+    const int c = tid;
+    bool fail = false;
+    for (int w = 0; w < THREADS / 32 && !fail; ++w) {
+      const uint32_t wm = Q.warpmeta[c][w];
+      if (wm == kMetaEmpty) continue;
+      if (wm != kMetaMixed && exp_of(s) == (int)wm) {
+        const double s2 = fadd(s, Q.warpD[c][w]);  // exact while it stays in the binade
+        if (exp_of(s2) == (int)wm) {
+          s = s2;
+          continue;
+        }
+      }
+      for (int i = w * 32; i < w * 32 + 32; ++i) {
+        const uint32_t m = Q.meta[c][i];
+        if (m == kMetaEmpty) continue;
+        if (m & kMetaUnsafe) {
+          const double *src = staged + (c * kParSlots + (int)((m >> 8) & 0xFFu)) * kPiece;
+          const int n = (int)(m & 0xFFu);
+          for (int k = 0; k < n; ++k) s = fadd(s, src[k]);
+        } else {
+          const double s2 = fadd(s, Q.pieceD[c][i]);
+          if (exp_of(s) != (int)m || exp_of(s2) != (int)m) {
+            fail = true;
+            break;
+          }
+          s = s2;
+        }
+      }
+    }
+    if (fail) Q.slots[7] = 1u;
+  }
+  __syncthreads();
+  const bool ok = Q.slots[7] == 0u;
+  __syncthreads();  // the table is free again
+  if (ok && tid < nchains) acc = s;
+  return ok;
+}
+
 // One pass: classify cur[0..cur_n) with pred (true = new side; `each` sees every point), then sum the new side's
 // terms in order.  Leaves chain[0..nchains) and new_size in S.  SOLO: executed by warp 0 only.
 // Chunks of (group size * kPiece) points: a thread owns a contiguous piece of each chunk so that the order survives.
@@ -200,7 +410,9 @@ __device__ __forceinline__ bool pass_sums(Shared &S, const Points &P, int cur_n,
     bool any_changed;
     group_ranks<THREADS, SOLO>(S, __popc(mask), changed, first, total, any_changed);
     same = same && !any_changed;
-    for (int tile = 0; tile < total; tile += kTile) {
+    bool summed = false;
+    if (!SOLO && P.in_global && total >= kParMinTerms) summed = chunk_sums_parallel<THREADS>(S, P, lo, hi, mask, nchains, acc);
+    for (int tile = 0; !summed && tile < total; tile += kTile) {
       // my new-side points have ranks [first, first + mine): stage those that fall into this tile
       int rank = first;
       for (int j0 = lo; j0 < hi; j0 += 4) {
@@ -307,7 +519,7 @@ __device__ __forceinline__ void split_passes(Shared &S, const Points &P, int cur
 // uniq / table: the histogram (unique colours in arrival order, counts; the counts are zeroed on the way);
 // first_seen[c]: smallest sample index of colour c; g_*: per-cluster scratch in global memory, used when K > 1024.
 template <int THREADS>
-__device__ void split_exact_body(const SplitArgs &A, int U, unsigned char *smem, unsigned char *scratch, const uint32_t *uniq,
+__device__ __noinline__ void split_exact_body(const SplitArgs &A, int U, unsigned char *smem, unsigned char *scratch, const uint32_t *uniq,
                                  uint32_t *table, const uint32_t *first_seen, double *g_weight, double *g_tse, double *g_mean,
                                  double *g_var, int32_t *g_size) {
   Shared &S = *reinterpret_cast<Shared *>(smem);
@@ -323,6 +535,7 @@ __device__ void split_exact_body(const SplitArgs &A, int U, unsigned char *smem,
   if (U <= kSmemPoints) {
     P.keys = S.keys, P.w = S.w, P.colour = S.colour, P.member = S.member, P.cur = S.cur;
     P.cur_shared_across_ctas = false;
+    P.in_global = false;
   } else {
     P.keys = reinterpret_cast<unsigned long long *>(scratch);
     P.w = reinterpret_cast<double *>(scratch + (size_t)kExactMaxPoints * 8);
@@ -330,6 +543,7 @@ __device__ void split_exact_body(const SplitArgs &A, int U, unsigned char *smem,
     P.cur = reinterpret_cast<uint32_t *>(scratch + (size_t)kExactMaxPoints * 20);
     P.member = reinterpret_cast<uint16_t *>(scratch + (size_t)kExactMaxPoints * 28);
     P.cur_shared_across_ctas = false;
+    P.in_global = true;
   }
 
   // ---- points in calc_color_table's emission order: (bucket asc, first seen desc) ----

@@ -43,12 +43,15 @@ __device__ __forceinline__ void derive_means(double tw, const double *tm, double
 // What every thread needs to classify a point in the current pass.
 struct PassParams {
   double a;     // pass 0: cut position; later: lhs (:616-619)
-  double tol;   // tie audit: a point whose test value is within tol of `a` is inside the reference's rounding noise (< 0: off)
   double r[3];  // rhs = old_mean - new_mean (:621-623)
   int32_t axis;
   int32_t buf;
   uint32_t begin;
   uint32_t size;
+  // tie audit: high word (+1) of the tolerance tie::PassExt::tol -- a point whose test value is within tol of `a` is
+  // inside the reference's rounding noise; negative when the audit is off
+  int32_t tol_hi;
+  int32_t pad;
 };
 
 // lhs / rhs of the hyperplane test from the two centres (:616-623)
@@ -104,11 +107,18 @@ __device__ __forceinline__ bool goes_new_audit(const PassParams &pp, const tie::
     x = fadd(fadd(fmul(pp.r[0], d.r), fmul(pp.r[1], d.g)), fmul(pp.r[2], d.b));
   }
   const double m = fsub(x, pp.a);
-  if (fabs(m) <= pp.tol) {  // inside the filter (a handful of points per frame): the bound for this very point decides
-    if (SPLIT) near = true;
-    else near = near || (fabs(m) <= tie::point_tol(*ext, d.r, d.g, d.b));
+  // The sign and the magnitude class of m are read off its high word on the integer pipe (which idles next to the FP64
+  // pipe here): m > 0 <=> hi > 0 (a non-zero difference of these operands is never below 2^-1022), and
+  // |m| <= tol  =>  (hi & 0x7fffffff) <= hi(tol), a filter that passes a handful of points per frame; the exact test
+  // and the bound for the very point follow only for those.  tol < 0 (audit off) has a negative high word: never passes.
+  const int hi = __double2hiint(m);
+  if ((hi & 0x7fffffff) <= pp.tol_hi) {
+    if (fabs(m) <= ext->tol) {
+      if (SPLIT) near = true;
+      else near = near || (fabs(m) <= tie::point_tol(*ext, d.r, d.g, d.b));
+    }
   }
-  return SPLIT ? (m > 0.0) : !(m > 0.0);
+  return SPLIT ? (hi > 0) : !(hi > 0);
 }
 // Accumulation stays on the integer pipe (IMAD.WIDE), which runs next to the FP64 pipe that classifies:
 // exact u64 sums of count*c and count*c*c.
@@ -204,14 +214,17 @@ __device__ __forceinline__ void make_children(const SplitNode &parent, int paren
   o.size = parent.size - size_new;  // size[old] = tmp_num_points - new_size (:819)
   n.begin = parent.begin + o.size;
   n.size = size_new;
-  o.eW = o.eM = o.eV = o.eT = n.eW = n.eM = n.eV = n.eT = 0.0;
+  o.eW = o.eS = o.eQ = o.eM = o.eV = o.eT = n.eW = n.eS = n.eQ = n.eM = n.eV = n.eT = 0.0;
   o.tie = n.tie = 0u;
   o.pad = n.pad = 0u;
   if (audit) {
-    const tie::PassErr fe = tie::pass_err(parent.eW, parent.eM, parent.tw, m.nw, m.ow, (double)size_new);
-    n.eW = fe.e_nw, n.eM = fe.e_nm, o.eW = fe.e_ow, o.eM = fe.e_om;
-    tie::child_var_bounds(fe, parent.eW, parent.eM, parent.eV, parent.tw, parent.tm, parent.tv, m.nw, m.ow, m.nm, m.om, n.tv,
-                          o.tv, (double)size_new, n.tse, o.tse, n.eV, o.eV, n.eT, o.eT);
+    const tie::PassErr fe = tie::pass_err(parent.eW, parent.eS, parent.tw, tie::max3abs(parent.tm), m.nw, tie::max3abs(m.nm), m.ow,
+                                          tie::max3abs(m.om), (double)size_new);
+    tie::Bounds bp, bn, bo;
+    bp.eW = parent.eW, bp.eS = parent.eS, bp.eQ = parent.eQ;
+    tie::child_bounds(bp, fe, parent.tw, parent.tm, parent.tv, m.nw, m.nm, n.tv, n.tse, m.ow, m.om, o.tv, o.tse, (double)size_new, bn, bo);
+    n.eW = bn.eW, n.eS = bn.eS, n.eQ = bn.eQ, n.eM = bn.eM, n.eV = bn.eV, n.eT = bn.eT;
+    o.eW = bo.eW, o.eS = bo.eS, o.eQ = bo.eQ, o.eM = bo.eM, o.eV = bo.eV, o.eT = bo.eT;
   }
   (void)child0;
 }

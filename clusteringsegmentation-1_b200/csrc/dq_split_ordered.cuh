@@ -91,6 +91,7 @@ __device__ bool split_node(const SplitArgs &A, Shared &S, const Scratch &G, int 
   P.keys = G.keys, P.w = G.w, P.colour = G.colour, P.member = nullptr;
   P.cur = G.idx[s_nd.buf] + s_nd.begin;
   P.cur_shared_across_ctas = true;
+  P.in_global = true;
   unsigned masks[kMaxChunks];
   const bool solo = cur_n <= kSolo;
   if (solo) {
@@ -233,7 +234,7 @@ __device__ int pick_leaf(const SplitArgs &A, const Scratch &G, int K) {
 
 // The whole divisive phase of one input on all CTAs.  Called by every thread of every CTA after the first-seen pass and
 // the grid barrier that follows it; state[] = kInvalid and counters[] = 0 were set before that barrier.
-__device__ void run(const SplitArgs &A, const Split2Extra &X, int U, unsigned char *smem, int b, int nctas, unsigned int &bar_target) {
+__device__ __noinline__ void run(const SplitArgs &A, const Split2Extra &X, int U, unsigned char *smem, int b, int nctas, unsigned int &bar_target) {
   Shared &S = *reinterpret_cast<Shared *>(smem);
   const Scratch G = carve(X.exact_scratch, A.node_cap);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -347,6 +348,7 @@ __device__ void run(const SplitArgs &A, const Split2Extra &X, int U, unsigned ch
   Points P;
   P.keys = G.keys, P.w = G.w, P.colour = G.colour, P.member = nullptr, P.cur = G.idx[0];
   P.cur_shared_across_ctas = true;
+  P.in_global = true;
   // cluster arrays of the reference (:296-324): cluster -> node and tse[]
   double *ctse = (K <= exact::kSmemColors) ? S.k_tse : X.exact_f64;
   int32_t *cnode = (K <= exact::kSmemColors) ? S.k_size : X.exact_i32;

@@ -8,12 +8,16 @@
 // split tree; a decision inside its bound raises a TieBit, and the host re-runs a flagged frame in the reference's own
 // summation order (the ordered path, dq_split_ordered.cuh).  A frame without a flag equals the reference bit for bit.
 //
-// Bounds are on |value here - value in the reference| with u = 2^-53:
-//   * a sequential sum of n rounded products: gamma(n) = min(n + 4, lambda sqrt(n + 4)) u relative.  n u is the worst
-//     case; rounding errors are not aligned, and lambda sqrt(n) u holds with probability 1 - 2 exp(-lambda^2 / 2)
-//     (Higham & Mary, "A new approach to probabilistic rounding error analysis", 2019); lambda = 8: 3e-14 per sum.
-//     The measured rms of such a sum's error is ~0.3 sqrt(n) u, so the bound sits ~25 sigma out.
-//   * every scalar formula propagates its operands' bounds to first order, with |channel| <= 256, |channel^2| <= 65536.
+// What is bounded, with u = 2^-53: for every cluster the absolute deviation between this kernel's and the reference's
+//   W = weight,  S_c = weight * mean_c,  Q_c = weight * (var_c + mean_c^2)          (eW, eS, eQ; max over channels)
+// i.e. of the three sums the statistics stand for.  In these variables a split is linear (old = parent - new: :579-581,
+// :844-855 are exact identities), so bounds simply add along the chain of "old" sides, plus a few u per formula step:
+//   * a fresh sequential sum of n rounded products deviates by gamma(n) = min(n + 4, lambda sqrt(n + 4)) u relative.
+//     n u is the worst case; rounding errors are not aligned, and lambda sqrt(n) u holds with probability
+//     1 - 2 exp(-lambda^2 / 2) (Higham & Mary, "A new approach to probabilistic rounding error analysis", SISC 2019);
+//     lambda = 8: 3e-14 per sum.  The rms of such a sum's error is ~0.3 sqrt(n) u, so the bound sits ~25 sigma out.
+//   * mean, variance and TSE bounds follow by first-order propagation: mean = S / W, var = Q / W - mean^2,
+//     TSE = sum_c Q_c - S_c^2 / W.
 // oracle/divquant_oracle.cpp (TieAudit) is the CPU model of exactly these formulas; tests compare the two.
 #pragma once
 
@@ -29,28 +33,69 @@ __host__ __device__ __forceinline__ double gamma_n(double n) {
   const double a = n + 4.0, b = kLambda * sqrt(n + 4.0);
   return (a < b ? a : b) * kU;
 }
-
-// Root statistics (DivQuantClusterInitMeanAndVar, :60-104): U sequential adds per sum.
-__host__ __device__ __forceinline__ void root_bounds(double U, double &eW, double &eM, double &eV) {
-  eW = 0.0;  // weight[0] = 1.0 in both
-  eM = gamma_n(U) * 256.0;
-  eV = (3.0 * gamma_n(U) + 8.0 * kU) * 65536.0;
+__host__ __device__ __forceinline__ double max3abs(const double *v) { return fmax(fabs(v[0]), fmax(fabs(v[1]), fabs(v[2]))); }
+// largest second moment var_c + mean_c^2 over the channels
+__host__ __device__ __forceinline__ double max3moment(const double *var, const double *mean) {
+  return fmax(fabs(var[0]) + mean[0] * mean[0], fmax(fabs(var[1]) + mean[1] * mean[1], fabs(var[2]) + mean[2] * mean[2]));
 }
 
-// Bounds of the centres after a pass whose new side has n_new points (:561-581, :780-810).
-struct PassErr {
-  double e_nw, e_nm, e_ow, e_om;
+// Bounds of one cluster: the three sums, and what follows for mean / variance / TSE.
+struct Bounds {
+  double eW, eS, eQ;
+  double eM, eV, eT;
 };
-__host__ __device__ __forceinline__ PassErr pass_err(double p_eW, double p_eM, double tw, double nw, double ow, double n_new) {
+__host__ __device__ __forceinline__ void derive(Bounds &b, double tw, const double *tm, const double *tv, double tse) {
+  const double m1 = max3abs(tm), m2 = max3moment(tv, tm), w = fabs(tw);
+  b.eM = (b.eS + m1 * b.eW) / w + 2.0 * kU * m1;
+  b.eV = (b.eQ + m2 * b.eW) / w + 2.0 * m1 * b.eM + 4.0 * kU * m2;
+  b.eT = 3.0 * (b.eQ + 2.0 * m1 * b.eS + m1 * m1 * b.eW) + 8.0 * kU * fabs(tse);
+}
+
+// Root statistics (DivQuantClusterInitMeanAndVar, :60-104): U sequential adds per sum; weight[0] = 1.0 in both.
+__host__ __device__ __forceinline__ Bounds root_bounds(double U, const double *tm, const double *tv) {
+  Bounds b;
+  b.eW = 0.0;
+  b.eS = (gamma_n(U) + 2.0 * kU) * max3abs(tm);
+  b.eQ = (gamma_n(U) + 4.0 * kU) * max3moment(tv, tm);
+  derive(b, 1.0, tm, tv, 0.0);
+  return b;
+}
+
+// Bounds of the two centres after a pass whose new side has n_new points (:561-581, :780-810).
+// m1_* = largest |mean_c| of the parent, the new and the old centre.
+struct PassErr {
+  double e_nw, eS_n, e_nm, e_ow, eS_o, e_om;
+};
+__host__ __device__ __forceinline__ PassErr pass_err(double p_eW, double p_eS, double tw, double m1_t, double nw, double m1_n, double ow,
+                                                     double m1_o, double n_new) {
   PassErr r;
   const double g = gamma_n(n_new);
   r.e_nw = g * nw;
-  r.e_nm = (2.0 * g + 4.0 * kU) * 256.0;
+  r.eS_n = (g + 2.0 * kU) * nw * m1_n;
+  r.e_nm = (2.0 * g + 4.0 * kU) * m1_n;  // = (eS_n + m1_n e_nw) / nw + 2 u m1_n
   r.e_ow = p_eW + r.e_nw + kU * fabs(ow);
-  const double e_num = p_eW * 256.0 + tw * p_eM + r.e_nw * 256.0 + nw * r.e_nm + 4.0 * kU * (tw + nw) * 256.0;
-  r.e_om = (e_num + 256.0 * r.e_ow) / fabs(ow) + 2.0 * kU * 256.0;
+  r.eS_o = p_eS + r.eS_n + 4.0 * kU * (tw * m1_t + nw * m1_n);
+  r.e_om = (r.eS_o + m1_o * r.e_ow) / fabs(ow) + 2.0 * kU * m1_o;
   return r;
 }
+#ifdef __CUDACC__
+// The same bounds for the per-pass tolerance, where they sit on the split's critical path: single-precision square root
+// and reciprocal rounded up (the results are bounds: a few ulp of float more is as good), no double division.
+__device__ __forceinline__ PassErr pass_err_fast(double p_eW, double p_eS, double tw, double m1_t, double nw, double m1_n, double ow,
+                                                 double m1_o, double n_new) {
+  PassErr r;
+  const float nf = __double2float_ru(n_new + 4.0);
+  const double g = (double)fminf(nf, __fmul_ru((float)kLambda, __fsqrt_ru(nf))) * kU;
+  const double inv_ow = (double)__frcp_ru(__double2float_rd(fabs(ow)));
+  r.e_nw = g * nw;
+  r.eS_n = (g + 2.0 * kU) * nw * m1_n;
+  r.e_nm = (2.0 * g + 4.0 * kU) * m1_n;
+  r.e_ow = p_eW + r.e_nw + kU * fabs(ow);
+  r.eS_o = p_eS + r.eS_n + 4.0 * kU * (tw * m1_t + nw * m1_n);
+  r.e_om = (r.eS_o + m1_o * r.e_ow) * inv_ow + 2.0 * kU * m1_o;
+  return r;
+}
+#endif
 
 // Tolerance of the hyperplane test  lhs < rhs . x  (:616-623, :683) for centres with these bounds.
 // dot - lhs = (|x - nm|^2 - |x - om|^2) / 2, so a perturbation of the centres moves it by
@@ -59,6 +104,7 @@ __host__ __device__ __forceinline__ PassErr pass_err(double p_eW, double p_eM, d
 __host__ __device__ __forceinline__ double hyperplane_tol(const PassErr &q) { return 1536.0 * (q.e_om + q.e_nm) + 8388608.0 * kU; }
 struct PassExt {  // centres and their bounds of the pass in flight (shared memory; read only for points inside the filter)
   double om[3], nm[3], e_om, e_nm;
+  double tol;  // the filter's threshold itself (its high word travels with the classification parameters)
 };
 __host__ __device__ __forceinline__ double point_tol(const PassExt &x, double r, double g, double b) {
   const double d_o = fabs(x.om[0] - r) + fabs(x.om[1] - g) + fabs(x.om[2] - b);
@@ -66,27 +112,21 @@ __host__ __device__ __forceinline__ double point_tol(const PassExt &x, double r,
   return d_o * x.e_om + d_n * x.e_nm + 8388608.0 * kU;
 }
 
-// Bounds of the two children's variance and TSE (:836-871).  nv/ov = the children's variances as computed.
-__host__ __device__ __forceinline__ void child_var_bounds(const PassErr &fe, double p_eW, double p_eM, double p_eV, double tw,
-                                                          const double *tm, const double *tv, double nw, double ow, const double *nm,
-                                                          const double *om, const double *nv, const double *ov, double n_new,
-                                                          double tse_new, double tse_old, double &eVn, double &eVo, double &eTn,
-                                                          double &eTo) {
-  eVn = (2.0 * gamma_n(n_new) + 8.0 * kU) * 65536.0 + 512.0 * fe.e_nm;
-  eVo = 0.0;
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    const double dn = fabs(nm[c] - tm[c]), dmo = fabs(om[c] - tm[c]);
-    const double inner = fabs(nv[c]) + dn * dn;
-    const double e_inner = eVn + 2.0 * dn * (fe.e_nm + p_eM) + 3.0 * kU * inner;
-    const double e_num = p_eW * fabs(tv[c]) + tw * p_eV + fe.e_nw * inner + nw * e_inner + 3.0 * kU * (tw * fabs(tv[c]) + nw * inner);
-    const double q = (tw * fabs(tv[c]) + nw * inner) / fabs(ow);
-    const double e_q = (e_num + q * fe.e_ow) / fabs(ow) + kU * q;
-    const double e = e_q + 2.0 * dmo * (fe.e_om + p_eM) + 3.0 * kU * (q + dmo * dmo);
-    if (!(e <= eVo)) eVo = e;  // NaN propagates
-  }
-  eTn = fe.e_nw * fabs(nv[0] + nv[1] + nv[2]) + nw * 3.0 * eVn + 4.0 * kU * fabs(tse_new);
-  eTo = fe.e_ow * fabs(ov[0] + ov[1] + ov[2]) + fabs(ow) * 3.0 * eVo + 4.0 * kU * fabs(tse_old);
+// Bounds of the two children of a finished split (:800-871) from the parent's and the last pass's.
+__host__ __device__ __forceinline__ void child_bounds(const Bounds &p, const PassErr &fe, double tw, const double *tm, const double *tv,
+                                                      double nw, const double *nm, const double *nv, double tse_n, double ow,
+                                                      const double *om, const double *ov, double tse_o, double n_new, Bounds &bn,
+                                                      Bounds &bo) {
+  bn.eW = fe.e_nw;
+  bn.eS = fe.eS_n;
+  bn.eQ = (gamma_n(n_new) + 4.0 * kU) * nw * max3moment(nv, nm);
+  bo.eW = fe.e_ow;
+  bo.eS = fe.eS_o;
+  bo.eQ = p.eQ + bn.eQ + 16.0 * kU * 65536.0 * (tw + nw);  // a dozen roundings of the combined-variance formula (:844-855)
+  derive(bn, nw, nm, nv, tse_n);
+  derive(bo, ow, om, ov, tse_o);
+  (void)tm;
+  (void)tv;
 }
 
 // D1: the comparisons choose_cut makes (:388-403).

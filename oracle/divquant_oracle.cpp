@@ -210,17 +210,27 @@ extern "C" int oracle_debug_convergence(int *out, int cap) {
 // ---------------------------------------------------------------------------------------------
 namespace {
 const double kU = 1.1102230246251565e-16;  // 2^-53
-const double kSafety = 1.0;
+const double kLambda = 8.0;
 // Rounding errors of a sequential sum of n terms: n*u is the worst case, but the errors are not aligned; the
 // probabilistic bound lambda*sqrt(n)*u (Higham & Mary 2019) fails with probability ~2 exp(-lambda^2/2) (3e-14 at 8).
-const double kLambda = 8.0;
 inline double gamma_n(double n) {
   const double a = n + 4.0, b = kLambda * std::sqrt(n + 4.0);
   return (a < b ? a : b) * kU;
 }
+inline double max3abs(const Vec3 &v) { return std::fmax(std::fabs(v.r), std::fmax(std::fabs(v.g), std::fabs(v.b))); }
+inline double max3moment(const Vec3 &var, const Vec3 &mean) {
+  return std::fmax(std::fabs(var.r) + mean.r * mean.r, std::fmax(std::fabs(var.g) + mean.g * mean.g, std::fabs(var.b) + mean.b * mean.b));
+}
+// bounds on |model - reference| of W, S = W*mean, Q = W*(var + mean^2) and what follows for mean / variance / TSE
 struct ClusterErr {
-  double eW, eM, eV, eT;
+  double eW, eS, eQ, eM, eV, eT;
 };
+inline void derive_err(ClusterErr &b, double tw, const Vec3 &tm, const Vec3 &tv, double tse) {
+  const double m1 = max3abs(tm), m2 = max3moment(tv, tm), w = std::fabs(tw);
+  b.eM = (b.eS + m1 * b.eW) / w + 2.0 * kU * m1;
+  b.eV = (b.eQ + m2 * b.eW) / w + 2.0 * m1 * b.eM + 4.0 * kU * m2;
+  b.eT = 3.0 * (b.eQ + 2.0 * m1 * b.eS + m1 * m1 * b.eW) + 8.0 * kU * std::fabs(tse);
+}
 struct TieAudit {
   uint32_t flags[6];  // [1..5] = D1..D5 counts, [0] = total
   void hit(int d) {
@@ -228,17 +238,19 @@ struct TieAudit {
     flags[0]++;
   }
 };
-// bounds after a pass: the new side has n_new points, the parent's bounds are pe
+// bounds after a pass: the new side has n_new points
 struct PassErr {
-  double e_nw, e_nm, e_ow, e_om;
+  double e_nw, eS_n, e_nm, e_ow, eS_o, e_om;
 };
-inline PassErr pass_err(const ClusterErr &pe, double tw, double nw, double ow, int n_new) {
+inline PassErr pass_err(const ClusterErr &pe, double tw, const Vec3 &tm, double nw, const Vec3 &nm, double ow, const Vec3 &om, int n_new) {
   PassErr r;
-  r.e_nw = gamma_n(n_new) * nw;
-  r.e_nm = (2.0 * gamma_n(n_new) + 4.0 * kU) * 256.0;
+  const double g = gamma_n(n_new), m1_t = max3abs(tm), m1_n = max3abs(nm), m1_o = max3abs(om);
+  r.e_nw = g * nw;
+  r.eS_n = (g + 2.0 * kU) * nw * m1_n;
+  r.e_nm = (r.eS_n + m1_n * r.e_nw) / nw + 2.0 * kU * m1_n;
   r.e_ow = pe.eW + r.e_nw + kU * std::fabs(ow);
-  const double e_num = pe.eW * 256.0 + tw * pe.eM + r.e_nw * 256.0 + nw * r.e_nm + 4.0 * kU * (tw + nw) * 256.0;
-  r.e_om = (e_num + 256.0 * r.e_ow) / std::fabs(ow) + 2.0 * kU * 256.0;
+  r.eS_o = pe.eS + r.eS_n + 4.0 * kU * (tw * m1_t + nw * m1_n);
+  r.e_om = (r.eS_o + m1_o * r.e_ow) / std::fabs(ow) + 2.0 * kU * m1_o;
   return r;
 }
 }  // namespace
@@ -300,7 +312,7 @@ static int varpart_impl(uint32_t num_pixels, const uint32_t *in, uint32_t num_ro
   std::vector<int> size(K, 0);
   std::vector<Vec3> mean(K, Vec3{0, 0, 0}), var(K, Vec3{0, 0, 0});
   std::vector<uint32_t> member(U, 0u);
-  std::vector<ClusterErr> cerr(K, ClusterErr{0, 0, 0, 0});
+  std::vector<ClusterErr> cerr(K, ClusterErr{0, 0, 0, 0, 0, 0});
   if (audit) memset(audit, 0, sizeof(*audit));
 
   // The cluster being split: `cur` lists original point indices in ascending order (the reference
@@ -321,8 +333,9 @@ static int varpart_impl(uint32_t num_pixels, const uint32_t *in, uint32_t num_ro
       initial_mean_and_var(s, &tm, &tv);
       // reference: U sequential adds of rounded products per sum
       cerr[0].eW = 0.0;
-      cerr[0].eM = gamma_n(U) * 256.0;
-      cerr[0].eV = (3.0 * gamma_n(U) + 8.0 * kU) * 65536.0;
+      cerr[0].eS = (gamma_n(U) + 2.0 * kU) * max3abs(tm);
+      cerr[0].eQ = (gamma_n(U) + 4.0 * kU) * max3moment(tv, tm);
+      derive_err(cerr[0], 1.0, tm, tv, 0.0);
     } else {
       tm = mean[old_index];
       tv = var[old_index];
@@ -334,13 +347,13 @@ static int varpart_impl(uint32_t num_pixels, const uint32_t *in, uint32_t num_ro
     int axis = 0;
     double cut = tm.r;
     const ClusterErr pe = cerr[old_index];
-    if (audit && std::fabs(best - tv.g) <= kSafety * 2.0 * pe.eV) audit->hit(1);
+    if (audit && std::fabs(best - tv.g) <= 2.0 * pe.eV) audit->hit(1);
     if (best < tv.g) {
       best = tv.g;
       axis = 1;
       cut = tm.g;
     }
-    if (audit && std::fabs(best - tv.b) <= kSafety * 2.0 * pe.eV) audit->hit(1);
+    if (audit && std::fabs(best - tv.b) <= 2.0 * pe.eV) audit->hit(1);
     if (best < tv.b) {
       axis = 2;
       cut = tm.b;
@@ -361,7 +374,7 @@ static int varpart_impl(uint32_t num_pixels, const uint32_t *in, uint32_t num_ro
         uint32_t p = s.data[idx];
         uint32_t R = chan_r(p), G = chan_g(p), B = chan_b(p);
         double proj = (axis == 0) ? R : ((axis == 1) ? G : B);
-        if (audit && std::fabs(proj - cut) <= kSafety * pe.eM) audit->hit(2);
+        if (audit && std::fabs(proj - cut) <= pe.eM) audit->hit(2);
         if (cut < proj) {
           ++cut_new;
           if (s.uniform) {
@@ -408,11 +421,11 @@ static int varpart_impl(uint32_t num_pixels, const uint32_t *in, uint32_t num_ro
           0.5 * (sq(om.r) - sq(nm.r) + sq(om.g) - sq(nm.g) + sq(om.b) - sq(nm.b));  // (:616-619)
       const double rr = om.r - nm.r, rg = om.g - nm.g, rb = om.b - nm.b;
       double eH = 0.0;
-      PassErr q = {0, 0, 0, 0};
+      PassErr q = {0, 0, 0, 0, 0, 0};
       const Vec3 om_pass = om, nm_pass = nm;  // the centres this pass classifies with
       if (audit) {
-        q = pass_err(pe, tw, nw, ow, new_size);
-        eH = kSafety * (1536.0 * (q.e_om + q.e_nm) + 8388608.0 * kU);  // filter: holds for any point
+        q = pass_err(pe, tw, tm, nw, nm, ow, om, new_size);
+        eH = 1536.0 * (q.e_om + q.e_nm) + 8388608.0 * kU;  // filter: holds for any point
       }
       nw = 0.0;
       new_size = 0;
@@ -496,13 +509,15 @@ static int varpart_impl(uint32_t num_pixels, const uint32_t *in, uint32_t num_ro
     size[old_index] = cur_n - new_size;
     size[new_index] = new_size;
     if (g_converged_n < 4096) g_converged_at[g_converged_n++] = converged_at;
-    PassErr fe = {0, 0, 0, 0};
+    PassErr fe = {0, 0, 0, 0, 0, 0};
     if (audit) {
-      fe = pass_err(pe, tw, nw, ow, new_size);
-      cerr[new_index].eW = fe.e_nw;
-      cerr[new_index].eM = fe.e_nm;
-      cerr[old_index].eW = fe.e_ow;
-      cerr[old_index].eM = fe.e_om;
+      fe = pass_err(pe, tw, tm, nw, nm, ow, om, new_size);
+      ClusterErr bn = {fe.e_nw, fe.eS_n, 0, 0, 0, 0}, bo = {fe.e_ow, fe.eS_o, pe.eQ, 0, 0, 0};
+      // the last split computes no variances (:823-832): the means' bounds are all that is read afterwards
+      derive_err(bn, nw, nm, Vec3{0, 0, 0}, 0.0);
+      derive_err(bo, ow, om, Vec3{0, 0, 0}, 0.0);
+      cerr[new_index] = bn;
+      cerr[old_index] = bo;
     }
 
     oracle_split_record rec;
@@ -541,26 +556,13 @@ static int varpart_impl(uint32_t num_pixels, const uint32_t *in, uint32_t num_ro
     tse[new_index] = nw * (nv.r + nv.g + nv.b);
 
     if (audit) {
-      // new side: sum(w c^2)/nw - nm^2 ; old side: combined variance (:836-855)
-      const double eVn = (2.0 * gamma_n(new_size) + 8.0 * kU) * 65536.0 + 512.0 * fe.e_nm;
-      double eVo = 0.0;
-      const double nvv[3] = {nv.r, nv.g, nv.b}, nmm[3] = {nm.r, nm.g, nm.b}, tmm[3] = {tm.r, tm.g, tm.b},
-                   tvv[3] = {tv.r, tv.g, tv.b}, omm[3] = {om.r, om.g, om.b};
-      for (int c = 0; c < 3; ++c) {
-        const double dn = std::fabs(nmm[c] - tmm[c]), dmo = std::fabs(omm[c] - tmm[c]);
-        const double inner = std::fabs(nvv[c]) + dn * dn;
-        const double e_inner = eVn + 2.0 * dn * (fe.e_nm + pe.eM) + 3.0 * kU * inner;
-        const double e_num = pe.eW * std::fabs(tvv[c]) + tw * pe.eV + fe.e_nw * inner + nw * e_inner +
-                             3.0 * kU * (tw * std::fabs(tvv[c]) + nw * inner);
-        const double q = (tw * std::fabs(tvv[c]) + nw * inner) / std::fabs(ow);
-        const double e_q = (e_num + q * fe.e_ow) / std::fabs(ow) + kU * q;
-        const double e = e_q + 2.0 * dmo * (fe.e_om + pe.eM) + 3.0 * kU * (q + dmo * dmo);
-        if (!(e <= eVo)) eVo = e;  // NaN propagates
-      }
-      cerr[new_index].eV = eVn;
-      cerr[old_index].eV = eVo;
-      cerr[new_index].eT = fe.e_nw * std::fabs(nv.r + nv.g + nv.b) + nw * 3.0 * eVn + 4.0 * kU * std::fabs(tse[new_index]);
-      cerr[old_index].eT = fe.e_ow * std::fabs(ov.r + ov.g + ov.b) + std::fabs(ow) * 3.0 * eVo + 4.0 * kU * std::fabs(tse[old_index]);
+      // Q = W (var + mean^2): fresh sum on the new side, parent - new on the old side (:836-855)
+      ClusterErr bn = {fe.e_nw, fe.eS_n, (gamma_n(new_size) + 4.0 * kU) * nw * max3moment(nv, nm), 0, 0, 0};
+      ClusterErr bo = {fe.e_ow, fe.eS_o, pe.eQ + bn.eQ + 16.0 * kU * 65536.0 * (tw + nw), 0, 0, 0};
+      derive_err(bn, nw, nm, nv, tse[new_index]);
+      derive_err(bo, ow, om, ov, tse[old_index]);
+      cerr[new_index] = bn;
+      cerr[old_index] = bo;
     }
     rec.new_var[0] = nv.r, rec.new_var[1] = nv.g, rec.new_var[2] = nv.b;
     rec.old_var[0] = ov.r, rec.old_var[1] = ov.g, rec.old_var[2] = ov.b;
@@ -580,9 +582,9 @@ static int varpart_impl(uint32_t num_pixels, const uint32_t *in, uint32_t num_ro
     }
     if (audit) {
       // D4: the winner must beat every other cluster (and DBL_MIN) by more than the bounds
-      bool tie = !(top - kSafety * cerr[old_index].eT > DBL_MIN);
+      bool tie = !(top - cerr[old_index].eT > DBL_MIN);
       for (int ic = 0; ic <= new_index && !tie; ++ic)
-        if (ic != old_index && !(top - tse[ic] > kSafety * (cerr[old_index].eT + cerr[ic].eT))) {
+        if (ic != old_index && !(top - tse[ic] > cerr[old_index].eT + cerr[ic].eT)) {
           tie = true;
           if (getenv("ORACLE_AUDIT_VERBOSE"))
             fprintf(stderr, "D4 step %d: top %.17g (cluster %d, eT %.3e size %d) vs %.17g (cluster %d, eT %.3e size %d) diff %.3e\n", new_index, top,
@@ -615,7 +617,7 @@ static int varpart_impl(uint32_t num_pixels, const uint32_t *in, uint32_t num_ro
         const double mm[3] = {mean[ic].r, mean[ic].g, mean[ic].b};
         for (int c = 0; c < 3; ++c) {
           const double v = mm[c] + 0.5;
-          if (std::fabs(v - std::rint(v)) <= kSafety * (cerr[ic].eM + 512.0 * kU)) audit->hit(5);
+          if (std::fabs(v - std::rint(v)) <= cerr[ic].eM + 512.0 * kU) audit->hit(5);
         }
       }
     } else {

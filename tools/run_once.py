@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Runs quant_recurse_device a few times on one synthetic frame (for ncu / sanitizer captures).
-usage: python tools/run_once.py [width height K reps kind]"""
+usage: python tools/run_once.py [width height K reps kind seed]"""
 import ctypes as C
 import importlib
 import os
@@ -13,12 +13,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import Oracle  # input generator only
 
-w, h, k, reps, kind = [int(x) for x in (sys.argv[1:6] + ["3840", "2160", "256", "3", "1"][len(sys.argv) - 1:])]
+w, h, k, reps, kind, seed = [int(x) for x in (sys.argv[1:7] + ["3840", "2160", "256", "3", "1", "12345"][len(sys.argv) - 1:])]
 pkg = importlib.import_module("clusteringsegmentation-1_b200")
 lib = pkg.load_library()
 lib.dq_set_display_timings(0)
 ctx = lib.dq_context_create(0)
-px = torch.from_numpy(Oracle().generate(kind, w, h).view(np.int32)).cuda()
+px = torch.from_numpy(Oracle().generate(kind, w, h, seed).view(np.int32)).cuda()
 out = torch.empty_like(px)
 ct = np.zeros(k, np.uint32)
 nk = C.c_uint32(k)
