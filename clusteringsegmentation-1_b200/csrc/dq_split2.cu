@@ -636,35 +636,25 @@ __device__ void fast_assignment(const SplitArgs &A, Shared2 &S, const Arrays &R)
     int above = n;
     if (t == t) {  // NaN is never selected (:882)
       above = 0;
-      if (!audit) {
 #pragma unroll 8
-        for (int m2 = 0; m2 < n; ++m2) above += (R.tse[m2] > t);
-      } else {
-        // tie audit, D4: does any other node's TSE come within the two bounds of this one?  (bit 30 of the rank word;
-        // whether that node matters to the reference's sequence is sorted out below, for the few nodes marked here)
-        const double e = R.terr[i];
-        int near = -1;  // the node itself always matches
-#pragma unroll 4
-        for (int m2 = 0; m2 < n; ++m2) {
-          const double o = R.tse[m2];
-          above += (o > t);
-          near += (fabs(o - t) <= e + R.terr[m2]);
-        }
-        if (near > 0) above |= 1 << 30;
-      }
+      for (int m2 = 0; m2 < n; ++m2) above += (R.tse[m2] > t);
     }
     R.rank[i] = above;
   }
   __syncthreads();
-  uint32_t near_mask = 0u;  // per thread: bit q = its q-th node was marked
+  uint32_t near_mask = 0u;  // per thread: bit q = its q-th node has another node's TSE within the two bounds
   if (audit) {
+    // tie audit, D4, for the nodes the reference pops: does any other node's TSE come within the two bounds of this one?
+    // (whether that node matters to the reference's sequence is sorted out below, for the few nodes marked here)
     int q = 0;
     for (int i = tid; i < n; i += T, ++q) {
-      if (R.rank[i] & (1 << 30)) near_mask |= 1u << (q & 31);
+      if (R.rank[i] >= K - 1 || i == 0) continue;
+      const double t = R.tse[i], e = R.terr[i];
+      int near = -1;  // the node itself always matches
+#pragma unroll 4
+      for (int m2 = 0; m2 < n; ++m2) near += (fabs(R.tse[m2] - t) <= e + R.terr[m2]);
+      if (near > 0) near_mask |= 1u << (q & 31);
     }
-    __syncthreads();
-    for (int i = tid; i < n; i += T) R.rank[i] &= ~(1 << 30);
-    __syncthreads();
   }
   for (int i = tid; i < n; i += T) {
     const double t = R.tse[i];
@@ -856,6 +846,12 @@ __device__ __forceinline__ unsigned narrow_pass(Shared2 &S, const uint2 (&p)[kNa
       }
     }
   }
+  if (near) {  // some point passed the audit's integer filter: settle it with the real test (cold)
+    near = false;
+#pragma unroll
+    for (int k = 0; k < kNarrowPPT; ++k)
+      if (k < ppt && ((validmask >> k) & 1u)) near = near || recheck_near<SPLIT>(pp, &S.ext, to_point(p[k]));
+  }
   uint64_t v[kAccWords];
   acc_words(acc, v);
   v[kAccPts] += (uint64_t)near << 32;  // tie audit (split_near_warp0)
@@ -914,6 +910,17 @@ __device__ __forceinline__ void wide_classify(const PassParams &pp, const tie::P
       for (int u = 0; u < 4; ++u) {
         if (q + (uint32_t)u * nthr < n_my && goes_new_audit<SPLIT>(pp, ext, to_point(raw[u]), near)) acc_add(acc, raw[u], FINAL);
       }
+    }
+  }
+  if (near) {  // some point passed the audit's integer filter: settle it with the real test (cold)
+    near = false;
+    for (uint32_t q = tid; q < n_my; q += nthr) {
+      const uint2 raw = (q < kWidePPT * nthr) ? pre[0] : ld_cg_u2(seg + offset_of(q));
+      uint2 pt = raw;
+#pragma unroll
+      for (int k = 0; k < kWidePPT; ++k)
+        if (q == tid + (uint32_t)k * nthr) pt = pre[k];
+      near = near || recheck_near<SPLIT>(pp, ext, to_point(pt));
     }
   }
   acc_words(acc, v);

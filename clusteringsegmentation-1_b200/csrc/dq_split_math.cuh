@@ -112,13 +112,22 @@ __device__ __forceinline__ bool goes_new_audit(const PassParams &pp, const tie::
   // |m| <= tol  =>  (hi & 0x7fffffff) <= hi(tol), a filter that passes a handful of points per frame; the exact test
   // and the bound for the very point follow only for those.  tol < 0 (audit off) has a negative high word: never passes.
   const int hi = __double2hiint(m);
-  if ((hi & 0x7fffffff) <= pp.tol_hi) {
-    if (fabs(m) <= ext->tol) {
-      if (SPLIT) near = true;
-      else near = near || (fabs(m) <= tie::point_tol(*ext, d.r, d.g, d.b));
-    }
-  }
+  near = near || ((hi & 0x7fffffff) <= pp.tol_hi);  // the filter only: recheck_near settles it, off the hot loop
+  (void)ext;
   return SPLIT ? (hi > 0) : !(hi > 0);
+}
+// Cold path of the audit: a point that passed the integer filter, tested for real.
+template <bool SPLIT>
+__device__ __forceinline__ bool recheck_near(const PassParams &pp, const tie::PassExt *ext, const PointD &d) {
+  double x;
+  if (SPLIT) {
+    x = (pp.axis == 0) ? d.r : ((pp.axis == 1) ? d.g : d.b);
+  } else {
+    x = fadd(fadd(fmul(pp.r[0], d.r), fmul(pp.r[1], d.g)), fmul(pp.r[2], d.b));
+  }
+  const double m = fabs(fsub(x, pp.a));
+  if (!(m <= ext->tol)) return false;
+  return SPLIT ? true : (m <= tie::point_tol(*ext, d.r, d.g, d.b));
 }
 // Accumulation stays on the integer pipe (IMAD.WIDE), which runs next to the FP64 pipe that classifies:
 // exact u64 sums of count*c and count*c*c.
@@ -218,11 +227,11 @@ __device__ __forceinline__ void make_children(const SplitNode &parent, int paren
   o.tie = n.tie = 0u;
   o.pad = n.pad = 0u;
   if (audit) {
-    const tie::PassErr fe = tie::pass_err(parent.eW, parent.eS, parent.tw, tie::max3abs(parent.tm), m.nw, tie::max3abs(m.nm), m.ow,
-                                          tie::max3abs(m.om), (double)size_new);
+    const tie::PassErr fe = tie::pass_err_fast(parent.eW, parent.eS, parent.tw, tie::max3abs(parent.tm), m.nw, tie::max3abs(m.nm), m.ow,
+                                               tie::max3abs(m.om), (double)size_new);
     tie::Bounds bp, bn, bo;
     bp.eW = parent.eW, bp.eS = parent.eS, bp.eQ = parent.eQ;
-    tie::child_bounds(bp, fe, parent.tw, parent.tm, parent.tv, m.nw, m.nm, n.tv, n.tse, m.ow, m.om, o.tv, o.tse, (double)size_new, bn, bo);
+    tie::child_bounds_fast(bp, fe, parent.tw, m.nw, m.nm, n.tv, n.tse, m.ow, m.om, o.tv, o.tse, (double)size_new, bn, bo);
     n.eW = bn.eW, n.eS = bn.eS, n.eQ = bn.eQ, n.eM = bn.eM, n.eV = bn.eV, n.eT = bn.eT;
     o.eW = bo.eW, o.eS = bo.eS, o.eQ = bo.eQ, o.eM = bo.eM, o.eV = bo.eV, o.eT = bo.eT;
   }

@@ -79,14 +79,25 @@ __host__ __device__ __forceinline__ PassErr pass_err(double p_eW, double p_eS, d
   return r;
 }
 #ifdef __CUDACC__
-// The same bounds for the per-pass tolerance, where they sit on the split's critical path: single-precision square root
-// and reciprocal rounded up (the results are bounds: a few ulp of float more is as good), no double division.
+// The same bounds on the device, where they sit on the split's critical path: single-precision square root and reciprocal
+// rounded UP (the results are bounds: a few ulp of float more is as good, and never less than the CPU model's), no
+// double-precision division or square root.
+__device__ __forceinline__ double gamma_fast(double n) {
+  const float nf = __double2float_ru(n + 4.0);
+  return (double)fminf(nf, __fmul_ru((float)kLambda, __fsqrt_ru(nf))) * kU;
+}
+__device__ __forceinline__ double rcp_up(double w) { return (double)__frcp_ru(__double2float_rd(fabs(w))); }
+__device__ __forceinline__ void derive_fast(Bounds &b, double tw, const double *tm, const double *tv, double tse) {
+  const double m1 = max3abs(tm), m2 = max3moment(tv, tm), iw = rcp_up(tw);
+  b.eM = (b.eS + m1 * b.eW) * iw + 2.0 * kU * m1;
+  b.eV = (b.eQ + m2 * b.eW) * iw + 2.0 * m1 * b.eM + 4.0 * kU * m2;
+  b.eT = 3.0 * (b.eQ + 2.0 * m1 * b.eS + m1 * m1 * b.eW) + 8.0 * kU * fabs(tse);
+}
 __device__ __forceinline__ PassErr pass_err_fast(double p_eW, double p_eS, double tw, double m1_t, double nw, double m1_n, double ow,
                                                  double m1_o, double n_new) {
   PassErr r;
-  const float nf = __double2float_ru(n_new + 4.0);
-  const double g = (double)fminf(nf, __fmul_ru((float)kLambda, __fsqrt_ru(nf))) * kU;
-  const double inv_ow = (double)__frcp_ru(__double2float_rd(fabs(ow)));
+  const double g = gamma_fast(n_new);
+  const double inv_ow = rcp_up(ow);
   r.e_nw = g * nw;
   r.eS_n = (g + 2.0 * kU) * nw * m1_n;
   r.e_nm = (2.0 * g + 4.0 * kU) * m1_n;
@@ -112,6 +123,20 @@ __host__ __device__ __forceinline__ double point_tol(const PassExt &x, double r,
   return d_o * x.e_om + d_n * x.e_nm + 8388608.0 * kU;
 }
 
+#ifdef __CUDACC__
+__device__ __forceinline__ void child_bounds_fast(const Bounds &p, const PassErr &fe, double tw, double nw, const double *nm,
+                                                  const double *nv, double tse_n, double ow, const double *om, const double *ov,
+                                                  double tse_o, double n_new, Bounds &bn, Bounds &bo) {
+  bn.eW = fe.e_nw;
+  bn.eS = fe.eS_n;
+  bn.eQ = (gamma_fast(n_new) + 4.0 * kU) * nw * max3moment(nv, nm);
+  bo.eW = fe.e_ow;
+  bo.eS = fe.eS_o;
+  bo.eQ = p.eQ + bn.eQ + 16.0 * kU * 65536.0 * (tw + nw);
+  derive_fast(bn, nw, nm, nv, tse_n);
+  derive_fast(bo, ow, om, ov, tse_o);
+}
+#endif
 // Bounds of the two children of a finished split (:800-871) from the parent's and the last pass's.
 __host__ __device__ __forceinline__ void child_bounds(const Bounds &p, const PassErr &fe, double tw, const double *tm, const double *tv,
                                                       double nw, const double *nm, const double *nv, double tse_n, double ow,
