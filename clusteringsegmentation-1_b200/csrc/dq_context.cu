@@ -103,6 +103,7 @@ struct dq_context {
   int exact_parallel = 1;  // the ordered path runs on all CTAs of the split kernel (DIVQUANT_B200_EXACT_PARALLEL=0: CTA 0 only)
   uint32_t exact_max_points = kExactDefaultPoints;  // ... up to this many unique colours (DIVQUANT_B200_EXACT_MAX)
   DevBuf<uint64_t> d_exact;
+  DevBuf<uint32_t> d_tie;  // [4 * kTieListCap] flagged clusters + [kTieListCap] resolver status words
   // Tie audit of the exact-integer split (dq_tie.cuh): 0 = off, 1 = report in dq_call_stats::tie_flags only,
   // 2 (default) = a flagged frame is computed again in the reference's summation order (DIVQUANT_B200_TIE)
   int tie_policy = 2;
@@ -274,6 +275,10 @@ uint32_t run_split(dq_context *ctx, uint32_t point_capacity, double norm, uint32
   const bool use_v2 = ctx->split_version == 2 && K <= kSplit2MaxColors;
   // weighted points on exact-integer sums: audit the decisions against the reference's rounding noise (dq_tie.cuh)
   a.tie_audit = (weighted && use_v2 && ctx->tie_policy != 0) ? 1u : 0u;
+  if (a.tie_audit) {
+    ctx->d_tie.ensure(5 * kTieListCap);
+    a.tie_list = ctx->d_tie.ptr;
+  }
   ctx->mark(2);
   const bool exact_path = exact != nullptr && collect_from_hist && K <= kExactMaxColors && ctx->exact_small && ctx->exact_max_points > 0;
   ExactSampling sampling;
@@ -524,7 +529,33 @@ bool quantize_device(dq_context *ctx, uint32_t n, const uint32_t *d_in, uint32_t
   *k_inout = run_split(ctx, point_cap, norm, K, max_iters, num_bits, colortable, records, mean_out, size_out, table_dirty,
                        table_dirty ? &src : nullptr, table_dirty);
   const uint32_t flags = ctx->stats.tie_flags;
-  if (flags != 0u && ctx->tie_policy == 2 && table_dirty && ctx->exact_small && ctx->stats.num_points <= kExactMaxPoints &&
+  bool resolved = false;
+  if (flags == (uint32_t)kTieRound && ctx->tie_policy == 2 && table_dirty && ctx->exact_small && records == nullptr && mean_out == nullptr) {
+    // Only palette roundings are in doubt (a cluster mean exactly on x.5: the commonest tie by far): the reference's own
+    // ordered sums are redone for just the flagged clusters (dq_resolve.cu), on top of a first-seen pass over the pixels.
+    const uint32_t count = ctx->h_cb->ctl[kCtlTieCount];
+    if (count >= 1 && count <= kTieListCap) {
+      first_seen_launch(exact_sampling(d_in, rows, cols, (uint32_t)dec, num_bits), ctx->d_map, ctx->stream);
+      uint32_t *d_status = ctx->d_tie.ptr + 4 * kTieListCap;
+      DQ_CUDA_CHECK(cudaMemsetAsync(d_status, 0, kTieListCap * sizeof(uint32_t), ctx->stream));
+      uint2 *pts[2] = {ctx->d_pts0.ptr, ctx->d_pts1.ptr};
+      tie_resolve_launch(ctx->d_nodes.ptr, pts, ctx->d_map, norm, 8 - num_bits, ctx->d_tie.ptr, count, ctx->d_palette.ptr, d_status,
+                         ctx->stream);
+      ctx->stats.kernel_launches += 2;
+      uint32_t status[kTieListCap];
+      ctx->ensure_small((size_t)K + 16);
+      DQ_CUDA_CHECK(cudaMemcpyAsync(status, d_status, count * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+      DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->h_small, ctx->d_palette.ptr, (size_t)*k_inout * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+      ctx->wait();
+      resolved = true;
+      for (uint32_t i = 0; i < count; ++i) resolved = resolved && status[i] == 1u;
+      if (resolved) {
+        memcpy(colortable, ctx->h_small, (size_t)*k_inout * sizeof(uint32_t));
+        ctx->stats.tie_resolved = count;
+      }
+    }
+  }
+  if (!resolved && flags != 0u && ctx->tie_policy == 2 && table_dirty && ctx->exact_small && ctx->stats.num_points <= kExactMaxPoints &&
       K <= kExactMaxColors && K <= kSplit2MaxColors && ctx->split_version == 2) {
     // Some decision of the exact-integer split sits inside the rounding noise of the reference's sequential sums:
     // the reference's own summation order decides.  The count table is all-zero again (the split kernel zeroed what
@@ -703,6 +734,7 @@ void dq_context_destroy(dq_context *ctx) {
   ctx->d_cursors.release();
   ctx->d_progress.release();
   ctx->d_exact.release();
+  ctx->d_tie.release();
   cudaFree(ctx->d_table);
   cudaFree(ctx->d_map);
   cudaFree(ctx->d_cb);

@@ -87,6 +87,7 @@ enum CtlSlot {
   kCtlSplits = 5,  // splits computed, including speculative ones (diagnostics)
   kCtlError = 6,   // non-zero = internal inconsistency
   kCtlTie = 8,     // tie audit: TieBit mask of the decisions that sit inside the reference's rounding noise (dq_tie.cuh)
+  kCtlTieCount = 9,  // tie audit: final clusters whose palette rounding is flagged (entries of SplitArgs::tie_list)
   kCtlWords = 12   // [kCtlWords - 1] = detail of an expired wait
 };
 
@@ -139,7 +140,11 @@ struct SplitArgs {
   uint32_t exact_small_max;
   // 1 = weighted path on exact-integer sums: audit every decision against the reference's rounding noise (dq_tie.cuh)
   uint32_t tie_audit;
+  // final clusters flagged kTieRound: {cluster index, node id, palette slot, 0} each, at most kTieListCap (dq_resolve.cu)
+  uint32_t *tie_list;
 };
+constexpr uint32_t kTieListCap = 16;
+
 
 // Largest input (unique colours) that takes the sequential-order path of dq_split_exact.cu.
 constexpr uint32_t kExactMaxPoints = 262144;       // compile-time ceiling; the run-time limit is SplitArgs::exact_small_max
@@ -152,6 +157,12 @@ struct ExactSampling {
   uint32_t samples_per_row, num_samples, num_rows, dec, word_mask, shift;
 };
 ExactSampling exact_sampling(const uint32_t *d_in, uint32_t num_rows, uint32_t num_cols, uint32_t dec, int bits);
+// dq_resolve.cu: a final cluster's mean in the reference's own arithmetic (ordered sums along its chain of splits), for the
+// clusters whose rounding the tie audit flagged.  d_status[i]: 1 = palette[slot] rewritten, 2 = not resolvable here.
+void tie_resolve_launch(const SplitNode *d_nodes, uint2 *const *pts, const uint32_t *d_first_seen, double norm, int shift,
+                        const uint32_t *d_list, uint32_t count, uint32_t *d_palette, uint32_t *d_status, cudaStream_t st);
+// first-seen pass alone (dq_split_exact.cu): smallest sample index of every colour into d_first_seen
+void first_seen_launch(const ExactSampling &q, uint32_t *d_first_seen, cudaStream_t st);
 size_t split_exact_smem_bytes();
 size_t split_exact_scratch_bytes();  // global scratch for the point arrays of inputs above 4096 colours
 // Stand-alone form (two launches that return at once for large inputs).  g_f64: 8*K doubles, g_i32: K ints of scratch.

@@ -539,11 +539,15 @@ __device__ __forceinline__ void publish_mailbox(const SplitArgs &A, uint32_t U) 
 // Palette = rounded means of the non-empty clusters in index order (:1030-1065). cnode[ic] = node of cluster ic.
 __device__ void emit_palette(const SplitArgs &A, Shared2 &S, const Arrays &R) {
   const int tid = threadIdx.x, lane = tid & 31, K = (int)A.num_colors;
-  if (tid == 0) S.scan_carry = 0;
+  if (tid == 0) {
+    S.scan_carry = 0;
+    S.cur_new = 0u;  // (free here) number of clusters whose rounding is flagged
+  }
   __syncthreads();
   for (int base = 0; base < K; base += T) {
     const int ic = base + tid;
     uint32_t colour = 0, size = 0;
+    bool flagged = false;
     if (ic < K) {
       double mean[3] = {0.0, 0.0, 0.0};  // K == 1 never assigns mean[0]
       if (K > 1) {
@@ -551,8 +555,10 @@ __device__ void emit_palette(const SplitArgs &A, Shared2 &S, const Arrays &R) {
         size = nd.size;
         mean[0] = nd.tm[0], mean[1] = nd.tm[1], mean[2] = nd.tm[2];
         if (A.tie_audit != 0u && size > 0 &&
-            (tie::round_tie(mean[0], nd.eM) || tie::round_tie(mean[1], nd.eM) || tie::round_tie(mean[2], nd.eM)))
+            (tie::round_tie(mean[0], nd.eM) || tie::round_tie(mean[1], nd.eM) || tie::round_tie(mean[2], nd.eM))) {
           atomicOr(&S.tie_total, (uint32_t)kTieRound);  // D5 (:1050-1052)
+          flagged = true;
+        }
       } else {
         size = S.num_points;
       }
@@ -573,6 +579,16 @@ __device__ void emit_palette(const SplitArgs &A, Shared2 &S, const Arrays &R) {
     int before = S.scan_carry;
     for (int w = 0; w < (tid >> 5); ++w) before += S.warp_tmp[w];
     if (size > 0) A.palette[before + __popc(ballot & ((1u << lane) - 1u))] = colour;
+    if (flagged && A.tie_list != nullptr) {  // for dq_resolve.cu: which cluster, which node, which palette word
+      const uint32_t at = atomicAdd(&S.cur_new, 1u);
+      if (at < kTieListCap) {
+        uint32_t *e = A.tie_list + 4 * at;
+        e[0] = (uint32_t)ic;
+        e[1] = (uint32_t)R.cnode[ic];
+        e[2] = (uint32_t)(before + __popc(ballot & ((1u << lane) - 1u)));
+        e[3] = 0u;
+      }
+    }
     __syncthreads();
     if (tid == 0) {
       int tot = 0;
@@ -584,6 +600,7 @@ __device__ void emit_palette(const SplitArgs &A, Shared2 &S, const Arrays &R) {
   if (tid == 0) {
     A.result[0] = (uint32_t)S.scan_carry;
     A.result[1] = (uint32_t)(K - S.scan_carry);
+    A.ctl[kCtlTieCount] = S.cur_new;
   }
 }
 

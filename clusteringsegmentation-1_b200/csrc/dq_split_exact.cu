@@ -3,6 +3,7 @@
 // runs the same body itself, without extra launches.
 #include "dq_split_exact.cuh"
 #include <atomic>
+#include <mutex>
 
 #include <algorithm>
 
@@ -46,6 +47,24 @@ ExactSampling exact_sampling(const uint32_t *d_in, uint32_t num_rows, uint32_t n
   q.word_mask = (byte_mask << 16) | (byte_mask << 8) | byte_mask;
   q.shift = shift;
   return q;
+}
+
+void first_seen_launch(const ExactSampling &q, uint32_t *d_first_seen, cudaStream_t st) {
+  static const uint32_t kNoLimit = 0xFFFFFFFFu;
+  static uint32_t *d_zero = nullptr;  // a device word holding 0: "U <= limit" is always true
+  static std::atomic<bool> ready{false};
+  if (!ready) {
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!d_zero) {
+      DQ_CUDA_CHECK(cudaMalloc(&d_zero, sizeof(uint32_t)));
+      DQ_CUDA_CHECK(cudaMemset(d_zero, 0, sizeof(uint32_t)));
+    }
+    ready = true;
+  }
+  const unsigned blocks = (unsigned)std::min<uint64_t>(((uint64_t)q.num_samples + 255) / 256, 1184u);
+  exact_first_seen_kernel<<<std::max(blocks, 1u), 256, 0, st>>>(q, d_zero, kNoLimit, d_first_seen);
+  DQ_CUDA_CHECK(cudaGetLastError());
 }
 
 void split_exact_launch(const SplitArgs &args, const ExactSampling &q, unsigned char *d_scratch, const uint32_t *d_uniq,

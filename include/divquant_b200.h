@@ -116,6 +116,9 @@ typedef struct {
    * summation order (so the result is the reference's as well). */
   uint32_t tie_flags;
   uint32_t ordered_rerun;
+  /* > 0: only palette roundings were flagged (bit 16) and that many cluster centres were recomputed in the reference's
+   * arithmetic by the resolver (csrc/dq_resolve.cu) instead of re-running the frame. */
+  uint32_t tie_resolved;
 } dq_call_stats;
 void dq_context_last_stats(const dq_context *ctx, dq_call_stats *out);
 /* Per-stage CUDA-event timing of dq_quant_recurse_device / _ctx calls (off by default). */

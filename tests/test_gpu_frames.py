@@ -1,9 +1,9 @@
 """GPU parity over EVERY frame of BASELINE config 4 (1024 x 1080p G1, K=64) and every frame bench.py times (4K G1, K=256),
 against fingerprints of the compiled reference (tests/golden/frames.npz, written by tests/golden/make_golden_frames.py
 from oracle/_ref).  All of them have more colours than the ordered path's default limit, so they run on the exact-integer
-kernels with the tie audit: frames whose decisions sit inside the reference's rounding noise (11 of the 1024, three of
+kernels with the tie audit: frames whose decisions sit inside the reference's rounding noise (4 of the 1024, three of
 which the integer sums alone would get wrong by one LSB: seeds 12410, 12830, 13124) must come back flagged AND equal to
-the reference, through the ordered re-run."""
+the reference -- through the resolver (palette roundings) or the ordered re-run (anything else)."""
 import os
 
 import numpy as np
@@ -35,16 +35,17 @@ def _check(dq, oracle, frames, tag, kind, w, h, k, count):
         assert (st["tie_flags"] & model) == model, (seed, st["tie_flags"], model)
         if st["tie_flags"]:
             flagged += 1
-            assert st["ordered_rerun"] == 1, seed
-            rerun += 1
+            assert st["ordered_rerun"] == 1 or st["tie_resolved"] > 0, seed
+            rerun += st["ordered_rerun"]
     assert not bad, bad
     return flagged, rerun
 
 
 def test_config4_all_1024_frames_bit_exact(dq, oracle, frames):
     flagged, rerun = _check(dq, oracle, frames, "c4", 1, 1920, 1080, 64, 1024)
-    assert flagged >= int((frames["c4_tie_mask"] != 0).sum()) == 11
-    assert flagged <= 40, flagged  # the audit must stay sharp: a few percent of the frames at most
+    assert flagged >= int((frames["c4_tie_mask"] != 0).sum()) == 4   # 12410, 12830, 13124 (x.5 roundings), 12832 (cut on an integer)
+    assert flagged <= 16, flagged  # the audit must stay sharp: about one percent of the frames at most
+    assert rerun <= 8, rerun       # and most flagged frames are settled by the resolver, not by a full ordered re-run
 
 
 def test_bench_frames_bit_exact(dq, oracle, frames):
