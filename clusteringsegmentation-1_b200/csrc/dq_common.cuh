@@ -20,7 +20,37 @@
     }                                                                                            \
   } while (0)
 
+#include <atomic>
+
 namespace dq {
+
+// Function attributes (the dynamic shared-memory limit) belong to a device's context: "already raised" is remembered
+// per device ordinal.  Several host threads (pipeline lanes) may ask at once: raising it twice is harmless.
+struct PerDeviceLimit {
+  std::atomic<size_t> raised[64];
+  PerDeviceLimit() {
+    for (auto &r : raised) r = 0;
+  }
+  // true when the caller has to raise the limit to `bytes` on the current device (and should call done afterwards)
+  bool needs(size_t bytes, int *device_out) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    *device_out = dev;
+    return dev < 0 || dev >= 64 || bytes > raised[dev];
+  }
+  void done(size_t bytes, int dev) {
+    if (dev >= 0 && dev < 64) raised[dev] = bytes;
+  }
+};
+#define DQ_RAISE_SMEM(kernel, bytes)                                                                              \
+  do {                                                                                                            \
+    static ::dq::PerDeviceLimit dq_lim__;                                                                         \
+    int dq_dev__ = 0;                                                                                             \
+    if ((bytes) > 48 * 1024 && dq_lim__.needs((bytes), &dq_dev__)) {                                              \
+      DQ_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));     \
+      dq_lim__.done((bytes), dq_dev__);                                                                           \
+    }                                                                                                             \
+  } while (0)
 
 // Number of 24-bit colours = bins of the direct-addressed table.
 constexpr uint32_t kColourBins = 1u << 24;

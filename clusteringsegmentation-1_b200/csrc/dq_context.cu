@@ -27,6 +27,7 @@
 #include "../../include/divquant_b200.h"
 #include "dq_kernels.cuh"
 #include "dq_split.cuh"
+#include "dq_stdsort.cuh"
 
 namespace {
 
@@ -104,6 +105,24 @@ struct dq_context {
   uint32_t exact_max_points = kExactDefaultPoints;  // ... up to this many unique colours (DIVQUANT_B200_EXACT_MAX)
   DevBuf<uint64_t> d_exact;
   DevBuf<uint32_t> d_tie;  // [4 * kTieListCap] flagged clusters + [kTieListCap] resolver status words
+  DevBuf<FrameResult> d_frame;  // frame pipeline: what palette_post hands back (device side)
+  // a split that has been launched but whose palette has not been collected yet (run_split / run_split_finish)
+  struct PendingSplit {
+    SplitArgs a;
+    bool use_v2 = false;
+    uint32_t K = 0;
+  } pend;
+  // a quantize call between its two halves (quantize_begin / quantize_finish)
+  struct QuantState {
+    uint32_t n = 0, rows = 0, cols = 0, K = 0, point_cap = 0;
+    const uint32_t *d_in = nullptr;
+    int num_bits = 8, dec = 1, max_iters = 10;
+    double norm = 0.0;
+    bool table_dirty = false;
+    dq_split_record *records = nullptr;
+    double *mean_out = nullptr;
+    uint32_t *size_out = nullptr;
+  } qs;
   // Tie audit of the exact-integer split (dq_tie.cuh): 0 = off, 1 = report in dq_call_stats::tie_flags only,
   // 2 (default) = a flagged frame is computed again in the reference's summation order (DIVQUANT_B200_TIE)
   int tie_policy = 2;
@@ -218,12 +237,16 @@ struct ExactSource {
 
 int plan_ctas_hint(const dq_context *ctx, uint32_t K) { return split2_plan(ctx->split_ctas, ctx->sm_count, K, true).grid; }
 
+uint32_t run_split_finish(dq_context *ctx, uint32_t *colortable_out, dq_split_record *records_out, double *mean_out,
+                          uint32_t *size_out);
+
 // Runs the divisive phase on ctx->d_pts0[0..U).  U is read on the device from d_cb->ucount.
 // Leaves palette/result/ctl in ctx->h_cb / ctx->h_small after a stream synchronisation.
 // Returns the number of palette entries.
 uint32_t run_split(dq_context *ctx, uint32_t point_capacity, double norm, uint32_t K, int max_iters, int num_bits,
                    uint32_t *colortable_out, dq_split_record *records_out, double *mean_out, uint32_t *size_out,
-                   bool collect_from_hist = false, const ExactSource *exact = nullptr, bool weighted = false) {
+                   bool collect_from_hist = false, const ExactSource *exact = nullptr, bool weighted = false,
+                   bool launch_only = false, bool defer = false) {
   if (max_iters < 1 || max_iters > kSplitMaxIters) {
     fprintf(stderr, "divquant_b200: max_iters ( %d ) must be in [1,%d] (the reference hard-wires local k-means on)\n",
             max_iters, kSplitMaxIters);
@@ -308,7 +331,7 @@ uint32_t run_split(dq_context *ctx, uint32_t point_capacity, double norm, uint32
     x.collect_table = collect_from_hist ? ctx->d_table : nullptr;
     if (getenv("DQ_PROFILE_NARROW")) DQ_CUDA_CHECK(cudaMemsetAsync(ctx->d_progress.ptr, 0, 1024 * sizeof(uint32_t), ctx->stream));
     const bool mail = ctx->use_mailbox && !ctx->blocking_wait && !ctx->trace_split && records_out == nullptr &&
-                      mean_out == nullptr && size_out == nullptr;
+                      mean_out == nullptr && size_out == nullptr && !launch_only;
     if (mail) {
       void *dev = nullptr;
       DQ_CUDA_CHECK(cudaHostGetDevicePointer(&dev, const_cast<uint32_t *>(ctx->mailbox), 0));
@@ -342,7 +365,27 @@ uint32_t run_split(dq_context *ctx, uint32_t point_capacity, double norm, uint32
   }
   ctx->mark(3);
   ctx->stats.kernel_launches++;
+  if (launch_only) return 0;  // frame pipeline: the palette stays on the device (palette_post), nothing to wait for
+  ctx->pend.a = a;
+  ctx->pend.use_v2 = use_v2;
+  ctx->pend.K = K;
+  if (defer) return 0;  // the caller polls split_ready() and collects with run_split_finish()
+  return run_split_finish(ctx, colortable_out, records_out, mean_out, size_out);
+}
 
+// Has the split launched last on this context delivered its palette?  (non-blocking; true when there is nothing to poll)
+bool split_ready(dq_context *ctx) {
+  const SplitArgs &a = ctx->pend.a;
+  if (a.mailbox == nullptr) return true;
+  if (ctx->mailbox[0] == a.mailbox_seq) return true;
+  return cudaStreamQuery(ctx->stream) != cudaErrorNotReady;  // an error exit leaves the stream idle without the number
+}
+
+uint32_t run_split_finish(dq_context *ctx, uint32_t *colortable_out, dq_split_record *records_out, double *mean_out,
+                          uint32_t *size_out) {
+  const SplitArgs &a = ctx->pend.a;
+  const bool use_v2 = ctx->pend.use_v2;
+  const uint32_t K = ctx->pend.K;
   ctx->ensure_small((size_t)K + 16);
   bool mailed = false;
   if (a.mailbox != nullptr) {
@@ -492,10 +535,9 @@ void check_quant_args(uint32_t n, uint32_t k, int num_bits) {
 
 // quant_varpart_fast on device-resident pixels; keeps the unique list (when one was built) valid for
 // a following table remap.  Returns true if such a unique list exists (d_uniq / d_cb->ucount).
-bool quantize_device(dq_context *ctx, uint32_t n, const uint32_t *d_in, uint32_t rows, uint32_t cols, uint32_t *k_inout,
-                     uint32_t *colortable, int num_bits, int dec, int max_iters, int all_unique, dq_split_record *records,
-                     double *mean_out, uint32_t *size_out) {
-  const uint32_t K = *k_inout;
+// First half: histogram (or points) and the split kernel are queued; nothing is waited for.
+void quantize_begin(dq_context *ctx, uint32_t n, const uint32_t *d_in, uint32_t rows, uint32_t cols, uint32_t K, int num_bits,
+                    int dec, int max_iters, int all_unique, dq_split_record *records, double *mean_out, uint32_t *size_out) {
   check_quant_args(n, K, num_bits);
   reset_control(ctx);
   ctx->mark(0);
@@ -526,8 +568,29 @@ bool quantize_device(dq_context *ctx, uint32_t n, const uint32_t *d_in, uint32_t
     point_cap = samples;
   }
   const ExactSource src = {d_in, rows, cols, (uint32_t)dec, num_bits};
-  *k_inout = run_split(ctx, point_cap, norm, K, max_iters, num_bits, colortable, records, mean_out, size_out, table_dirty,
-                       table_dirty ? &src : nullptr, table_dirty);
+  uint32_t unused = 0;
+  run_split(ctx, point_cap, norm, K, max_iters, num_bits, &unused, records, mean_out, size_out, table_dirty,
+            table_dirty ? &src : nullptr, table_dirty, false, /*defer=*/true);
+  dq_context::QuantState &q = ctx->qs;
+  q.n = n, q.rows = rows, q.cols = cols, q.K = K, q.point_cap = point_cap, q.d_in = d_in;
+  q.num_bits = num_bits, q.dec = dec, q.max_iters = max_iters, q.norm = norm, q.table_dirty = table_dirty;
+  q.records = records, q.mean_out = mean_out, q.size_out = size_out;
+}
+
+// Second half: the palette (waits for it unless split_ready() said it is there), and what the tie audit asks for.
+// Returns true if a unique list exists (d_uniq / d_cb->ucount) for a following table remap.
+bool quantize_finish(dq_context *ctx, uint32_t *k_inout, uint32_t *colortable) {
+  const dq_context::QuantState q = ctx->qs;
+  const uint32_t n = q.n, rows = q.rows, cols = q.cols, K = q.K, point_cap = q.point_cap;
+  const uint32_t *d_in = q.d_in;
+  const int num_bits = q.num_bits, dec = q.dec, max_iters = q.max_iters;
+  const double norm = q.norm;
+  const bool table_dirty = q.table_dirty;
+  dq_split_record *records = q.records;
+  double *mean_out = q.mean_out;
+  uint32_t *size_out = q.size_out;
+  const ExactSource src = {d_in, rows, cols, (uint32_t)dec, num_bits};
+  *k_inout = run_split_finish(ctx, colortable, records, mean_out, size_out);
   const uint32_t flags = ctx->stats.tie_flags;
   bool resolved = false;
   if (flags == (uint32_t)kTieRound && ctx->tie_policy == 2 && table_dirty && ctx->exact_small && records == nullptr && mean_out == nullptr) {
@@ -572,11 +635,25 @@ bool quantize_device(dq_context *ctx, uint32_t n, const uint32_t *d_in, uint32_t
   return table_dirty;
 }
 
-void quant_recurse_device_impl(dq_context *ctx, uint32_t n, const uint32_t *d_in, uint32_t *d_out, uint32_t *k_inout,
-                               uint32_t *colortable, int all_unique, double *ms_quant, double *ms_map, bool final_sync = true) {
-  auto t0 = std::chrono::steady_clock::now();
-  const bool dirty = quantize_device(ctx, n, d_in, 1, n, k_inout, colortable, 8, 1, 10, all_unique, nullptr, nullptr, nullptr);
-  auto t1 = std::chrono::steady_clock::now();
+bool quantize_device(dq_context *ctx, uint32_t n, const uint32_t *d_in, uint32_t rows, uint32_t cols, uint32_t *k_inout,
+                     uint32_t *colortable, int num_bits, int dec, int max_iters, int all_unique, dq_split_record *records,
+                     double *mean_out, uint32_t *size_out) {
+  quantize_begin(ctx, n, d_in, rows, cols, *k_inout, num_bits, dec, max_iters, all_unique, records, mean_out, size_out);
+  return quantize_finish(ctx, k_inout, colortable);
+}
+
+// quant_recurse on device pixels in two halves, so that one host thread can keep several contexts busy: recurse_begin
+// queues histogram + split; once split_ready(ctx), recurse_remap collects the palette, handles it exactly as the
+// reference's host code does (duplicates, std::sort, lut_init) and queues the remap.  Neither waits for the GPU unless
+// the tie audit flagged the frame.
+void recurse_begin(dq_context *ctx, uint32_t n, const uint32_t *d_in, uint32_t K, int all_unique) {
+  quantize_begin(ctx, n, d_in, 1, n, K, 8, 1, 10, all_unique, nullptr, nullptr, nullptr);
+}
+
+void recurse_remap(dq_context *ctx, uint32_t n, const uint32_t *d_in, uint32_t *d_out, uint32_t *k_inout, uint32_t *colortable,
+                   std::chrono::steady_clock::time_point *t_palette = nullptr) {
+  const bool dirty = quantize_finish(ctx, k_inout, colortable);
+  if (t_palette) *t_palette = std::chrono::steady_clock::now();
   uint32_t k = dedup_palette(colortable, *k_inout);
   *k_inout = k;
   ctx->stats.actual_colors = k;
@@ -603,6 +680,14 @@ void quant_recurse_device_impl(dq_context *ctx, uint32_t n, const uint32_t *d_in
     upload_search_tables(ctx, colortable, (int)k);
     remap_bruteforce(ctx, d_in, n, d_out, (int)k);
   }
+}
+
+void quant_recurse_device_impl(dq_context *ctx, uint32_t n, const uint32_t *d_in, uint32_t *d_out, uint32_t *k_inout,
+                               uint32_t *colortable, int all_unique, double *ms_quant, double *ms_map, bool final_sync = true) {
+  auto t0 = std::chrono::steady_clock::now();
+  recurse_begin(ctx, n, d_in, *k_inout, all_unique);
+  auto t1 = t0;
+  recurse_remap(ctx, n, d_in, d_out, k_inout, colortable, &t1);  // waits for the palette, then queues the remap
   if (final_sync || ctx->profiling) ctx->wait();
   if (ctx->profiling) {
     auto span = [&](int a, int b) {
@@ -621,6 +706,57 @@ void quant_recurse_device_impl(dq_context *ctx, uint32_t n, const uint32_t *d_in
   auto t2 = std::chrono::steady_clock::now();
   if (ms_quant) *ms_quant = std::chrono::duration<double, std::milli>(t1 - t0).count();
   if (ms_map) *ms_map = std::chrono::duration<double, std::milli>(t2 - t1).count();
+}
+
+// Frame pipeline: the whole of one quant_recurse queued on the context's stream without a single host wait -- histogram,
+// split, palette handling on the device (duplicates, the reference's std::sort order, lut_init: palette_post), remap
+// through the unique-colour table, and one small copy of the FrameResult to pinned host memory.  The host looks at the
+// frame only once it is complete (frame_async_collect).
+bool frame_async_supported(const dq_context *ctx, uint32_t K, int all_unique) {
+  return !all_unique && ctx->split_version == 2 && K <= kSplit2MaxColors && K <= (uint32_t)kFrameMaxColors && K >= 1;
+}
+
+void frame_async_enqueue(dq_context *ctx, uint32_t n, const uint32_t *d_in, uint32_t *d_out, uint32_t K, FrameResult *h_frame) {
+  check_quant_args(n, K, 8);
+  reset_control(ctx);
+  ctx->d_pts0.ensure(n);
+  run_histogram(ctx, d_in, n, 1, n, 1, 8);
+  const ExactSource src = {d_in, 1, n, 1, 8};
+  uint32_t unused = 0;
+  run_split(ctx, n, sample_norm(1, n, 1), K, 10, 8, &unused, nullptr, nullptr, nullptr, true, &src, true, /*launch_only=*/true);
+  ctx->d_sorted.ensure((size_t)K + kLutEntries);
+  ctx->d_frame.ensure(1);
+  palette_post(ctx->d_palette.ptr, ctx->d_cb->result, ctx->d_cb->ctl, &ctx->d_cb->ucount, (int)K, ctx->d_sorted.ptr, ctx->d_frame.ptr,
+               ctx->stream);
+  map_unique_dev(ctx->d_uniq.ptr, &ctx->d_cb->ucount, n, ctx->d_map, ctx->d_sorted.ptr, (int)K, ctx->d_frame.ptr, ctx->sm_count,
+                 ctx->stream);
+  map_gather(d_in, n, d_out, ctx->d_map, ctx->sm_count, ctx->stream);
+  DQ_CUDA_CHECK(cudaMemcpyAsync(h_frame, ctx->d_frame.ptr, sizeof(FrameResult), cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->stats.kernel_launches += 3;
+}
+
+// The frame is complete (its stream position has been waited for).  Returns true when the palette in h_frame is final;
+// false when the tie audit flagged the frame (the caller runs it again through the synchronous path, which resolves it).
+bool frame_async_collect(dq_context *ctx, const FrameResult *h_frame, uint32_t K, uint32_t *k_out, uint32_t *colortable) {
+  if (h_frame->ctl[kCtlError] != 0) {
+    fprintf(stderr, "divquant_b200: split controller failed (code %u, frame pipeline; internal error)\n", h_frame->ctl[kCtlError]);
+    abort();
+  }
+  const uint32_t flags = (ctx->tie_policy != 0) ? h_frame->ctl[kCtlTie] : 0u;
+  if (flags != 0u && ctx->tie_policy == 2) return false;
+  const uint32_t k = h_frame->num_colors;
+  if (h_frame->result[1]) fprintf(stderr, "# empty clusters: %d\n", (int)h_frame->result[1]);  // (:1067-1070)
+  memcpy(colortable, h_frame->palette, (size_t)k * sizeof(uint32_t));
+  *k_out = k;
+  ctx->stats.num_points = h_frame->num_points;
+  ctx->stats.requested_colors = K;
+  ctx->stats.actual_colors = k;
+  ctx->stats.empty_clusters = h_frame->result[1];
+  ctx->stats.split_rounds = h_frame->ctl[kCtlRounds];
+  ctx->stats.splits_computed = h_frame->ctl[kCtlSplits];
+  ctx->stats.tie_flags = flags;
+  ctx->stats.remap_path = 2;
+  return true;
 }
 
 std::mutex g_default_mutex;
@@ -648,6 +784,21 @@ uint32_t dq_host_dedup_palette(uint32_t *colortable, uint32_t num_colors) { retu
 
 void dq_host_build_search_tables(const uint32_t *colortable, int num_colors, uint32_t *sorted_out, int32_t *lut_init_out) {
   build_search_tables(colortable, num_colors, sorted_out, lut_init_out);
+}
+
+void dq_host_sort_permutation(const uint32_t *keys, int n, int use_replay, uint32_t *perm_out) {
+  if (n <= 0) return;
+  if (use_replay) {  // csrc/dq_stdsort.cuh, the code the device runs
+    std::vector<uint32_t> v((size_t)n);
+    for (int i = 0; i < n; ++i) v[i] = (keys[i] << 16) | (uint32_t)i;
+    stdsort::sort(v.data(), n);
+    for (int i = 0; i < n; ++i) perm_out[i] = v[i] & 0xFFFFu;
+  } else {  // std::sort on the reference's element type and comparator
+    std::vector<PaletteEntry> v((size_t)n);
+    for (int i = 0; i < n; ++i) v[i].red = i, v[i].green = v[i].blue = 0, v[i].weight = (int)keys[i];
+    std::sort(v.begin(), v.end(), palette_less);
+    for (int i = 0; i < n; ++i) perm_out[i] = (uint32_t)v[i].red;
+  }
 }
 
 dq_context *dq_context_create(int device) {
@@ -735,6 +886,7 @@ void dq_context_destroy(dq_context *ctx) {
   ctx->d_progress.release();
   ctx->d_exact.release();
   ctx->d_tie.release();
+  ctx->d_frame.release();
   cudaFree(ctx->d_table);
   cudaFree(ctx->d_map);
   cudaFree(ctx->d_cb);
@@ -1144,7 +1296,13 @@ struct dq_pipeline {
     uint32_t *d_in = nullptr, *d_out = nullptr;
     cudaEvent_t begin = nullptr, end = nullptr;
     bool have_begin = false;
-    std::thread worker;
+    FrameResult *h_frame[2] = {nullptr, nullptr};  // pinned: result of the frame queued on the lane's stream (asynchronous chain)
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    // dispatcher state
+    int state = 0;
+    bool async_chain = false;
+    uint64_t launches = 0;
+    Job job;
   };
   int device = 0;
   uint32_t max_pixels = 0;
@@ -1156,52 +1314,151 @@ struct dq_pipeline {
   uint64_t submitted = 0, low_water = 0;  // every ticket < low_water has completed
   bool stop = false;
   std::atomic<uint64_t> launches{0};
+  std::atomic<uint64_t> flagged_frames{0};  // frames the tie audit sent through the synchronous path
+  // DIVQUANT_B200_ASYNC=1: the whole chain of a frame is queued without a host wait (palette handling on the device,
+  // palette_post).  Off by default: measured at 4K, 12 lanes, it is slower than the host round trip (0.184-0.22 against
+  // 0.166 ms/frame): the one-thread std::sort replay costs 93 us per frame on the lane's chain and the lanes' throughput
+  // is bounded by the histogram / remap kernels sharing the SMs the split kernels leave free, not by the host.
+  int async_frames = 0;
+  int poll_sleep = 0;    // the dispatcher sleeps 20 us between polling rounds instead of spinning (dq_pipeline_set_blocking_wait)
+  std::vector<std::thread> dispatchers;
   float last_ms = 0.f;
 };
 
 namespace {
 
-void pipeline_worker(dq_pipeline *p, int lane_index) {
-  dq_pipeline::Lane &lane = p->lanes[lane_index];
+void pipeline_complete(dq_pipeline *p, uint64_t ticket, uint64_t launches) {
+  p->launches += launches;
+  {
+    std::lock_guard<std::mutex> lock(p->mu);
+    p->done_above.insert(ticket);
+    while (!p->done_above.empty() && *p->done_above.begin() == p->low_water) {
+      p->done_above.erase(p->done_above.begin());
+      p->low_water++;
+    }
+  }
+  p->cv_done.notify_all();
+}
+
+// One frame through the blocking path, start to end (frames the tie audit flagged in the asynchronous chain).
+void pipeline_run_sync(dq_pipeline *p, dq_pipeline::Lane &lane, const dq_pipeline::Job &job) {
   dq_context *ctx = lane.ctx;
-  require_device(ctx);
+  const uint32_t *d_in = job.in;
+  uint32_t *d_out = job.out;
+  if (!job.device_ptrs) {
+    d_in = lane.d_in;
+    d_out = lane.d_out;
+    DQ_CUDA_CHECK(cudaMemcpyAsync(lane.d_in, job.in, (size_t)job.n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  memset(&ctx->stats, 0, sizeof(ctx->stats));
+  ctx->stats.num_pixels = job.n;
+  quant_recurse_device_impl(ctx, job.n, d_in, d_out, job.k_ptr, job.colortable, job.all_unique, nullptr, nullptr, false);
+  if (!job.device_ptrs)
+    DQ_CUDA_CHECK(cudaMemcpyAsync(job.out, lane.d_out, (size_t)job.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  DQ_CUDA_CHECK(cudaEventRecord(lane.end, ctx->stream));
+  ctx->wait();
+  pipeline_complete(p, job.ticket, ctx->stats.kernel_launches);
+}
+
+// The dispatcher: ONE host thread walks the frames of all its lanes through the GPU.  A lane is a small state machine
+//   idle -> [H2D] histogram + split queued -> (palette arrives in the lane's mailbox) host palette handling, remap [+ D2H]
+//        queued -> (the lane's event fires) frame complete -> idle
+// and the thread only ever polls: mailboxes are host memory, events are cudaEventQuery.  Nothing sleeps on the GPU and
+// nothing spins per lane, so the pipeline needs one busy host core per dispatcher however many lanes it feeds (round 1
+// had a spinning thread per lane, and lost a quarter of its throughput where ranks had fewer cores than lanes).
+void pipeline_dispatcher(dq_pipeline *p, int first_lane, int lane_step) {
+  require_device(p->lanes[first_lane].ctx);
+  enum { kIdle = 0, kWaitSplit = 1, kWaitDone = 2 };
   for (;;) {
-    dq_pipeline::Job job;
-    {
+    bool progress = false;
+    int busy = 0;
+    for (size_t li = (size_t)first_lane; li < p->lanes.size(); li += (size_t)lane_step) {
+      dq_pipeline::Lane &lane = p->lanes[li];
+      dq_context *ctx = lane.ctx;
+      if (lane.state == kWaitDone) {
+        if (cudaEventQuery(lane.done[0]) == cudaErrorNotReady) {
+          ++busy;
+          continue;
+        }
+        progress = true;
+        lane.state = kIdle;
+        if (lane.async_chain) {
+          uint32_t k = 0;
+          if (frame_async_collect(ctx, lane.h_frame[0], *lane.job.k_ptr, &k, lane.job.colortable)) {
+            *lane.job.k_ptr = k;
+            pipeline_complete(p, lane.job.ticket, lane.launches);
+          } else {
+            p->flagged_frames++;
+            pipeline_run_sync(p, lane, lane.job);
+          }
+        } else {
+          if (ctx->stats.tie_flags) p->flagged_frames++;
+          pipeline_complete(p, lane.job.ticket, ctx->stats.kernel_launches);
+        }
+      } else if (lane.state == kWaitSplit) {
+        ++busy;
+        if (!split_ready(ctx)) continue;
+        progress = true;
+        const dq_pipeline::Job &job = lane.job;
+        const uint32_t *d_in = job.device_ptrs ? job.in : lane.d_in;
+        uint32_t *d_out = job.device_ptrs ? job.out : lane.d_out;
+        recurse_remap(ctx, job.n, d_in, d_out, job.k_ptr, job.colortable);
+        if (!job.device_ptrs)
+          DQ_CUDA_CHECK(cudaMemcpyAsync(job.out, lane.d_out, (size_t)job.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        DQ_CUDA_CHECK(cudaEventRecord(lane.done[0], ctx->stream));
+        DQ_CUDA_CHECK(cudaEventRecord(lane.end, ctx->stream));
+        lane.state = kWaitDone;
+      }
+    }
+    // new frames for the idle lanes
+    for (size_t li = (size_t)first_lane; li < p->lanes.size(); li += (size_t)lane_step) {
+      dq_pipeline::Lane &lane = p->lanes[li];
+      if (lane.state != kIdle) continue;
+      {
+        std::lock_guard<std::mutex> lock(p->mu);
+        if (p->queue.empty()) break;
+        lane.job = p->queue.front();
+        p->queue.pop_front();
+      }
+      progress = true;
+      ++busy;
+      dq_context *ctx = lane.ctx;
+      const dq_pipeline::Job &job = lane.job;
+      if (!lane.have_begin) {
+        DQ_CUDA_CHECK(cudaEventRecord(lane.begin, ctx->stream));
+        lane.have_begin = true;
+      }
+      const uint32_t *d_in = job.in;
+      uint32_t *d_out = job.out;
+      if (!job.device_ptrs) {
+        d_in = lane.d_in;
+        d_out = lane.d_out;
+        DQ_CUDA_CHECK(cudaMemcpyAsync(lane.d_in, job.in, (size_t)job.n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+      }
+      memset(&ctx->stats, 0, sizeof(ctx->stats));
+      ctx->stats.num_pixels = job.n;
+      lane.async_chain = p->async_frames && frame_async_supported(ctx, *job.k_ptr, job.all_unique);
+      if (lane.async_chain) {
+        frame_async_enqueue(ctx, job.n, d_in, d_out, *job.k_ptr, lane.h_frame[0]);
+        if (!job.device_ptrs)
+          DQ_CUDA_CHECK(cudaMemcpyAsync(job.out, lane.d_out, (size_t)job.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        DQ_CUDA_CHECK(cudaEventRecord(lane.done[0], ctx->stream));
+        DQ_CUDA_CHECK(cudaEventRecord(lane.end, ctx->stream));
+        lane.launches = ctx->stats.kernel_launches;
+        lane.state = kWaitDone;
+      } else {
+        recurse_begin(ctx, job.n, d_in, *job.k_ptr, job.all_unique);
+        lane.state = kWaitSplit;
+      }
+    }
+    if (progress) continue;
+    if (busy == 0) {
       std::unique_lock<std::mutex> lock(p->mu);
       p->cv_work.wait(lock, [&] { return p->stop || !p->queue.empty(); });
       if (p->queue.empty()) return;  // stop requested and nothing left
-      job = p->queue.front();
-      p->queue.pop_front();
+    } else if (p->poll_sleep) {
+      std::this_thread::sleep_for(std::chrono::microseconds(20));
     }
-    if (!lane.have_begin) {
-      DQ_CUDA_CHECK(cudaEventRecord(lane.begin, ctx->stream));
-      lane.have_begin = true;
-    }
-    const uint32_t *d_in = job.in;
-    uint32_t *d_out = job.out;
-    if (!job.device_ptrs) {
-      d_in = lane.d_in;
-      d_out = lane.d_out;
-      DQ_CUDA_CHECK(cudaMemcpyAsync(lane.d_in, job.in, (size_t)job.n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-    }
-    memset(&ctx->stats, 0, sizeof(ctx->stats));
-    ctx->stats.num_pixels = job.n;
-    quant_recurse_device_impl(ctx, job.n, d_in, d_out, job.k_ptr, job.colortable, job.all_unique, nullptr, nullptr, false);
-    if (!job.device_ptrs)
-      DQ_CUDA_CHECK(cudaMemcpyAsync(job.out, lane.d_out, (size_t)job.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    DQ_CUDA_CHECK(cudaEventRecord(lane.end, ctx->stream));
-    ctx->wait();
-    p->launches += ctx->stats.kernel_launches;
-    {
-      std::lock_guard<std::mutex> lock(p->mu);
-      p->done_above.insert(job.ticket);
-      while (!p->done_above.empty() && *p->done_above.begin() == p->low_water) {
-        p->done_above.erase(p->done_above.begin());
-        p->low_water++;
-      }
-    }
-    p->cv_done.notify_all();
   }
 }
 
@@ -1254,14 +1511,21 @@ dq_pipeline *dq_pipeline_create_lanes(int device, uint32_t max_pixels, int lanes
     }
     DQ_CUDA_CHECK(cudaEventCreate(&lane.begin));
     DQ_CUDA_CHECK(cudaEventCreate(&lane.end));
+    for (int s = 0; s < 2; ++s) {
+      DQ_CUDA_CHECK(cudaMallocHost(&lane.h_frame[s], sizeof(FrameResult)));
+      DQ_CUDA_CHECK(cudaEventCreateWithFlags(&lane.done[s], cudaEventBlockingSync | cudaEventDisableTiming));
+    }
   }
-  for (int i = 0; i < lanes; ++i) p->lanes[i].worker = std::thread(pipeline_worker, p, i);
+  if (const char *e = getenv("DIVQUANT_B200_ASYNC")) p->async_frames = (e[0] != '0');
+  int n_disp = 1;  // host threads that drive the lanes (each polls its share of them)
+  if (const char *e = getenv("DIVQUANT_B200_DISPATCHERS")) n_disp = std::min(std::max(atoi(e), 1), lanes);
+  for (int i = 0; i < n_disp; ++i) p->dispatchers.emplace_back(pipeline_dispatcher, p, i, n_disp);
   return p;
 }
 
 void dq_pipeline_set_blocking_wait(dq_pipeline *p, int enabled) {
   dq_pipeline_flush(p);
-  for (auto &lane : p->lanes) lane.ctx->blocking_wait = enabled ? 1 : 0;
+  p->poll_sleep = enabled ? 1 : 0;
 }
 
 dq_pipeline *dq_pipeline_create(int device, uint32_t max_pixels, int depth) {
@@ -1278,13 +1542,17 @@ void dq_pipeline_destroy(dq_pipeline *p) {
     p->stop = true;
   }
   p->cv_work.notify_all();
-  for (auto &lane : p->lanes) lane.worker.join();
+  for (auto &t : p->dispatchers) t.join();
   for (auto &lane : p->lanes) {
     require_device(lane.ctx);
     cudaFree(lane.d_in);
     cudaFree(lane.d_out);
     cudaEventDestroy(lane.begin);
     cudaEventDestroy(lane.end);
+    for (int s = 0; s < 2; ++s) {
+      cudaFreeHost(lane.h_frame[s]);
+      cudaEventDestroy(lane.done[s]);
+    }
     dq_context_destroy(lane.ctx);
   }
   delete p;
@@ -1331,6 +1599,7 @@ void dq_pipeline_flush(dq_pipeline *p) {
 float dq_pipeline_last_elapsed_ms(const dq_pipeline *p) { return p->last_ms; }
 dq_context *dq_pipeline_context(dq_pipeline *p) { return p->lanes[0].ctx; }
 uint64_t dq_pipeline_kernel_launches(const dq_pipeline *p) { return p->launches.load(); }
+uint64_t dq_pipeline_flagged_frames(const dq_pipeline *p) { return p->flagged_frames.load(); }
 int dq_pipeline_lanes(const dq_pipeline *p) { return (int)p->lanes.size(); }
 
 // ---- test hooks ----

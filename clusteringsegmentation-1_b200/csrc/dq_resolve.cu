@@ -198,13 +198,7 @@ __global__ void __launch_bounds__(kResolveThreads) tie_resolve_kernel(const Spli
 
 void tie_resolve_launch(const SplitNode *d_nodes, uint2 *const *pts, const uint32_t *d_first_seen, double norm, int shift,
                         const uint32_t *d_list, uint32_t count, uint32_t *d_palette, uint32_t *d_status, cudaStream_t st) {
-  static bool configured[64] = {};
-  int dev = 0;
-  DQ_CUDA_CHECK(cudaGetDevice(&dev));
-  if (dev < 64 && !configured[dev]) {
-    DQ_CUDA_CHECK(cudaFuncSetAttribute(tie_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ResolveShared)));
-    configured[dev] = true;
-  }
+  DQ_RAISE_SMEM(tie_resolve_kernel, sizeof(ResolveShared));
   tie_resolve_kernel<<<count, kResolveThreads, sizeof(ResolveShared), st>>>(d_nodes, pts[0], pts[1], d_first_seen, norm, shift,
                                                                             d_list, d_palette, d_status);
   DQ_CUDA_CHECK(cudaGetLastError());

@@ -626,11 +626,7 @@ void split_launch(const SplitArgs &args_in, const SplitLaunch &plan, cudaStream_
   const uint32_t K = args.num_colors;
   size_t base = ((sizeof(CtaShared) + 15) & ~size_t(15)) + (((size_t)(K + 1) * 4 + 15) & ~size_t(15));
   args.use_smem_ctl = plan.smem_bytes > base ? 1 : 0;
-  static std::atomic<size_t> configured{0};  // lanes call this from several host threads
-  if (plan.smem_bytes > configured) {
-    DQ_CUDA_CHECK(cudaFuncSetAttribute(split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes));
-    configured = plan.smem_bytes;
-  }
+  DQ_RAISE_SMEM(split_kernel, plan.smem_bytes);
   void *kargs[] = {(void *)&args};
   DQ_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)split_kernel, dim3(plan.grid), dim3(kSplitThreads), kargs,
                                             plan.smem_bytes, stream));

@@ -1590,16 +1590,19 @@ size_t split2_slot_capacity(uint32_t point_capacity, uint32_t num_colors, int sm
 
 // CTAs of the split kernel that can be co-resident on the device (cooperative launch limit) for this K.
 int split2_max_ctas(int sm_count, uint32_t num_colors) {
+  // (occupancy and the raised shared-memory limit belong to the device: keyed by device ordinal as well)
   static std::mutex mu;
-  static std::map<size_t, int> cache;
+  static std::map<std::pair<int, size_t>, int> cache;
   const size_t smem = split2_smem_bytes(num_colors, 8 * num_colors + 16);
+  int dev = 0;
+  DQ_CUDA_CHECK(cudaGetDevice(&dev));
   std::lock_guard<std::mutex> lock(mu);
-  auto it = cache.find(smem);
+  auto it = cache.find(std::make_pair(dev, smem));
   if (it == cache.end()) {
     int per_sm = 0;
     DQ_CUDA_CHECK(cudaFuncSetAttribute(split2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)(216 * 1024))));
     DQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, split2_kernel, T, smem));
-    it = cache.emplace(smem, std::max(per_sm, 1)).first;
+    it = cache.emplace(std::make_pair(dev, smem), std::max(per_sm, 1)).first;
   }
   return it->second * sm_count;
 }

@@ -71,11 +71,7 @@ void split_exact_launch(const SplitArgs &args, const ExactSampling &q, unsigned 
                         uint32_t *d_table, uint32_t *d_first_seen, double *g_f64, int32_t *g_i32, cudaStream_t st) {
   const unsigned blocks = (unsigned)std::min<uint64_t>(((uint64_t)q.num_samples + 255) / 256, 64u);
   exact_first_seen_kernel<<<std::max(blocks, 1u), 256, 0, st>>>(q, args.num_points_dev, args.exact_small_max, d_first_seen);
-  static std::atomic<bool> configured{false};  // lanes call this from several host threads
-  if (!configured) {
-    DQ_CUDA_CHECK(cudaFuncSetAttribute(split_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(exact::Shared)));
-    configured = true;
-  }
+  DQ_RAISE_SMEM(split_exact_kernel, sizeof(exact::Shared));
   const size_t K = args.num_colors;
   split_exact_kernel<<<1, kExactThreads, sizeof(exact::Shared), st>>>(args, d_scratch, d_uniq, d_table, d_first_seen, g_f64, g_f64 + K,
                                                                            g_f64 + 2 * K, g_f64 + 5 * K, g_i32);

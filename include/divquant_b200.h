@@ -272,6 +272,8 @@ float dq_pipeline_last_elapsed_ms(const dq_pipeline *pipe);
 dq_context *dq_pipeline_context(dq_pipeline *pipe);
 /* Kernels launched since creation (sum over frames and lanes). */
 uint64_t dq_pipeline_kernel_launches(const dq_pipeline *pipe);
+/* Frames whose tie audit raised a flag and that therefore went through the synchronous path a second time. */
+uint64_t dq_pipeline_flagged_frames(const dq_pipeline *pipe);
 int dq_pipeline_lanes(const dq_pipeline *pipe);
 /* Lane threads spin while they wait for the GPU (lowest latency; default) or, with enabled = 1, sleep on an event:
  * use it when the pipeline has more lanes than the process has free host cores (several ranks on one host). */
@@ -315,6 +317,11 @@ uint32_t dq_debug_split_timeline(dq_context *ctx, int enable, uint64_t *pairs_ou
  *   dq_host_build_search_tables sorted palette (the reference's std::sort by r+g+b) and lut_init[766]
  *                               (DivQuantMapColors.cpp:267-383). */
 uint32_t dq_host_dedup_palette(uint32_t *colortable, uint32_t num_colors);
+/* Permutation that sorting n <= 65536 entries by keys[i] (< 65536) produces: perm_out[j] = original index of the entry
+ * that ends at position j.  use_replay = 0: std::sort on the reference's Pixel_Int / comparator (what the host shim
+ * calls); 1: the step-for-step replay of libstdc++'s introsort that the device runs (csrc/dq_stdsort.cuh).  The two
+ * must agree for every input, equal keys included -- tests/test_stdsort.py. */
+void dq_host_sort_permutation(const uint32_t *keys, int n, int use_replay, uint32_t *perm_out);
 void dq_host_build_search_tables(const uint32_t *colortable, int num_colors, uint32_t *sorted_out, int32_t *lut_init_out);
 
 const char *dq_version(void);
