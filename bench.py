@@ -4,11 +4,12 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
-One "step" = one batch of --frames-per-step (12) synthetic 3840x2160 frames (generator G1 of SURVEY.md 8d,
+One "step" = one batch of --frames-per-step (192) synthetic 3840x2160 frames (generator G1 of SURVEY.md 8d,
 seed 12345+frame), each a whole quant_recurse (24-bit histogram -> divisive split with 10 local 2-means
 iterations -> palette dedup/sort -> remap), pushed through the frame pipeline (`lanes` frames in flight
-on the GPU).  N > 1: every rank owns one GPU and its own stream of frames (frame-sharded, no collective:
-weak scaling); value = all ranks' pixels / max-over-ranks device time.
+on the GPU, one dispatcher thread on the host).  N > 1: every rank owns one GPU and its own stream of frames
+(frame-sharded, no collective: weak scaling); value = all ranks' pixels / max-over-ranks device time.
+Every distinct frame that is timed is checked against the compiled reference's fingerprints (tests/golden/frames.npz).
 
 Printed JSON line (rank 0): see the task contract.  value = device-resident throughput (inputs in HBM,
 CUDA events on the lanes' streams); e2e = the same stream through the host-pointer API with pinned host
@@ -107,6 +108,13 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def workload_config():
+    """The `config` key: names the workload, identical in both arms."""
+    return {"workload": f"{WIDTH}x{HEIGHT} RGBA G1 natural-like, K={K}, quant_recurse (histogram + split with 10 LKM iterations + remap)",
+            "width": WIDTH, "height": HEIGHT, "colors": K, "generator": "G1 (SURVEY.md 8d), frame f of rank r: seed 12345 + r*ring + f",
+            "all_pixels_unique": 0}
+
+
 def traffic_bytes():
     """DRAM bytes of one frame from the committed ncu capture (never measured under the timed run): (total, note)."""
     path = os.path.join(ROOT, "profiles", "r01_traffic.json")
@@ -129,8 +137,13 @@ def measured_peaks():
 # ------------------------------------------------------------------------------------------------
 # reference arm: the reference's own CPU implementation on the host cores
 # ------------------------------------------------------------------------------------------------
+_REF_FRAMES = {}
+
+
 def _ref_worker(args):
-    seed, frames = args
+    """One process: quant_recurse of `frames` frames.  The synthetic frames are generated (and kept) OUTSIDE the timed
+    region; only the reference's own call is timed."""
+    seed, frames, width, height, k = args
     from oracle import Oracle, Reference, muted
     o = Oracle()
     try:
@@ -138,25 +151,29 @@ def _ref_worker(args):
         kind = "reference"
     except FileNotFoundError:
         r, kind = o, "port"
-    done = 0
-    t0 = time.perf_counter()
+    pxs = []
     for f in range(frames):
-        px = o.generate(1, WIDTH, HEIGHT, seed + f)
-        with muted():
-            r.quant_recurse(px, K, 0)
-        done += 1
-    return kind, done, time.perf_counter() - t0
-
-
-def cpu_reference_time(frames_per_worker, workers, pool=None):
-    """Frame-parallel over `workers` processes (the reference itself is single-threaded)."""
+        key = (width, height, seed + f)
+        if key not in _REF_FRAMES:
+            _REF_FRAMES[key] = o.generate(1, width, height, seed + f)
+        pxs.append(_REF_FRAMES[key])
     t0 = time.perf_counter()
+    for px in pxs:
+        with muted():
+            r.quant_recurse(px, k, 0)
+    return kind, frames, time.perf_counter() - t0
+
+
+def cpu_reference_time(frames_per_worker, workers, pool=None, width=None, height=None, k=None):
+    """Frame-parallel over `workers` processes (the reference itself is single-threaded).  Returns (kind, frames,
+    seconds) with seconds = the slowest worker's time inside the reference's calls (input generation and process
+    dispatch are outside)."""
+    width, height, k = width or WIDTH, height or HEIGHT, k or K
     if workers == 1 or pool is None:
-        res = [_ref_worker((12345, frames_per_worker))]
+        res = [_ref_worker((12345, frames_per_worker, width, height, k))]
     else:
-        res = pool.map(_ref_worker, [(12345 + 1000 * w, frames_per_worker) for w in range(workers)])
-    wall = time.perf_counter() - t0
-    return res[0][0], sum(r[1] for r in res), wall
+        res = pool.map(_ref_worker, [(12345 + 1000 * w, frames_per_worker, width, height, k) for w in range(workers)])
+    return res[0][0], sum(r[1] for r in res), max(r[2] for r in res)
 
 
 def run_reference(args, rank, world):
@@ -168,23 +185,23 @@ def run_reference(args, rank, world):
     workers = os.cpu_count() or 1
     steps, warmup = args.steps, max(args.warmup, 0)
     pool = mp.get_context("fork").Pool(workers) if workers > 1 else None
-    for _ in range(min(warmup, 1)):
+    for _ in range(max(min(warmup, 1), 1)):  # also generates (and caches) every worker's frame outside the timed steps
         cpu_reference_time(1, workers, pool)
-    t0 = time.perf_counter()
     total_frames = 0
+    wall = 0.0
     kind = "reference"
     for _ in range(steps):
-        kind, frames, _ = cpu_reference_time(1, workers, pool)
+        kind, frames, secs = cpu_reference_time(1, workers, pool)
         total_frames += frames
-    wall = time.perf_counter() - t0
+        wall += secs
     if pool:
         pool.close()
     value = total_frames * NPIX / wall / 1e6
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Mpixels/s", "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": 1e3 * wall / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64+u32", "data": "synthetic",
-            "config": {"workload": f"{WIDTH}x{HEIGHT} RGBA G1 natural-like, K={K}, quant_recurse (10 LKM iterations)",
-                       "frames_per_step": workers},
+            "config": workload_config(),
+            "run": {"frames_per_step": workers, "timed": "only the reference's quant_recurse calls (slowest worker per step); frames generated beforehand"},
             "cpu_baseline": {"value": value, "unit": "Mpixels/s", "cores": workers, "kind": kind,
                              "sample": f"{workers} processes x 1 frame per step, {steps} steps, reference compiled from its own sources"},
             "e2e": {"value": value, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -263,20 +280,51 @@ def run_ours(args, rank, world, local_rank):
 
     steps, warmup = args.steps, max(args.warmup, 3)
 
-    # -- parity spot check before timing anything (rank 0, one frame, against the reference build) --
+    # -- parity before timing anything: EVERY distinct frame this rank times, against the compiled reference's
+    #    fingerprints (tests/golden/frames.npz, written by tests/golden/make_golden_frames.py from oracle/_ref); a frame
+    #    without a fingerprint (other --width/--height/--colors) is computed by oracle/_ref here (frame 0 only) --
     step_device(0)
     torch.cuda.synchronize()
     parity = None
-    if rank == 0 and not args.skip_parity:
-        try:
-            checker, kind = Reference(), "reference"
-        except FileNotFoundError:
-            checker, kind = o, "port"
-        with muted():
-            ref_out, ref_pal = checker.quant_recurse(host_frames[0].numpy().view(np.uint32), K, 0)
-        got = dev_out.cpu().numpy().view(np.uint32)
-        parity = bool(np.array_equal(ref_pal, ct[:nk.value]) and np.array_equal(ref_out, got))
-        log(f"[bench] parity vs {kind}: {'bit-exact' if parity else 'MISMATCH'}")
+    parity_info = {"frames_checked": 0, "against": None}
+    if not args.skip_parity:
+        golden = None
+        gpath = os.path.join(ROOT, "tests", "golden", "frames.npz")
+        if (WIDTH, HEIGHT, K) == (3840, 2160, 256) and os.path.exists(gpath):
+            golden = np.load(gpath)
+        ok_all = True
+        for s_i in range(RING):
+            seed = 12345 + rank * RING + s_i
+            step_device(s_i)
+            torch.cuda.synchronize()
+            got_pal, got = ct[:nk.value].copy(), dev_out.cpu().numpy().view(np.uint32)
+            idx = np.where(golden["bench_seeds"] == seed)[0] if golden is not None else []
+            if len(idx):
+                i0 = int(idx[0])
+                ok = (o.hash_words(got_pal) == int(golden["bench_pal_hash"][i0]) and o.hash_words(got) == int(golden["bench_out_hash"][i0]))
+                parity_info["against"] = "tests/golden/frames.npz (oracle/_ref fingerprints)"
+            elif s_i == 0 and rank == 0:
+                try:
+                    checker, parity_info["against"] = Reference(), "oracle/_ref run here"
+                except FileNotFoundError:
+                    checker, parity_info["against"] = o, "oracle port run here"
+                with muted():
+                    ref_out, ref_pal = checker.quant_recurse(host_frames[0].numpy().view(np.uint32), K, 0)
+                ok = bool(np.array_equal(ref_pal, got_pal) and np.array_equal(ref_out, got))
+            else:
+                continue
+            parity_info["frames_checked"] += 1
+            ok_all = ok_all and ok
+            if not ok:
+                log(f"[bench] rank {rank}: frame seed {seed} MISMATCH")
+        parity = bool(ok_all and parity_info["frames_checked"] > 0)
+        if dist:
+            t = torch.tensor([1.0 if parity else 0.0], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            parity = bool(t.item() > 0.5)
+        if rank == 0:
+            log(f"[bench] parity of every distinct timed frame ({parity_info['frames_checked']} on rank 0) vs {parity_info['against']}: "
+                f"{'bit-exact' if parity else 'MISMATCH'}")
 
     # -- frame pipeline (the public API for a stream of frames): `lanes` frames in flight on one GPU, each lane a
     #    context + host thread walking one frame at a time through [H2D ->] kernels [-> D2H]; split kernels of
@@ -332,14 +380,11 @@ def run_ours(args, rank, world, local_rank):
         return ms, n_launch, ok
 
     FPS = args.frames_per_step
-    # every lane has a host thread that waits on its stream: leave one core per rank for the submitting thread
+    # The pipeline has ONE dispatcher thread per GPU that polls the lanes (it spins), next to this submitting thread
+    # (which sleeps in flush): two host threads per rank whatever the lane count.  Only a rank with a single core lets
+    # the dispatcher sleep between its polling rounds.
     cpus = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    # lane threads spin on their stream (lowest latency) when every one of them can have a core, with one left for the
-    # submitting thread; otherwise they sleep on an event and a few more lanes hide the later wake-up (tools/lanes_check.py)
-    spin_lanes = min(args.lanes, cpus // world - 1)
-    blocking = 0 if spin_lanes >= 8 else 1
-    args.lanes = spin_lanes if not blocking else max(args.lanes, 12)
-    args.e2e_lanes = min(args.e2e_lanes, max(spin_lanes, 2)) if not blocking else args.e2e_lanes
+    blocking = 1 if cpus // world < 2 else 0
     clocks = ClockSampler(local_rank)
     clocks.start()
     # -- device-resident throughput (frames already in HBM, results left in HBM) --
@@ -399,6 +444,17 @@ def run_ours(args, rank, world, local_rank):
         shard = torch.from_numpy(full[r0 * WIDTH:r1 * WIDTH].view(np.int32).copy()).cuda()
         ws = {}
         out_s, pal_s = pkg.row_sharded_quant_recurse(lib, ctx, shard, NPIX, K, dist, ws)
+        # parity of the sharded result: palette and this rank's rows against one whole-image call on this GPU
+        full_dev = torch.from_numpy(full.view(np.int32)).cuda()
+        nk.value = K
+        lib.dq_quant_recurse_device(ctx, NPIX, full_dev.data_ptr(), dev_out.data_ptr(), C.byref(nk), ctp, 0)
+        torch.cuda.synchronize()
+        rows_ok = bool(np.array_equal(pal_s, ct[:nk.value]) and
+                       torch.equal(out_s.view(torch.int32), dev_out[r0 * WIDTH:r1 * WIDTH]))
+        t_ok = torch.tensor([1.0 if rows_ok else 0.0], device="cuda")
+        dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+        rows_ok = bool(t_ok.item() > 0.5)
+        del full_dev
         for _ in range(2):
             pkg.row_sharded_quant_recurse(lib, ctx, shard, NPIX, K, dist, ws)
         barrier()
@@ -412,12 +468,125 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         rows_info = {"ms_per_image": float(t.item()), "value": NPIX / (float(t.item()) * 1e-3) / 1e6, "unit": "Mpixels/s",
                      "scaling": "strong", "collective": "1 x all_gather of (colour,count) lists (+ sizes) over NCCL per image",
-                     "palette_entries": int(pal_s.size)}
+                     "palette_entries": int(pal_s.size), "matches_single_gpu_call": rows_ok}
+
+    # -- BASELINE config 4: a batch of 1024 synthetic 1080p frames, K=64, frame-sharded over the ranks (no collective),
+    #    host-fed: pinned host frames in, pinned host frames out, H2D and D2H of every frame inside the timed region --
+    batch_info = None
+    if not args.skip_batch:
+        BW, BH, BK, BN = 1920, 1080, 64, 1024
+        bpix = BW * BH
+        mine = pkg.frames_for_rank(BN, world, rank)
+        ties = [f for f in (65, 485, 779, 487) if f in mine]  # seeds 12410 / 12830 / 13124 / 12832: the frames the tie audit flags
+        ring_frames = list(mine)[:max(args.batch_ring - len(ties), 1)]
+        distinct = list(dict.fromkeys(ring_frames + ties))
+        # frame i of the batch reads ring slot i % len(ring), except the tie frames, which are themselves exactly once
+        slot_of = {f: j for j, f in enumerate(distinct)}
+        frame_slot = [slot_of[f] if f in ties else slot_of[ring_frames[i % len(ring_frames)]] for i, f in enumerate(mine)]
+        bgold = np.load(os.path.join(ROOT, "tests", "golden", "frames.npz")) if os.path.exists(os.path.join(ROOT, "tests", "golden", "frames.npz")) else None
+        b_in = [torch.from_numpy(o.generate(1, BW, BH, 12345 + f).view(np.int32)).pin_memory() for f in distinct]
+        b_lanes = args.lanes
+        pipe = lib.dq_pipeline_create_lanes(local_rank, bpix, b_lanes, 0)
+        lib.dq_pipeline_set_blocking_wait(pipe, blocking)
+        b_outs = [torch.empty(bpix, dtype=torch.int32).pin_memory() for _ in range(b_lanes + 2)]
+        # correctness pass: every distinct frame of the ring against the reference's fingerprints
+        b_ok, b_checked = True, 0
+        for j, f in enumerate(distinct):
+            nkb, ctb = C.c_uint32(BK), np.zeros(BK, np.uint32)
+            lib.dq_pipeline_submit(pipe, bpix, C.cast(b_in[j].data_ptr(), u32p), C.cast(b_outs[0].data_ptr(), u32p), C.byref(nkb),
+                                   ctb.ctypes.data_as(u32p), 0)
+            lib.dq_pipeline_flush(pipe)
+            if bgold is not None:
+                b_checked += 1
+                b_ok = b_ok and (o.hash_words(ctb[:nkb.value]) == int(bgold["c4_pal_hash"][f]) and
+                                 o.hash_words(b_outs[0].numpy().view(np.uint32)) == int(bgold["c4_out_hash"][f]))
+        flagged0 = lib.dq_pipeline_flagged_frames(pipe)
+
+        def run_batch(n_frames):
+            nks_b = [C.c_uint32(BK) for _ in range(n_frames)]
+            cts_b = [np.zeros(BK, np.uint32) for _ in range(n_frames)]
+            tickets = []
+            nbuf = len(b_outs)
+            for i in range(n_frames):
+                if i >= nbuf:
+                    lib.dq_pipeline_wait(pipe, tickets[i - nbuf])
+                tickets.append(lib.dq_pipeline_submit(pipe, bpix, C.cast(b_in[frame_slot[i]].data_ptr(), u32p),
+                                                      C.cast(b_outs[i % nbuf].data_ptr(), u32p), C.byref(nks_b[i]),
+                                                      cts_b[i].ctypes.data_as(u32p), 0))
+            lib.dq_pipeline_flush(pipe)
+            return float(lib.dq_pipeline_last_elapsed_ms(pipe))
+
+        run_batch(min(len(mine), 64))
+        barrier()
+        ms_batch = run_batch(len(mine))
+        barrier()
+        if dist:
+            t = torch.tensor([ms_batch], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_batch = float(t.item())
+            t_ok = torch.tensor([1.0 if b_ok else 0.0], device="cuda")
+            dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+            b_ok = bool(t_ok.item() > 0.5)
+        lib.dq_pipeline_destroy(pipe)
+        batch_info = {"workload": f"BASELINE config 4: {BN} frames {BW}x{BH} G1 (frame f: seed 12345+f), K={BK}, frame-sharded over {world} GPU(s), no collective, host-fed (pinned)",
+                      "value": BN * bpix / (ms_batch * 1e-3) / 1e6, "unit": "Mpixels/s", "ms_total": ms_batch, "ms_per_frame": ms_batch / BN,
+                      "frames_per_rank": len(mine), "distinct_frames_per_rank": len(distinct),
+                      "ring_note": "frames cycle through the first ring slots of the rank's range; the frames the tie audit flags (f = 65, 485, 487, 779) are in the batch exactly once each, as in the real batch",
+                      "h2d_bytes_per_frame": bpix * 4, "d2h_bytes_per_frame": bpix * 4 + BK * 4 + 4,
+                      "every_distinct_frame_matches_reference": bool(b_ok) if b_checked else None, "frames_checked_rank0": b_checked,
+                      "tie_flagged_frames_in_check_pass_rank0": int(flagged0), "lanes": b_lanes, "scaling": "strong (fixed batch)"}
+        del b_in, b_outs
 
     if rank != 0:
         if dist:
             dist.destroy_process_group()
         return
+
+    # -- latency of small inputs (the reference's real callers pass region-sized pixel lists, K = 4 .. 125): one blocking
+    #    call through the reference-signature entry point with host buffers, next to the reference's own CPU time --
+    small_table = None
+    pageable_ms = None
+    if not args.skip_small:
+        dq = pkg.DivQuant(lib, timings=False)
+        try:
+            refc = Reference()
+        except FileNotFoundError:
+            refc = o
+        small_table = []
+        for (sw, sh) in ((4, 4), (40, 25), (400, 250)):
+            px = o.generate(1, sw, sh, 777)
+            for sk in (4, 125):
+                with muted():
+                    for _ in range(3):
+                        dq.quant_recurse(px, sk, 0)
+                    tg = []
+                    for _ in range(15):
+                        t0 = time.perf_counter()
+                        dq.quant_recurse(px, sk, 0)
+                        tg.append(time.perf_counter() - t0)
+                    tc = []
+                    for _ in range(5):
+                        t0 = time.perf_counter()
+                        refc.quant_recurse(px, sk, 0)
+                        tc.append(time.perf_counter() - t0)
+                small_table.append({"pixels": sw * sh, "colors": sk, "unique_colours": int(np.unique(px & 0xFFFFFF).size),
+                                    "gpu_ms": 1e3 * statistics.median(tg), "cpu_reference_ms": 1e3 * statistics.median(tc)})
+        # one 4K call through the literal `quant_recurse` symbol with PAGEABLE host buffers (what a relinked caller does)
+        px = host_frames[0].numpy().view(np.uint32).copy()
+        outp = np.zeros_like(px)
+        ctq = np.zeros(K, np.uint32)
+        qr = lib.quant_recurse
+        qr.restype = None
+        qr.argtypes = [C.c_uint32, u32p, u32p, u32p, u32p, C.c_int]
+        tq = []
+        with muted():
+            for i in range(6):
+                nkq = C.c_uint32(K)
+                t0 = time.perf_counter()
+                qr(px.size, px.ctypes.data_as(u32p), outp.ctypes.data_as(u32p), C.byref(nkq), ctq.ctypes.data_as(u32p), 0)
+                if i:
+                    tq.append(time.perf_counter() - t0)
+        pageable_ms = 1e3 * statistics.median(tq)
 
     peak, peak_src = measured_peaks()
     ms_step = ms_dev / steps
@@ -456,8 +625,9 @@ def run_ours(args, rank, world, local_rank):
         "metric": METRIC, "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32+f64",
         "data": "synthetic",
-        "config": {"workload": f"{WIDTH}x{HEIGHT} RGBA G1 natural-like, K={K}, quant_recurse (histogram + split with 10 LKM iterations + remap)",
-                   "frames_per_step": FPS, "lanes": args.lanes, "lane_threads_wait": "sleep on an event" if blocking else "spin",
+        "config": workload_config(),
+        "run": {"frames_per_step": FPS, "lanes": args.lanes, "host_threads_per_gpu": "1 dispatcher (polls the lanes) + the submitting thread",
+                   "dispatcher_wait": "sleeps 20 us between polling rounds" if blocking else "spins",
                    "host_cores_per_rank": cpus // world,
                    "api": "dq_pipeline_submit_device/flush: a stream of independent frames, `lanes` in flight on one GPU (each frame is one unmodified quant_recurse; split kernels of different frames on disjoint SM groups)",
                    "distinct_frames_per_rank": RING, "sharding": "frames (one stream of frames per GPU, no collective)" if world > 1 else "single GPU",
@@ -472,6 +642,8 @@ def run_ours(args, rank, world, local_rank):
                 "copy_floor_note": "H2D + D2H of one frame each, concurrently on two streams, no kernels: what PCIe alone allows on this rank",
                 "api": "dq_pipeline_submit/flush (H2D, kernels and D2H of different frames overlap)",
                 "single_call_ms": ms_e2e_single / steps, "single_call_value": world * steps * NPIX / (ms_e2e_single * 1e-3) / 1e6,
+                "pageable_single_call_ms": pageable_ms,
+                "pageable_note": "one call of the exported `quant_recurse` symbol with pageable (numpy) buffers, host clock, median of 5",
                 "matches_single_call": e2e_parity},
         "single_call": {"api": "dq_quant_recurse_device, one frame at a time (latency of one call, all SMs on one frame)",
                         "ms": ms_single_frame, "value": world * NPIX / (ms_single_frame * 1e-3) / 1e6, "unit": "Mpixels/s",
@@ -489,8 +661,13 @@ def run_ours(args, rank, world, local_rank):
                           "basis": "per frame at the throughput of `value` (lanes frames in flight); frac_single_call is the same bound against the latency of one isolated call",
                           "note": "config.remap_variant says which formulation produced the time: the unique-colour table does U*K, not N*K, evaluations (an algorithmic win, not pipe efficiency)"},
         "stage_ms": stage_ms,
-        "parity": parity, "pipeline_matches_single_call": dev_parity,
+        "parity": parity, "parity_detail": parity_info, "pipeline_matches_single_call": dev_parity,
     }
+    if batch_info:
+        line["batch1080"] = batch_info
+    if small_table:
+        line["small_inputs"] = {"api": "dq_quant_recurse (host pointers, blocking), median of 15 calls; CPU: oracle/_ref, median of 5",
+                                "rows": small_table}
     if rows_info:
         line["row_sharded"] = rows_info
     if cpu:
@@ -509,8 +686,12 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=10, help="frames of the single-thread CPU baseline sample")
     ap.add_argument("--lanes", type=int, default=12, help="frames in flight per GPU, device-resident leg")
     ap.add_argument("--e2e-lanes", type=int, default=6, help="frames in flight per GPU, host-buffer leg")
-    ap.add_argument("--frames-per-step", type=int, default=12, help="frames in one step (one batch; a multiple of the lanes keeps them evenly loaded)")
+    ap.add_argument("--frames-per-step", type=int, default=192,
+                    help="frames in one step (one batch; a multiple of the lanes keeps them evenly loaded; 20 steps x 192 frames keep the timed region above 0.5 s)")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-batch", action="store_true", help="skip the BASELINE config-4 leg (1024 x 1080p, K=64, host-fed)")
+    ap.add_argument("--skip-small", action="store_true", help="skip the small-input latency table")
+    ap.add_argument("--batch-ring", type=int, default=48, help="distinct pinned host frames the config-4 leg cycles through")
     ap.add_argument("--skip-parity", action="store_true")
     ap.add_argument("--width", type=int, default=3840, help="frame width (default: the BASELINE.json headline config)")
     ap.add_argument("--height", type=int, default=2160)
@@ -531,12 +712,15 @@ def main():
     sys.stdout.flush()
     _JSON_FD = os.dup(1)
     os.dup2(2, 1)
+    if args.impl == "reference":
+        # the reference arm only ever touches the checker side: nothing of the product is built, loaded or called
+        if rank == 0:
+            subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "all"], check=True, stdout=subprocess.DEVNULL)
+        run_reference(args, rank, world)
+        return
     import __graft_entry__ as entry
     if local_rank == 0:
         entry.build()
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-        return
     run_ours(args, rank, world, local_rank)
 
 

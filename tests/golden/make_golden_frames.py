@@ -5,7 +5,7 @@
 
 Writes tests/golden/frames.npz:
   c4_*     the 1024 frames of config 4: 1920x1080 G1, K=64, frame f has seed 12345+f  
-  bench_*  the frames bench.py times: 3840x2160 G1, K=256, seeds 12345..12345+31
+  bench_*  the frames bench.py times: 3840x2160 G1, K=256, seeds 12345..12345+63 (8 ranks x 7 ring slots and a margin)
   g2_*     the stress inputs of SURVEY.md 8c/8d: G2 uniform-random 1920x1080 (and 3840x2160 with --g2-4k, ~6 min)
 For each frame: palette hash, out hash (oracle.hash_words, FNV-1a over u32 words), palette size, and the TieBit mask
 the CPU model of the device's tie audit raises (oracle_quant_varpart_fast_exact_audit; 0 = the exact-integer path is
@@ -61,7 +61,7 @@ def main():
     out = {}
     with Pool(8) as pool:
         for tag, kind, w, h, k, seeds in (("c4", 1, 1920, 1080, 64, range(12345, 12345 + 1024)),
-                                          ("bench", 1, 3840, 2160, 256, range(12345, 12345 + 32)),
+                                          ("bench", 1, 3840, 2160, 256, range(12345, 12345 + 64)),
                                           ("g2", 2, 1920, 1080, 256, range(12345, 12346))):
             for key, val in run(pool, kind, w, h, k, seeds).items():
                 out[f"{tag}_{key}"] = val
