@@ -122,7 +122,10 @@ struct dq_context {
     dq_split_record *records = nullptr;
     double *mean_out = nullptr;
     uint32_t *size_out = nullptr;
+    int phase = 0;  // quantize_step
+    uint32_t flags = 0, tie_count = 0, k_first = 0;
   } qs;
+  cudaEvent_t tie_ev = nullptr;
   // Tie audit of the exact-integer split (dq_tie.cuh): 0 = off, 1 = report in dq_call_stats::tie_flags only,
   // 2 (default) = a flagged frame is computed again in the reference's summation order (DIVQUANT_B200_TIE)
   int tie_policy = 2;
@@ -575,64 +578,108 @@ void quantize_begin(dq_context *ctx, uint32_t n, const uint32_t *d_in, uint32_t 
   q.n = n, q.rows = rows, q.cols = cols, q.K = K, q.point_cap = point_cap, q.d_in = d_in;
   q.num_bits = num_bits, q.dec = dec, q.max_iters = max_iters, q.norm = norm, q.table_dirty = table_dirty;
   q.records = records, q.mean_out = mean_out, q.size_out = size_out;
+  q.phase = 0;
+  q.flags = q.tie_count = q.k_first = 0;
 }
 
-// Second half: the palette (waits for it unless split_ready() said it is there), and what the tie audit asks for.
-// Returns true if a unique list exists (d_uniq / d_cb->ucount) for a following table remap.
-bool quantize_finish(dq_context *ctx, uint32_t *k_inout, uint32_t *colortable) {
-  const dq_context::QuantState q = ctx->qs;
-  const uint32_t n = q.n, rows = q.rows, cols = q.cols, K = q.K, point_cap = q.point_cap;
-  const uint32_t *d_in = q.d_in;
-  const int num_bits = q.num_bits, dec = q.dec, max_iters = q.max_iters;
-  const double norm = q.norm;
-  const bool table_dirty = q.table_dirty;
-  dq_split_record *records = q.records;
-  double *mean_out = q.mean_out;
-  uint32_t *size_out = q.size_out;
-  const ExactSource src = {d_in, rows, cols, (uint32_t)dec, num_bits};
-  *k_inout = run_split_finish(ctx, colortable, records, mean_out, size_out);
-  const uint32_t flags = ctx->stats.tie_flags;
-  bool resolved = false;
-  if (flags == (uint32_t)kTieRound && ctx->tie_policy == 2 && table_dirty && ctx->exact_small && records == nullptr && mean_out == nullptr) {
-    // Only palette roundings are in doubt (a cluster mean exactly on x.5: the commonest tie by far): the reference's own
-    // ordered sums are redone for just the flagged clusters (dq_resolve.cu), on top of a first-seen pass over the pixels.
-    const uint32_t count = ctx->h_cb->ctl[kCtlTieCount];
-    if (count >= 1 && count <= kTieListCap) {
-      first_seen_launch(exact_sampling(d_in, rows, cols, (uint32_t)dec, num_bits), ctx->d_map, ctx->stream);
-      uint32_t *d_status = ctx->d_tie.ptr + 4 * kTieListCap;
-      DQ_CUDA_CHECK(cudaMemsetAsync(d_status, 0, kTieListCap * sizeof(uint32_t), ctx->stream));
-      uint2 *pts[2] = {ctx->d_pts0.ptr, ctx->d_pts1.ptr};
-      tie_resolve_launch(ctx->d_nodes.ptr, pts, ctx->d_map, norm, 8 - num_bits, ctx->d_tie.ptr, count, ctx->d_palette.ptr, d_status,
-                         ctx->stream);
-      ctx->stats.kernel_launches += 2;
-      uint32_t status[kTieListCap];
-      ctx->ensure_small((size_t)K + 16);
-      DQ_CUDA_CHECK(cudaMemcpyAsync(status, d_status, count * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-      DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->h_small, ctx->d_palette.ptr, (size_t)*k_inout * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-      ctx->wait();
-      resolved = true;
-      for (uint32_t i = 0; i < count; ++i) resolved = resolved && status[i] == 1u;
-      if (resolved) {
-        memcpy(colortable, ctx->h_small, (size_t)*k_inout * sizeof(uint32_t));
-        ctx->stats.tie_resolved = count;
-      }
-    }
-  }
-  if (!resolved && flags != 0u && ctx->tie_policy == 2 && table_dirty && ctx->exact_small && ctx->stats.num_points <= kExactMaxPoints &&
-      K <= kExactMaxColors && K <= kSplit2MaxColors && ctx->split_version == 2) {
+// Second half, as a small state machine so that a host thread that drives several contexts never has to wait inside it:
+//   phase 0  the split's palette is collected; a clean frame is done.  A flagged frame (tie audit, dq_tie.cuh) either gets
+//            the resolver queued (only palette roundings in doubt: dq_resolve.cu) -> phase 1, or is queued once more on
+//            the ordered path -> phase 2
+//   phase 1  the resolver's verdict: palette words patched, done -- or not resolvable there -> phase 2
+//   phase 2  the ordered re-run's palette is collected, done
+// quantize_step() advances one phase and says what to poll next; quantize_pending_ready() is the non-blocking poll.
+enum QuantStepResult { kQuantDone = 0, kQuantPending = 1 };
+
+bool quantize_pending_ready(dq_context *ctx) {
+  if (ctx->qs.phase == 1) return cudaEventQuery(ctx->tie_ev) != cudaErrorNotReady;
+  return split_ready(ctx);
+}
+
+QuantStepResult quantize_step(dq_context *ctx, uint32_t *k_inout, uint32_t *colortable) {
+  dq_context::QuantState &q = ctx->qs;
+  const uint32_t K = q.K;
+  const ExactSource src = {q.d_in, q.rows, q.cols, (uint32_t)q.dec, q.num_bits};
+  auto queue_rerun = [&]() {
     // Some decision of the exact-integer split sits inside the rounding noise of the reference's sequential sums:
     // the reference's own summation order decides.  The count table is all-zero again (the split kernel zeroed what
     // it collected), so the frame simply goes through the histogram and the split once more, on the ordered path.
     const uint32_t keep = ctx->exact_max_points;
     ctx->exact_max_points = kExactMaxPoints;
     reset_control(ctx);
-    run_histogram(ctx, d_in, n, rows, cols, (uint32_t)dec, num_bits);
-    *k_inout = run_split(ctx, point_cap, norm, K, max_iters, num_bits, colortable, records, mean_out, size_out, true, &src, true);
+    run_histogram(ctx, q.d_in, q.n, q.rows, q.cols, (uint32_t)q.dec, q.num_bits);
+    uint32_t unused = 0;
+    run_split(ctx, q.point_cap, q.norm, K, q.max_iters, q.num_bits, &unused, q.records, q.mean_out, q.size_out, true, &src, true,
+              false, /*defer=*/true);
     ctx->exact_max_points = keep;
-    ctx->stats.tie_flags = flags;
-    ctx->stats.ordered_rerun = 1;
+    q.phase = 2;
+  };
+  const bool can_rerun = ctx->tie_policy == 2 && q.table_dirty && ctx->exact_small && K <= kExactMaxColors && K <= kSplit2MaxColors &&
+                         ctx->split_version == 2;
+  if (q.phase == 0) {
+    *k_inout = run_split_finish(ctx, colortable, q.records, q.mean_out, q.size_out);
+    q.flags = ctx->stats.tie_flags;
+    if (q.flags == 0u) return kQuantDone;
+    if (q.flags == (uint32_t)kTieRound && ctx->tie_policy == 2 && q.table_dirty && ctx->exact_small && q.records == nullptr &&
+        q.mean_out == nullptr) {
+      // Only palette roundings are in doubt (a cluster mean exactly on x.5: the commonest tie by far): the reference's own
+      // ordered sums are redone for just the flagged clusters (dq_resolve.cu), on top of a first-seen pass over the pixels.
+      q.tie_count = ctx->h_cb->ctl[kCtlTieCount];
+      if (q.tie_count >= 1 && q.tie_count <= kTieListCap) {
+        first_seen_launch(exact_sampling(q.d_in, q.rows, q.cols, (uint32_t)q.dec, q.num_bits), ctx->d_map, ctx->stream);
+        uint32_t *d_status = ctx->d_tie.ptr + 4 * kTieListCap;
+        DQ_CUDA_CHECK(cudaMemsetAsync(d_status, 0, kTieListCap * sizeof(uint32_t), ctx->stream));
+        uint2 *pts[2] = {ctx->d_pts0.ptr, ctx->d_pts1.ptr};
+        tie_resolve_launch(ctx->d_nodes.ptr, pts, ctx->d_map, q.norm, 8 - q.num_bits, ctx->d_tie.ptr, q.tie_count, ctx->d_palette.ptr,
+                           d_status, ctx->stream);
+        ctx->stats.kernel_launches += 2;
+        ctx->ensure_small((size_t)K + 16 + kTieListCap);
+        q.k_first = *k_inout;
+        DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->h_small + K, d_status, q.tie_count * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->h_small, ctx->d_palette.ptr, (size_t)q.k_first * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                      ctx->stream));
+        if (!ctx->tie_ev) DQ_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->tie_ev, cudaEventDisableTiming));
+        DQ_CUDA_CHECK(cudaEventRecord(ctx->tie_ev, ctx->stream));
+        q.phase = 1;
+        return kQuantPending;
+      }
+    }
+    if (can_rerun && ctx->stats.num_points <= kExactMaxPoints) {
+      queue_rerun();
+      return kQuantPending;
+    }
+    return kQuantDone;  // flagged and not resolvable here (more colours than the ordered path takes): reported in the stats
   }
-  return table_dirty;
+  if (q.phase == 1) {
+    DQ_CUDA_CHECK(cudaEventSynchronize(ctx->tie_ev));  // (already complete when the caller polled)
+    bool resolved = true;
+    for (uint32_t i = 0; i < q.tie_count; ++i) resolved = resolved && ctx->h_small[K + i] == 1u;
+    if (resolved) {
+      memcpy(colortable, ctx->h_small, (size_t)q.k_first * sizeof(uint32_t));
+      *k_inout = q.k_first;
+      ctx->stats.tie_resolved = q.tie_count;
+      return kQuantDone;
+    }
+    if (can_rerun && ctx->stats.num_points <= kExactMaxPoints) {
+      queue_rerun();
+      return kQuantPending;
+    }
+    return kQuantDone;
+  }
+  // phase 2
+  const uint32_t launches = ctx->stats.kernel_launches;
+  *k_inout = run_split_finish(ctx, colortable, q.records, q.mean_out, q.size_out);
+  ctx->stats.kernel_launches = launches;
+  ctx->stats.tie_flags = q.flags;
+  ctx->stats.ordered_rerun = 1;
+  return kQuantDone;
+}
+
+// Blocking form.  Returns true if a unique list exists (d_uniq / d_cb->ucount) for a following table remap.
+bool quantize_finish(dq_context *ctx, uint32_t *k_inout, uint32_t *colortable) {
+  while (quantize_step(ctx, k_inout, colortable) != kQuantDone) {
+  }
+  return ctx->qs.table_dirty;
 }
 
 bool quantize_device(dq_context *ctx, uint32_t n, const uint32_t *d_in, uint32_t rows, uint32_t cols, uint32_t *k_inout,
@@ -650,10 +697,18 @@ void recurse_begin(dq_context *ctx, uint32_t n, const uint32_t *d_in, uint32_t K
   quantize_begin(ctx, n, d_in, 1, n, K, 8, 1, 10, all_unique, nullptr, nullptr, nullptr);
 }
 
+void recurse_remap_tail(dq_context *ctx, uint32_t n, const uint32_t *d_in, uint32_t *d_out, uint32_t *k_inout, uint32_t *colortable);
+
 void recurse_remap(dq_context *ctx, uint32_t n, const uint32_t *d_in, uint32_t *d_out, uint32_t *k_inout, uint32_t *colortable,
                    std::chrono::steady_clock::time_point *t_palette = nullptr) {
-  const bool dirty = quantize_finish(ctx, k_inout, colortable);
+  quantize_finish(ctx, k_inout, colortable);
   if (t_palette) *t_palette = std::chrono::steady_clock::now();
+  recurse_remap_tail(ctx, n, d_in, d_out, k_inout, colortable);
+}
+
+// The palette is final: the reference's host handling of it and the remap kernels (queued, not waited for).
+void recurse_remap_tail(dq_context *ctx, uint32_t n, const uint32_t *d_in, uint32_t *d_out, uint32_t *k_inout, uint32_t *colortable) {
+  const bool dirty = ctx->qs.table_dirty;
   uint32_t k = dedup_palette(colortable, *k_inout);
   *k_inout = k;
   ctx->stats.actual_colors = k;
@@ -895,6 +950,7 @@ void dq_context_destroy(dq_context *ctx) {
   if (ctx->mailbox) cudaFreeHost(const_cast<uint32_t *>(ctx->mailbox));
   for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->ev[i]);
   if (ctx->wait_ev) cudaEventDestroy(ctx->wait_ev);
+  if (ctx->tie_ev) cudaEventDestroy(ctx->tie_ev);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -1397,12 +1453,14 @@ void pipeline_dispatcher(dq_pipeline *p, int first_lane, int lane_step) {
         }
       } else if (lane.state == kWaitSplit) {
         ++busy;
-        if (!split_ready(ctx)) continue;
+        if (!quantize_pending_ready(ctx)) continue;
         progress = true;
         const dq_pipeline::Job &job = lane.job;
+        // (a frame the tie audit flagged comes back here once or twice more: resolver verdict, ordered re-run)
+        if (quantize_step(ctx, job.k_ptr, job.colortable) != kQuantDone) continue;
         const uint32_t *d_in = job.device_ptrs ? job.in : lane.d_in;
         uint32_t *d_out = job.device_ptrs ? job.out : lane.d_out;
-        recurse_remap(ctx, job.n, d_in, d_out, job.k_ptr, job.colortable);
+        recurse_remap_tail(ctx, job.n, d_in, d_out, job.k_ptr, job.colortable);
         if (!job.device_ptrs)
           DQ_CUDA_CHECK(cudaMemcpyAsync(job.out, lane.d_out, (size_t)job.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
         DQ_CUDA_CHECK(cudaEventRecord(lane.done[0], ctx->stream));
