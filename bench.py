@@ -35,7 +35,7 @@ if ROOT not in sys.path:
 
 WIDTH, HEIGHT, K = 3840, 2160, 256
 NPIX = WIDTH * HEIGHT
-RING = 6  # distinct frames resident in HBM: 6 x 33 MB = 199 MB > 126 MB of L2
+RING = 32  # distinct frames resident in HBM per rank: 32 x 33 MB = 1.06 GB >> 126 MB of L2
 METRIC = "Mpixels/sec DivQuant quantize+map (K=256, 4K)"
 
 
@@ -435,40 +435,61 @@ def run_ours(args, rank, world, local_rank):
     lib.dq_context_last_stats(ctx, C.byref(stats))
     info = stats.as_dict()
 
-    # -- pixel-row sharded variant of the same workload (ONE 4K frame spread over all ranks, one all-gather of
-    #    the per-shard (colour, count) lists; strong scaling of a sub-millisecond job, reported next to the main line)
+    # -- pixel-row sharded variant (BASELINE config 3): ONE image spread over all ranks by rows, the exchange inside the
+    #    library (dq_rows_*: one grouped ncclAllGather of the per-shard (colour, count) lists per image, no host wait
+    #    before the palette), merged split replicated, rows remapped locally.  Strong scaling of one image: reported next
+    #    to the time of the same image on one GPU alone, at 4K and at a size where the rows carry enough work to shard.
     rows_info = None
-    if dist:
-        full = o.generate(1, WIDTH, HEIGHT, 12345)
-        r0, r1 = pkg.rows_for_rank(HEIGHT, world, rank)
-        shard = torch.from_numpy(full[r0 * WIDTH:r1 * WIDTH].view(np.int32).copy()).cuda()
-        ws = {}
-        out_s, pal_s = pkg.row_sharded_quant_recurse(lib, ctx, shard, NPIX, K, dist, ws)
-        # parity of the sharded result: palette and this rank's rows against one whole-image call on this GPU
-        full_dev = torch.from_numpy(full.view(np.int32)).cuda()
-        nk.value = K
-        lib.dq_quant_recurse_device(ctx, NPIX, full_dev.data_ptr(), dev_out.data_ptr(), C.byref(nk), ctp, 0)
-        torch.cuda.synchronize()
-        rows_ok = bool(np.array_equal(pal_s, ct[:nk.value]) and
-                       torch.equal(out_s.view(torch.int32), dev_out[r0 * WIDTH:r1 * WIDTH]))
-        t_ok = torch.tensor([1.0 if rows_ok else 0.0], device="cuda")
-        dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
-        rows_ok = bool(t_ok.item() > 0.5)
-        del full_dev
-        for _ in range(2):
-            pkg.row_sharded_quant_recurse(lib, ctx, shard, NPIX, K, dist, ws)
-        barrier()
-        r_e0, r_e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        r_e0.record()
-        for _ in range(steps):
-            pkg.row_sharded_quant_recurse(lib, ctx, shard, NPIX, K, dist, ws)
-        r_e1.record()
-        barrier()
-        t = torch.tensor([r_e0.elapsed_time(r_e1) / steps], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        rows_info = {"ms_per_image": float(t.item()), "value": NPIX / (float(t.item()) * 1e-3) / 1e6, "unit": "Mpixels/s",
-                     "scaling": "strong", "collective": "1 x all_gather of (colour,count) lists (+ sizes) over NCCL per image",
-                     "palette_entries": int(pal_s.size), "matches_single_gpu_call": rows_ok}
+    if dist and not args.skip_rows:
+        rows = pkg.RowShards(lib, ctx, dist, list_capacity=1 << 18)
+        rows_info = {"api": "dq_rows_quant_recurse (exchange inside the library)", "collective": "1 grouped ncclAllGather of fixed-capacity (colour,count) slices per image",
+                     "scaling": "strong", "sizes": []}
+        for (rw, rh) in ((WIDTH, HEIGHT), (16384, 16384)):
+            npix = rw * rh
+            full = o.generate(1, rw, rh, 12345)
+            r0, r1 = pkg.rows_for_rank(rh, world, rank)
+            shard = torch.from_numpy(full[r0 * rw:r1 * rw].view(np.int32).copy()).cuda()
+            out_s = torch.empty_like(shard)
+            full_dev = torch.from_numpy(full.view(np.int32)).cuda()
+            full_out = torch.empty_like(full_dev)
+            out_s, pal_s = rows.quant_recurse(shard, npix, K, out_s)
+            nk.value = K
+            lib.dq_quant_recurse_device(ctx, npix, full_dev.data_ptr(), full_out.data_ptr(), C.byref(nk), ctp, 0)
+            torch.cuda.synchronize()
+            rows_ok = bool(np.array_equal(pal_s, ct[:nk.value]) and torch.equal(out_s, full_out[r0 * rw:r1 * rw]))
+
+            def timed_calls(fn, reps):
+                for _ in range(2):
+                    fn()
+                barrier()
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
+                for _ in range(reps):
+                    fn()
+                ev1.record()
+                barrier()
+                t = torch.tensor([ev0.elapsed_time(ev1) / reps], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                return float(t.item())
+
+            def one_gpu():
+                nk.value = K
+                lib.dq_quant_recurse_device(ctx, npix, full_dev.data_ptr(), full_out.data_ptr(), C.byref(nk), ctp, 0)
+
+            reps = steps if npix <= NPIX else max(steps // 4, 3)
+            ms_rows = timed_calls(lambda: rows.quant_recurse(shard, npix, K, out_s), reps)
+            ms_one = timed_calls(one_gpu, reps)
+            t_ok = torch.tensor([1.0 if rows_ok else 0.0], device="cuda")
+            dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+            rows_info["sizes"].append({"width": rw, "height": rh, "ms_per_image": ms_rows, "value": npix / (ms_rows * 1e-3) / 1e6,
+                                       "unit": "Mpixels/s", "one_gpu_alone_ms": ms_one, "speedup_vs_one_gpu": ms_one / ms_rows,
+                                       "matches_single_gpu_call": bool(t_ok.item() > 0.5), "palette_entries": int(pal_s.size)})
+            del full_dev, full_out, shard, out_s, full
+        rows.close()
+        rows_info["ms_per_image"] = rows_info["sizes"][0]["ms_per_image"]
+        rows_info["value"] = rows_info["sizes"][0]["value"]
+        rows_info["unit"] = "Mpixels/s"
+        rows_info["matches_single_gpu_call"] = all(x["matches_single_gpu_call"] for x in rows_info["sizes"])
 
     # -- BASELINE config 4: a batch of 1024 synthetic 1080p frames, K=64, frame-sharded over the ranks (no collective),
     #    host-fed: pinned host frames in, pinned host frames out, H2D and D2H of every frame inside the timed region --
@@ -688,9 +709,11 @@ def main():
     ap.add_argument("--e2e-lanes", type=int, default=6, help="frames in flight per GPU, host-buffer leg")
     ap.add_argument("--frames-per-step", type=int, default=192,
                     help="frames in one step (one batch; a multiple of the lanes keeps them evenly loaded; 20 steps x 192 frames keep the timed region above 0.5 s)")
+    ap.add_argument("--ring", type=int, default=32, help="distinct frames per rank (resident in HBM and in pinned host memory)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-batch", action="store_true", help="skip the BASELINE config-4 leg (1024 x 1080p, K=64, host-fed)")
     ap.add_argument("--skip-small", action="store_true", help="skip the small-input latency table")
+    ap.add_argument("--skip-rows", action="store_true", help="skip the pixel-row sharded leg (N > 1)")
     ap.add_argument("--batch-ring", type=int, default=48, help="distinct pinned host frames the config-4 leg cycles through")
     ap.add_argument("--skip-parity", action="store_true")
     ap.add_argument("--width", type=int, default=3840, help="frame width (default: the BASELINE.json headline config)")
@@ -700,7 +723,9 @@ def main():
     global WIDTH, HEIGHT, K, NPIX, METRIC, RING
     WIDTH, HEIGHT, K = args.width, args.height, args.colors
     NPIX = WIDTH * HEIGHT
-    RING = max(6, -(-200_000_000 // (NPIX * 4)))  # enough distinct frames to exceed the 126 MB L2
+    # A stream of DISTINCT frames (rank r: seeds 12345 + 32 r ...): far beyond the 126 MB L2, and frames the tie audit
+    # flags turn up at their natural rate (about one 4K frame in a hundred) instead of once per lap of a short ring.
+    RING = max(args.ring, -(-200_000_000 // (NPIX * 4)))
     if (WIDTH, HEIGHT, K) != (3840, 2160, 256):
         METRIC = f"Mpixels/sec DivQuant quantize+map (K={K}, {WIDTH}x{HEIGHT})"
     rank = int(os.environ.get("RANK", "0"))

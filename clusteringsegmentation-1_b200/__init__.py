@@ -99,6 +99,10 @@ def load_library(path=LIB_PATH):
         "dq_colortable_indexes_device": (None, [vp, vp, C.c_uint32, _u32p, C.c_int, vp, C.c_int]),
         "dq_shard_histogram": (C.c_uint32, [vp, vp, C.c_uint32, vp, vp]),
         "dq_shard_quantize_map": (None, [vp, vp, vp, C.c_uint32, C.c_uint64, vp, C.c_uint32, vp, _u32p, _u32p]),
+        "dq_rows_unique_id": (None, [vp]),
+        "dq_rows_create": (vp, [vp, C.c_int, C.c_int, vp, C.c_uint32]),
+        "dq_rows_destroy": (None, [vp]),
+        "dq_rows_quant_recurse": (None, [vp, vp, C.c_uint32, C.c_uint64, vp, _u32p, _u32p]),
         "dq_pipeline_create": (vp, [C.c_int, C.c_uint32, C.c_int]),
         "dq_pipeline_destroy": (None, [vp]),
         "dq_pipeline_create_lanes": (vp, [C.c_int, C.c_uint32, C.c_int, C.c_int]),
@@ -132,7 +136,7 @@ EXPORTED_C_SYMBOLS = [
     "dq_get_double_scale", "dq_validate_num_bits", "dq_set_display_timings", "dq_context_create", "dq_context_destroy",
     "dq_default_context", "dq_context_stream", "dq_context_synchronize", "dq_context_last_stats", "dq_context_set_profiling",
     "dq_quant_recurse_device", "dq_map_colors_device", "dq_quant_varpart_device", "dq_quant_recurse_ctx",
-    "dq_srm_num_pairs", "dq_srm_sorted_edges", "dq_srm_sorted_edges_device", "dq_context_set_split_ctas", "dq_context_set_exact_small", "dq_context_set_exact_max_points", "dq_context_set_tie_policy", "dq_pixel_histogram", "dq_block_vote", "dq_block_vote_device", "dq_quant_blocks", "dq_colortable_indexes", "dq_colortable_indexes_device", "dq_shard_histogram", "dq_shard_quantize_map", "dq_pipeline_create", "dq_pipeline_create_lanes", "dq_pipeline_destroy", "dq_pipeline_submit", "dq_pipeline_submit_device", "dq_pipeline_wait", "dq_pipeline_lanes", "dq_pipeline_set_blocking_wait", "dq_pipeline_flush", "dq_pipeline_last_elapsed_ms",
+    "dq_srm_num_pairs", "dq_srm_sorted_edges", "dq_srm_sorted_edges_device", "dq_context_set_split_ctas", "dq_context_set_exact_small", "dq_context_set_exact_max_points", "dq_context_set_tie_policy", "dq_pixel_histogram", "dq_block_vote", "dq_block_vote_device", "dq_quant_blocks", "dq_colortable_indexes", "dq_colortable_indexes_device", "dq_shard_histogram", "dq_shard_quantize_map", "dq_rows_unique_id", "dq_rows_create", "dq_rows_destroy", "dq_rows_quant_recurse", "dq_pipeline_create", "dq_pipeline_create_lanes", "dq_pipeline_destroy", "dq_pipeline_submit", "dq_pipeline_submit_device", "dq_pipeline_wait", "dq_pipeline_lanes", "dq_pipeline_set_blocking_wait", "dq_pipeline_flush", "dq_pipeline_last_elapsed_ms",
     "dq_pipeline_context", "dq_pipeline_kernel_launches", "dq_pipeline_flagged_frames",
     "dq_debug_split_points", "dq_debug_histogram", "dq_debug_split_timeline", "dq_host_dedup_palette", "dq_host_sort_permutation", "dq_host_build_search_tables",
 ]
@@ -382,3 +386,37 @@ def row_sharded_quant_recurse(lib, ctx, shard, total_pixels, k, dist=None, works
     lib.dq_shard_quantize_map(ctx, all_colours.data_ptr(), all_counts.data_ptr(), entries, total_pixels, shard.data_ptr(), n,
                               out.data_ptr(), C.byref(nk), _p(ct))
     return out, ct[:nk.value].copy()
+
+
+class RowShards:
+    """dq_rows: quant_recurse of ONE image whose pixel rows are spread over the ranks of a torch.distributed group, the
+    exchange (one grouped ncclAllGather per image) inside the library.  torch.distributed only carries the 128-byte NCCL
+    id from rank 0 to the others when the object is created."""
+
+    def __init__(self, lib, ctx, dist=None, list_capacity=1 << 18):
+        import torch
+        self.lib, self.ctx = lib, ctx
+        world = dist.get_world_size() if dist is not None else 1
+        rank = dist.get_rank() if dist is not None else 0
+        ident = (C.c_ubyte * 128)()
+        if world > 1:
+            if rank == 0:
+                lib.dq_rows_unique_id(ident)
+            t = torch.tensor(list(ident), dtype=torch.uint8, device="cuda")
+            dist.broadcast(t, 0)
+            ident = (C.c_ubyte * 128)(*t.cpu().tolist())
+        self.handle = lib.dq_rows_create(ctx, world, rank, ident, list_capacity)
+
+    def quant_recurse(self, shard, total_pixels, k, out=None):
+        """shard: this rank's rows as a flat CUDA int32 tensor.  Returns (out_shard, palette)."""
+        import torch
+        out = torch.empty_like(shard) if out is None else out
+        ct = np.zeros(max(int(k), 1), np.uint32)
+        nk = C.c_uint32(k)
+        self.lib.dq_rows_quant_recurse(self.handle, shard.data_ptr(), shard.numel(), total_pixels, out.data_ptr(), C.byref(nk), _p(ct))
+        return out, ct[:nk.value].copy()
+
+    def close(self):
+        if self.handle:
+            self.lib.dq_rows_destroy(self.handle)
+            self.handle = None

@@ -630,8 +630,8 @@ QuantStepResult quantize_step(dq_context *ctx, uint32_t *k_inout, uint32_t *colo
         uint32_t *d_status = ctx->d_tie.ptr + 4 * kTieListCap;
         DQ_CUDA_CHECK(cudaMemsetAsync(d_status, 0, kTieListCap * sizeof(uint32_t), ctx->stream));
         uint2 *pts[2] = {ctx->d_pts0.ptr, ctx->d_pts1.ptr};
-        tie_resolve_launch(ctx->d_nodes.ptr, pts, ctx->d_map, q.norm, 8 - q.num_bits, ctx->d_tie.ptr, q.tie_count, ctx->d_palette.ptr,
-                           d_status, ctx->stream);
+        tie_resolve_launch(ctx->d_nodes.ptr, ctx->h_cb->ctl[kCtlNodes], pts, ctx->d_map, q.norm, 8 - q.num_bits, ctx->d_tie.ptr,
+                           q.tie_count, ctx->d_palette.ptr, d_status, ctx->stream);
         ctx->stats.kernel_launches += 2;
         ctx->ensure_small((size_t)K + 16 + kTieListCap);
         q.k_first = *k_inout;
@@ -1735,6 +1735,187 @@ uint32_t dq_pixel_histogram(const uint32_t *pixels, uint32_t numPixels, uint32_t
     countsOut[i] = pts[i].y;
   }
   return U;
+}
+
+}  // extern "C"
+
+// ---- pixel-row sharding of one image, exchange inside the library (NCCL) ---------------------------------------------
+// BASELINE config 3.  Every rank histograms its own rows; the per-shard (colour, count) lists are exchanged with ONE
+// grouped ncclAllGather on the context's stream (fixed-capacity slices, unused entries carry count 0, so no sizes have to
+// travel first and nothing waits on the host); every rank merges the lists into its direct table and runs the split
+// replicated -- exact integer sums: identical decisions from identical integers on every GPU -- and remaps its own rows.
+// NCCL is looked up at run time (dlopen of libnccl.so.2: the copy the process already has, e.g. PyTorch's, or the
+// system's), so the library itself has no link-time dependency on it.
+#include <dlfcn.h>
+#include <nccl.h>
+
+namespace {
+
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+NcclApi *nccl_api() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) {
+      fprintf(stderr, "divquant_b200: the row-sharded path needs NCCL (libnccl.so.2 not found: %s)\n", dlerror());
+      abort();
+    }
+    auto sym = [&](const char *name) {
+      void *p = dlsym(h, name);
+      if (!p) {
+        fprintf(stderr, "divquant_b200: %s missing from libnccl\n", name);
+        abort();
+      }
+      return p;
+    };
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+    api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
+    api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
+    api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+  });
+  return &api;
+}
+
+void nccl_check(ncclResult_t r, const char *what) {
+  if (r != ncclSuccess) {
+    fprintf(stderr, "divquant_b200: NCCL error in %s: %s\n", what, nccl_api()->GetErrorString(r));
+    abort();
+  }
+}
+
+}  // namespace
+
+struct dq_rows {
+  dq_context *ctx = nullptr;
+  ncclComm_t comm = nullptr;
+  int world = 1, rank = 0;
+  uint32_t cap = 0;              // list entries per rank
+  uint32_t *d_colours = nullptr;  // [world][cap]
+  uint32_t *d_counts = nullptr;   // [world][cap]
+  uint32_t *d_overflow = nullptr;
+};
+
+extern "C" {
+
+void dq_rows_unique_id(void *out128) {
+  ncclUniqueId id;
+  nccl_check(nccl_api()->GetUniqueId(&id), "ncclGetUniqueId");
+  memcpy(out128, &id, sizeof(id));
+}
+
+dq_rows *dq_rows_create(dq_context *ctx, int world, int rank, const void *unique_id128, uint32_t list_capacity) {
+  require_device(ctx);
+  if (world < 1 || rank < 0 || rank >= world || list_capacity == 0) {
+    fprintf(stderr, "divquant_b200: dq_rows_create needs 0 <= rank < world and a positive list capacity\n");
+    abort();
+  }
+  dq_rows *r = new dq_rows();
+  r->ctx = ctx;
+  r->world = world;
+  r->rank = rank;
+  r->cap = list_capacity;
+  if (world > 1) {
+    ncclUniqueId id;
+    memcpy(&id, unique_id128, sizeof(id));
+    nccl_check(nccl_api()->CommInitRank(&r->comm, world, id, rank), "ncclCommInitRank");
+  }
+  DQ_CUDA_CHECK(cudaMalloc(&r->d_colours, (size_t)world * list_capacity * sizeof(uint32_t)));
+  DQ_CUDA_CHECK(cudaMalloc(&r->d_counts, (size_t)world * list_capacity * sizeof(uint32_t)));
+  DQ_CUDA_CHECK(cudaMalloc(&r->d_overflow, sizeof(uint32_t)));
+  DQ_CUDA_CHECK(cudaMemset(r->d_overflow, 0, sizeof(uint32_t)));
+  return r;
+}
+
+void dq_rows_destroy(dq_rows *r) {
+  if (!r) return;
+  require_device(r->ctx);
+  cudaStreamSynchronize(r->ctx->stream);
+  if (r->comm) nccl_api()->CommDestroy(r->comm);
+  cudaFree(r->d_colours);
+  cudaFree(r->d_counts);
+  cudaFree(r->d_overflow);
+  delete r;
+}
+
+void dq_rows_quant_recurse(dq_rows *r, const uint32_t *d_shard, uint32_t n_shard, uint64_t total_pixels, uint32_t *d_out_shard,
+                           uint32_t *numClustersPtr, uint32_t *outColortablePtr) {
+  dq_context *ctx = r->ctx;
+  require_device(ctx);
+  memset(&ctx->stats, 0, sizeof(ctx->stats));
+  ctx->stats.num_pixels = n_shard;
+  const uint32_t K = *numClustersPtr;
+  if (total_pixels == 0 || total_pixels > 0x7fffffffull || K == 0) {
+    fprintf(stderr, "divquant_b200: row-sharded call needs 0 < total_pixels < 2^31 and K > 0\n");
+    abort();
+  }
+  const uint32_t cap = r->cap;
+  const size_t entries = (size_t)r->world * cap;
+  uint32_t *my_colours = r->d_colours + (size_t)r->rank * cap, *my_counts = r->d_counts + (size_t)r->rank * cap;
+  // 1. this rank's rows -> (colour, count) list in its slice (an empty shard is a list of zero counts)
+  reset_control(ctx);
+  ctx->d_pts0.ensure(std::max<size_t>(n_shard, entries));
+  ctx->d_uniq.ensure(std::max<size_t>(n_shard, entries));
+  if (n_shard) {
+    run_histogram(ctx, d_shard, n_shard, 1, n_shard, 1, 8);
+    hist_collect(ctx->d_uniq.ptr, &ctx->d_cb->ucount, n_shard, ctx->d_table, ctx->d_pts0.ptr, true, ctx->sm_count, ctx->stream);
+    ctx->stats.kernel_launches++;
+  }
+  hist_export_padded(ctx->d_pts0.ptr, &ctx->d_cb->ucount, cap, my_colours, my_counts, r->d_overflow, ctx->sm_count, ctx->stream);
+  ctx->stats.kernel_launches++;
+  // 2. the one exchange of the data path
+  if (r->world > 1) {
+    NcclApi *nc = nccl_api();
+    nccl_check(nc->GroupStart(), "ncclGroupStart");
+    nccl_check(nc->AllGather(my_colours, r->d_colours, cap, ncclUint32, r->comm, ctx->stream), "ncclAllGather(colours)");
+    nccl_check(nc->AllGather(my_counts, r->d_counts, cap, ncclUint32, r->comm, ctx->stream), "ncclAllGather(counts)");
+    nccl_check(nc->GroupEnd(), "ncclGroupEnd");
+  }
+  // 3. merged histogram of the whole image in this rank's direct table, split replicated, own rows remapped
+  reset_control(ctx);
+  hist_merge(r->d_colours, r->d_counts, (uint32_t)entries, ctx->d_table, ctx->d_uniq.ptr, &ctx->d_cb->ucount, ctx->sm_count, ctx->stream);
+  ctx->stats.kernel_launches++;
+  const double norm = sample_norm(1, (uint32_t)total_pixels, 1);  // 1 / N of the WHOLE image (:172)
+  uint32_t k = run_split(ctx, (uint32_t)entries, norm, K, 10, 8, outColortablePtr, nullptr, nullptr, nullptr, true, nullptr, true);
+  k = dedup_palette(outColortablePtr, k);
+  *numClustersPtr = k;
+  ctx->stats.actual_colors = k;
+  if (n_shard) {
+    if (k <= 256) {
+      MapTablesParam tables;
+      int lut[kLutEntries];
+      build_search_tables(outColortablePtr, (int)k, tables.sorted, lut);
+      for (int i = 0; i < kLutEntries; ++i) tables.lut[i] = (uint16_t)lut[i];
+      map_unique_params(tables, ctx->d_uniq.ptr, &ctx->d_cb->ucount, ctx->stats.num_points, ctx->d_map, (int)k, ctx->sm_count, ctx->stream);
+      map_gather(d_shard, n_shard, d_out_shard, ctx->d_map, ctx->sm_count, ctx->stream);
+      ctx->stats.kernel_launches += 2;
+      ctx->stats.remap_path = 2;
+    } else {
+      upload_search_tables(ctx, outColortablePtr, (int)k);
+      remap_through_table(ctx, d_shard, n_shard, d_out_shard, (int)k, ctx->stats.num_points);
+    }
+  }
+  uint32_t overflow = 0;
+  DQ_CUDA_CHECK(cudaMemcpyAsync(&overflow, r->d_overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  if (overflow) {
+    fprintf(stderr, "divquant_b200: a shard has %u unique colours, more than the %u entries per rank the row exchange was created with\n",
+            overflow, cap);
+    abort();
+  }
 }
 
 }  // extern "C"

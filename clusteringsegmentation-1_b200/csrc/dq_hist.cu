@@ -187,6 +187,23 @@ __global__ void __launch_bounds__(256) hist_export_kernel(const uint2 *__restric
   }
 }
 
+// Same into a fixed-capacity slice of the exchange buffers: entries beyond the shard's U get count 0 (the merge skips
+// them), a shard with more than `cap` colours raises *overflow (the caller sized the exchange too small).
+__global__ void __launch_bounds__(256) hist_export_padded_kernel(const uint2 *__restrict__ pts, const uint32_t *ucount, uint32_t cap,
+                                                                uint32_t *colours, uint32_t *counts, uint32_t *overflow) {
+  const uint32_t u = *ucount;
+  if (u > cap && blockIdx.x == 0 && threadIdx.x == 0) *overflow = u;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
+    if (i < u) {
+      const uint2 p = pts[i];
+      colours[i] = p.x;
+      counts[i] = p.y;
+    } else {
+      counts[i] = 0u;
+    }
+  }
+}
+
 // Merge of gathered per-shard lists into the direct table: counts add up exactly; the entry that bumps a
 // counter from 0 appends the colour to the merged unique list.
 __global__ void __launch_bounds__(256) hist_merge_kernel(const uint32_t *__restrict__ colours, const uint32_t *__restrict__ counts,
@@ -253,6 +270,12 @@ void table_clear(const uint32_t *d_uniq, const uint32_t *d_ucount, uint32_t u_hi
 void hist_export(const uint2 *d_pts, const uint32_t *d_ucount, uint32_t u_hint, uint32_t *d_colours, uint32_t *d_counts,
                  int sm_count, cudaStream_t st) {
   hist_export_kernel<<<blocks_for(u_hint, 256, sm_count, 8), 256, 0, st>>>(d_pts, d_ucount, d_colours, d_counts);
+  DQ_CUDA_CHECK(cudaGetLastError());
+}
+
+void hist_export_padded(const uint2 *d_pts, const uint32_t *d_ucount, uint32_t cap, uint32_t *d_colours, uint32_t *d_counts,
+                        uint32_t *d_overflow, int sm_count, cudaStream_t st) {
+  hist_export_padded_kernel<<<blocks_for(cap, 256, sm_count, 8), 256, 0, st>>>(d_pts, d_ucount, cap, d_colours, d_counts, d_overflow);
   DQ_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -21,6 +21,8 @@ void order_keys(const uint32_t *d_in, uint32_t num_rows, uint32_t num_cols, uint
 
 void hist_export(const uint2 *d_pts, const uint32_t *d_ucount, uint32_t u_hint, uint32_t *d_colours, uint32_t *d_counts,
                  int sm_count, cudaStream_t st);
+void hist_export_padded(const uint2 *d_pts, const uint32_t *d_ucount, uint32_t cap, uint32_t *d_colours, uint32_t *d_counts,
+                        uint32_t *d_overflow, int sm_count, cudaStream_t st);
 void hist_merge(const uint32_t *d_colours, const uint32_t *d_counts, uint32_t num_entries, uint32_t *d_table, uint32_t *d_uniq,
                 uint32_t *d_ucount, int sm_count, cudaStream_t st);
 

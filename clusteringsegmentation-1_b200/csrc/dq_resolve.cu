@@ -24,10 +24,24 @@ constexpr int kResolveThreads = 512;
 constexpr int kResolveMax = 8192;   // points of the chain's top node
 constexpr int kResolveChain = 24;   // "old" steps between the flagged cluster and the top node
 constexpr int kResolveLeaves = 1024;
+constexpr int kResolveNodes = 8 * 512 + 16;  // node table of the split kernel for K <= kSplit2MaxColors
 
 struct ResolveShared {
-  unsigned long long keys[kResolveMax];
-  uint2 pts[kResolveMax];         // (colour, count) by position inside the top node's range
+  union {
+    unsigned long long keys[kResolveMax];  // sort keys; afterwards ...
+    double w_sorted[kResolveMax];          // ... the weights in emission order
+  };
+  union {
+    uint2 pts[kResolveMax];         // (colour, count) by position inside the top node's range; afterwards ...
+    struct {
+      uint32_t colour_sorted[kResolveMax];  // ... colours and positions in emission order
+      uint16_t pos_sorted[kResolveMax];
+    } so;
+  };
+  // the split tree's links and segments, staged once (walking them in global memory costs a round trip per step)
+  uint32_t nd_begin[kResolveNodes], nd_size[kResolveNodes];
+  int16_t nd_parent[kResolveNodes], nd_child[kResolveNodes];  // node ids fit: < 4112
+  uint8_t nd_buf[kResolveNodes];
   double sums[kResolveChain + 1][4];
   int32_t leaf[kResolveLeaves];
   int32_t sib[kResolveChain];
@@ -46,12 +60,26 @@ __device__ __forceinline__ SplitNode load_node_g(const SplitNode *nodes, int id)
 
 __global__ void __launch_bounds__(kResolveThreads) tie_resolve_kernel(const SplitNode *nodes, uint2 *pts0, uint2 *pts1,
                                                                       const uint32_t *first_seen, double norm, int shift,
-                                                                      const uint32_t *list, uint32_t *palette, uint32_t *status) {
+                                                                      const uint32_t *list, uint32_t num_nodes, uint32_t *palette,
+                                                                      uint32_t *status) {
   extern __shared__ __align__(16) unsigned char resolve_smem[];
   ResolveShared &S = *reinterpret_cast<ResolveShared *>(resolve_smem);
   const int tid = threadIdx.x, item = blockIdx.x;
   const int node_x = (int)list[4 * item + 1], slot = (int)list[4 * item + 2];
 
+  if (num_nodes > (uint32_t)kResolveNodes) {
+    if (tid == 0) status[item] = 2u;
+    return;
+  }
+  for (uint32_t i = tid; i < num_nodes; i += kResolveThreads) {
+    const SplitNode *nd = nodes + i;
+    S.nd_begin[i] = __ldcg(&nd->begin);
+    S.nd_size[i] = __ldcg(&nd->size);
+    S.nd_parent[i] = (int16_t)__ldcg(&nd->parent);
+    S.nd_child[i] = (int16_t)__ldcg(&nd->child);
+    S.nd_buf[i] = (uint8_t)__ldcg(&nd->buf);
+  }
+  __syncthreads();
   // ---- the chain of "old" sides above the flagged cluster, and the leaves below its top node ----
   if (tid == 0) {
     S.fail = 0;
@@ -59,12 +87,12 @@ __global__ void __launch_bounds__(kResolveThreads) tie_resolve_kernel(const Spli
     S.top_is_root = 0;
     int cur = node_x;
     for (;;) {
-      const int p = __ldcg(&nodes[cur].parent);
+      const int p = S.nd_parent[cur];
       if (p < 0) {  // the root: its statistics are sums over every point (:60-104)
         S.top_is_root = 1;
         break;
       }
-      const int child0 = __ldcg(&nodes[p].child);
+      const int child0 = S.nd_child[p];
       if (cur == child0 + 1) break;  // a "new" side: its statistics are its own sums
       if (S.n_sib >= kResolveChain) {
         S.fail = 1;
@@ -74,13 +102,12 @@ __global__ void __launch_bounds__(kResolveThreads) tie_resolve_kernel(const Spli
       cur = p;
     }
     S.top = cur;
-    const SplitNode top = load_node_g(nodes, cur);
-    if (top.size > (uint32_t)kResolveMax || top.size == 0u) S.fail = 1;
-    S.sib_begin[0] = top.begin;
-    S.sib_size[0] = top.size;
+    if (S.nd_size[cur] > (uint32_t)kResolveMax || S.nd_size[cur] == 0u) S.fail = 1;
+    S.sib_begin[0] = S.nd_begin[cur];
+    S.sib_size[0] = S.nd_size[cur];
     for (int k = 0; k < S.n_sib && !S.fail; ++k) {
-      S.sib_begin[k + 1] = __ldcg(&nodes[S.sib[k]].begin);
-      S.sib_size[k + 1] = __ldcg(&nodes[S.sib[k]].size);
+      S.sib_begin[k + 1] = S.nd_begin[S.sib[k]];
+      S.sib_size[k + 1] = S.nd_size[S.sib[k]];
     }
     // leaves below the top node (depth-first, explicit stack)
     S.n_leaves = 0;
@@ -89,7 +116,7 @@ __global__ void __launch_bounds__(kResolveThreads) tie_resolve_kernel(const Spli
       stack[sp++] = cur;
       while (sp > 0) {
         const int nd = stack[--sp];
-        const int ch = __ldcg(&nodes[nd].child);
+        const int ch = S.nd_child[nd];
         if (ch < 0) {
           if (S.n_leaves >= kResolveLeaves) {
             S.fail = 1;
@@ -115,9 +142,9 @@ __global__ void __launch_bounds__(kResolveThreads) tie_resolve_kernel(const Spli
   const uint32_t base = S.sib_begin[0], n = S.sib_size[0];
   // ---- the top node's points: every leaf keeps its segment in its own buffer ----
   for (int l = 0; l < S.n_leaves; ++l) {
-    const SplitNode *lf = nodes + S.leaf[l];
-    const uint32_t lb = __ldcg(&lf->begin), ls = __ldcg(&lf->size);
-    const uint2 *src = (__ldcg(&lf->buf) ? pts1 : pts0) + lb;
+    const int lf = S.leaf[l];
+    const uint32_t lb = S.nd_begin[lf], ls = S.nd_size[lf];
+    const uint2 *src = (S.nd_buf[lf] ? pts1 : pts0) + lb;
     for (uint32_t i = tid; i < ls; i += kResolveThreads) S.pts[lb - base + i] = __ldcg(src + i);
   }
   __syncthreads();
@@ -150,19 +177,62 @@ __global__ void __launch_bounds__(kResolveThreads) tie_resolve_kernel(const Spli
       __syncthreads();
     }
   }
-  // ---- the reference's sums: thread (set, chain) adds its terms one after the other ----
+  // ---- weights, colours and positions in emission order (through registers: the arrays alias keys / pts) ----
+  {
+    constexpr int kPer = kResolveMax / kResolveThreads;
+    double w_r[kPer];
+    uint32_t c_r[kPer];
+    uint16_t i_r[kPer];
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+      const int r = tid + q * kResolveThreads;
+      w_r[q] = 0.0, c_r[q] = 0u, i_r[q] = 0;
+      if (r < (int)n) {
+        const uint32_t i = (uint32_t)(S.keys[r] & 0x1FFFull);
+        const uint2 p = S.pts[i];
+        w_r[q] = fmul(norm, (double)(int)p.y);  // weights[i] = norm * count (MapColors.cpp:185)
+        c_r[q] = p.x;
+        i_r[q] = (uint16_t)i;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+      const int r = tid + q * kResolveThreads;
+      if (r < (int)n) {
+        S.w_sorted[r] = w_r[q];
+        S.so.colour_sorted[r] = c_r[q];
+        S.so.pos_sorted[r] = i_r[q];
+      }
+    }
+    __syncthreads();
+  }
+  // ---- the reference's sums: thread (set, chain) adds its terms one after the other; a point outside the set adds +0.0,
+  //      which leaves a non-negative sum as it is, so every thread walks the same list ----
   const int n_sets = S.n_sib + 1;
   if (tid < 4 * n_sets) {
     const int set = tid >> 2, chain = tid & 3;
     const uint32_t lo = S.sib_begin[set] - base, hi = lo + S.sib_size[set];
+    const int sh = 16 - 8 * chain;
     double acc = 0.0;
-    for (uint32_t r = 0; r < n; ++r) {
-      const uint32_t i = (uint32_t)(S.keys[r] & 0x1FFFull);
-      if (i < lo || i >= hi) continue;
-      const uint2 p = S.pts[i];
-      const double w = fmul(norm, (double)(int)p.y);  // weights[i] = norm * count (MapColors.cpp:185)
-      const double t = (chain == 3) ? w : fmul(w, byte_to_double((p.x >> (16 - 8 * chain)) & 0xFFu));
-      acc = fadd(acc, t);
+    uint32_t r = 0;
+    for (; r + 4 <= n; r += 4) {
+      double t[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t i = S.so.pos_sorted[r + q];
+        const double w = S.w_sorted[r + q];
+        const double term = (chain == 3) ? w : fmul(w, byte_to_double((S.so.colour_sorted[r + q] >> sh) & 0xFFu));
+        t[q] = (i >= lo && i < hi) ? term : 0.0;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc = fadd(acc, t[q]);
+    }
+    for (; r < n; ++r) {
+      const uint32_t i = S.so.pos_sorted[r];
+      const double w = S.w_sorted[r];
+      const double term = (chain == 3) ? w : fmul(w, byte_to_double((S.so.colour_sorted[r] >> sh) & 0xFFu));
+      acc = fadd(acc, (i >= lo && i < hi) ? term : 0.0);
     }
     S.sums[set][chain] = acc;
   }
@@ -196,11 +266,11 @@ __global__ void __launch_bounds__(kResolveThreads) tie_resolve_kernel(const Spli
 
 }  // namespace
 
-void tie_resolve_launch(const SplitNode *d_nodes, uint2 *const *pts, const uint32_t *d_first_seen, double norm, int shift,
-                        const uint32_t *d_list, uint32_t count, uint32_t *d_palette, uint32_t *d_status, cudaStream_t st) {
+void tie_resolve_launch(const SplitNode *d_nodes, uint32_t num_nodes, uint2 *const *pts, const uint32_t *d_first_seen, double norm,
+                        int shift, const uint32_t *d_list, uint32_t count, uint32_t *d_palette, uint32_t *d_status, cudaStream_t st) {
   DQ_RAISE_SMEM(tie_resolve_kernel, sizeof(ResolveShared));
   tie_resolve_kernel<<<count, kResolveThreads, sizeof(ResolveShared), st>>>(d_nodes, pts[0], pts[1], d_first_seen, norm, shift,
-                                                                            d_list, d_palette, d_status);
+                                                                            d_list, num_nodes, d_palette, d_status);
   DQ_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -159,8 +159,8 @@ struct ExactSampling {
 ExactSampling exact_sampling(const uint32_t *d_in, uint32_t num_rows, uint32_t num_cols, uint32_t dec, int bits);
 // dq_resolve.cu: a final cluster's mean in the reference's own arithmetic (ordered sums along its chain of splits), for the
 // clusters whose rounding the tie audit flagged.  d_status[i]: 1 = palette[slot] rewritten, 2 = not resolvable here.
-void tie_resolve_launch(const SplitNode *d_nodes, uint2 *const *pts, const uint32_t *d_first_seen, double norm, int shift,
-                        const uint32_t *d_list, uint32_t count, uint32_t *d_palette, uint32_t *d_status, cudaStream_t st);
+void tie_resolve_launch(const SplitNode *d_nodes, uint32_t num_nodes, uint2 *const *pts, const uint32_t *d_first_seen, double norm,
+                        int shift, const uint32_t *d_list, uint32_t count, uint32_t *d_palette, uint32_t *d_status, cudaStream_t st);
 // first-seen pass alone (dq_split_exact.cu): smallest sample index of every colour into d_first_seen
 void first_seen_launch(const ExactSampling &q, uint32_t *d_first_seen, cudaStream_t st);
 size_t split_exact_smem_bytes();

@@ -233,6 +233,26 @@ void dq_shard_quantize_map(dq_context *ctx, const uint32_t *d_all_colours, const
                            uint64_t total_pixels, const uint32_t *d_shard, uint32_t n_shard, uint32_t *d_out_shard,
                            uint32_t *numClustersPtr, uint32_t *outColortablePtr);
 
+/* The same with the exchange INSIDE the library (NCCL over NVLink, looked up with dlopen("libnccl.so.2") at run time, so
+ * the copy the process already has -- e.g. PyTorch's -- is used and the library has no link-time dependency on it).
+ *   rank 0:      dq_rows_unique_id(id)            -> hand the 128 bytes to every rank (any side channel)
+ *   every rank:  rows = dq_rows_create(ctx, world, rank, id, list_capacity)          (collective: ncclCommInitRank)
+ *   per image:   dq_rows_quant_recurse(rows, d_shard, n_shard, N_total, d_out_shard, &K, palette)
+ * One grouped ncclAllGather of fixed-capacity (colour, count) slices per image on the context's stream (unused entries carry
+ * count 0: no sizes travel first, no host synchronisation before the palette); list_capacity >= the largest number of
+ * unique colours in any shard (a shard that exceeds it is fatal: message + abort).  world = 1 needs no id and no NCCL.
+ * Result: the palette and this rank's rows of dq_quant_recurse of the whole image, PROVIDED the single-GPU call takes the
+ * exact-integer kernels for it (more unique colours than dq_context_set_exact_max_points, default 65 536: every BASELINE
+ * configuration).  Below that limit the single-GPU call adds in the reference's order, which needs the first-seen index of
+ * every colour over the WHOLE image; the sharded call does not exchange those and stays on exact integer sums: it then
+ * equals the reference unless dq_call_stats::tie_flags says a decision sat inside the reference's rounding noise. */
+typedef struct dq_rows dq_rows;
+void dq_rows_unique_id(void *out128);
+dq_rows *dq_rows_create(dq_context *ctx, int world, int rank, const void *unique_id128, uint32_t list_capacity);
+void dq_rows_destroy(dq_rows *rows);
+void dq_rows_quant_recurse(dq_rows *rows, const uint32_t *d_shard, uint32_t n_shard, uint64_t total_pixels, uint32_t *d_out_shard,
+                           uint32_t *numClustersPtr, uint32_t *outColortablePtr);
+
 /* ------------------------------------------------------------------------------------------------
  * 2b. Frame pipeline: quant_recurse over a stream of frames (BASELINE.json config 4, "batch of frames", and both
  *     legs of bench.py).  Frames are independent units and one frame's critical path (the chain of dependent

@@ -5,8 +5,8 @@
 
 Writes tests/golden/frames.npz:
   c4_*     the 1024 frames of config 4: 1920x1080 G1, K=64, frame f has seed 12345+f  
-  bench_*  the frames bench.py times: 3840x2160 G1, K=256, seeds 12345..12345+63 (8 ranks x 7 ring slots and a margin)
-  g2_*     the stress inputs of SURVEY.md 8c/8d: G2 uniform-random 1920x1080 (and 3840x2160 with --g2-4k, ~6 min)
+  bench_*  the frames bench.py times: 3840x2160 G1, K=256, seeds 12345..12345+255 (8 ranks x 32 ring slots)
+  g2_*     the stress inputs of SURVEY.md 8c/8d: G2 uniform-random 1920x1080; g2_4k_*: 3840x2160 (--g2-4k, ~6 min)
 For each frame: palette hash, out hash (oracle.hash_words, FNV-1a over u32 words), palette size, and the TieBit mask
 the CPU model of the device's tie audit raises (oracle_quant_varpart_fast_exact_audit; 0 = the exact-integer path is
 guaranteed to equal the reference).
@@ -58,24 +58,36 @@ def run(pool, kind, w, h, k, seeds):
 
 
 def main():
+    """--only TAG[,TAG...] (c4, bench, g2, g2_4k) recomputes just those sets and keeps the rest of an existing frames.npz."""
+    path = os.path.join(HERE, "frames.npz")
+    only = None
+    if "--only" in sys.argv:
+        only = set(sys.argv[sys.argv.index("--only") + 1].split(","))
     out = {}
+    if only is not None and os.path.exists(path):
+        out = dict(np.load(path))
+    sets = (("c4", 1, 1920, 1080, 64, range(12345, 12345 + 1024)),
+            ("bench", 1, 3840, 2160, 256, range(12345, 12345 + 256)),
+            ("g2", 2, 1920, 1080, 256, range(12345, 12346)),
+            ("g2_4k", 2, 3840, 2160, 256, range(12345, 12346)))  # ~6 min of CPU: only with --g2-4k or --only g2_4k
     with Pool(8) as pool:
-        for tag, kind, w, h, k, seeds in (("c4", 1, 1920, 1080, 64, range(12345, 12345 + 1024)),
-                                          ("bench", 1, 3840, 2160, 256, range(12345, 12345 + 64)),
-                                          ("g2", 2, 1920, 1080, 256, range(12345, 12346))):
+        for tag, kind, w, h, k, seeds in sets:
+            if only is not None and tag not in only:
+                continue
+            if only is None and tag == "g2_4k" and "--g2-4k" not in sys.argv:
+                continue
             for key, val in run(pool, kind, w, h, k, seeds).items():
                 out[f"{tag}_{key}"] = val
             print(tag, "frames", len(out[f"{tag}_seeds"]), "flagged", int((out[f"{tag}_tie_mask"] != 0).sum()),
                   "model != reference", int((out[f"{tag}_model_equal"] == 0).sum()), flush=True)
-        if "--g2-4k" in sys.argv:
-            for key, val in run(pool, 2, 3840, 2160, 256, range(12345, 12346)).items():
-                out[f"g2_4k_{key}"] = val
     # an unflagged frame must equal the reference: the audit's contract
-    for tag in ("c4", "bench", "g2"):
+    for tag in ("c4", "bench", "g2", "g2_4k"):
+        if f"{tag}_seeds" not in out:
+            continue
         bad = (out[f"{tag}_model_equal"] == 0) & (out[f"{tag}_tie_mask"] == 0)
         assert not bad.any(), (tag, out[f"{tag}_seeds"][bad])
-    np.savez_compressed(os.path.join(HERE, "frames.npz"), **out)
-    print("written", os.path.join(HERE, "frames.npz"))
+    np.savez_compressed(path, **out)
+    print("written", path)
 
 
 if __name__ == "__main__":

@@ -28,6 +28,12 @@ def test_row_sharded_single_rank(built):
     _run(1, 640, 360, 64)
 
 
+def test_row_sharded_few_colours_single_rank(built):
+    # 320x180 G1 has 43 411 colours: below the ordered path's limit the sharded call stays on exact integer sums (it has
+    # no whole-image first-seen order); rows_check fails if that ever differs from the single-GPU call without a tie flag
+    _run(1, 320, 180, 64)
+
+
 def test_row_sharded_all_gpus(built):
     import torch
     n = torch.cuda.device_count()

@@ -23,7 +23,8 @@ o = Oracle()
 lib = pkg.load_library()
 lib.dq_set_display_timings(0)
 ring = max(6, -(-200_000_000 // (N * 4)))
-host = [torch.from_numpy(o.generate(1, W, H, 12345 + s).view(np.int32)).pin_memory() for s in range(ring)]
+SEED0 = int(os.environ.get("LANES_SEED0", "12345"))
+host = [torch.from_numpy(o.generate(1, W, H, SEED0 + s).view(np.int32)).pin_memory() for s in range(ring)]
 dev = [h.cuda() for h in host]
 u32p = C.POINTER(C.c_uint32)
 ref = {}
@@ -65,6 +66,7 @@ def run(lanes, ctas, on_device):
           f"{N * FR / ms / 1e6:.2f} Gpix/s  same={ref[tag] == (key, last)}", flush=True)
     st = pkg.CallStats()
     lib.dq_context_last_stats(lib.dq_pipeline_context(pipe), C.byref(st))
+    print("      flagged frames:", lib.dq_pipeline_flagged_frames(pipe), flush=True)
     print("      lane 0, last frame, stage ms:", " ".join(f"{n}={v:.3f}" for n, v in zip(pkg.CallStats.STAGES, st.stage_ms)), flush=True)
     lib.dq_pipeline_destroy(pipe)
 

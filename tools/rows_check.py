@@ -1,6 +1,8 @@
 #!/usr/bin/env python
-"""Row-sharded quant_recurse of one image over the ranks of a torchrun job, checked against the
-single-GPU result of the whole image.  usage: torchrun --nproc-per-node N tools/rows_check.py [w h K reps]"""
+"""Row-sharded quant_recurse of one image over the ranks of a torchrun job, checked against the single-GPU result of the
+whole image and timed next to it.  Two forms: the in-library exchange (dq_rows_*, one grouped ncclAllGather per image,
+no host wait before the palette) and the caller-owned exchange (dq_shard_* + torch.distributed all-gather).
+usage: torchrun --nproc-per-node N tools/rows_check.py [w h K reps]"""
 import ctypes as C
 import importlib
 import os
@@ -27,29 +29,58 @@ img = Oracle().generate(1, w, h)
 r0, r1 = pkg.rows_for_rank(h, world, rank)
 shard = torch.from_numpy(img[r0 * w:r1 * w].view(np.int32).copy()).cuda()
 d = dist if world > 1 else None
-out, pal = pkg.row_sharded_quant_recurse(lib, ctx, shard, w * h, k, d)
+rows = pkg.RowShards(lib, ctx, d, list_capacity=1 << 18)
+out, pal = rows.quant_recurse(shard, w * h, k)
+out_py, pal_py = pkg.row_sharded_quant_recurse(lib, ctx, shard, w * h, k, d)
 # reference: the whole image on this GPU alone
 full = torch.from_numpy(img.view(np.int32)).cuda()
 full_out = torch.empty_like(full)
 ct = np.zeros(k, np.uint32)
 nk = C.c_uint32(k)
-lib.dq_quant_recurse_device(ctx, full.numel(), full.data_ptr(), full_out.data_ptr(), C.byref(nk), ct.ctypes.data_as(C.POINTER(C.c_uint32)), 0)
-ok = np.array_equal(pal, ct[:nk.value]) and torch.equal(out, full_out[r0 * w:r1 * w])
-# timing: max over ranks of the device time of `reps` sharded calls
-torch.cuda.synchronize()
-if d: d.barrier()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(reps):
-    pkg.row_sharded_quant_recurse(lib, ctx, shard, w * h, k, d)
-e1.record()
-torch.cuda.synchronize()
-ms = torch.tensor([e0.elapsed_time(e1) / reps], device="cuda")
+u32p = C.POINTER(C.c_uint32)
+
+
+def single():
+    nk.value = k
+    lib.dq_quant_recurse_device(ctx, full.numel(), full.data_ptr(), full_out.data_ptr(), C.byref(nk), ct.ctypes.data_as(u32p), 0)
+
+
+single()
+ok = (np.array_equal(pal, ct[:nk.value]) and torch.equal(out, full_out[r0 * w:r1 * w]) and
+      np.array_equal(pal_py, ct[:nk.value]) and torch.equal(out_py, full_out[r0 * w:r1 * w]))
+
+
+def timed(fn):
+    """max over ranks of the device time per call (CUDA events on torch's stream bracket the library's stream: the
+    library's calls are synchronous with respect to the host)."""
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    if d:
+        d.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / reps], device="cuda")
+    if d:
+        d.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+
+ws = {}
+ms_lib = timed(lambda: rows.quant_recurse(shard, w * h, k, out))
+ms_py = timed(lambda: pkg.row_sharded_quant_recurse(lib, ctx, shard, w * h, k, d, ws))
+ms_one = timed(single)
 flag = torch.tensor([1 if ok else 0], device="cuda")
 if d:
-    d.all_reduce(ms, op=dist.ReduceOp.MAX)
     d.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print(f"rows x{world}: {'bit-exact vs single GPU' if flag.item() else 'MISMATCH'}; {ms.item():.3f} ms/image = {w*h/ms.item()/1e3:.0f} Mpix/s", flush=True)
-if d: d.destroy_process_group()
+    print(f"rows x{world} {w}x{h} K={k}: {'bit-exact vs single GPU' if flag.item() else 'MISMATCH'}; in-library exchange {ms_lib:.3f} ms/image, "
+          f"caller-owned exchange {ms_py:.3f}, one GPU alone {ms_one:.3f}", flush=True)
+rows.close()
+if d:
+    d.destroy_process_group()
 sys.exit(0 if flag.item() else 1)
