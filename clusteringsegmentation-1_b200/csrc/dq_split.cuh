@@ -148,7 +148,12 @@ constexpr uint32_t kTieListCap = 16;
 
 // Largest input (unique colours) that takes the sequential-order path of dq_split_exact.cu.
 constexpr uint32_t kExactMaxPoints = 262144;       // compile-time ceiling; the run-time limit is SplitArgs::exact_small_max
-constexpr uint32_t kExactDefaultPoints = 65536;    // its default
+// Its default.  Above it the exact-integer kernels run with the tie audit (dq_tie.cuh) and only flagged frames come back
+// to the ordered path; 4096 is where the ordered path stops being the cheaper way to be right: up to there ties are the
+// rule (tiny clusters) and the whole input sits in shared memory (~1 ms); at 40 000 colours it costs 20 ms against 0.35.
+// (36 natural crops of 4 000..60 000 colours, tools/limit_check.py: limit 65536 3.3 ms per crop, 4096 1.3 ms, all
+// bit-exact either way.)
+constexpr uint32_t kExactDefaultPoints = 4096;
 constexpr uint32_t kExactMaxColors = 4096;
 // Small weighted inputs in the reference's own summation order (dq_split_exact.cuh).
 // The sampled pixels behind the histogram: needed to put the unique colours into calc_color_table's emission order.

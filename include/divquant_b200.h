@@ -131,13 +131,12 @@ void dq_context_set_split_ctas(dq_context *ctx, int num_ctas);
 /* Weighted inputs (allPixelsUnique = 0) of at most `max_points` unique colours (and K <= 4096) are split by code that
  * adds in the reference's own order (calc_color_table emission order, one sequential double sum per accumulator), so
  * that even decisions that sit exactly on a tie come out as in the reference: bit-exact palettes.  Larger inputs use
- * exact integer sums: identical unless such a tie occurs (DESIGN.md 5.2 has the measured rates).  The ordered path
- * adds sequential chains, one CTA per cluster: ~0.2 ms for 100 colours, ~1.2 ms for 4096, ~3 ms for 16384, 6-10 ms
- * for 65536 (K = 256).
- * max_points: 0..262144, default 65536 (environment DIVQUANT_B200_EXACT_MAX) -- every BASELINE performance config has more
- * colours than the default (G1 1080p 118 773, 4K 125 712) and stays on the exact-integer kernels; raising the limit puts them
- * on the ordered path too (~8 ms per 4K frame instead of 0.47); dq_context_set_exact_small(ctx, 0)
- * (environment DIVQUANT_B200_EXACT_SMALL=0) turns the ordered path off altogether. */
+ * exact integer sums with the tie audit below, which sends the frames that need it back to the ordered path (it takes up
+ * to 262144 colours) -- so the palette is the reference's either way and this limit is a performance knob: the ordered
+ * path costs ~0.2 ms for 100 colours, ~1.2 ms for 4096, ~3 ms for 16384, 20 ms for 40 000 (K = 256, sequential chains),
+ * the audited integer kernels 0.3-0.5 ms whatever the size.
+ * max_points: 0..262144, default 4096 (environment DIVQUANT_B200_EXACT_MAX); dq_context_set_exact_small(ctx, 0)
+ * (environment DIVQUANT_B200_EXACT_SMALL=0) turns the ordered path off altogether (flagged frames are then only reported). */
 void dq_context_set_exact_max_points(dq_context *ctx, uint32_t max_points);
 void dq_context_set_exact_small(dq_context *ctx, int enabled);
 /* Inputs above that limit run on exact integer sums, which equal the reference's sequential double sums up to the
@@ -242,7 +241,7 @@ void dq_shard_quantize_map(dq_context *ctx, const uint32_t *d_all_colours, const
  * count 0: no sizes travel first, no host synchronisation before the palette); list_capacity >= the largest number of
  * unique colours in any shard (a shard that exceeds it is fatal: message + abort).  world = 1 needs no id and no NCCL.
  * Result: the palette and this rank's rows of dq_quant_recurse of the whole image, PROVIDED the single-GPU call takes the
- * exact-integer kernels for it (more unique colours than dq_context_set_exact_max_points, default 65 536: every BASELINE
+ * exact-integer kernels for it (more unique colours than dq_context_set_exact_max_points, default 4096: every BASELINE
  * configuration).  Below that limit the single-GPU call adds in the reference's order, which needs the first-seen index of
  * every colour over the WHOLE image; the sharded call does not exchange those and stays on exact integer sums: it then
  * equals the reference unless dq_call_stats::tie_flags says a decision sat inside the reference's rounding noise. */

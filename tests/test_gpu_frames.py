@@ -57,6 +57,13 @@ def test_g2_1080p_bit_exact(dq, oracle, frames):
     _check(dq, oracle, frames, "g2", 2, 1920, 1080, 256, 1)
 
 
+def test_g2_4k_bit_exact(dq, oracle, frames):
+    # 6.5 M unique colours: the largest stress input of SURVEY.md 8c/8d (the reference needs ~6 minutes for it)
+    if "g2_4k_seeds" not in frames.files:
+        pytest.skip("g2_4k fingerprints not generated (make_golden_frames.py --only g2_4k)")
+    _check(dq, oracle, frames, "g2_4k", 2, 3840, 2160, 256, 1)
+
+
 def test_audit_off_reproduces_the_known_mismatch(dq, oracle, frames):
     """With the audit off, seed 12410 is one LSB off in one palette entry: the reason the audit exists."""
     lib = dq.lib

@@ -74,7 +74,12 @@ def test_small_cases_uniform_path_bit_exact_vs_reference(dq, golden):
         assert np.array_equal(out, golden[f"small{i}_u1_out"]), i
 
 
-EXACT_MAX_POINTS = 65536  # kExactMaxPoints (csrc/dq_split.cuh): inputs up to this many unique colours are summed in the reference's order
+# Up to this many unique colours the tests demand the reference's result bit for bit on EVERY input, ties included: the
+# ordered path sums in the reference's order up to its default limit (4096, kExactDefaultPoints in csrc/dq_split.cuh);
+# above it the exact-integer kernels run with the tie audit, and flagged frames are settled by the resolver or re-run on
+# the ordered path (which takes up to 262 144 colours).
+EXACT_MAX_POINTS = 65536
+EXACT_DEFAULT_LIMIT = 4096
 
 
 def test_small_cases_weighted_path(dq, oracle, golden):
@@ -547,7 +552,7 @@ def test_ordered_path_limits_and_large_k(dq, oracle):
         assert np.array_equal(pal, ref_pal) and empty == ref_empty
         assert st["tie_flags"] == 0 or st["ordered_rerun"] == 1 or st["tie_resolved"] > 0
     finally:
-        dq.lib.dq_context_set_exact_max_points(ctx, 65536)
+        dq.lib.dq_context_set_exact_max_points(ctx, EXACT_DEFAULT_LIMIT)
         dq.lib.dq_context_set_tie_policy(ctx, 2)
 
 
@@ -569,7 +574,7 @@ def test_ordered_path_above_the_default_limit(dq, oracle, golden):
         assert np.array_equal(pal, golden["g1_1080_k64_palette"])
         assert oracle.hash_words(out) == int(golden["g1_1080_k64_out_hash"][0])
     finally:
-        dq.lib.dq_context_set_exact_max_points(ctx, 65536)
+        dq.lib.dq_context_set_exact_max_points(ctx, EXACT_DEFAULT_LIMIT)
 
 
 def test_frame_pipeline_device_side_palette_chain(dq, pkg, oracle, monkeypatch):
