@@ -129,6 +129,7 @@ struct dq_context {
   // Tie audit of the exact-integer split (dq_tie.cuh): 0 = off, 1 = report in dq_call_stats::tie_flags only,
   // 2 (default) = a flagged frame is computed again in the reference's summation order (DIVQUANT_B200_TIE)
   int tie_policy = 2;
+  long long spin_cycles = 0;  // DIVQUANT_B200_SPIN_MS: bound of the split kernel's waits on other CTAs (0 = built-in 0.2 s)
   int split_version = 2;  // 1 = generic kernel, 2 = latency-optimised kernel (falls back to 1 when it cannot run)
   int trace_split = 0;
   int *d_lut = nullptr;
@@ -300,6 +301,7 @@ uint32_t run_split(dq_context *ctx, uint32_t point_capacity, double norm, uint32
 
   const bool use_v2 = ctx->split_version == 2 && K <= kSplit2MaxColors;
   // weighted points on exact-integer sums: audit the decisions against the reference's rounding noise (dq_tie.cuh)
+  a.spin_cycles = ctx->spin_cycles;
   a.tie_audit = (weighted && use_v2 && ctx->tie_policy != 0) ? 1u : 0u;
   if (a.tie_audit) {
     ctx->d_tie.ensure(5 * kTieListCap);
@@ -816,6 +818,13 @@ bool frame_async_collect(dq_context *ctx, const FrameResult *h_frame, uint32_t K
 
 std::mutex g_default_mutex;
 dq_context *g_default = nullptr;
+// The reference's functions are re-entrant; the entry points that run on the one lazily created default context are
+// serialised instead: each holds this lock for the whole call (recursive: dq_quant_blocks calls other entry points).
+std::recursive_mutex g_default_call_mutex;
+struct DefaultLock {
+  std::lock_guard<std::recursive_mutex> guard;
+  DefaultLock() : guard(g_default_call_mutex) {}
+};
 int g_display_timings = -1;
 
 int display_timings_default() {
@@ -896,6 +905,7 @@ dq_context *dq_context_create(int device) {
   ctx->display_timings = display_timings_default();
   if (const char *e = getenv("DIVQUANT_B200_SPLIT")) ctx->split_version = (e[0] == '1') ? 1 : 2;
   if (const char *e = getenv("DIVQUANT_B200_TIE")) ctx->tie_policy = std::min(std::max(atoi(e), 0), 2);
+  if (const char *e = getenv("DIVQUANT_B200_SPIN_MS")) ctx->spin_cycles = (long long)std::max(atol(e), 0l) * 2000000ll;  // ~2 GHz
   if (const char *e = getenv("DIVQUANT_B200_EXACT_SMALL")) ctx->exact_small = (e[0] != '0');
   if (const char *e = getenv("DIVQUANT_B200_EXACT_PARALLEL")) ctx->exact_parallel = (e[0] != '0');
   if (const char *e = getenv("DIVQUANT_B200_EXACT_MAX")) ctx->exact_max_points = (uint32_t)std::min<long>(std::max<long>(atol(e), 0), kExactMaxPoints);
@@ -1068,6 +1078,7 @@ void dq_quant_recurse_ctx(dq_context *ctx, uint32_t numPixels, const uint32_t *i
 
 void dq_quant_recurse(uint32_t numPixels, const uint32_t *inPixelsPtr, uint32_t *outPixelsPtr, uint32_t *numClustersPtr,
                       uint32_t *outColortablePtr, int allPixelsUnique) {
+  DefaultLock lock;
   dq_quant_recurse_ctx(dq_default_context(), numPixels, inPixelsPtr, outPixelsPtr, numClustersPtr, outColortablePtr,
                        allPixelsUnique);
 }
@@ -1076,6 +1087,7 @@ void dq_quant_varpart_fast(uint32_t numPixels, const uint32_t *inPixels, uint32_
                            uint32_t numCols, uint32_t *numClustersPtr, uint32_t *colortablePtr, int num_bits, int dec_factor,
                            int max_iters, int allPixelsUnique) {
   dq_context *ctx = dq_default_context();
+  DefaultLock lock;
   require_device(ctx);
   ctx->d_in.ensure(numPixels);
   DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->d_in.ptr, inPixels, (size_t)numPixels * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -1086,6 +1098,7 @@ void dq_quant_varpart_fast(uint32_t numPixels, const uint32_t *inPixels, uint32_
 void dq_map_colors_mps(const uint32_t *inPixelsPtr, uint32_t numPixels, uint32_t *outPixelsPtr, const uint32_t *colortablePtr,
                        int colormapSize) {
   dq_context *ctx = dq_default_context();
+  DefaultLock lock;
   require_device(ctx);
   if (numPixels == 0) return;
   ctx->d_in.ensure(numPixels);
@@ -1102,6 +1115,7 @@ void dq_cut_bits(const uint32_t *inPixels, uint32_t numPixels, uint32_t *outPixe
     return;  // silent return after the message, like the reference (DivQuantUni.cpp:41-46)
   if (numPixels == 0) return;
   dq_context *ctx = dq_default_context();
+  DefaultLock lock;
   require_device(ctx);
   ctx->d_in.ensure(numPixels);
   ctx->d_out.ensure(numPixels);
@@ -1118,6 +1132,7 @@ int dq_calc_color_table(const uint32_t *inPixels, uint32_t numPixels, uint32_t *
     return -1;
   }
   dq_context *ctx = dq_default_context();
+  DefaultLock lock;
   require_device(ctx);
   memset(&ctx->stats, 0, sizeof(ctx->stats));
   const uint32_t dec = (uint32_t)dec_factor;
@@ -1172,7 +1187,12 @@ void dq_block_vote_device(dq_context *ctx, const uint32_t *d_quantPixels, uint32
 }
 
 void dq_block_vote(const uint32_t *quantPixels, uint32_t width, uint32_t height, uint32_t superpixelDim, uint32_t *blocksOut) {
+  if (superpixelDim < 1 || superpixelDim > 8 || width == 0 || height == 0) {
+    fprintf(stderr, "divquant_b200: block vote needs a non-empty image and superpixelDim in 1..8\n");
+    abort();
+  }
   dq_context *ctx = dq_default_context();
+  DefaultLock lock;
   require_device(ctx);
   const uint32_t n = width * height;
   const uint32_t nb = ((width + superpixelDim - 1) / superpixelDim) * ((height + superpixelDim - 1) / superpixelDim);
@@ -1186,7 +1206,12 @@ void dq_block_vote(const uint32_t *quantPixels, uint32_t width, uint32_t height,
 
 void dq_quant_blocks(const uint32_t *inPixels, uint32_t width, uint32_t height, uint32_t superpixelDim, const uint32_t *colortable,
                      int colormapSize, uint32_t *quantOut, uint32_t *blocksOut) {
+  if (superpixelDim < 1 || superpixelDim > 8 || width == 0 || height == 0) {
+    fprintf(stderr, "divquant_b200: block vote needs a non-empty image and superpixelDim in 1..8\n");
+    abort();
+  }
   dq_context *ctx = dq_default_context();
+  DefaultLock lock;
   require_device(ctx);
   const uint32_t n = width * height;
   const uint32_t nb = ((width + superpixelDim - 1) / superpixelDim) * ((height + superpixelDim - 1) / superpixelDim);
@@ -1221,6 +1246,7 @@ void dq_srm_sorted_edges_device(dq_context *ctx, const uint8_t *d_in, uint32_t w
 void dq_srm_sorted_edges(const uint8_t *in, uint32_t width, uint32_t height, uint32_t channels, uint32_t widthStep,
                          dq_srm_pair *orderedPairs) {
   dq_context *ctx = dq_default_context();
+  DefaultLock lock;
   require_device(ctx);
   const size_t bytes = (size_t)height * widthStep;
   const uint32_t n = srm_num_pairs(width, height);
@@ -1273,6 +1299,7 @@ void dq_colortable_indexes(const uint32_t *quantPixels, uint32_t numPixels, cons
                            uint32_t *labelsOut, int asGreyscale) {
   if (numPixels == 0) return;
   dq_context *ctx = dq_default_context();
+  DefaultLock lock;
   require_device(ctx);
   ctx->d_in.ensure(numPixels);
   ctx->d_out.ensure(numPixels);
@@ -1716,6 +1743,7 @@ uint32_t dq_debug_histogram(dq_context *ctx, const uint32_t *inPixels, uint32_t 
 
 uint32_t dq_pixel_histogram(const uint32_t *pixels, uint32_t numPixels, uint32_t *pixelsOut, uint32_t *countsOut, uint32_t capacity) {
   dq_context *ctx = dq_default_context();
+  DefaultLock lock;
   require_device(ctx);
   if (numPixels == 0) return 0;
   ctx->d_in.ensure(numPixels);

@@ -142,6 +142,8 @@ struct SplitArgs {
   uint32_t tie_audit;
   // final clusters flagged kTieRound: {cluster index, node id, palette slot, 0} each, at most kTieListCap (dq_resolve.cu)
   uint32_t *tie_list;
+  // SM cycles a wait on another CTA may last before it is declared stuck (0 = the built-in 0.2 s)
+  long long spin_cycles;
 };
 constexpr uint32_t kTieListCap = 16;
 

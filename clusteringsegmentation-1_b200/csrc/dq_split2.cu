@@ -122,12 +122,14 @@ __device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int *p) {
 // Every wait on another CTA is bounded: a persistent spinning kernel must never be able to wedge the
 // device.  After kSpinCycles without progress the waiter records where it was stuck in ctl[] and
 // raises ctl[kCtlError]; every other waiter sees the flag and leaves too, and the host reports it.
-constexpr long long kSpinCycles = 400000000ll;  // ~0.2 s at 1.9 GHz; a healthy wait is microseconds
+constexpr long long kSpinCycles = 400000000ll;  // default: ~0.2 s at 1.9 GHz; a healthy wait is microseconds
+// (SplitArgs::spin_cycles, DIVQUANT_B200_SPIN_MS, replaces it: compute-sanitizer, cuda-gdb or heavy time-slicing can make a
+// healthy wait long)
 
 __device__ __forceinline__ bool spin_expired(const SplitArgs &A, long long t0, unsigned &polls, int what, int arg) {
   if ((++polls & 1023u) != 0) return false;
   if (ld_relaxed_u32(A.ctl + kCtlError) != 0) return true;
-  if (clock64() - t0 > kSpinCycles) {
+  if (clock64() - t0 > (A.spin_cycles > 0 ? A.spin_cycles : kSpinCycles)) {
     if (atomicCAS(A.ctl + kCtlError, 0u, 3u) == 0u) {
       A.ctl[kCtlWords - 1] = (uint32_t)what;
       A.ctl[kCtlJobs] = (uint32_t)arg;

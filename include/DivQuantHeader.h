@@ -59,7 +59,15 @@ double *calc_color_table(const uint32_t *inPixels, const uint32_t numPixels, uin
 void cut_bits(const uint32_t *inPixels, const uint32_t numPixels, uint32_t *outPixels, const uchar num_bits_red,
               const uchar num_bits_green, const uchar num_bits_blue);
 
-/* DivQuantCluster.cpp:1099-1179 */
+/* DivQuantCluster.cpp:1099-1179.
+ * Deviations from the reference, both fatal here instead of silently degenerate there:
+ *  - max_iters must be in 1..32.  The reference accepts 0, but its KM template flag is hard-wired true (:1154-1166), so
+ *    with no local k-means pass member[] is never written: every split leaves all points in the old cluster and the call
+ *    returns one colour plus "# empty clusters: K-1" (SURVEY.md 7).  Nothing calls it that way (quant_util.cpp:31 ships 10).
+ *  - dec_factor <= 0: message + abort (the reference dereferences the NULL calc_color_table returns, :1136).
+ * The entry points of this header run on one lazily created context and are serialised by a lock: safe to call from
+ * several threads, but one call runs at a time (the reference's functions are re-entrant); concurrent streams of frames go
+ * through divquant_b200.h (dq_context_create / dq_pipeline_*). */
 void quant_varpart_fast(const uint32_t numPixels, const uint32_t *inPixels, uint32_t *tmpPixels,
                         const uint32_t numRows, const uint32_t numCols, uint32_t *numClustersPtr,
                         uint32_t *colortablePtr, const int num_bits, const int dec_factor, const int max_iters,
