@@ -102,6 +102,7 @@ struct Arrays {
   int32_t *cand;       // [K]
   int32_t *rank;       // [cap]  number of known nodes with a larger TSE (final assignment)
   double *terr;        // [cap]  tie audit: bound of the node's TSE
+  int32_t *byrank;     // [cap]  tie audit: node of every TSE rank (final assignment)
   uint8_t *jobtie;     // [K]    tie audit: TieBit mask of this round's wide jobs (owner CTA)
 };
 
@@ -353,7 +354,11 @@ __device__ __forceinline__ void derive_params_warp0(Shared2 &S, const JobConst &
     const double a = fsq(om), b = fsq(nm);
     const double a1 = __shfl_sync(0xffffffffu, a, 1), b1 = __shfl_sync(0xffffffffu, b, 1);
     const double a2 = __shfl_sync(0xffffffffu, a, 2), b2 = __shfl_sync(0xffffffffu, b, 2);
-    if (threadIdx.x < 3) S.pp.r[c] = fsub(om, nm);
+    if (threadIdx.x < 3) {
+      S.pp.r[c] = fsub(om, nm);
+      S.ext.om[c] = om;  // (tie audit: the centres themselves, for the cold per-point re-check)
+      S.ext.nm[c] = nm;
+    }
     if (threadIdx.x == 0) {
       double l = fsub(a, b);  // (:616-619), left to right
       l = fadd(l, a1);
@@ -394,24 +399,13 @@ __device__ __forceinline__ void derive_audit_warp1(Shared2 &S, const JobConst &j
       }
       return;
     }
-    const int c = min(lane, 2);
+    // Only the new side's weight and point count are needed: the centres' magnitudes enter the bounds as 256 (they are
+    // means of bytes), so no division happens here and this warp is never the one the pass waits for.
     const uint64_t t_cnt = warp_total_row(S, lane, rows, kAccCnt), t_pts = warp_total_row(S, lane, rows, kAccPts);
-    const uint64_t t_r = warp_total_row(S, lane, rows, kAccR), t_g = warp_total_row(S, lane, rows, kAccG),
-                   t_b = warp_total_row(S, lane, rows, kAccB);
-    const uint64_t t_c = (c == 0) ? t_r : ((c == 1) ? t_g : t_b);
     const double nw = fmul(u52_to_double(t_cnt), norm);
-    const double nm = fdiv(fmul(u52_to_double(t_c), norm), nw);
     const double ow = fsub(jc.tw, nw);
-    const double om = fdiv(fsub(fmul(jc.tw, jc.tm[c]), fmul(nw, nm)), ow);
-    const double om1 = __shfl_sync(0xffffffffu, om, 1), nm1 = __shfl_sync(0xffffffffu, nm, 1);
-    const double om2 = __shfl_sync(0xffffffffu, om, 2), nm2 = __shfl_sync(0xffffffffu, nm, 2);
-    if (lane < 3) {
-      S.ext.om[c] = om;
-      S.ext.nm[c] = nm;
-    }
     if (lane == 0) {
-      const tie::PassErr q = tie::pass_err_fast(aud->eW, aud->eS, jc.tw, aud->m1, nw, fmax(fabs(nm), fmax(fabs(nm1), fabs(nm2))), ow,
-                                                fmax(fabs(om), fmax(fabs(om1), fabs(om2))), (double)(uint32_t)t_pts);
+      const tie::PassErr q = tie::pass_err_fast(aud->eW, aud->eS, jc.tw, aud->m1, nw, 256.0, ow, 256.0, (double)(uint32_t)t_pts);
       const double tol = tie::hyperplane_tol(q);
       S.ext.e_om = q.e_om;
       S.ext.e_nm = q.e_nm;
@@ -661,18 +655,46 @@ __device__ void fast_assignment(const SplitArgs &A, Shared2 &S, const Arrays &R)
     R.rank[i] = above;
   }
   __syncthreads();
-  uint32_t near_mask = 0u;  // per thread: bit q = its q-th node has another node's TSE within the two bounds
+  uint32_t near_mask = 0u;  // per thread: bit q = its q-th node may have another node's TSE within the two bounds
   if (audit) {
     // tie audit, D4, for the nodes the reference pops: does any other node's TSE come within the two bounds of this one?
-    // (whether that node matters to the reference's sequence is sorted out below, for the few nodes marked here)
+    // The ranks just computed ARE the descending TSE order, so only a node's neighbours in that order can be that close:
+    // byrank[] inverts the ranks (equal TSEs share a rank and collide there: a tie by definition), and a node is marked
+    // when a neighbour lies within its own bound plus the LARGEST bound of any node -- a superset of the exact pairwise
+    // test, which follows below for the few nodes marked here (together with whether the other node matters at all).
+    for (int i = tid; i < n; i += T) R.byrank[i] = -1;
+    __shared__ double s_emax;
+    if (tid == 0) s_emax = 0.0;
+    __syncthreads();
+    double emax = 0.0;
+    for (int i = tid; i < n; i += T) {
+      const int r = R.rank[i];
+      if (r < n) R.byrank[r] = i;
+      const double e = R.terr[i];
+      if (e > emax || e != e) emax = (e != e) ? __longlong_as_double(0x7ff0000000000000ll) : e;
+    }
+    if (emax > 0.0) atomicMax(reinterpret_cast<unsigned long long *>(&s_emax), (unsigned long long)__double_as_longlong(emax));
+    __syncthreads();
+    emax = s_emax;
     int q = 0;
     for (int i = tid; i < n; i += T, ++q) {
-      if (R.rank[i] >= K - 1 || i == 0) continue;
-      const double t = R.tse[i], e = R.terr[i];
-      int near = -1;  // the node itself always matches
-#pragma unroll 4
-      for (int m2 = 0; m2 < n; ++m2) near += (fabs(R.tse[m2] - t) <= e + R.terr[m2]);
-      if (near > 0) near_mask |= 1u << (q & 31);
+      const int r = R.rank[i];
+      if (r >= K - 1 || i == 0) continue;
+      const double t = R.tse[i], tol = R.terr[i] + emax;
+      bool near = R.byrank[r] != i;  // somebody with an equal TSE took the slot
+      for (int d = r - 1; d >= 0 && !near; --d) {  // next node above (slots emptied by equal TSEs are skipped)
+        const int j = R.byrank[d];
+        if (j < 0) continue;
+        near = fabs(R.tse[j] - t) <= tol;
+        break;
+      }
+      for (int d = r + 1; d < n && !near; ++d) {  // next node below
+        const int j = R.byrank[d];
+        if (j < 0) continue;
+        near = fabs(R.tse[j] - t) <= tol;
+        break;
+      }
+      if (near) near_mask |= 1u << (q & 31);
     }
   }
   for (int i = tid; i < n; i += T) {
@@ -991,6 +1013,8 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
     cur += (size_t)K;
     cur = smem_raw + (((size_t)(cur - smem_raw) + 15) & ~size_t(15));
     R.terr = reinterpret_cast<double *>(cur);
+    cur += (size_t)cap * 8;
+    R.byrank = reinterpret_cast<int32_t *>(cur);
   }
   const bool audit = A.tie_audit != 0u;
 
@@ -1578,7 +1602,7 @@ size_t split2_smem_bytes(uint32_t K, uint32_t cap) {
   s += (size_t)K * (8 + 4 + 4 + 4);
   s += (size_t)(K + 1) * 4 * 3;
   s += (size_t)K * 2 * 2;
-  s += (size_t)K + 16 + (size_t)cap * 8;  // tie audit: jobtie, terr
+  s += (size_t)K + 16 + (size_t)cap * (8 + 4);  // tie audit: jobtie, terr, byrank
   return s + 64;
 }
 

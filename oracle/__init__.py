@@ -213,6 +213,19 @@ class ReferenceSRM:
         self.lib.ref_srm_sorted_edges.restype = C.c_uint
         self.lib.ref_srm_sorted_edges.argtypes = [C.c_double, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p, _u32p]
 
+    def run_with_pairs(self, image, pairs, q=128.0):
+        """The reference's SRM (initialize, union-find merge loop srm.c:179-190, merge_small_regions, finalize) driven by a
+        SUPPLIED sorted edge list (n_pairs, 3) uint32 instead of the one segmentation() builds.  Returns the segmented image."""
+        im = np.ascontiguousarray(image, np.uint8).copy()
+        h, w, ch = im.shape
+        out_img = np.zeros_like(im)
+        pr = np.ascontiguousarray(pairs, np.uint32)
+        fn = self.lib.ref_srm_run_with_pairs
+        fn.restype = None
+        fn.argtypes = [C.c_double, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p, _u32p]
+        fn(q, w, h, ch, w * ch, im.ctypes.data, out_img.ctypes.data, _ptr(pr.reshape(-1)))
+        return out_img
+
     def sorted_edges(self, image, q=32.0):
         im = np.ascontiguousarray(image, np.uint8).copy()
         h, w, ch = im.shape
