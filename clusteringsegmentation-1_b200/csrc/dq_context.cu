@@ -1151,23 +1151,23 @@ int dq_calc_color_table(const uint32_t *inPixels, uint32_t numPixels, uint32_t *
   DQ_CUDA_CHECK(cudaMemcpyAsync(&ctx->h_cb->ucount, &ctx->d_cb->ucount, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   const uint32_t U = ctx->h_cb->ucount;
-  // emission order of the reference: (bucket asc, first-seen desc) keys computed on the device
-  ctx->d_keys.ensure(U);
+  // emission order of the reference: (bucket asc, first-seen desc) keys, sorted, and the colours / weights written out in
+  // that order -- all on the device; the host only copies the two result arrays back
+  uint32_t n_pow2 = 2;
+  while (n_pow2 < U) n_pow2 <<= 1;
+  ctx->d_keys.ensure(n_pow2);
+  ctx->d_out.ensure(std::max<size_t>(n_pow2, numPixels));                     // payload of the sort
+  ctx->d_exact.ensure((size_t)U + 2);                                         // U doubles: the weights
   order_keys(ctx->d_in.ptr, numRows, numCols, dec, 8, ctx->d_uniq.ptr, ctx->d_pts0.ptr, U, ctx->d_table, ctx->d_keys.ptr,
              ctx->sm_count, ctx->stream);
-  std::vector<uint64_t> keys(U);
-  std::vector<uint2> pts(U);
-  DQ_CUDA_CHECK(cudaMemcpyAsync(keys.data(), ctx->d_keys.ptr, (size_t)U * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-  DQ_CUDA_CHECK(cudaMemcpyAsync(pts.data(), ctx->d_pts0.ptr, (size_t)U * sizeof(uint2), cudaMemcpyDeviceToHost, ctx->stream));
-  DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-  std::vector<uint32_t> order(U);
-  for (uint32_t i = 0; i < U; ++i) order[i] = i;
-  std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
   const double norm = sample_norm(numRows, numCols, dec_factor);
-  for (uint32_t i = 0; i < U; ++i) {
-    outPixels[i] = pts[order[i]].x;
-    if (weightsOut) weightsOut[i] = norm * (int)pts[order[i]].y;  // (:185)
-  }
+  uint32_t *d_colours = ctx->d_uniq.ptr;  // (the arrival-order list is not needed any more)
+  double *d_weights = reinterpret_cast<double *>(ctx->d_exact.ptr);
+  order_sort_emit(ctx->d_pts0.ptr, U, ctx->d_keys.ptr, ctx->d_out.ptr, norm, d_colours, d_weights, ctx->sm_count, ctx->stream);
+  DQ_CUDA_CHECK(cudaMemcpyAsync(outPixels, d_colours, (size_t)U * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  if (weightsOut)
+    DQ_CUDA_CHECK(cudaMemcpyAsync(weightsOut, d_weights, (size_t)U * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  DQ_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   *num_colors = (int)U;
   ctx->stats.num_points = U;
   return 0;

@@ -176,6 +176,37 @@ __global__ void __launch_bounds__(256) order_keys_kernel(const uint2 *__restrict
   }
 }
 
+// ---- emission order on the device: bitonic sort of the (unique) keys with the point index as payload, then the
+//      unique colours and their weights count * (1/N) written out in that order (calc_color_table :172-198) ----
+__global__ void __launch_bounds__(256) order_pad_kernel(uint64_t *keys, uint32_t *vals, uint32_t u, uint32_t n_pow2) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pow2; i += gridDim.x * blockDim.x) {
+    vals[i] = i;
+    if (i >= u) keys[i] = ~0ull;  // padding sorts to the end
+  }
+}
+__global__ void __launch_bounds__(256) bitonic_step_kernel(uint64_t *keys, uint32_t *vals, uint32_t n_pow2, uint32_t j, uint32_t k) {
+  const uint32_t half = n_pow2 >> 1;
+  for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < half; p += gridDim.x * blockDim.x) {
+    const uint32_t i = ((p & ~(j - 1u)) << 1) | (p & (j - 1u));  // the p-th index whose bit j is clear
+    const uint64_t a = keys[i], b = keys[i | j];
+    if ((a > b) == ((i & k) == 0u)) {
+      keys[i] = b;
+      keys[i | j] = a;
+      const uint32_t va = vals[i];
+      vals[i] = vals[i | j];
+      vals[i | j] = va;
+    }
+  }
+}
+__global__ void __launch_bounds__(256) order_emit_kernel(const uint2 *__restrict__ pts, const uint32_t *__restrict__ vals, uint32_t u,
+                                                        double norm, uint32_t *colours, double *weights) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < u; i += gridDim.x * blockDim.x) {
+    const uint2 p = pts[vals[i]];
+    colours[i] = p.x;
+    weights[i] = __dmul_rn(norm, (double)(int)p.y);  // weights[i] = norm_factor * bucket->value (:185), value is an int
+  }
+}
+
 // (colour, count) points -> two plain arrays (the exchange format of the row-sharded path)
 __global__ void __launch_bounds__(256) hist_export_kernel(const uint2 *__restrict__ pts, const uint32_t *ucount,
                                                          uint32_t *colours, uint32_t *counts) {
@@ -264,6 +295,19 @@ void hist_collect(const uint32_t *d_uniq, const uint32_t *d_ucount, uint32_t u_h
 void table_clear(const uint32_t *d_uniq, const uint32_t *d_ucount, uint32_t u_hint, uint32_t *d_table, int sm_count,
                  cudaStream_t st) {
   table_clear_kernel<<<blocks_for(u_hint, 256, sm_count, 8), 256, 0, st>>>(d_uniq, d_ucount, d_table);
+  DQ_CUDA_CHECK(cudaGetLastError());
+}
+
+void order_sort_emit(const uint2 *d_pts, uint32_t u, uint64_t *d_keys, uint32_t *d_vals, double norm, uint32_t *d_colours,
+                     double *d_weights, int sm_count, cudaStream_t st) {
+  if (u == 0) return;
+  uint32_t n_pow2 = 2;
+  while (n_pow2 < u) n_pow2 <<= 1;
+  order_pad_kernel<<<blocks_for(n_pow2, 256, sm_count, 8), 256, 0, st>>>(d_keys, d_vals, u, n_pow2);
+  for (uint32_t k = 2; k <= n_pow2; k <<= 1)
+    for (uint32_t j = k >> 1; j > 0; j >>= 1)
+      bitonic_step_kernel<<<blocks_for(n_pow2 >> 1, 256, sm_count, 8), 256, 0, st>>>(d_keys, d_vals, n_pow2, j, k);
+  order_emit_kernel<<<blocks_for(u, 256, sm_count, 8), 256, 0, st>>>(d_pts, d_vals, u, norm, d_colours, d_weights);
   DQ_CUDA_CHECK(cudaGetLastError());
 }
 

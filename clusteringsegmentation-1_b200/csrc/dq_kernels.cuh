@@ -19,6 +19,10 @@ void cut_bits_device(const uint32_t *d_in, uint32_t n, uint32_t *d_out, int rbit
 void order_keys(const uint32_t *d_in, uint32_t num_rows, uint32_t num_cols, uint32_t dec, int num_bits, const uint32_t *d_uniq,
                 const uint2 *d_pts, uint32_t u, uint32_t *d_table, uint64_t *d_keys, int sm_count, cudaStream_t st);
 
+// Sorts the u (unique) keys of order_keys with their point index (d_keys / d_vals need room for the next power of two),
+// then writes the unique colours and their weights norm * count in that order: calc_color_table's output, on the device.
+void order_sort_emit(const uint2 *d_pts, uint32_t u, uint64_t *d_keys, uint32_t *d_vals, double norm, uint32_t *d_colours,
+                     double *d_weights, int sm_count, cudaStream_t st);
 void hist_export(const uint2 *d_pts, const uint32_t *d_ucount, uint32_t u_hint, uint32_t *d_colours, uint32_t *d_counts,
                  int sm_count, cudaStream_t st);
 void hist_export_padded(const uint2 *d_pts, const uint32_t *d_ucount, uint32_t cap, uint32_t *d_colours, uint32_t *d_counts,
