@@ -117,7 +117,7 @@ def workload_config():
 
 def traffic_bytes():
     """DRAM bytes of one frame from the committed ncu capture (never measured under the timed run): (total, note)."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    path = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if os.path.exists(path):
         with open(path) as f:
             t = json.load(f)
