@@ -109,7 +109,7 @@ struct dq_context {
   // a split that has been launched but whose palette has not been collected yet (run_split / run_split_finish)
   struct PendingSplit {
     SplitArgs a;
-    bool use_v2 = false;
+    bool use_v2 = false, unaudited = false;
     uint32_t K = 0;
   } pend;
   // a quantize call between its two halves (quantize_begin / quantize_finish)
@@ -316,6 +316,8 @@ uint32_t run_split(dq_context *ctx, uint32_t point_capacity, double norm, uint32
     ctx->d_ctl_f64.ensure((size_t)8 * K + node_cap + 16);
     a.g_cluster_tse = ctx->d_ctl_f64.ptr;
     a.exact_small_max = std::min<uint32_t>(ctx->exact_max_points, kExactMaxPoints);
+    // the generic kernel (K > kSplit2MaxColors) carries no tie audit: everything the ordered path can hold goes there
+    if (weighted && !use_v2 && ctx->tie_policy != 0) a.exact_small_max = kExactMaxPoints;
     ctx->d_exact.ensure((split_exact_scratch_bytes() + ((size_t)8 * K + 16 + 64) * sizeof(uint32_t)) / 8 + 2);
     sampling = exact_sampling(exact->d_in, exact->rows, exact->cols, exact->dec, exact->bits);
   }
@@ -374,6 +376,7 @@ uint32_t run_split(dq_context *ctx, uint32_t point_capacity, double norm, uint32
   ctx->pend.a = a;
   ctx->pend.use_v2 = use_v2;
   ctx->pend.K = K;
+  ctx->pend.unaudited = weighted && !a.tie_audit && ctx->tie_policy != 0;
   if (defer) return 0;  // the caller polls split_ready() and collects with run_split_finish()
   return run_split_finish(ctx, colortable_out, records_out, mean_out, size_out);
 }
@@ -456,6 +459,8 @@ uint32_t run_split_finish(dq_context *ctx, uint32_t *colortable_out, dq_split_re
   ctx->stats.split_rounds = ctx->h_cb->ctl[kCtlRounds];
   ctx->stats.splits_computed = ctx->h_cb->ctl[kCtlSplits];
   ctx->stats.tie_flags = a.tie_audit ? ctx->h_cb->ctl[kCtlTie] : 0u;
+  // exact-integer sums without an audit (the generic kernel beyond the ordered path's reach): say so
+  if (ctx->pend.unaudited && ctx->h_cb->ucount > a.exact_small_max) ctx->stats.tie_flags |= (uint32_t)kTieUnaudited;
   if (records_out && K > 1)
     DQ_CUDA_CHECK(cudaMemcpy(records_out, ctx->d_records.ptr, (size_t)(K - 1) * sizeof(SplitRecord), cudaMemcpyDeviceToHost));
   if (mean_out) DQ_CUDA_CHECK(cudaMemcpy(mean_out, ctx->d_cluster_mean.ptr, (size_t)3 * K * sizeof(double), cudaMemcpyDeviceToHost));

@@ -4,7 +4,7 @@
 // by r+g+b, starts at lut_init[r+g+b] and walks up/down alternately, pruning with (delta sum)^2/3.
 // Its result is exactly  argmin_k (dist(k), rank(k))  over the WHOLE sorted palette, with
 // rank(s)=0, rank(s+d)=2d-1, rank(s-d)=2d (re-verified against the compiled reference
-// in tests/test_oracle_vs_ref.py), because the prune bound never exceeds the true distance and a
+// in tests/test_oracle_golden.py), because the prune bound never exceeds the true distance and a
 // candidate only replaces the incumbent when strictly closer.
 //
 // The sorted palette and lut_init come from the host shim, which calls the same std::sort as the
@@ -112,6 +112,73 @@ __device__ __forceinline__ void stage_palette_fast(const uint32_t *sorted, int n
   __syncthreads();
 }
 
+
+// ---- integer formulation (K <= 512) -------------------------------------------------------------------------
+// With the colour bytes packed in one word,  p.c_k  is ONE dp4a, and  2 p.c_k - |c_k|^2 = |p|^2 - dist(k)  grows as the
+// distance shrinks.  The entry index rides in the low 9 bits of the key, so the arg-min needs no second pass:
+//   key_lo = (2 p.c_k - |c_k|^2) * 512 + (511 - k) : the maximum names the SMALLEST k at the minimal distance,
+//   key_hi = (2 p.c_k - |c_k|^2) * 512 + k         : ... the LARGEST.
+// Both are dot * 1024 + a per-entry constant: per (pixel, entry) 1 IDP4A + 2 multiply/shift-adds, and a 3-input maximum
+// takes two entries at a time.  |2 p.c - |c|^2| <= 390150 < 2^22, so the keys fit 32 bits.  Almost always the two
+// indices agree (one entry at the minimum) and that is the answer; if they differ, every entry at the minimum lies
+// between them and the reference's visiting order (start, +1, -1, +2, ...) decides among those.
+constexpr int kIntColors = 512;
+constexpr int kIntSentinel = -(1 << 30);  // pads an odd palette: loses against every real key (>= -2^27)
+
+__device__ __forceinline__ void stage_palette_int(const uint32_t *sorted, int num_colors, int4 *s_ent) {
+  const int padded = (num_colors + 1) & ~1;
+  for (int k = threadIdx.x; k < padded; k += blockDim.x) {
+    if (k < num_colors) {
+      const uint32_t c = sorted[k] & 0x00FFFFFFu;
+      const int r = (c >> 16) & 0xFF, g = (c >> 8) & 0xFF, b = c & 0xFF;
+      const int sq = -(r * r + g * g + b * b) * 512;
+      s_ent[k] = make_int4((int)c, sq + (511 - k), sq + k, (int)c);
+    } else {
+      s_ent[k] = make_int4(0, kIntSentinel, kIntSentinel, 0);
+    }
+  }
+}
+
+template <int PIX>
+__device__ __forceinline__ void nearest_int(const int4 *s_ent, int num_colors, const uint32_t (&c)[PIX], int (&lo)[PIX], int (&hi)[PIX]) {
+#pragma unroll
+  for (int i = 0; i < PIX; ++i) lo[i] = hi[i] = kIntSentinel;
+  const int padded = (num_colors + 1) & ~1;
+#pragma unroll 4
+  for (int k = 0; k < padded; k += 2) {
+    const int4 e0 = s_ent[k], e1 = s_ent[k + 1];
+#pragma unroll
+    for (int i = 0; i < PIX; ++i) {
+      const int d0 = (int)__dp4a(c[i], (uint32_t)e0.x, 0u) << 10, d1 = (int)__dp4a(c[i], (uint32_t)e1.x, 0u) << 10;
+      lo[i] = max(lo[i], max(d0 + e0.y, d1 + e1.y));
+      hi[i] = max(hi[i], max(d0 + e0.z, d1 + e1.z));
+    }
+  }
+}
+
+// The palette word for one colour from its two keys; s = the reference's start index for it.
+__device__ __forceinline__ uint32_t resolve_int(const int4 *s_ent, uint32_t c, int s, int lo, int hi) {
+  const int ka = 511 - (lo & 511), kb = hi & 511;
+  int win = ka;
+  if (ka != kb) {
+    // entries at the minimal distance: ka < ... < kb.  Above the start the rank grows with k, below it falls with k.
+    if (s <= ka) {
+      win = ka;
+    } else if (s > kb) {
+      win = kb;
+    } else {
+      const int want = lo >> 9;
+      win = -1;
+      for (int d = 0; win < 0; ++d) {
+        const int up = s + d, down = s - d;
+        if (up <= kb && ((((int)__dp4a(c, (uint32_t)s_ent[up].x, 0u) << 10) + s_ent[up].y) >> 9) == want) win = up;
+        else if (d > 0 && down >= ka && ((((int)__dp4a(c, (uint32_t)s_ent[down].x, 0u) << 10) + s_ent[down].y) >> 9) == want) win = down;
+      }
+    }
+  }
+  return (uint32_t)s_ent[win].w;
+}
+
 constexpr int kFastPix = 8;  // pixels per thread per iteration: two 128-bit loads
 
 __global__ void __launch_bounds__(kMapThreads) map_pixels_fast_kernel(const uint32_t *__restrict__ in, uint32_t n,
@@ -121,10 +188,38 @@ __global__ void __launch_bounds__(kMapThreads) map_pixels_fast_kernel(const uint
   float4 *s_pal = reinterpret_cast<float4 *>(smem);
   uint32_t *s_word = reinterpret_cast<uint32_t *>(smem + (size_t)num_colors * 16);
   int *s_lut = reinterpret_cast<int *>(smem + (size_t)num_colors * 20);
-  stage_palette_fast(sorted, num_colors, lut_init, s_pal, s_word, s_lut);
   const uint32_t nblk = n / kFastPix;
   const uint4 *in4 = reinterpret_cast<const uint4 *>(in);
   uint4 *out4 = reinterpret_cast<uint4 *>(out);
+  if (num_colors <= kIntColors) {
+    int4 *s_ent = reinterpret_cast<int4 *>(smem);
+    s_lut = reinterpret_cast<int *>(smem + (size_t)((num_colors + 1) & ~1) * 16);
+    stage_palette_int(sorted, num_colors, s_ent);
+    for (int i = threadIdx.x; i < (int)kLutEntries; i += blockDim.x) s_lut[i] = lut_init[i];
+    __syncthreads();
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nblk; t += gridDim.x * blockDim.x) {
+      const uint4 a = __ldcs(in4 + 2 * t), c = __ldcs(in4 + 2 * t + 1);
+      const uint32_t w[kFastPix] = {a.x & 0xFFFFFFu, a.y & 0xFFFFFFu, a.z & 0xFFFFFFu, a.w & 0xFFFFFFu,
+                                    c.x & 0xFFFFFFu, c.y & 0xFFFFFFu, c.z & 0xFFFFFFu, c.w & 0xFFFFFFu};
+      int lo[kFastPix], hi[kFastPix];
+      nearest_int<kFastPix>(s_ent, num_colors, w, lo, hi);
+      uint32_t res[kFastPix];
+#pragma unroll
+      for (int i = 0; i < kFastPix; ++i)
+        res[i] = resolve_int(s_ent, w[i], s_lut[((w[i] >> 16) & 0xFF) + ((w[i] >> 8) & 0xFF) + (w[i] & 0xFF)], lo[i], hi[i]);
+      __stcs(out4 + 2 * t, make_uint4(res[0], res[1], res[2], res[3]));
+      __stcs(out4 + 2 * t + 1, make_uint4(res[4], res[5], res[6], res[7]));
+    }
+    const uint32_t tail = nblk * kFastPix;
+    if (blockIdx.x == 0 && tail + threadIdx.x < n) {
+      const uint32_t w[1] = {in[tail + threadIdx.x] & 0xFFFFFFu};
+      int lo[1], hi[1];
+      nearest_int<1>(s_ent, num_colors, w, lo, hi);
+      out[tail + threadIdx.x] = resolve_int(s_ent, w[0], s_lut[((w[0] >> 16) & 0xFF) + ((w[0] >> 8) & 0xFF) + (w[0] & 0xFF)], lo[0], hi[0]);
+    }
+    return;
+  }
+  stage_palette_fast(sorted, num_colors, lut_init, s_pal, s_word, s_lut);
   for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nblk; t += gridDim.x * blockDim.x) {
     const uint4 a = __ldcs(in4 + 2 * t), c = __ldcs(in4 + 2 * t + 1);
     const uint32_t w[kFastPix] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
@@ -156,6 +251,7 @@ __global__ void __launch_bounds__(kMapThreads) map_pixels_fast_kernel(const uint
   }
 }
 
+constexpr int kUniqInt = 2;  // colours per thread of the integer formulation (4K K=256, 125 712 colours: 1 -> 25 us, 2 -> 22 us, 4 -> 29 us)
 constexpr int kUniqPix = 2;  // colours per thread (measured at 4K, K=256: 4 -> 26 us, 2 -> 22 us, 1 -> 25 us)
 
 // One evaluation per unique colour: body shared by the two ways the tables arrive.
@@ -166,9 +262,33 @@ __device__ __forceinline__ void map_unique_fast_body(const uint32_t *__restrict_
   float4 *s_pal = reinterpret_cast<float4 *>(smem);
   uint32_t *s_word = reinterpret_cast<uint32_t *>(smem + (size_t)num_colors * 16);
   int *s_lut = reinterpret_cast<int *>(smem + (size_t)num_colors * 20);
-  stage_palette_fast(sorted, num_colors, lut_init, s_pal, s_word, s_lut);
   const uint32_t u = *ucount;
   const uint32_t stride = gridDim.x * blockDim.x;
+  if (num_colors <= kIntColors) {
+    int4 *s_ent = reinterpret_cast<int4 *>(smem);
+    s_lut = reinterpret_cast<int *>(smem + (size_t)((num_colors + 1) & ~1) * 16);
+    stage_palette_int(sorted, num_colors, s_ent);
+    for (int i = threadIdx.x; i < (int)kLutEntries; i += blockDim.x) s_lut[i] = (int)lut_init[i];
+    __syncthreads();
+    for (uint32_t base = blockIdx.x * blockDim.x + threadIdx.x; base < u; base += kUniqInt * stride) {
+      uint32_t c[kUniqInt];
+      int lo[kUniqInt], hi[kUniqInt];
+#pragma unroll
+      for (int i = 0; i < kUniqInt; ++i) {
+        const uint32_t idx = base + (uint32_t)i * stride;
+        c[i] = idx < u ? (uniq[idx] & 0xFFFFFFu) : 0u;
+      }
+      nearest_int<kUniqInt>(s_ent, num_colors, c, lo, hi);
+#pragma unroll
+      for (int i = 0; i < kUniqInt; ++i) {
+        if (base + (uint32_t)i * stride < u)
+          table[c[i]] = 0x80000000u |
+                        resolve_int(s_ent, c[i], s_lut[((c[i] >> 16) & 0xFF) + ((c[i] >> 8) & 0xFF) + (c[i] & 0xFF)], lo[i], hi[i]);
+      }
+    }
+    return;
+  }
+  stage_palette_fast(sorted, num_colors, lut_init, s_pal, s_word, s_lut);
   // every thread takes kUniqPix colours a stride apart (coalesced loads of the unique list)
   for (uint32_t base = blockIdx.x * blockDim.x + threadIdx.x; base < u; base += kUniqPix * stride) {
     uint32_t c[kUniqPix];
@@ -284,7 +404,7 @@ __global__ void __launch_bounds__(kMapThreads) map_unique_fast_param_kernel(cons
   map_unique_fast_body(uniq, ucount, table, tables.sorted, num_colors, tables.lut);
 }
 
-inline size_t fast_smem_bytes(int num_colors) { return (size_t)num_colors * 20 + kLutEntries * 4 + 16; }
+inline size_t fast_smem_bytes(int num_colors) { return (size_t)num_colors * 20 + kLutEntries * 4 + 64; }  // covers both layouts
 
 // Brute force over pixels, palette staged in shared memory.
 __global__ void __launch_bounds__(kMapThreads) map_pixels_kernel(const uint32_t *__restrict__ in, uint32_t n,

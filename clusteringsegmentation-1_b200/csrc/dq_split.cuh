@@ -99,7 +99,8 @@ enum TieBit {
   kTieHyperplane = 4u,  // D3: lhs < rhs . x (:683)
   kTieTse = 8u,         // D4: arg-max of the TSEs (:876-887), incl. the DBL_MIN seed
   kTieRound = 16u,      // D5: (uint8)(mean + 0.5) (:1050-1052)
-  kTieReplay = 32u      // the sequential replay of the selection ran (degenerate TSE order): not audited, always flagged
+  kTieReplay = 32u,     // the sequential replay of the selection ran (degenerate TSE order): not audited, always flagged
+  kTieUnaudited = 64u   // set by the host: exact-integer sums WITHOUT an audit (K > kSplit2MaxColors beyond the ordered path)
 };
 
 struct SplitArgs {

@@ -111,7 +111,9 @@ typedef struct {
   float stage_ms[7];
   /* Tie audit of the exact-integer split (inputs above the ordered path's limit): bit d-1 set = a decision of kind d
    * sat inside the rounding noise of the reference's sequential sums (1 axis :388-403, 2 cut :473, 4 hyperplane :683,
-   * 8 TSE arg-max :876-887, 16 palette rounding :1050-1052, 32 degenerate TSE order).  0 = the result is the
+   * 8 TSE arg-max :876-887, 16 palette rounding :1050-1052, 32 degenerate TSE order; 64 = NOT audited: more
+   * than 512 colours requested on more than 262144 distinct colours, where neither the audited kernel nor the ordered
+   * path applies -- requests above 512 colours otherwise always take the ordered path).  0 = the result is the
    * reference's bit for bit.  ordered_rerun = 1: the frame was flagged and computed again in the reference's
    * summation order (so the result is the reference's as well). */
   uint32_t tie_flags;

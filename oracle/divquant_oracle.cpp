@@ -5,7 +5,7 @@
 //   (1) against the seven known-answer palettes of the reference's Test/DivQuantTest.m
 //       (tests/golden/divquant_kat.json), and
 //   (2) against the UNMODIFIED reference sources compiled from /root/reference into
-//       oracle/_ref/libdivquant_ref.so (tests/test_oracle_vs_ref.py; fixtures in tests/golden/).
+//       oracle/_ref/libdivquant_ref.so (tests/test_oracle_golden.py; fixtures in tests/golden/).
 // Parity status: PINNED (both of the above pass bit-for-bit, including the floating-point
 // summation order of the weighted path, which this file follows operation by operation).
 //

@@ -530,6 +530,15 @@ def test_ordered_path_limits_and_large_k(dq, oracle):
         with muted((2,)):
             out, pal = dq.quant_recurse(px, k, 0)
         assert np.array_equal(pal, ref_pal) and np.array_equal(out, ref_out), k
+    # K > 512 above the default limit: the generic kernel has no tie audit, so the ordered path takes the input whatever the
+    # limit says (19 256 random colours at K = 700 differ from the reference in a palette entry on exact-integer sums)
+    px = np.random.default_rng(9).integers(0, 1 << 24, 19300, dtype=np.uint32)
+    with muted():
+        ref_out, ref_pal = oracle.quant_recurse(px, 700, 0)
+    with muted((2,)):
+        out, pal = dq.quant_recurse(px, 700, 0)
+    assert np.array_equal(pal, ref_pal) and np.array_equal(out, ref_out)
+    assert dq.last_stats()["tie_flags"] == 0
     ctx = dq.lib.dq_default_context()
     px = rng.integers(0, 1 << 24, 6000, dtype=np.uint32)
     with muted():
