@@ -85,6 +85,8 @@ struct dq_context {
   ControlBlock *h_cb = nullptr;  // pinned
   DevBuf<uint32_t> d_in, d_out, d_uniq;
   DevBuf<uint2> d_pts0, d_pts1;
+  DevBuf<uint2> d_flat;         // large tie resolver: the points by position
+  DevBuf<uint32_t> d_sortvals;  // ... and the payload of its sort
   DevBuf<uint64_t> d_keys;
   // sized by K
   DevBuf<SplitNode> d_nodes;
@@ -104,7 +106,7 @@ struct dq_context {
   int exact_parallel = 1;  // the ordered path runs on all CTAs of the split kernel (DIVQUANT_B200_EXACT_PARALLEL=0: CTA 0 only)
   uint32_t exact_max_points = kExactDefaultPoints;  // ... up to this many unique colours (DIVQUANT_B200_EXACT_MAX)
   DevBuf<uint64_t> d_exact;
-  DevBuf<uint32_t> d_tie;  // [4 * kTieListCap] flagged clusters + [kTieListCap] resolver status words
+  DevBuf<uint32_t> d_tie;  // [4 * kTieListCap] flagged clusters + [kTieListCap] resolver status words + a counter
   DevBuf<FrameResult> d_frame;  // frame pipeline: what palette_post hands back (device side)
   // a split that has been launched but whose palette has not been collected yet (run_split / run_split_finish)
   struct PendingSplit {
@@ -129,6 +131,7 @@ struct dq_context {
   // Tie audit of the exact-integer split (dq_tie.cuh): 0 = off, 1 = report in dq_call_stats::tie_flags only,
   // 2 (default) = a flagged frame is computed again in the reference's summation order (DIVQUANT_B200_TIE)
   int tie_policy = 2;
+  int resolve_mode = 3;  // bit 0: the resolver's shared-memory form, bit 1: its large form (DIVQUANT_B200_RESOLVE; testing)
   long long spin_cycles = 0;  // DIVQUANT_B200_SPIN_MS: bound of the split kernel's waits on other CTAs (0 = built-in 0.2 s)
   int split_version = 2;  // 1 = generic kernel, 2 = latency-optimised kernel (falls back to 1 when it cannot run)
   int trace_split = 0;
@@ -304,7 +307,7 @@ uint32_t run_split(dq_context *ctx, uint32_t point_capacity, double norm, uint32
   a.spin_cycles = ctx->spin_cycles;
   a.tie_audit = (weighted && use_v2 && ctx->tie_policy != 0) ? 1u : 0u;
   if (a.tie_audit) {
-    ctx->d_tie.ensure(5 * kTieListCap);
+    ctx->d_tie.ensure(5 * kTieListCap + 4);
     a.tie_list = ctx->d_tie.ptr;
   }
   ctx->mark(2);
@@ -599,7 +602,7 @@ void quantize_begin(dq_context *ctx, uint32_t n, const uint32_t *d_in, uint32_t 
 enum QuantStepResult { kQuantDone = 0, kQuantPending = 1 };
 
 bool quantize_pending_ready(dq_context *ctx) {
-  if (ctx->qs.phase == 1) return cudaEventQuery(ctx->tie_ev) != cudaErrorNotReady;
+  if (ctx->qs.phase == 1 || ctx->qs.phase == 3) return cudaEventQuery(ctx->tie_ev) != cudaErrorNotReady;
   return split_ready(ctx);
 }
 
@@ -621,6 +624,29 @@ QuantStepResult quantize_step(dq_context *ctx, uint32_t *k_inout, uint32_t *colo
     ctx->exact_max_points = keep;
     q.phase = 2;
   };
+  auto queue_big_resolve = [&]() {
+    // the resolver's large form (dq_resolve.cu): chains through nodes of any size, a global sort instead of one in shared memory
+    const uint32_t U = ctx->stats.num_points;
+    uint32_t n_pow2 = 2;
+    while (n_pow2 < U) n_pow2 <<= 1;
+    ctx->d_keys.ensure(n_pow2);
+    ctx->d_sortvals.ensure(n_pow2);
+    ctx->d_flat.ensure(U);
+    uint32_t *d_status = ctx->d_tie.ptr + 4 * kTieListCap;
+    DQ_CUDA_CHECK(cudaMemsetAsync(d_status, 0, kTieListCap * sizeof(uint32_t), ctx->stream));
+    uint2 *pts[2] = {ctx->d_pts0.ptr, ctx->d_pts1.ptr};
+    tie_resolve_big_launch(ctx->d_nodes.ptr, ctx->h_cb->ctl[kCtlNodes], pts, ctx->d_map, U, q.norm, 8 - q.num_bits, ctx->d_tie.ptr,
+                           q.tie_count, ctx->d_keys.ptr, ctx->d_sortvals.ptr, ctx->d_flat.ptr, ctx->d_tie.ptr + 5 * kTieListCap,
+                           ctx->d_palette.ptr, d_status, ctx->sm_count, ctx->stream);
+    uint32_t steps = 0;
+    for (uint32_t k = 2; k <= n_pow2; k <<= 1) steps += (uint32_t)__builtin_ctz(k);
+    ctx->stats.kernel_launches += 3 + steps;
+    DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->h_small + K, d_status, q.tie_count * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->h_small, ctx->d_palette.ptr, (size_t)q.k_first * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    DQ_CUDA_CHECK(cudaEventRecord(ctx->tie_ev, ctx->stream));
+    q.phase = 3;
+  };
   const bool can_rerun = ctx->tie_policy == 2 && q.table_dirty && ctx->exact_small && K <= kExactMaxColors && K <= kSplit2MaxColors &&
                          ctx->split_version == 2;
   if (q.phase == 0) {
@@ -632,20 +658,25 @@ QuantStepResult quantize_step(dq_context *ctx, uint32_t *k_inout, uint32_t *colo
       // Only palette roundings are in doubt (a cluster mean exactly on x.5: the commonest tie by far): the reference's own
       // ordered sums are redone for just the flagged clusters (dq_resolve.cu), on top of a first-seen pass over the pixels.
       q.tie_count = ctx->h_cb->ctl[kCtlTieCount];
-      if (q.tie_count >= 1 && q.tie_count <= kTieListCap) {
+      if (q.tie_count >= 1 && q.tie_count <= kTieListCap && ctx->resolve_mode != 0) {
         first_seen_launch(exact_sampling(q.d_in, q.rows, q.cols, (uint32_t)q.dec, q.num_bits), ctx->d_map, ctx->stream);
+        ctx->stats.kernel_launches++;
+        ctx->ensure_small((size_t)K + 16 + kTieListCap);
+        q.k_first = *k_inout;
+        if (!ctx->tie_ev) DQ_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->tie_ev, cudaEventDisableTiming));
+        if ((ctx->resolve_mode & 1) == 0) {
+          queue_big_resolve();
+          return kQuantPending;
+        }
         uint32_t *d_status = ctx->d_tie.ptr + 4 * kTieListCap;
         DQ_CUDA_CHECK(cudaMemsetAsync(d_status, 0, kTieListCap * sizeof(uint32_t), ctx->stream));
         uint2 *pts[2] = {ctx->d_pts0.ptr, ctx->d_pts1.ptr};
         tie_resolve_launch(ctx->d_nodes.ptr, ctx->h_cb->ctl[kCtlNodes], pts, ctx->d_map, q.norm, 8 - q.num_bits, ctx->d_tie.ptr,
                            q.tie_count, ctx->d_palette.ptr, d_status, ctx->stream);
-        ctx->stats.kernel_launches += 2;
-        ctx->ensure_small((size_t)K + 16 + kTieListCap);
-        q.k_first = *k_inout;
+        ctx->stats.kernel_launches++;
         DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->h_small + K, d_status, q.tie_count * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
         DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->h_small, ctx->d_palette.ptr, (size_t)q.k_first * sizeof(uint32_t), cudaMemcpyDeviceToHost,
                                       ctx->stream));
-        if (!ctx->tie_ev) DQ_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->tie_ev, cudaEventDisableTiming));
         DQ_CUDA_CHECK(cudaEventRecord(ctx->tie_ev, ctx->stream));
         q.phase = 1;
         return kQuantPending;
@@ -657,7 +688,7 @@ QuantStepResult quantize_step(dq_context *ctx, uint32_t *k_inout, uint32_t *colo
     }
     return kQuantDone;  // flagged and not resolvable here (more colours than the ordered path takes): reported in the stats
   }
-  if (q.phase == 1) {
+  if (q.phase == 1 || q.phase == 3) {
     DQ_CUDA_CHECK(cudaEventSynchronize(ctx->tie_ev));  // (already complete when the caller polled)
     bool resolved = true;
     for (uint32_t i = 0; i < q.tie_count; ++i) resolved = resolved && ctx->h_small[K + i] == 1u;
@@ -666,6 +697,10 @@ QuantStepResult quantize_step(dq_context *ctx, uint32_t *k_inout, uint32_t *colo
       *k_inout = q.k_first;
       ctx->stats.tie_resolved = q.tie_count;
       return kQuantDone;
+    }
+    if (q.phase == 1 && (ctx->resolve_mode & 2)) {  // a chain through a large node: the resolver's large form
+      queue_big_resolve();
+      return kQuantPending;
     }
     if (can_rerun && ctx->stats.num_points <= kExactMaxPoints) {
       queue_rerun();
@@ -910,6 +945,7 @@ dq_context *dq_context_create(int device) {
   ctx->display_timings = display_timings_default();
   if (const char *e = getenv("DIVQUANT_B200_SPLIT")) ctx->split_version = (e[0] == '1') ? 1 : 2;
   if (const char *e = getenv("DIVQUANT_B200_TIE")) ctx->tie_policy = std::min(std::max(atoi(e), 0), 2);
+  if (const char *e = getenv("DIVQUANT_B200_RESOLVE")) ctx->resolve_mode = atoi(e) & 3;
   if (const char *e = getenv("DIVQUANT_B200_SPIN_MS")) ctx->spin_cycles = (long long)std::max(atol(e), 0l) * 2000000ll;  // ~2 GHz
   if (const char *e = getenv("DIVQUANT_B200_EXACT_SMALL")) ctx->exact_small = (e[0] != '0');
   if (const char *e = getenv("DIVQUANT_B200_EXACT_PARALLEL")) ctx->exact_parallel = (e[0] != '0');
@@ -956,6 +992,8 @@ void dq_context_destroy(dq_context *ctx) {
   ctx->d_progress.release();
   ctx->d_exact.release();
   ctx->d_tie.release();
+  ctx->d_flat.release();
+  ctx->d_sortvals.release();
   ctx->d_frame.release();
   cudaFree(ctx->d_table);
   cudaFree(ctx->d_map);

@@ -298,8 +298,8 @@ void table_clear(const uint32_t *d_uniq, const uint32_t *d_ucount, uint32_t u_hi
   DQ_CUDA_CHECK(cudaGetLastError());
 }
 
-void order_sort_emit(const uint2 *d_pts, uint32_t u, uint64_t *d_keys, uint32_t *d_vals, double norm, uint32_t *d_colours,
-                     double *d_weights, int sm_count, cudaStream_t st) {
+// Sorts d_keys[0..u) ascending with d_vals = the index each key came from (both arrays hold the power of two >= u entries).
+void order_sort(uint64_t *d_keys, uint32_t *d_vals, uint32_t u, int sm_count, cudaStream_t st) {
   if (u == 0) return;
   uint32_t n_pow2 = 2;
   while (n_pow2 < u) n_pow2 <<= 1;
@@ -307,6 +307,13 @@ void order_sort_emit(const uint2 *d_pts, uint32_t u, uint64_t *d_keys, uint32_t 
   for (uint32_t k = 2; k <= n_pow2; k <<= 1)
     for (uint32_t j = k >> 1; j > 0; j >>= 1)
       bitonic_step_kernel<<<blocks_for(n_pow2 >> 1, 256, sm_count, 8), 256, 0, st>>>(d_keys, d_vals, n_pow2, j, k);
+  DQ_CUDA_CHECK(cudaGetLastError());
+}
+
+void order_sort_emit(const uint2 *d_pts, uint32_t u, uint64_t *d_keys, uint32_t *d_vals, double norm, uint32_t *d_colours,
+                     double *d_weights, int sm_count, cudaStream_t st) {
+  if (u == 0) return;
+  order_sort(d_keys, d_vals, u, sm_count, st);
   order_emit_kernel<<<blocks_for(u, 256, sm_count, 8), 256, 0, st>>>(d_pts, d_vals, u, norm, d_colours, d_weights);
   DQ_CUDA_CHECK(cudaGetLastError());
 }

@@ -21,6 +21,7 @@ void order_keys(const uint32_t *d_in, uint32_t num_rows, uint32_t num_cols, uint
 
 // Sorts the u (unique) keys of order_keys with their point index (d_keys / d_vals need room for the next power of two),
 // then writes the unique colours and their weights norm * count in that order: calc_color_table's output, on the device.
+void order_sort(uint64_t *d_keys, uint32_t *d_vals, uint32_t u, int sm_count, cudaStream_t st);
 void order_sort_emit(const uint2 *d_pts, uint32_t u, uint64_t *d_keys, uint32_t *d_vals, double norm, uint32_t *d_colours,
                      double *d_weights, int sm_count, cudaStream_t st);
 void hist_export(const uint2 *d_pts, const uint32_t *d_ucount, uint32_t u_hint, uint32_t *d_colours, uint32_t *d_counts,

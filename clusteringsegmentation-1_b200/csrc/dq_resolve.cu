@@ -11,10 +11,13 @@
 // and all of them lie inside the top node of that chain.  So one CTA per flagged cluster: collect the top node's points
 // from the leaves below it, sort them into emission order (first-seen index from the first-seen pass), add the chains
 // sequentially -- one thread per (set, accumulator) -- and replay the scalar formulas down the chain.
-// Chains through large nodes (more than kResolveMax points, e.g. the ever-shrinking cluster 0 of a 4K frame) are not
-// handled here: status 2, and the host re-runs the frame on the ordered path.
+// Chains through large nodes (more than kResolveMax points, e.g. the ever-shrinking cluster 0 of a 4K frame) get status 2
+// from that kernel and go through the large form below: the points under the top nodes are put into emission order by a
+// global sort (any number of them), and one warp per 8 sets streams the sorted list, lane = (set, accumulator).
+#include <algorithm>
 #include <cfloat>
 
+#include "dq_kernels.cuh"
 #include "dq_split_math.cuh"
 
 namespace dq {
@@ -49,13 +52,75 @@ struct ResolveShared {
   int32_t n_leaves, n_sib, top, fail, top_is_root;
 };
 
-__device__ __forceinline__ SplitNode load_node_g(const SplitNode *nodes, int id) {
-  SplitNode nd;
-  const double *src = reinterpret_cast<const double *>(nodes + id);
-  double *dst = reinterpret_cast<double *>(&nd);
-#pragma unroll
-  for (int i = 0; i < (int)(sizeof(SplitNode) / 8); ++i) dst[i] = __ldcg(src + i);
-  return nd;
+// The chain of "old" sides above node_x: S.sib[] = the "new" siblings whose sums the chain was derived from, S.top = the node
+// whose statistics are its own sums (a "new" side, or the root), S.sib_begin/size[0] = its range, [k + 1] = sibling k's.
+// Thread 0 only.
+template <class SH>
+__device__ __forceinline__ void walk_chain(SH &S, int node_x) {
+  S.fail = 0;
+  S.n_sib = 0;
+  S.top_is_root = 0;
+  int cur = node_x;
+  for (;;) {
+    const int p = S.nd_parent[cur];
+    if (p < 0) {  // the root: its statistics are sums over every point (:60-104)
+      S.top_is_root = 1;
+      break;
+    }
+    const int child0 = S.nd_child[p];
+    if (cur == child0 + 1) break;  // a "new" side: its statistics are its own sums
+    if (S.n_sib >= kResolveChain) {
+      S.fail = 1;
+      break;
+    }
+    S.sib[S.n_sib++] = child0 + 1;  // the sibling whose sums this "old" side was derived from
+    cur = p;
+  }
+  S.top = cur;
+  if (S.nd_size[cur] == 0u) S.fail = 1;
+  S.sib_begin[0] = S.nd_begin[cur];
+  S.sib_size[0] = S.nd_size[cur];
+  for (int k = 0; k < S.n_sib && !S.fail; ++k) {
+    S.sib_begin[k + 1] = S.nd_begin[S.sib[k]];
+    S.sib_size[k + 1] = S.nd_size[S.sib[k]];
+  }
+}
+
+template <class SH>
+__device__ __forceinline__ void stage_nodes(SH &S, const SplitNode *nodes, uint32_t num_nodes, int tid, int threads) {
+  for (uint32_t i = tid; i < num_nodes; i += threads) {
+    const SplitNode *nd = nodes + i;
+    S.nd_begin[i] = __ldcg(&nd->begin);
+    S.nd_size[i] = __ldcg(&nd->size);
+    S.nd_parent[i] = (int16_t)__ldcg(&nd->parent);
+    S.nd_child[i] = (int16_t)__ldcg(&nd->child);
+  }
+}
+
+// The scalar formulas down the chain from S.sums (set 0 = the top node), and the palette word (:1050-1052).
+template <class SH>
+__device__ __forceinline__ uint32_t replay_chain(const SH &S, int shift) {
+  double tw, tm[3];
+  if (S.top_is_root) {
+    tw = 1.0;  // weight[0] = 1.0 (:343); the root's means are the plain sums (:107-112)
+    for (int c = 0; c < 3; ++c) tm[c] = S.sums[0][c];
+  } else {
+    tw = S.sums[0][3];
+    for (int c = 0; c < 3; ++c) tm[c] = fdiv(S.sums[0][c], tw);
+  }
+  for (int k = S.n_sib - 1; k >= 0; --k) {  // from the top node down to the flagged cluster
+    const double nw = S.sums[k + 1][3];
+    const double ow = fsub(tw, nw);
+    for (int c = 0; c < 3; ++c) {
+      const double nm = fdiv(S.sums[k + 1][c], nw);
+      tm[c] = fdiv(fsub(fmul(tw, tm[c]), fmul(nw, nm)), ow);  // 'combined mean' (:579-581, :805-810)
+    }
+    tw = ow;
+  }
+  const uint32_t Rr = (__double2uint_rz(fadd(tm[0], 0.5)) & 0xFFu) << shift;
+  const uint32_t Gg = (__double2uint_rz(fadd(tm[1], 0.5)) & 0xFFu) << shift;
+  const uint32_t Bb = (__double2uint_rz(fadd(tm[2], 0.5)) & 0xFFu) << shift;
+  return (Rr << 16) | (Gg << 8) | Bb;
 }
 
 __global__ void __launch_bounds__(kResolveThreads) tie_resolve_kernel(const SplitNode *nodes, uint2 *pts0, uint2 *pts1,
@@ -82,33 +147,9 @@ __global__ void __launch_bounds__(kResolveThreads) tie_resolve_kernel(const Spli
   __syncthreads();
   // ---- the chain of "old" sides above the flagged cluster, and the leaves below its top node ----
   if (tid == 0) {
-    S.fail = 0;
-    S.n_sib = 0;
-    S.top_is_root = 0;
-    int cur = node_x;
-    for (;;) {
-      const int p = S.nd_parent[cur];
-      if (p < 0) {  // the root: its statistics are sums over every point (:60-104)
-        S.top_is_root = 1;
-        break;
-      }
-      const int child0 = S.nd_child[p];
-      if (cur == child0 + 1) break;  // a "new" side: its statistics are its own sums
-      if (S.n_sib >= kResolveChain) {
-        S.fail = 1;
-        break;
-      }
-      S.sib[S.n_sib++] = child0 + 1;  // the sibling whose sums this "old" side was derived from
-      cur = p;
-    }
-    S.top = cur;
-    if (S.nd_size[cur] > (uint32_t)kResolveMax || S.nd_size[cur] == 0u) S.fail = 1;
-    S.sib_begin[0] = S.nd_begin[cur];
-    S.sib_size[0] = S.nd_size[cur];
-    for (int k = 0; k < S.n_sib && !S.fail; ++k) {
-      S.sib_begin[k + 1] = S.nd_begin[S.sib[k]];
-      S.sib_size[k + 1] = S.nd_size[S.sib[k]];
-    }
+    walk_chain(S, node_x);
+    const int cur = S.top;
+    if (S.nd_size[cur] > (uint32_t)kResolveMax) S.fail = 1;
     // leaves below the top node (depth-first, explicit stack)
     S.n_leaves = 0;
     if (!S.fail) {
@@ -239,27 +280,145 @@ __global__ void __launch_bounds__(kResolveThreads) tie_resolve_kernel(const Spli
   __syncthreads();
   // ---- the scalar formulas down the chain ----
   if (tid == 0) {
-    double tw, tm[3];
-    if (S.top_is_root) {
-      tw = 1.0;  // weight[0] = 1.0 (:343); the root's means are the plain sums (:107-112)
-      for (int c = 0; c < 3; ++c) tm[c] = S.sums[0][c];
-    } else {
-      tw = S.sums[0][3];
-      for (int c = 0; c < 3; ++c) tm[c] = fdiv(S.sums[0][c], tw);
+    palette[slot] = replay_chain(S, shift);
+    status[item] = 1u;
+  }
+}
+
+
+// ---- large form -------------------------------------------------------------------------------------------------------
+// Three steps on the stream, any number of points:
+//   flatten   every leaf copies its segment to one flat array (a node's range [begin, begin + size) is the same in either
+//             buffer, so position p names a point and a set is a range of positions); points under the top node of some
+//             flagged cluster get their emission-order key (bucket asc, first seen desc), all others the padding key
+//   sort      keys with the position as payload (order_sort: global bitonic network, dq_hist.cu)
+//   stream    one CTA per flagged cluster; lane = (set, accumulator) as above, 32 of them per warp; a warp reads the sorted
+//             positions 32 at a time, gathers their points (one ahead), and hands the ones inside the top node's range
+//             around by shuffle, each lane adding its term or +0.0 -- the reference's sum, add for add.
+constexpr int kBigThreads = 32 * ((4 * (kResolveChain + 1) + 31) / 32);  // every (set, accumulator) has a lane
+
+struct BigShared {
+  uint32_t nd_begin[kResolveNodes], nd_size[kResolveNodes];
+  int16_t nd_parent[kResolveNodes], nd_child[kResolveNodes];
+  double sums[kResolveChain + 1][4];
+  int32_t sib[kResolveChain];
+  uint32_t sib_begin[kResolveChain + 1], sib_size[kResolveChain + 1];
+  int32_t n_sib, top, fail, top_is_root;
+  uint32_t range_lo[kTieListCap], range_hi[kTieListCap];
+  int32_t n_ranges;
+};
+
+__global__ void __launch_bounds__(256) resolve_flatten_kernel(const SplitNode *nodes, uint32_t num_nodes, const uint2 *pts0,
+                                                             const uint2 *pts1, const uint32_t *first_seen, const uint32_t *list,
+                                                             uint32_t count, unsigned long long *keys, uint2 *flat,
+                                                             uint32_t *in_range_total) {
+  extern __shared__ __align__(16) unsigned char resolve_smem[];
+  BigShared &S = *reinterpret_cast<BigShared *>(resolve_smem);
+  const int tid = threadIdx.x;
+  if (num_nodes > (uint32_t)kResolveNodes) return;  // (the stream kernel reports it)
+  stage_nodes(S, nodes, num_nodes, tid, 256);
+  __syncthreads();
+  if (tid == 0) {
+    S.n_ranges = 0;
+    for (uint32_t it = 0; it < count; ++it) {
+      walk_chain(S, (int)list[4 * it + 1]);
+      if (S.fail) continue;
+      S.range_lo[S.n_ranges] = S.sib_begin[0];
+      S.range_hi[S.n_ranges] = S.sib_begin[0] + S.sib_size[0];
+      S.n_ranges++;
     }
-    for (int k = S.n_sib - 1; k >= 0; --k) {  // from the top node down to the flagged cluster
-      const double nw = S.sums[k + 1][3];
-      const double ow = fsub(tw, nw);
-      for (int c = 0; c < 3; ++c) {
-        const double nm = fdiv(S.sums[k + 1][c], nw);
-        tm[c] = fdiv(fsub(fmul(tw, tm[c]), fmul(nw, nm)), ow);  // 'combined mean' (:579-581, :805-810)
+  }
+  __syncthreads();
+  const int n_ranges = S.n_ranges;
+  uint32_t mine = 0;
+  for (uint32_t nd = blockIdx.x; nd < num_nodes; nd += gridDim.x) {
+    if (S.nd_child[nd] >= 0) continue;  // leaves only
+    const uint32_t lb = S.nd_begin[nd], ls = S.nd_size[nd];
+    const uint2 *src = (__ldcg(&nodes[nd].buf) ? pts1 : pts0) + lb;
+    for (uint32_t i = tid; i < ls; i += 256) {
+      const uint2 p = __ldcg(src + i);
+      const uint32_t pos = lb + i;
+      flat[pos] = p;
+      bool wanted = false;
+      for (int r = 0; r < n_ranges; ++r) wanted = wanted || (pos >= S.range_lo[r] && pos < S.range_hi[r]);
+      unsigned long long key = ~0ull;
+      if (wanted) {
+        const uint32_t c = p.x;
+        const long R = (c >> 16) & 0xFF, G = (c >> 8) & 0xFF, B = c & 0xFF;
+        const unsigned long long bucket = (unsigned long long)(((R * 33023 + G * 30013 + B * 27011) & 0x7fffffff) % 20023);
+        key = (bucket << 31) | (unsigned long long)(0x7FFFFFFFu - __ldcg(first_seen + c));
+        ++mine;
       }
-      tw = ow;
+      keys[pos] = key;
     }
-    const uint32_t Rr = (__double2uint_rz(fadd(tm[0], 0.5)) & 0xFFu) << shift;
-    const uint32_t Gg = (__double2uint_rz(fadd(tm[1], 0.5)) & 0xFFu) << shift;
-    const uint32_t Bb = (__double2uint_rz(fadd(tm[2], 0.5)) & 0xFFu) << shift;
-    palette[slot] = (Rr << 16) | (Gg << 8) | Bb;
+  }
+  // how many keys are real: the stream stops there
+  for (int off = 16; off > 0; off >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, off);
+  if ((tid & 31) == 0 && mine) atomicAdd(in_range_total, mine);
+}
+
+__global__ void __launch_bounds__(kBigThreads) tie_resolve_big_kernel(const SplitNode *nodes, uint32_t num_nodes,
+                                                                      const uint32_t *__restrict__ sorted_pos,
+                                                                      const uint2 *__restrict__ flat, const uint32_t *in_range_total,
+                                                                      double norm, int shift, const uint32_t *list,
+                                                                      uint32_t *palette, uint32_t *status) {
+  extern __shared__ __align__(16) unsigned char resolve_smem[];
+  BigShared &S = *reinterpret_cast<BigShared *>(resolve_smem);
+  const int tid = threadIdx.x, lane = tid & 31, item = blockIdx.x;
+  const int node_x = (int)list[4 * item + 1], slot = (int)list[4 * item + 2];
+  if (num_nodes > (uint32_t)kResolveNodes) {
+    if (tid == 0) status[item] = 2u;
+    return;
+  }
+  stage_nodes(S, nodes, num_nodes, tid, kBigThreads);
+  __syncthreads();
+  if (tid == 0) walk_chain(S, node_x);
+  __syncthreads();
+  if (S.fail) {
+    if (tid == 0) status[item] = 2u;
+    return;
+  }
+  const uint32_t total = __ldcg(in_range_total);
+  const uint32_t t_lo = S.sib_begin[0], t_hi = t_lo + S.sib_size[0];
+  const int n_sets = S.n_sib + 1;
+  const int set = tid >> 2, chain = tid & 3;
+  const bool live = set < n_sets;
+  const uint32_t lo = live ? S.sib_begin[set] : 0u, hi = live ? lo + S.sib_size[set] : 0u;
+  const int sh = 16 - 8 * chain;
+  if ((tid & ~31) < 4 * n_sets) {  // warps with at least one live lane
+    double acc = 0.0;
+    // one block of 32 sorted positions ahead: its gather is in flight while the current block is added
+    uint32_t pos_n = 0xFFFFFFFFu;
+    uint2 pt_n = make_uint2(0u, 0u);
+    if ((uint32_t)lane < total) {
+      pos_n = __ldg(sorted_pos + lane);
+      if (pos_n >= t_lo && pos_n < t_hi) pt_n = __ldg(flat + pos_n);
+    }
+    for (uint32_t r0 = 0; r0 < total; r0 += 32) {
+      const uint32_t pos = pos_n;
+      const uint2 pt = pt_n;
+      pos_n = 0xFFFFFFFFu;
+      if (r0 + 32 + lane < total) {
+        pos_n = __ldg(sorted_pos + r0 + 32 + lane);
+        if (pos_n >= t_lo && pos_n < t_hi) pt_n = __ldg(flat + pos_n);
+      }
+      const double w = fmul(norm, (double)(int)pt.y);  // weights[i] = norm * count (MapColors.cpp:185)
+      unsigned inside = __ballot_sync(0xffffffffu, pos >= t_lo && pos < t_hi);
+      while (inside) {
+        const int q = __ffs(inside) - 1;
+        inside &= inside - 1u;
+        const uint32_t pq = __shfl_sync(0xffffffffu, pos, q);
+        const uint32_t cq = __shfl_sync(0xffffffffu, pt.x, q);
+        const double wq = __shfl_sync(0xffffffffu, w, q);
+        const double term = (chain == 3) ? wq : fmul(wq, byte_to_double((cq >> sh) & 0xFFu));
+        acc = fadd(acc, (pq >= lo && pq < hi) ? term : 0.0);
+      }
+    }
+    if (live) S.sums[set][chain] = acc;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    palette[slot] = replay_chain(S, shift);
     status[item] = 1u;
   }
 }
@@ -271,6 +430,22 @@ void tie_resolve_launch(const SplitNode *d_nodes, uint32_t num_nodes, uint2 *con
   DQ_RAISE_SMEM(tie_resolve_kernel, sizeof(ResolveShared));
   tie_resolve_kernel<<<count, kResolveThreads, sizeof(ResolveShared), st>>>(d_nodes, pts[0], pts[1], d_first_seen, norm, shift,
                                                                             d_list, num_nodes, d_palette, d_status);
+  DQ_CUDA_CHECK(cudaGetLastError());
+}
+
+// The large form: d_keys [n_pow2], d_vals [n_pow2], d_flat [U], d_counter [1] are scratch; n_pow2 = the power of two >= U.
+void tie_resolve_big_launch(const SplitNode *d_nodes, uint32_t num_nodes, uint2 *const *pts, const uint32_t *d_first_seen, uint32_t u,
+                            double norm, int shift, const uint32_t *d_list, uint32_t count, uint64_t *d_keys, uint32_t *d_vals,
+                            uint2 *d_flat, uint32_t *d_counter, uint32_t *d_palette, uint32_t *d_status, int sm_count,
+                            cudaStream_t st) {
+  DQ_CUDA_CHECK(cudaMemsetAsync(d_counter, 0, sizeof(uint32_t), st));
+  DQ_RAISE_SMEM(resolve_flatten_kernel, sizeof(BigShared));
+  DQ_RAISE_SMEM(tie_resolve_big_kernel, sizeof(BigShared));
+  resolve_flatten_kernel<<<std::min<uint32_t>(num_nodes, (uint32_t)(4 * sm_count)), 256, sizeof(BigShared), st>>>(
+      d_nodes, num_nodes, pts[0], pts[1], d_first_seen, d_list, count, reinterpret_cast<unsigned long long *>(d_keys), d_flat, d_counter);
+  order_sort(d_keys, d_vals, u, sm_count, st);
+  tie_resolve_big_kernel<<<count, kBigThreads, sizeof(BigShared), st>>>(d_nodes, num_nodes, d_vals, d_flat, d_counter, norm, shift, d_list, d_palette,
+                                                        d_status);
   DQ_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -169,6 +169,12 @@ ExactSampling exact_sampling(const uint32_t *d_in, uint32_t num_rows, uint32_t n
 // clusters whose rounding the tie audit flagged.  d_status[i]: 1 = palette[slot] rewritten, 2 = not resolvable here.
 void tie_resolve_launch(const SplitNode *d_nodes, uint32_t num_nodes, uint2 *const *pts, const uint32_t *d_first_seen, double norm,
                         int shift, const uint32_t *d_list, uint32_t count, uint32_t *d_palette, uint32_t *d_status, cudaStream_t st);
+// The same for chains through nodes of any size (global sort of the points under the top nodes, one streaming pass).
+// Scratch: d_keys / d_vals hold the power of two >= u entries, d_flat u points, d_counter one word.
+void tie_resolve_big_launch(const SplitNode *d_nodes, uint32_t num_nodes, uint2 *const *pts, const uint32_t *d_first_seen, uint32_t u,
+                            double norm, int shift, const uint32_t *d_list, uint32_t count, uint64_t *d_keys, uint32_t *d_vals,
+                            uint2 *d_flat, uint32_t *d_counter, uint32_t *d_palette, uint32_t *d_status, int sm_count,
+                            cudaStream_t st);
 // first-seen pass alone (dq_split_exact.cu): smallest sample index of every colour into d_first_seen
 void first_seen_launch(const ExactSampling &q, uint32_t *d_first_seen, cudaStream_t st);
 size_t split_exact_smem_bytes();

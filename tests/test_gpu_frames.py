@@ -80,3 +80,21 @@ def test_audit_off_reproduces_the_known_mismatch(dq, oracle, frames):
         assert st["tie_flags"] & 16 and st["ordered_rerun"] == 0
     finally:
         lib.dq_context_set_tie_policy(ctx, 2)
+
+
+def test_resolver_large_form_alone(frames):
+    """DIVQUANT_B200_RESOLVE=2 skips the resolver's shared-memory form, so every palette-rounding flag goes through the
+    large one (global sort + streaming chains, csrc/dq_resolve.cu), which otherwise only serves chains through nodes of more
+    than 8192 points: the three flagged config-4 frames and a flagged 4K bench frame must still equal the reference."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, DIVQUANT_B200_RESOLVE="2")
+    for tag, seeds in (("c4", ["12410", "12830", "13124"]), ("bench", ["12359"])):
+        res = subprocess.run([sys.executable, os.path.join(root, "tools", "check_seeds.py"), tag] + seeds, env=env,
+                             capture_output=True, text=True, timeout=600)
+        assert res.returncode == 0, res.stderr[-1500:]
+        lines = [ln for ln in res.stdout.splitlines() if ln[:5].isdigit()]
+        assert len(lines) == len(seeds), res.stdout
+        for ln in lines:
+            assert "pal ok" in ln and "out ok" in ln and "'tie_resolved': 0" not in ln and "'ordered_rerun': 0" in ln, ln
