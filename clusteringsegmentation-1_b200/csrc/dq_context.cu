@@ -106,7 +106,7 @@ struct dq_context {
   int exact_parallel = 1;  // the ordered path runs on all CTAs of the split kernel (DIVQUANT_B200_EXACT_PARALLEL=0: CTA 0 only)
   uint32_t exact_max_points = kExactDefaultPoints;  // ... up to this many unique colours (DIVQUANT_B200_EXACT_MAX)
   DevBuf<uint64_t> d_exact;
-  DevBuf<uint32_t> d_tie;  // [4 * kTieListCap] flagged clusters + [kTieListCap] resolver status words + a counter
+  DevBuf<uint32_t> d_tie;  // flagged clusters / nodes, resolver status words, a counter (layout: dq_split.cuh, kTieListWords)
   DevBuf<FrameResult> d_frame;  // frame pipeline: what palette_post hands back (device side)
   // a split that has been launched but whose palette has not been collected yet (run_split / run_split_finish)
   struct PendingSplit {
@@ -125,7 +125,7 @@ struct dq_context {
     double *mean_out = nullptr;
     uint32_t *size_out = nullptr;
     int phase = 0;  // quantize_step
-    uint32_t flags = 0, tie_count = 0, k_first = 0;
+    uint32_t flags = 0, tie_count = 0, cut_count = 0, k_first = 0;
   } qs;
   cudaEvent_t tie_ev = nullptr;
   // Tie audit of the exact-integer split (dq_tie.cuh): 0 = off, 1 = report in dq_call_stats::tie_flags only,
@@ -307,7 +307,7 @@ uint32_t run_split(dq_context *ctx, uint32_t point_capacity, double norm, uint32
   a.spin_cycles = ctx->spin_cycles;
   a.tie_audit = (weighted && use_v2 && ctx->tie_policy != 0) ? 1u : 0u;
   if (a.tie_audit) {
-    ctx->d_tie.ensure(5 * kTieListCap + 4);
+    ctx->d_tie.ensure(kTieListWords);
     a.tie_list = ctx->d_tie.ptr;
   }
   ctx->mark(2);
@@ -589,7 +589,7 @@ void quantize_begin(dq_context *ctx, uint32_t n, const uint32_t *d_in, uint32_t 
   q.num_bits = num_bits, q.dec = dec, q.max_iters = max_iters, q.norm = norm, q.table_dirty = table_dirty;
   q.records = records, q.mean_out = mean_out, q.size_out = size_out;
   q.phase = 0;
-  q.flags = q.tie_count = q.k_first = 0;
+  q.flags = q.tie_count = q.cut_count = q.k_first = 0;
 }
 
 // Second half, as a small state machine so that a host thread that drives several contexts never has to wait inside it:
@@ -632,16 +632,17 @@ QuantStepResult quantize_step(dq_context *ctx, uint32_t *k_inout, uint32_t *colo
     ctx->d_keys.ensure(n_pow2);
     ctx->d_sortvals.ensure(n_pow2);
     ctx->d_flat.ensure(U);
-    uint32_t *d_status = ctx->d_tie.ptr + 4 * kTieListCap;
-    DQ_CUDA_CHECK(cudaMemsetAsync(d_status, 0, kTieListCap * sizeof(uint32_t), ctx->stream));
+    uint32_t *d_status = ctx->d_tie.ptr + kTieStatus;
+    DQ_CUDA_CHECK(cudaMemsetAsync(d_status, 0, 2 * kTieListCap * sizeof(uint32_t), ctx->stream));
     uint2 *pts[2] = {ctx->d_pts0.ptr, ctx->d_pts1.ptr};
     tie_resolve_big_launch(ctx->d_nodes.ptr, ctx->h_cb->ctl[kCtlNodes], pts, ctx->d_map, U, q.norm, 8 - q.num_bits, ctx->d_tie.ptr,
-                           q.tie_count, ctx->d_keys.ptr, ctx->d_sortvals.ptr, ctx->d_flat.ptr, ctx->d_tie.ptr + 5 * kTieListCap,
-                           ctx->d_palette.ptr, d_status, ctx->sm_count, ctx->stream);
+                           q.tie_count, q.cut_count, ctx->d_keys.ptr, ctx->d_sortvals.ptr, ctx->d_flat.ptr,
+                           ctx->d_tie.ptr + kTieCounter, ctx->d_palette.ptr, d_status, ctx->sm_count, ctx->stream);
     uint32_t steps = 0;
     for (uint32_t k = 2; k <= n_pow2; k <<= 1) steps += (uint32_t)__builtin_ctz(k);
     ctx->stats.kernel_launches += 3 + steps;
-    DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->h_small + K, d_status, q.tie_count * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->h_small + K, d_status, (q.tie_count + q.cut_count) * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                  ctx->stream));
     DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->h_small, ctx->d_palette.ptr, (size_t)q.k_first * sizeof(uint32_t), cudaMemcpyDeviceToHost,
                                   ctx->stream));
     DQ_CUDA_CHECK(cudaEventRecord(ctx->tie_ev, ctx->stream));
@@ -653,28 +654,34 @@ QuantStepResult quantize_step(dq_context *ctx, uint32_t *k_inout, uint32_t *colo
     *k_inout = run_split_finish(ctx, colortable, q.records, q.mean_out, q.size_out);
     q.flags = ctx->stats.tie_flags;
     if (q.flags == 0u) return kQuantDone;
-    if (q.flags == (uint32_t)kTieRound && ctx->tie_policy == 2 && q.table_dirty && ctx->exact_small && q.records == nullptr &&
-        q.mean_out == nullptr) {
+    if ((q.flags & ~(uint32_t)(kTieRound | kTieCut)) == 0u && ctx->tie_policy == 2 && q.table_dirty && ctx->exact_small &&
+        q.records == nullptr && q.mean_out == nullptr) {
       // Only palette roundings are in doubt (a cluster mean exactly on x.5: the commonest tie by far): the reference's own
       // ordered sums are redone for just the flagged clusters (dq_resolve.cu), on top of a first-seen pass over the pixels.
+      // Palette roundings and cuts are in doubt, nothing else (by far the commonest flags): both hang on the mean of ONE node,
+      // which the resolver recomputes in the reference's arithmetic (dq_resolve.cu) on top of a first-seen pass over the pixels.
+      // A rounding is rewritten; a cut either separates the same points as the reference's (nothing to do) or it does not
+      // (status 3: the frame has to be computed again).
       q.tie_count = ctx->h_cb->ctl[kCtlTieCount];
-      if (q.tie_count >= 1 && q.tie_count <= kTieListCap && ctx->resolve_mode != 0) {
+      q.cut_count = ctx->h_cb->ctl[kCtlCutCount];
+      if (q.tie_count + q.cut_count >= 1 && q.tie_count <= kTieListCap && q.cut_count <= kTieListCap && ctx->resolve_mode != 0) {
         first_seen_launch(exact_sampling(q.d_in, q.rows, q.cols, (uint32_t)q.dec, q.num_bits), ctx->d_map, ctx->stream);
         ctx->stats.kernel_launches++;
-        ctx->ensure_small((size_t)K + 16 + kTieListCap);
+        ctx->ensure_small((size_t)K + 16 + 2 * kTieListCap);
         q.k_first = *k_inout;
         if (!ctx->tie_ev) DQ_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->tie_ev, cudaEventDisableTiming));
         if ((ctx->resolve_mode & 1) == 0) {
           queue_big_resolve();
           return kQuantPending;
         }
-        uint32_t *d_status = ctx->d_tie.ptr + 4 * kTieListCap;
-        DQ_CUDA_CHECK(cudaMemsetAsync(d_status, 0, kTieListCap * sizeof(uint32_t), ctx->stream));
+        uint32_t *d_status = ctx->d_tie.ptr + kTieStatus;
+        DQ_CUDA_CHECK(cudaMemsetAsync(d_status, 0, 2 * kTieListCap * sizeof(uint32_t), ctx->stream));
         uint2 *pts[2] = {ctx->d_pts0.ptr, ctx->d_pts1.ptr};
         tie_resolve_launch(ctx->d_nodes.ptr, ctx->h_cb->ctl[kCtlNodes], pts, ctx->d_map, q.norm, 8 - q.num_bits, ctx->d_tie.ptr,
-                           q.tie_count, ctx->d_palette.ptr, d_status, ctx->stream);
+                           q.tie_count, q.cut_count, ctx->d_palette.ptr, d_status, ctx->stream);
         ctx->stats.kernel_launches++;
-        DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->h_small + K, d_status, q.tie_count * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->h_small + K, d_status, (q.tie_count + q.cut_count) * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                      ctx->stream));
         DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->h_small, ctx->d_palette.ptr, (size_t)q.k_first * sizeof(uint32_t), cudaMemcpyDeviceToHost,
                                       ctx->stream));
         DQ_CUDA_CHECK(cudaEventRecord(ctx->tie_ev, ctx->stream));
@@ -690,15 +697,18 @@ QuantStepResult quantize_step(dq_context *ctx, uint32_t *k_inout, uint32_t *colo
   }
   if (q.phase == 1 || q.phase == 3) {
     DQ_CUDA_CHECK(cudaEventSynchronize(ctx->tie_ev));  // (already complete when the caller polled)
-    bool resolved = true;
-    for (uint32_t i = 0; i < q.tie_count; ++i) resolved = resolved && ctx->h_small[K + i] == 1u;
+    bool resolved = true, differs = false;
+    for (uint32_t i = 0; i < q.tie_count + q.cut_count; ++i) {
+      resolved = resolved && ctx->h_small[K + i] == 1u;
+      differs = differs || ctx->h_small[K + i] == 3u;  // a cut the reference makes elsewhere: only a re-run helps
+    }
     if (resolved) {
       memcpy(colortable, ctx->h_small, (size_t)q.k_first * sizeof(uint32_t));
       *k_inout = q.k_first;
-      ctx->stats.tie_resolved = q.tie_count;
+      ctx->stats.tie_resolved = q.tie_count + q.cut_count;
       return kQuantDone;
     }
-    if (q.phase == 1 && (ctx->resolve_mode & 2)) {  // a chain through a large node: the resolver's large form
+    if (q.phase == 1 && !differs && (ctx->resolve_mode & 2)) {  // a chain through a large node: the resolver's large form
       queue_big_resolve();
       return kQuantPending;
     }

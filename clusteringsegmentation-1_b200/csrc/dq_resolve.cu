@@ -97,10 +97,10 @@ __device__ __forceinline__ void stage_nodes(SH &S, const SplitNode *nodes, uint3
   }
 }
 
-// The scalar formulas down the chain from S.sums (set 0 = the top node), and the palette word (:1050-1052).
+// The scalar formulas down the chain from S.sums (set 0 = the top node): the node's mean as the reference holds it.
 template <class SH>
-__device__ __forceinline__ uint32_t replay_chain(const SH &S, int shift) {
-  double tw, tm[3];
+__device__ __forceinline__ void replay_chain(const SH &S, double *tm) {
+  double tw;
   if (S.top_is_root) {
     tw = 1.0;  // weight[0] = 1.0 (:343); the root's means are the plain sums (:107-112)
     for (int c = 0; c < 3; ++c) tm[c] = S.sums[0][c];
@@ -108,7 +108,7 @@ __device__ __forceinline__ uint32_t replay_chain(const SH &S, int shift) {
     tw = S.sums[0][3];
     for (int c = 0; c < 3; ++c) tm[c] = fdiv(S.sums[0][c], tw);
   }
-  for (int k = S.n_sib - 1; k >= 0; --k) {  // from the top node down to the flagged cluster
+  for (int k = S.n_sib - 1; k >= 0; --k) {  // from the top node down to the flagged node
     const double nw = S.sums[k + 1][3];
     const double ow = fsub(tw, nw);
     for (int c = 0; c < 3; ++c) {
@@ -117,20 +117,46 @@ __device__ __forceinline__ uint32_t replay_chain(const SH &S, int shift) {
     }
     tw = ow;
   }
+}
+
+// What the resolved mean settles.  A rounding entry (item < n_round): the palette word (:1050-1052), status 1.
+// A cut entry: the split of this node sent a point to the new side iff  cut_pos < value  (:473) with cut_pos = the mean on
+// the cut axis; the values are integers, so the reference's cut and this kernel's separate the same points iff they
+// have the same floor: status 1 (nothing to change) or 3 (the reference splits this node differently).
+template <class SH>
+__device__ __forceinline__ void settle(const SH &S, const SplitNode *nodes, int node_x, bool is_cut, int slot, int shift,
+                                       uint32_t *palette, uint32_t *status_word) {
+  double tm[3];
+  replay_chain(S, tm);
+  if (is_cut) {
+    const int axis = __ldcg(&nodes[node_x].axis);
+    const double cut_here = __ldcg(&nodes[node_x].cut);
+    *status_word = (floor(tm[axis]) == floor(cut_here)) ? 1u : 3u;
+    return;
+  }
   const uint32_t Rr = (__double2uint_rz(fadd(tm[0], 0.5)) & 0xFFu) << shift;
   const uint32_t Gg = (__double2uint_rz(fadd(tm[1], 0.5)) & 0xFFu) << shift;
   const uint32_t Bb = (__double2uint_rz(fadd(tm[2], 0.5)) & 0xFFu) << shift;
-  return (Rr << 16) | (Gg << 8) | Bb;
+  palette[slot] = (Rr << 16) | (Gg << 8) | Bb;
+  *status_word = 1u;
+}
+// item -> (node, palette slot, kind) from the two lists
+__device__ __forceinline__ void item_of(const uint32_t *list, uint32_t n_round, int item, int &node_x, int &slot, bool &is_cut) {
+  is_cut = (uint32_t)item >= n_round;
+  node_x = is_cut ? (int)list[kTieCutList + (uint32_t)item - n_round] : (int)list[4 * item + 1];
+  slot = is_cut ? 0 : (int)list[4 * item + 2];
 }
 
 __global__ void __launch_bounds__(kResolveThreads) tie_resolve_kernel(const SplitNode *nodes, uint2 *pts0, uint2 *pts1,
                                                                       const uint32_t *first_seen, double norm, int shift,
-                                                                      const uint32_t *list, uint32_t num_nodes, uint32_t *palette,
-                                                                      uint32_t *status) {
+                                                                      const uint32_t *list, uint32_t n_round, uint32_t num_nodes,
+                                                                      uint32_t *palette, uint32_t *status) {
   extern __shared__ __align__(16) unsigned char resolve_smem[];
   ResolveShared &S = *reinterpret_cast<ResolveShared *>(resolve_smem);
   const int tid = threadIdx.x, item = blockIdx.x;
-  const int node_x = (int)list[4 * item + 1], slot = (int)list[4 * item + 2];
+  int node_x, slot;
+  bool is_cut;
+  item_of(list, n_round, item, node_x, slot, is_cut);
 
   if (num_nodes > (uint32_t)kResolveNodes) {
     if (tid == 0) status[item] = 2u;
@@ -279,10 +305,7 @@ __global__ void __launch_bounds__(kResolveThreads) tie_resolve_kernel(const Spli
   }
   __syncthreads();
   // ---- the scalar formulas down the chain ----
-  if (tid == 0) {
-    palette[slot] = replay_chain(S, shift);
-    status[item] = 1u;
-  }
+  if (tid == 0) settle(S, nodes, node_x, is_cut, slot, shift, palette, status + item);
 }
 
 
@@ -304,14 +327,14 @@ struct BigShared {
   int32_t sib[kResolveChain];
   uint32_t sib_begin[kResolveChain + 1], sib_size[kResolveChain + 1];
   int32_t n_sib, top, fail, top_is_root;
-  uint32_t range_lo[kTieListCap], range_hi[kTieListCap];
+  uint32_t range_lo[2 * kTieListCap], range_hi[2 * kTieListCap];
   int32_t n_ranges;
 };
 
 __global__ void __launch_bounds__(256) resolve_flatten_kernel(const SplitNode *nodes, uint32_t num_nodes, const uint2 *pts0,
                                                              const uint2 *pts1, const uint32_t *first_seen, const uint32_t *list,
-                                                             uint32_t count, unsigned long long *keys, uint2 *flat,
-                                                             uint32_t *in_range_total) {
+                                                             uint32_t n_round, uint32_t count, unsigned long long *keys,
+                                                             uint2 *flat, uint32_t *in_range_total) {
   extern __shared__ __align__(16) unsigned char resolve_smem[];
   BigShared &S = *reinterpret_cast<BigShared *>(resolve_smem);
   const int tid = threadIdx.x;
@@ -321,7 +344,10 @@ __global__ void __launch_bounds__(256) resolve_flatten_kernel(const SplitNode *n
   if (tid == 0) {
     S.n_ranges = 0;
     for (uint32_t it = 0; it < count; ++it) {
-      walk_chain(S, (int)list[4 * it + 1]);
+      int node_x, slot;
+      bool is_cut;
+      item_of(list, n_round, (int)it, node_x, slot, is_cut);
+      walk_chain(S, node_x);
       if (S.fail) continue;
       S.range_lo[S.n_ranges] = S.sib_begin[0];
       S.range_hi[S.n_ranges] = S.sib_begin[0] + S.sib_size[0];
@@ -361,11 +387,13 @@ __global__ void __launch_bounds__(kBigThreads) tie_resolve_big_kernel(const Spli
                                                                       const uint32_t *__restrict__ sorted_pos,
                                                                       const uint2 *__restrict__ flat, const uint32_t *in_range_total,
                                                                       double norm, int shift, const uint32_t *list,
-                                                                      uint32_t *palette, uint32_t *status) {
+                                                                      uint32_t n_round, uint32_t *palette, uint32_t *status) {
   extern __shared__ __align__(16) unsigned char resolve_smem[];
   BigShared &S = *reinterpret_cast<BigShared *>(resolve_smem);
   const int tid = threadIdx.x, lane = tid & 31, item = blockIdx.x;
-  const int node_x = (int)list[4 * item + 1], slot = (int)list[4 * item + 2];
+  int node_x, slot;
+  bool is_cut;
+  item_of(list, n_round, item, node_x, slot, is_cut);
   if (num_nodes > (uint32_t)kResolveNodes) {
     if (tid == 0) status[item] = 2u;
     return;
@@ -417,35 +445,36 @@ __global__ void __launch_bounds__(kBigThreads) tie_resolve_big_kernel(const Spli
     if (live) S.sums[set][chain] = acc;
   }
   __syncthreads();
-  if (tid == 0) {
-    palette[slot] = replay_chain(S, shift);
-    status[item] = 1u;
-  }
+  if (tid == 0) settle(S, nodes, node_x, is_cut, slot, shift, palette, status + item);
 }
 
 }  // namespace
 
 void tie_resolve_launch(const SplitNode *d_nodes, uint32_t num_nodes, uint2 *const *pts, const uint32_t *d_first_seen, double norm,
-                        int shift, const uint32_t *d_list, uint32_t count, uint32_t *d_palette, uint32_t *d_status, cudaStream_t st) {
+                        int shift, const uint32_t *d_list, uint32_t n_round, uint32_t n_cut, uint32_t *d_palette, uint32_t *d_status,
+                        cudaStream_t st) {
   DQ_RAISE_SMEM(tie_resolve_kernel, sizeof(ResolveShared));
-  tie_resolve_kernel<<<count, kResolveThreads, sizeof(ResolveShared), st>>>(d_nodes, pts[0], pts[1], d_first_seen, norm, shift,
-                                                                            d_list, num_nodes, d_palette, d_status);
+  tie_resolve_kernel<<<n_round + n_cut, kResolveThreads, sizeof(ResolveShared), st>>>(d_nodes, pts[0], pts[1], d_first_seen, norm,
+                                                                                      shift, d_list, n_round, num_nodes, d_palette,
+                                                                                      d_status);
   DQ_CUDA_CHECK(cudaGetLastError());
 }
 
 // The large form: d_keys [n_pow2], d_vals [n_pow2], d_flat [U], d_counter [1] are scratch; n_pow2 = the power of two >= U.
 void tie_resolve_big_launch(const SplitNode *d_nodes, uint32_t num_nodes, uint2 *const *pts, const uint32_t *d_first_seen, uint32_t u,
-                            double norm, int shift, const uint32_t *d_list, uint32_t count, uint64_t *d_keys, uint32_t *d_vals,
-                            uint2 *d_flat, uint32_t *d_counter, uint32_t *d_palette, uint32_t *d_status, int sm_count,
-                            cudaStream_t st) {
+                            double norm, int shift, const uint32_t *d_list, uint32_t n_round, uint32_t n_cut, uint64_t *d_keys,
+                            uint32_t *d_vals, uint2 *d_flat, uint32_t *d_counter, uint32_t *d_palette, uint32_t *d_status,
+                            int sm_count, cudaStream_t st) {
+  const uint32_t count = n_round + n_cut;
   DQ_CUDA_CHECK(cudaMemsetAsync(d_counter, 0, sizeof(uint32_t), st));
   DQ_RAISE_SMEM(resolve_flatten_kernel, sizeof(BigShared));
   DQ_RAISE_SMEM(tie_resolve_big_kernel, sizeof(BigShared));
   resolve_flatten_kernel<<<std::min<uint32_t>(num_nodes, (uint32_t)(4 * sm_count)), 256, sizeof(BigShared), st>>>(
-      d_nodes, num_nodes, pts[0], pts[1], d_first_seen, d_list, count, reinterpret_cast<unsigned long long *>(d_keys), d_flat, d_counter);
+      d_nodes, num_nodes, pts[0], pts[1], d_first_seen, d_list, n_round, count, reinterpret_cast<unsigned long long *>(d_keys), d_flat,
+      d_counter);
   order_sort(d_keys, d_vals, u, sm_count, st);
-  tie_resolve_big_kernel<<<count, kBigThreads, sizeof(BigShared), st>>>(d_nodes, num_nodes, d_vals, d_flat, d_counter, norm, shift, d_list, d_palette,
-                                                        d_status);
+  tie_resolve_big_kernel<<<count, kBigThreads, sizeof(BigShared), st>>>(d_nodes, num_nodes, d_vals, d_flat, d_counter, norm, shift, d_list, n_round,
+                                                                        d_palette, d_status);
   DQ_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -88,6 +88,7 @@ enum CtlSlot {
   kCtlError = 6,   // non-zero = internal inconsistency
   kCtlTie = 8,     // tie audit: TieBit mask of the decisions that sit inside the reference's rounding noise (dq_tie.cuh)
   kCtlTieCount = 9,  // tie audit: final clusters whose palette rounding is flagged (entries of SplitArgs::tie_list)
+  kCtlCutCount = 10,  // tie audit: consumed splits whose cut is flagged (entries of the second list of tie_list)
   kCtlWords = 12   // [kCtlWords - 1] = detail of an expired wait
 };
 
@@ -147,6 +148,10 @@ struct SplitArgs {
   long long spin_cycles;
 };
 constexpr uint32_t kTieListCap = 16;
+// layout of the tie_list buffer (words): [0, 4 cap) rounding entries | [4 cap, 6 cap) resolver status, roundings then cuts |
+// [6 cap, 6 cap + 4) a counter of the resolver | [kTieCutList, + cap) nodes whose cut is flagged
+constexpr uint32_t kTieStatus = 4 * kTieListCap, kTieCounter = 6 * kTieListCap, kTieCutList = 6 * kTieListCap + 4;
+constexpr uint32_t kTieListWords = kTieCutList + kTieListCap;
 
 
 // Largest input (unique colours) that takes the sequential-order path of dq_split_exact.cu.
@@ -166,15 +171,18 @@ struct ExactSampling {
 };
 ExactSampling exact_sampling(const uint32_t *d_in, uint32_t num_rows, uint32_t num_cols, uint32_t dec, int bits);
 // dq_resolve.cu: a final cluster's mean in the reference's own arithmetic (ordered sums along its chain of splits), for the
-// clusters whose rounding the tie audit flagged.  d_status[i]: 1 = palette[slot] rewritten, 2 = not resolvable here.
+// clusters whose rounding the tie audit flagged (n_round entries) and the nodes whose cut it flagged (n_cut entries).
+// d_status[i]: 1 = settled (palette[slot] rewritten / the cut separates the same points), 2 = not resolvable here,
+// 3 = the reference cuts this node differently.
 void tie_resolve_launch(const SplitNode *d_nodes, uint32_t num_nodes, uint2 *const *pts, const uint32_t *d_first_seen, double norm,
-                        int shift, const uint32_t *d_list, uint32_t count, uint32_t *d_palette, uint32_t *d_status, cudaStream_t st);
+                        int shift, const uint32_t *d_list, uint32_t n_round, uint32_t n_cut, uint32_t *d_palette, uint32_t *d_status,
+                        cudaStream_t st);
 // The same for chains through nodes of any size (global sort of the points under the top nodes, one streaming pass).
 // Scratch: d_keys / d_vals hold the power of two >= u entries, d_flat u points, d_counter one word.
 void tie_resolve_big_launch(const SplitNode *d_nodes, uint32_t num_nodes, uint2 *const *pts, const uint32_t *d_first_seen, uint32_t u,
-                            double norm, int shift, const uint32_t *d_list, uint32_t count, uint64_t *d_keys, uint32_t *d_vals,
-                            uint2 *d_flat, uint32_t *d_counter, uint32_t *d_palette, uint32_t *d_status, int sm_count,
-                            cudaStream_t st);
+                            double norm, int shift, const uint32_t *d_list, uint32_t n_round, uint32_t n_cut, uint64_t *d_keys,
+                            uint32_t *d_vals, uint2 *d_flat, uint32_t *d_counter, uint32_t *d_palette, uint32_t *d_status,
+                            int sm_count, cudaStream_t st);
 // first-seen pass alone (dq_split_exact.cu): smallest sample index of every colour into d_first_seen
 void first_seen_launch(const ExactSampling &q, uint32_t *d_first_seen, cudaStream_t st);
 size_t split_exact_smem_bytes();

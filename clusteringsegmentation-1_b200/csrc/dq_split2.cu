@@ -84,6 +84,7 @@ struct Shared2 {
   uint32_t near;      // tie audit: points of the pass just reduced / gathered that sit inside the noise bound
   uint32_t job_tie;   // TieBit mask of the narrow job in flight
   uint32_t tie_total; // TieBit mask of the frame (CTA 0, final assignment + palette)
+  uint32_t cut_count; // consumed splits whose cut is flagged (kTieCut): entries of the second list of SplitArgs::tie_list
 };
 
 struct Arrays {
@@ -597,6 +598,7 @@ __device__ void emit_palette(const SplitArgs &A, Shared2 &S, const Arrays &R) {
     A.result[0] = (uint32_t)S.scan_carry;
     A.result[1] = (uint32_t)(K - S.scan_carry);
     A.ctl[kCtlTieCount] = S.cur_new;
+    A.ctl[kCtlCutCount] = (A.tie_audit != 0u && S.mode == 0) ? S.cut_count : 0u;
   }
 }
 
@@ -664,7 +666,7 @@ __device__ void fast_assignment(const SplitArgs &A, Shared2 &S, const Arrays &R)
     // test, which follows below for the few nodes marked here (together with whether the other node matters at all).
     for (int i = tid; i < n; i += T) R.byrank[i] = -1;
     __shared__ double s_emax;
-    if (tid == 0) s_emax = 0.0;
+    if (tid == 0) s_emax = 0.0, S.cut_count = 0u;
     __syncthreads();
     double emax = 0.0;
     for (int i = tid; i < n; i += T) {
@@ -725,7 +727,12 @@ __device__ void fast_assignment(const SplitArgs &A, Shared2 &S, const Arrays &R)
     int q = 0;
     for (int i = tid; i < n; i += T, ++q) {
       if (R.rank[i] >= K - 1) continue;
-      bits |= __ldcg(&A.nodes[i].tie);
+      const uint32_t node_bits = __ldcg(&A.nodes[i].tie);
+      bits |= node_bits;
+      if ((node_bits & (uint32_t)kTieCut) && A.tie_list != nullptr) {  // for dq_resolve.cu: whose mean decides the cut
+        const uint32_t at = atomicAdd(&S.cut_count, 1u);
+        if (at < kTieListCap && blockIdx.x == 0) A.tie_list[kTieCutList + at] = (uint32_t)i;
+      }
       if (i == 0) continue;  // the root is split first, unconditionally
       const double t = R.tse[i], e = R.terr[i];
       if (!(t - e > DBL_MIN)) bits |= (uint32_t)kTieTse;
@@ -1120,6 +1127,7 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
     S.root = root;
     if (b == 0) A.nodes[0] = root;
     S.tie_total = 0u;
+    S.cut_count = 0u;
     R.terr[0] = 0.0;
     R.tse[0] = __longlong_as_double(0x7ff0000000000000ll);  // +inf: the first split is unconditional
     R.child[0] = -1;

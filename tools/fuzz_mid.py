@@ -21,6 +21,7 @@ o = Oracle()
 ref = Reference()
 bad = flagged = rerun = resolved = 0
 hist_u = []
+masks = {}
 for t in range(trials):
     gen = 1 + (t % 2)
     img = o.generate(gen, 1920, 1080, int(rng.integers(1, 1 << 20))).reshape(1080, 1920)
@@ -38,6 +39,10 @@ for t in range(trials):
         out, pal = dq.quant_recurse(px, k, 0)
     st = dq.last_stats()
     flagged += st["tie_flags"] != 0
+    if st["tie_flags"]:
+        key = (st["tie_flags"], "perturbed" if t % 5 == 4 else "plain", "U>262144" if u > 262144 else "U<=262144",
+               "resolved" if st["tie_resolved"] else "rerun" if st["ordered_rerun"] else "reported")
+        masks[key] = masks.get(key, 0) + 1
     rerun += st["ordered_rerun"]
     resolved += st["tie_resolved"] > 0
     hist_u.append(u)
@@ -49,3 +54,5 @@ hu = np.array(hist_u)
 print(f"{trials} mid-size inputs against the reference: {bad} mismatches; U min/median/max {hu.min()}/{int(np.median(hu))}/{hu.max()}, "
       f"{int((hu > 4096).sum())} above the ordered path's default limit; tie audit flagged {flagged} "
       f"({resolved} resolved in place, {rerun} re-run in the reference's order)")
+for key in sorted(masks):
+    print("  flags", key, masks[key])
