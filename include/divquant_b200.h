@@ -118,8 +118,10 @@ typedef struct {
    * summation order (so the result is the reference's as well). */
   uint32_t tie_flags;
   uint32_t ordered_rerun;
-  /* > 0: only palette roundings were flagged (bit 16) and that many cluster centres were recomputed in the reference's
-   * arithmetic by the resolver (csrc/dq_resolve.cu) instead of re-running the frame. */
+  /* > 0: only palette roundings (bit 16) and / or cuts (bit 2) were flagged and that many of them were settled by the
+   * resolver (csrc/dq_resolve.cu), which recomputes the one node mean each of them hangs on in the reference's own
+   * arithmetic: a rounding is rewritten, a cut is confirmed to separate the same points as the reference's.  The result is
+   * the reference's, without a re-run.  (A cut that does NOT separate the same points sends the frame to the re-run.) */
   uint32_t tie_resolved;
 } dq_call_stats;
 void dq_context_last_stats(const dq_context *ctx, dq_call_stats *out);
@@ -144,8 +146,8 @@ void dq_context_set_exact_small(dq_context *ctx, int enabled);
 /* Inputs above that limit run on exact integer sums, which equal the reference's sequential double sums up to the
  * reference's own rounding noise.  The split kernel audits every decision it takes (axis, cut, hyperplane, TSE
  * arg-max, palette rounding) against first-order bounds of that noise (csrc/dq_tie.cuh).  policy 2 (default): a frame
- * with a decision inside its bound is computed again on the ordered path (up to 262144 colours), so the palette is
- * the reference's either way; 1: only report (dq_call_stats::tie_flags); 0: no audit.  Environment: DIVQUANT_B200_TIE. */
+ * with a decision inside its bound is settled by the resolver (flagged roundings and cuts: any number of colours) or
+ * computed again on the ordered path (anything else: up to 262144 colours), so the palette is the reference's either way; 1: only report (dq_call_stats::tie_flags); 0: no audit.  Environment: DIVQUANT_B200_TIE. */
 void dq_context_set_tie_policy(dq_context *ctx, int policy);
 
 /* quant_recurse with pixels already resident in HBM.  d_in / d_out are device pointers on the
