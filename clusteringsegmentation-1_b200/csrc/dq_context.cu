@@ -443,11 +443,12 @@ uint32_t run_split_finish(dq_context *ctx, uint32_t *colortable_out, dq_split_re
   if (use_v2 && getenv("DQ_PROFILE_NARROW")) {
     uint32_t prof[8];
     cudaMemcpy(prof, ctx->d_progress.ptr + 756, sizeof(prof), cudaMemcpyDeviceToHost);
-    uint32_t wp[6];
+    uint32_t wp[9];
     cudaMemcpy(wp, ctx->d_progress.ptr + 764, sizeof(wp), cudaMemcpyDeviceToHost);
     if (wp[3])
-      fprintf(stderr, "wide profile (cycles per job-pass, thread 0 of every participant): gather %.0f derive+sync %.0f classify+reduce+publish %.0f (classify %.0f, stage1+sync %.0f) ; %u job-passes\n",
-              (double)wp[0] / wp[3], (double)wp[1] / wp[3], (double)wp[2] / wp[3], (double)wp[4] / wp[3], (double)wp[5] / wp[3], wp[3]);
+      fprintf(stderr, "wide profile (cycles per job-pass, thread 0 of every participant): gather %.0f derive+sync %.0f classify+reduce+publish %.0f (classify %.0f, stage1+sync %.0f, stage2 %.0f, publish %.0f, closing barrier %.0f) ; %u job-passes\n",
+              (double)wp[0] / wp[3], (double)wp[1] / wp[3], (double)wp[2] / wp[3], (double)wp[4] / wp[3], (double)wp[5] / wp[3],
+              (double)wp[6] / wp[3], (double)wp[7] / wp[3], (double)wp[8] / wp[3], wp[3]);
     if (prof[4])
       fprintf(stderr, "narrow profile (cycles per pass, thread 0): classify %.0f stage1+sync %.0f warp0(stage2+derive) %.0f sync %.0f ; %u passes, %u points\n",
               (double)prof[0] / prof[4], (double)prof[1] / prof[4], (double)prof[2] / prof[4], (double)prof[3] / prof[4], prof[4], prof[5]);

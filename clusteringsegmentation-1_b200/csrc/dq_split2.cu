@@ -1430,12 +1430,28 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
           if (tid == 0 && pass > 0) atomicAdd(X.progress + 769, (uint32_t)(clock64() - w3));  // stage 1 + sync
 #endif
           if (tid < 32) {
+#ifdef DQ_PROFILE_NARROW
+            const long long w4 = clock64();
+#endif
             reduce_stage2_warp0<5>(S, (int)(nthr >> 5));
+#ifdef DQ_PROFILE_NARROW
+            const long long w5 = clock64();
+#endif
             publish<5>(slots_w, R.slot0[j] + me, S, (seq0 + pass) & 0xFFFFu);
+#ifdef DQ_PROFILE_NARROW
+            if (tid == 0 && pass > 0) {
+              atomicAdd(X.progress + 770, (uint32_t)(w5 - w4));          // stage 2
+              atomicAdd(X.progress + 771, (uint32_t)(clock64() - w5));   // publish
+            }
+#endif
           }
         }
+#ifdef DQ_PROFILE_NARROW
+        const long long w6 = clock64();
+#endif
         __syncthreads();
 #ifdef DQ_PROFILE_NARROW
+        if (tid == 0 && pass > 0) atomicAdd(X.progress + 772, (uint32_t)(clock64() - w6));  // closing barrier
         if (tid == 0 && pass > 0) atomicAdd(X.progress + 768, (uint32_t)(w3 - w2));  // classification only
         if (tid == 0 && pass > 0) {
           atomicAdd(X.progress + 764, (uint32_t)(w1 - w0));            // gather (wait + reduce)
