@@ -571,6 +571,7 @@ def run_ours(args, rank, world, local_rank):
     #    call through the reference-signature entry point with host buffers, next to the reference's own CPU time --
     small_table = None
     pageable_ms = None
+    g2_info = None
     if not args.skip_small:
         dq = pkg.DivQuant(lib, timings=False)
         try:
@@ -612,6 +613,40 @@ def run_ours(args, rank, world, local_rank):
                 if i:
                     tq.append(time.perf_counter() - t0)
         pageable_ms = 1e3 * statistics.median(tq)
+        # G2 stress input of SURVEY.md 8c/8d at 1080p (uniform-random pixels, ~1.95 M distinct colours of 2.07 M: no colour
+        # repetition to exploit, so the remap is the brute-force N*K kernel): one device-resident call, CUDA events
+        gpath2 = os.path.join(ROOT, "tests", "golden", "frames.npz")
+        gold2 = np.load(gpath2) if os.path.exists(gpath2) else None
+        if rank == 0 and gold2 is not None and "g2_seeds" in gold2.files:
+            seed2 = int(gold2["g2_seeds"][0])
+            g2 = torch.from_numpy(o.generate(2, 1920, 1080, seed2).view(np.int32)).cuda()
+            g2_out = torch.empty_like(g2)
+            ct2 = np.zeros(K, np.uint32)
+            lib.dq_context_set_profiling(ctx, 1)
+            tg2 = []
+            for i in range(6):
+                nk2 = C.c_uint32(K)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                e0.record(stream)
+                lib.dq_quant_recurse_device(ctx, g2.numel(), g2.data_ptr(), g2_out.data_ptr(), C.byref(nk2), ct2.ctypes.data_as(u32p), 0)
+                e1.record(stream)
+                torch.cuda.synchronize()
+                if i:
+                    tg2.append(e0.elapsed_time(e1))
+            st2 = pkg.CallStats()
+            lib.dq_context_last_stats(ctx, C.byref(st2))
+            lib.dq_context_set_profiling(ctx, 0)
+            d2 = st2.as_dict()
+            ok2 = (o.hash_words(ct2[:nk2.value]) == int(gold2["g2_pal_hash"][0]) and
+                   o.hash_words(g2_out.cpu().numpy().view(np.uint32)) == int(gold2["g2_out_hash"][0]))
+            g2_info = {"workload": f"quant_recurse 1920x1080 K={K}, generator G2 seed {seed2} (uniform-random pixels)",
+                       "unique_colours": d2["num_points"], "ms": statistics.median(tg2), "value": 1920 * 1080 / (statistics.median(tg2) * 1e-3) / 1e6,
+                       "unit": "Mpixels/s", "remap_variant": "brute force N*K" if d2["remap_path"] != 2 else "unique-colour table",
+                       "stage_ms": d2["stage_ms"], "tie_flags": d2["tie_flags"], "parity": bool(ok2),
+                       "parity_against": "tests/golden/frames.npz (oracle/_ref fingerprint of the same frame)",
+                       "cpu_reference_s": 22.5, "cpu_reference_note": "SURVEY.md 5 / BASELINE.md: the reference needs 22.5 s for this input (hash-chain pathology), measured once in the survey, not re-timed here"}
+            del g2, g2_out
 
     peak, peak_src = measured_peaks()
     ms_step = ms_dev / steps
@@ -696,6 +731,8 @@ def run_ours(args, rank, world, local_rank):
     if small_table:
         line["small_inputs"] = {"api": "dq_quant_recurse (host pointers, blocking), median of 15 calls; CPU: oracle/_ref, median of 5",
                                 "rows": small_table}
+    if g2_info:
+        line["g2_stress"] = g2_info
     if rows_info:
         line["row_sharded"] = rows_info
     if cpu:
