@@ -39,7 +39,7 @@ class CallStats(C.Structure):
                 ("actual_colors", C.c_uint32), ("empty_clusters", C.c_uint32), ("split_rounds", C.c_uint32),
                 ("splits_computed", C.c_uint32), ("remap_path", C.c_uint32), ("kernel_launches", C.c_uint32),
                 ("stage_ms", C.c_float * 7), ("tie_flags", C.c_uint32), ("ordered_rerun", C.c_uint32),
-                ("tie_resolved", C.c_uint32)]
+                ("tie_resolved", C.c_uint32), ("cut_overrides", C.c_uint32)]
 
     STAGES = ("hist_insert", "hist_collect", "split", "map_unique_or_bruteforce", "map_gather", "table_clear", "total")
 

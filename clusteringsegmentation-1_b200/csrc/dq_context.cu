@@ -87,6 +87,9 @@ struct dq_context {
   DevBuf<uint2> d_pts0, d_pts1;
   DevBuf<uint2> d_flat;         // large tie resolver: the points by position
   DevBuf<uint32_t> d_sortvals;  // ... and the payload of its sort
+  DevBuf<uint32_t> d_ovr;       // cuts taken from the resolver (SplitArgs::cut_overrides) of the call in flight
+  CutOverride h_ovr[kCutOverrideCap];
+  uint32_t n_ovr = 0;
   DevBuf<uint64_t> d_keys;
   // sized by K
   DevBuf<SplitNode> d_nodes;
@@ -125,7 +128,7 @@ struct dq_context {
     double *mean_out = nullptr;
     uint32_t *size_out = nullptr;
     int phase = 0;  // quantize_step
-    uint32_t flags = 0, tie_count = 0, cut_count = 0, k_first = 0;
+    uint32_t flags = 0, flags_all = 0, tie_count = 0, cut_count = 0, k_first = 0, resplits = 0;
   } qs;
   cudaEvent_t tie_ev = nullptr;
   // Tie audit of the exact-integer split (dq_tie.cuh): 0 = off, 1 = report in dq_call_stats::tie_flags only,
@@ -309,6 +312,10 @@ uint32_t run_split(dq_context *ctx, uint32_t point_capacity, double norm, uint32
   if (a.tie_audit) {
     ctx->d_tie.ensure(kTieListWords);
     a.tie_list = ctx->d_tie.ptr;
+    if (ctx->n_ovr) {
+      a.cut_overrides = reinterpret_cast<const CutOverride *>(ctx->d_ovr.ptr);
+      a.num_cut_overrides = ctx->n_ovr;
+    }
   }
   ctx->mark(2);
   const bool exact_path = exact != nullptr && collect_from_hist && K <= kExactMaxColors && ctx->exact_small && ctx->exact_max_points > 0;
@@ -590,7 +597,8 @@ void quantize_begin(dq_context *ctx, uint32_t n, const uint32_t *d_in, uint32_t 
   q.num_bits = num_bits, q.dec = dec, q.max_iters = max_iters, q.norm = norm, q.table_dirty = table_dirty;
   q.records = records, q.mean_out = mean_out, q.size_out = size_out;
   q.phase = 0;
-  q.flags = q.tie_count = q.cut_count = q.k_first = 0;
+  q.flags = q.flags_all = q.tie_count = q.cut_count = q.k_first = q.resplits = 0;
+  ctx->n_ovr = 0;
 }
 
 // Second half, as a small state machine so that a host thread that drives several contexts never has to wait inside it:
@@ -625,6 +633,20 @@ QuantStepResult quantize_step(dq_context *ctx, uint32_t *k_inout, uint32_t *colo
     ctx->exact_max_points = keep;
     q.phase = 2;
   };
+  auto queue_resplit = [&]() {
+    // The reference cuts some node on the other side of an integer than the exact mean does (the resolver found out, and
+    // what the reference's mean is): the exact-integer split runs again with that node cut where the reference cuts it
+    // (SplitArgs::cut_overrides).  Everything outside the node's subtree comes out as before.
+    ctx->d_ovr.ensure(kCutOverrideCap * sizeof(CutOverride) / sizeof(uint32_t));
+    DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->d_ovr.ptr, ctx->h_ovr, ctx->n_ovr * sizeof(CutOverride), cudaMemcpyHostToDevice, ctx->stream));
+    reset_control(ctx);
+    run_histogram(ctx, q.d_in, q.n, q.rows, q.cols, (uint32_t)q.dec, q.num_bits);
+    uint32_t unused = 0;
+    run_split(ctx, q.point_cap, q.norm, K, q.max_iters, q.num_bits, &unused, q.records, q.mean_out, q.size_out, true, &src, true,
+              false, /*defer=*/true);
+    q.resplits++;
+    q.phase = 0;
+  };
   auto queue_big_resolve = [&]() {
     // the resolver's large form (dq_resolve.cu): chains through nodes of any size, a global sort instead of one in shared memory
     const uint32_t U = ctx->stats.num_points;
@@ -644,6 +666,9 @@ QuantStepResult quantize_step(dq_context *ctx, uint32_t *k_inout, uint32_t *colo
     ctx->stats.kernel_launches += 3 + steps;
     DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->h_small + K, d_status, (q.tie_count + q.cut_count) * sizeof(uint32_t), cudaMemcpyDeviceToHost,
                                   ctx->stream));
+    if (q.cut_count)
+      DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->h_small + K + 2 * kTieListCap, ctx->d_tie.ptr + kTieRefCut, q.cut_count * sizeof(CutOverride),
+                                    cudaMemcpyDeviceToHost, ctx->stream));
     DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->h_small, ctx->d_palette.ptr, (size_t)q.k_first * sizeof(uint32_t), cudaMemcpyDeviceToHost,
                                   ctx->stream));
     DQ_CUDA_CHECK(cudaEventRecord(ctx->tie_ev, ctx->stream));
@@ -654,6 +679,9 @@ QuantStepResult quantize_step(dq_context *ctx, uint32_t *k_inout, uint32_t *colo
   if (q.phase == 0) {
     *k_inout = run_split_finish(ctx, colortable, q.records, q.mean_out, q.size_out);
     q.flags = ctx->stats.tie_flags;
+    q.flags_all |= q.flags;
+    ctx->stats.tie_flags = q.flags_all;  // (a frame that needed forced cuts stays marked as flagged)
+    ctx->stats.cut_overrides = ctx->n_ovr;
     if (q.flags == 0u) return kQuantDone;
     if ((q.flags & ~(uint32_t)(kTieRound | kTieCut)) == 0u && ctx->tie_policy == 2 && q.table_dirty && ctx->exact_small &&
         q.records == nullptr && q.mean_out == nullptr) {
@@ -668,7 +696,7 @@ QuantStepResult quantize_step(dq_context *ctx, uint32_t *k_inout, uint32_t *colo
       if (q.tie_count + q.cut_count >= 1 && q.tie_count <= kTieListCap && q.cut_count <= kTieListCap && ctx->resolve_mode != 0) {
         first_seen_launch(exact_sampling(q.d_in, q.rows, q.cols, (uint32_t)q.dec, q.num_bits), ctx->d_map, ctx->stream);
         ctx->stats.kernel_launches++;
-        ctx->ensure_small((size_t)K + 16 + 2 * kTieListCap);
+        ctx->ensure_small((size_t)K + 16 + 8 * kTieListCap + 2);
         q.k_first = *k_inout;
         if (!ctx->tie_ev) DQ_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->tie_ev, cudaEventDisableTiming));
         if ((ctx->resolve_mode & 1) == 0) {
@@ -683,6 +711,9 @@ QuantStepResult quantize_step(dq_context *ctx, uint32_t *k_inout, uint32_t *colo
         ctx->stats.kernel_launches++;
         DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->h_small + K, d_status, (q.tie_count + q.cut_count) * sizeof(uint32_t), cudaMemcpyDeviceToHost,
                                       ctx->stream));
+        if (q.cut_count)
+          DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->h_small + K + 2 * kTieListCap, ctx->d_tie.ptr + kTieRefCut,
+                                        q.cut_count * sizeof(CutOverride), cudaMemcpyDeviceToHost, ctx->stream));
         DQ_CUDA_CHECK(cudaMemcpyAsync(ctx->h_small, ctx->d_palette.ptr, (size_t)q.k_first * sizeof(uint32_t), cudaMemcpyDeviceToHost,
                                       ctx->stream));
         DQ_CUDA_CHECK(cudaEventRecord(ctx->tie_ev, ctx->stream));
@@ -708,6 +739,27 @@ QuantStepResult quantize_step(dq_context *ctx, uint32_t *k_inout, uint32_t *colo
       *k_inout = q.k_first;
       ctx->stats.tie_resolved = q.tie_count + q.cut_count;
       return kQuantDone;
+    }
+    if (differs && q.resplits < 8) {
+      // status-3 cut entries whose range is not inside another one's (a cut below a cut that changes is decided next time)
+      const CutOverride *rec = reinterpret_cast<const CutOverride *>(ctx->h_small + K + 2 * kTieListCap);
+      const uint32_t *st = ctx->h_small + K + q.tie_count;
+      uint32_t added = 0;
+      for (uint32_t i = 0; i < q.cut_count; ++i) {
+        if (st[i] != 3u) continue;
+        bool nested = false;
+        for (uint32_t j = 0; j < q.cut_count; ++j)
+          nested = nested || (j != i && st[j] == 3u && rec[j].begin <= rec[i].begin &&
+                              rec[i].begin + rec[i].size <= rec[j].begin + rec[j].size &&
+                              (rec[j].size > rec[i].size || j < i));
+        if (nested || ctx->n_ovr >= kCutOverrideCap) continue;
+        ctx->h_ovr[ctx->n_ovr++] = rec[i];
+        ++added;
+      }
+      if (added) {
+        queue_resplit();
+        return kQuantPending;
+      }
     }
     if (q.phase == 1 && !differs && (ctx->resolve_mode & 2)) {  // a chain through a large node: the resolver's large form
       queue_big_resolve();
@@ -1003,6 +1055,7 @@ void dq_context_destroy(dq_context *ctx) {
   ctx->d_progress.release();
   ctx->d_exact.release();
   ctx->d_tie.release();
+  ctx->d_ovr.release();
   ctx->d_flat.release();
   ctx->d_sortvals.release();
   ctx->d_frame.release();

@@ -125,12 +125,17 @@ __device__ __forceinline__ void replay_chain(const SH &S, double *tm) {
 // have the same floor: status 1 (nothing to change) or 3 (the reference splits this node differently).
 template <class SH>
 __device__ __forceinline__ void settle(const SH &S, const SplitNode *nodes, int node_x, bool is_cut, int slot, int shift,
-                                       uint32_t *palette, uint32_t *status_word) {
+                                       uint32_t *palette, uint32_t *status_word, CutOverride *ref_cut) {
   double tm[3];
   replay_chain(S, tm);
   if (is_cut) {
     const int axis = __ldcg(&nodes[node_x].axis);
     const double cut_here = __ldcg(&nodes[node_x].cut);
+    // what the host needs to have this node cut where the reference cuts it (SplitArgs::cut_overrides)
+    ref_cut->begin = __ldcg(&nodes[node_x].begin);
+    ref_cut->size = __ldcg(&nodes[node_x].size);
+    ref_cut->mean_here = cut_here;
+    ref_cut->mean_ref = tm[axis];
     *status_word = (floor(tm[axis]) == floor(cut_here)) ? 1u : 3u;
     return;
   }
@@ -150,7 +155,7 @@ __device__ __forceinline__ void item_of(const uint32_t *list, uint32_t n_round, 
 __global__ void __launch_bounds__(kResolveThreads) tie_resolve_kernel(const SplitNode *nodes, uint2 *pts0, uint2 *pts1,
                                                                       const uint32_t *first_seen, double norm, int shift,
                                                                       const uint32_t *list, uint32_t n_round, uint32_t num_nodes,
-                                                                      uint32_t *palette, uint32_t *status) {
+                                                                      uint32_t *palette, uint32_t *status, CutOverride *ref_cuts) {
   extern __shared__ __align__(16) unsigned char resolve_smem[];
   ResolveShared &S = *reinterpret_cast<ResolveShared *>(resolve_smem);
   const int tid = threadIdx.x, item = blockIdx.x;
@@ -305,7 +310,7 @@ __global__ void __launch_bounds__(kResolveThreads) tie_resolve_kernel(const Spli
   }
   __syncthreads();
   // ---- the scalar formulas down the chain ----
-  if (tid == 0) settle(S, nodes, node_x, is_cut, slot, shift, palette, status + item);
+  if (tid == 0) settle(S, nodes, node_x, is_cut, slot, shift, palette, status + item, ref_cuts + (is_cut ? (uint32_t)item - n_round : 0u));
 }
 
 
@@ -387,7 +392,8 @@ __global__ void __launch_bounds__(kBigThreads) tie_resolve_big_kernel(const Spli
                                                                       const uint32_t *__restrict__ sorted_pos,
                                                                       const uint2 *__restrict__ flat, const uint32_t *in_range_total,
                                                                       double norm, int shift, const uint32_t *list,
-                                                                      uint32_t n_round, uint32_t *palette, uint32_t *status) {
+                                                                      uint32_t n_round, uint32_t *palette, uint32_t *status,
+                                                                      CutOverride *ref_cuts) {
   extern __shared__ __align__(16) unsigned char resolve_smem[];
   BigShared &S = *reinterpret_cast<BigShared *>(resolve_smem);
   const int tid = threadIdx.x, lane = tid & 31, item = blockIdx.x;
@@ -445,10 +451,15 @@ __global__ void __launch_bounds__(kBigThreads) tie_resolve_big_kernel(const Spli
     if (live) S.sums[set][chain] = acc;
   }
   __syncthreads();
-  if (tid == 0) settle(S, nodes, node_x, is_cut, slot, shift, palette, status + item);
+  if (tid == 0) settle(S, nodes, node_x, is_cut, slot, shift, palette, status + item, ref_cuts + (is_cut ? (uint32_t)item - n_round : 0u));
 }
 
 }  // namespace
+
+// the cut entries' records inside the tie_list buffer (layout: dq_split.cuh)
+static inline CutOverride *ref_cuts_of(const uint32_t *d_list) {
+  return reinterpret_cast<CutOverride *>(const_cast<uint32_t *>(d_list) + kTieRefCut);
+}
 
 void tie_resolve_launch(const SplitNode *d_nodes, uint32_t num_nodes, uint2 *const *pts, const uint32_t *d_first_seen, double norm,
                         int shift, const uint32_t *d_list, uint32_t n_round, uint32_t n_cut, uint32_t *d_palette, uint32_t *d_status,
@@ -456,7 +467,7 @@ void tie_resolve_launch(const SplitNode *d_nodes, uint32_t num_nodes, uint2 *con
   DQ_RAISE_SMEM(tie_resolve_kernel, sizeof(ResolveShared));
   tie_resolve_kernel<<<n_round + n_cut, kResolveThreads, sizeof(ResolveShared), st>>>(d_nodes, pts[0], pts[1], d_first_seen, norm,
                                                                                       shift, d_list, n_round, num_nodes, d_palette,
-                                                                                      d_status);
+                                                                                      d_status, ref_cuts_of(d_list));
   DQ_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -474,7 +485,7 @@ void tie_resolve_big_launch(const SplitNode *d_nodes, uint32_t num_nodes, uint2 
       d_counter);
   order_sort(d_keys, d_vals, u, sm_count, st);
   tie_resolve_big_kernel<<<count, kBigThreads, sizeof(BigShared), st>>>(d_nodes, num_nodes, d_vals, d_flat, d_counter, norm, shift, d_list, n_round,
-                                                                        d_palette, d_status);
+                                                                        d_palette, d_status, ref_cuts_of(d_list));
   DQ_CUDA_CHECK(cudaGetLastError());
 }
 

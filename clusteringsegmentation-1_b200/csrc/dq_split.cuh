@@ -104,6 +104,12 @@ enum TieBit {
   kTieUnaudited = 64u   // set by the host: exact-integer sums WITHOUT an audit (K > kSplit2MaxColors beyond the ordered path)
 };
 
+struct CutOverride {
+  uint32_t begin, size;
+  double mean_here, mean_ref;
+};
+constexpr uint32_t kCutOverrideCap = 16;
+
 struct SplitArgs {
   uint2 *pts[2];        // (colour 0x00RRGGBB, count) double buffer, capacity U each
   uint32_t num_points;  // U (ignored when num_points_dev != nullptr)
@@ -146,12 +152,19 @@ struct SplitArgs {
   uint32_t *tie_list;
   // SM cycles a wait on another CTA may last before it is declared stuck (0 = the built-in 0.2 s)
   long long spin_cycles;
+  // Cuts taken from the resolver (dq_resolve.cu): a node whose range is [begin, begin + size) and whose own mean on the cut
+  // axis is exactly `mean_here` is cut at `mean_ref`, the mean the reference holds for it, and its cut is not audited again.
+  const CutOverride *cut_overrides;
+  uint32_t num_cut_overrides;
 };
 constexpr uint32_t kTieListCap = 16;
 // layout of the tie_list buffer (words): [0, 4 cap) rounding entries | [4 cap, 6 cap) resolver status, roundings then cuts |
 // [6 cap, 6 cap + 4) a counter of the resolver | [kTieCutList, + cap) nodes whose cut is flagged
 constexpr uint32_t kTieStatus = 4 * kTieListCap, kTieCounter = 6 * kTieListCap, kTieCutList = 6 * kTieListCap + 4;
-constexpr uint32_t kTieListWords = kTieCutList + kTieListCap;
+// [kTieRefCut, + 6 cap) one CutOverride per cut entry, written by the resolver (8-byte aligned offset)
+constexpr uint32_t kTieRefCut = kTieCutList + kTieListCap;
+static_assert(kTieRefCut % 2 == 0 && sizeof(CutOverride) == 24, "records with doubles inside the tie_list buffer");
+constexpr uint32_t kTieListWords = kTieRefCut + 6 * kTieListCap;
 
 
 // Largest input (unique colours) that takes the sequential-order path of dq_split_exact.cu.

@@ -49,6 +49,7 @@ struct JobConst {
   double tw, tm[3], cut;
   int32_t axis, buf;
   uint32_t begin, size;
+  int32_t forced, pad;  // forced: the cut comes from SplitArgs::cut_overrides (not audited: it IS the reference's)
 };
 // Tie audit: what the bounds of a job's passes need from its node (dq_tie.cuh).  Lives in shared memory only; warp 1 and
 // thread 0 read it, nobody keeps it in registers.  eM < 0 = audit off.
@@ -85,6 +86,8 @@ struct Shared2 {
   uint32_t job_tie;   // TieBit mask of the narrow job in flight
   uint32_t tie_total; // TieBit mask of the frame (CTA 0, final assignment + palette)
   uint32_t cut_count; // consumed splits whose cut is flagged (kTieCut): entries of the second list of SplitArgs::tie_list
+  CutOverride ovr[kCutOverrideCap];  // SplitArgs::cut_overrides, staged
+  uint32_t n_ovr;
 };
 
 struct Arrays {
@@ -419,8 +422,8 @@ __device__ __forceinline__ void derive_audit_warp1(Shared2 &S, const JobConst &j
 __device__ __forceinline__ void set_split_params(Shared2 &S, const JobConst &jc, const JobAudit *aud) {
   if (threadIdx.x == 0) {
     S.pp.a = jc.cut;
-    const double eM = aud ? aud->eM : __longlong_as_double(0x7ff0000000000000ll);
-    S.ext.tol = eM;  // tie audit of the cut test (:473): the cut is the node's mean
+    const double eM = jc.forced ? -1.0 : (aud ? aud->eM : __longlong_as_double(0x7ff0000000000000ll));
+    S.ext.tol = eM;  // tie audit of the cut test (:473): the cut is the node's mean (a forced cut is the reference's own)
     S.pp.tol_hi = __double2hiint(eM) + (eM >= 0.0 ? 1 : 0);
     S.pp.r[0] = S.pp.r[1] = S.pp.r[2] = 0.0;
     S.pp.axis = jc.axis;
@@ -446,6 +449,17 @@ __device__ __forceinline__ JobConst job_const_of(const SplitNode &nd) {
   jc.buf = nd.buf;
   jc.begin = nd.begin;
   jc.size = nd.size;
+  jc.forced = 0, jc.pad = 0;
+  return jc;
+}
+__device__ __forceinline__ JobConst job_const_of(const Shared2 &S, const SplitNode &nd) {
+  JobConst jc = job_const_of(nd);
+  for (uint32_t i = 0; i < S.n_ovr; ++i) {
+    if (S.ovr[i].begin == jc.begin && S.ovr[i].size == jc.size && S.ovr[i].mean_here == jc.cut) {
+      jc.cut = S.ovr[i].mean_ref;
+      jc.forced = 1;
+    }
+  }
   return jc;
 }
 
@@ -1103,6 +1117,7 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
   trace2(A, kTraceRootBarrier, 0);
   trace2(A, kTraceRoot, 0);
 
+  if (A.cut_overrides != nullptr && (uint32_t)tid < min(A.num_cut_overrides, kCutOverrideCap)) S.ovr[tid] = A.cut_overrides[tid];
   if (tid == 0) {
     SplitNode root;
     root.tw = 1.0;  // weight[0] = 1.0 (:343)
@@ -1128,6 +1143,7 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
     if (b == 0) A.nodes[0] = root;
     S.tie_total = 0u;
     S.cut_count = 0u;
+    S.n_ovr = (A.cut_overrides != nullptr) ? min(A.num_cut_overrides, kCutOverrideCap) : 0u;
     R.terr[0] = 0.0;
     R.tse[0] = __longlong_as_double(0x7ff0000000000000ll);  // +inf: the first split is unconditional
     R.child[0] = -1;
@@ -1314,7 +1330,7 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
     for (int mw = tid; mw < min(n_mywide, kAudCache); mw += T) {
       // (executed by a few threads) constants of the first few wide jobs stay in shared memory
       const SplitNode nd = load_node(A, S, R.jobnode[R.mywide[mw]]);
-      if (mw < kWideCache) S.wide[mw] = job_const_of(nd);
+      if (mw < kWideCache) S.wide[mw] = job_const_of(S, nd);
       S.wide_aud[mw] = job_audit_of(nd, audit);
       if (audit && tie::axis_tie(nd.tv, nd.eV)) R.jobtie[R.mywide[mw]] |= (uint8_t)kTieAxis;  // D1 (:388-403)
     }
@@ -1329,7 +1345,7 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
     const unsigned seq0 = 1u + (unsigned)round * (unsigned)(P + 1);
     auto wide_const = [&](int mw) -> JobConst {
       if (mw < kWideCache) return S.wide[mw];
-      return job_const_of(load_node(A, S, R.jobnode[R.mywide[mw]]));
+      return job_const_of(S, load_node(A, S, R.jobnode[R.mywide[mw]]));
     };
     // This CTA's share of wide job j: participants, my rank among them, my first point and how many.
     struct Share {
@@ -1561,7 +1577,7 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
         S.job_tie = (audit && tie::axis_tie(S.cur.tv, S.cur.eV)) ? (uint32_t)kTieAxis : 0u;  // D1 (:388-403)
       }
       __syncthreads();
-      const JobConst jc = job_const_of(S.cur);
+      const JobConst jc = job_const_of(S, S.cur);
       // all warps the job has points for; up to kNarrowPPT points per thread, held in registers for every pass
       const uint32_t nthr = min((uint32_t)T, max(32u, (jc.size + 31u) & ~31u));
       const int nwarps = (int)(nthr >> 5);

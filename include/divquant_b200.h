@@ -123,6 +123,9 @@ typedef struct {
    * arithmetic: a rounding is rewritten, a cut is confirmed to separate the same points as the reference's.  The result is
    * the reference's, without a re-run.  (A cut that does NOT separate the same points sends the frame to the re-run.) */
   uint32_t tie_resolved;
+  /* > 0: that many nodes were cut where the resolver found the reference cuts them (a mean on an integer that the
+   * reference's rounding noise puts on the other side), by running the exact-integer split again with those cuts forced. */
+  uint32_t cut_overrides;
 } dq_call_stats;
 void dq_context_last_stats(const dq_context *ctx, dq_call_stats *out);
 /* Per-stage CUDA-event timing of dq_quant_recurse_device / _ctx calls (off by default). */

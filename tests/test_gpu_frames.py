@@ -3,7 +3,8 @@ against fingerprints of the compiled reference (tests/golden/frames.npz, written
 from oracle/_ref).  All of them have more colours than the ordered path's default limit, so they run on the exact-integer
 kernels with the tie audit: frames whose decisions sit inside the reference's rounding noise (4 of the 1024, three of
 which the integer sums alone would get wrong by one LSB: seeds 12410, 12830, 13124) must come back flagged AND equal to
-the reference -- through the resolver (palette roundings) or the ordered re-run (anything else)."""
+the reference -- through the resolver (palette roundings and cuts; a cut the reference makes on the other side of an integer
+is forced and the split run again: seed 12832) or the ordered re-run (anything else)."""
 import os
 
 import numpy as np
@@ -35,7 +36,7 @@ def _check(dq, oracle, frames, tag, kind, w, h, k, count):
         assert (st["tie_flags"] & model) == model, (seed, st["tie_flags"], model)
         if st["tie_flags"]:
             flagged += 1
-            assert st["ordered_rerun"] == 1 or st["tie_resolved"] > 0, seed
+            assert st["ordered_rerun"] == 1 or st["tie_resolved"] > 0 or st["cut_overrides"] > 0, seed
             rerun += st["ordered_rerun"]
     assert not bad, bad
     return flagged, rerun
@@ -98,3 +99,16 @@ def test_resolver_large_form_alone(frames):
         assert len(lines) == len(seeds), res.stdout
         for ln in lines:
             assert "pal ok" in ln and "out ok" in ln and "'tie_resolved': 0" not in ln and "'ordered_rerun': 0" in ln, ln
+
+
+def test_forced_cut_instead_of_ordered_rerun(dq, oracle, frames):
+    """Config-4 frame 487 (seed 12832): the exact mean of one node on its cut axis is an integer, the reference's rounding noise
+    puts its own mean on the other side, so the reference sends the points AT that integer to the other child.  The resolver
+    finds the reference's mean, the split runs again with that node cut there (dq_call_stats::cut_overrides), and the result
+    is the reference's without the 20 ms ordered re-run."""
+    i = 12832 - 12345
+    px = oracle.generate(1, 1920, 1080, 12832)
+    out, pal = dq.quant_recurse(px, 64, 0)
+    st = dq.last_stats()
+    assert oracle.hash_words(pal) == int(frames["c4_pal_hash"][i]) and oracle.hash_words(out) == int(frames["c4_out_hash"][i])
+    assert st["tie_flags"] & 2 and st["cut_overrides"] >= 1 and st["ordered_rerun"] == 0

@@ -24,4 +24,4 @@ for seed in (int(x) for x in sys.argv[2:]):
     st = dq.last_stats()
     print(seed, "pal ok" if o.hash_words(pal) == int(fr[f"{tag}_pal_hash"][i]) else "PAL DIFF",
           "out ok" if o.hash_words(out) == int(fr[f"{tag}_out_hash"][i]) else "OUT DIFF",
-          {k2: st[k2] for k2 in ("tie_flags", "ordered_rerun", "tie_resolved")}, "model mask", int(fr[f"{tag}_tie_mask"][i]), flush=True)
+          {k2: st[k2] for k2 in ("tie_flags", "ordered_rerun", "tie_resolved", "cut_overrides")}, "model mask", int(fr[f"{tag}_tie_mask"][i]), flush=True)

@@ -16,6 +16,8 @@ from oracle import Oracle, Reference, muted  # noqa: E402
 pkg = importlib.import_module("clusteringsegmentation-1_b200")
 trials = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+MIN_U = int(os.environ.get("FUZZ_MIN_U", "0"))     # skip inputs with fewer distinct colours (e.g. 262144: beyond the ordered path)
+KMAX = int(os.environ.get("FUZZ_KMAX", "100000"))  # clamp the requested colours (e.g. 512: the audited kernel only)
 dq = pkg.DivQuant()
 o = Oracle()
 ref = Reference()
@@ -32,7 +34,10 @@ for t in range(trials):
     if t % 5 == 4:  # quantise the low bits: many equal colours, symmetric clusters, more exact ties
         px = px & np.uint32(0xFFF8F8F8 if t % 10 == 4 else 0xFFFCFCFC)
     k = int(rng.choice([16, 64, 256, 256, 300, 512, 700]))
+    k = min(k, KMAX)
     u = np.unique(px & 0xFFFFFF).size
+    if u < MIN_U:
+        continue
     with muted():
         r_out, r_pal = ref.quant_recurse(px, k, 0)
     with muted((2,)):
@@ -41,7 +46,7 @@ for t in range(trials):
     flagged += st["tie_flags"] != 0
     if st["tie_flags"]:
         key = (st["tie_flags"], "perturbed" if t % 5 == 4 else "plain", "U>262144" if u > 262144 else "U<=262144",
-               "resolved" if st["tie_resolved"] else "rerun" if st["ordered_rerun"] else "reported")
+               "rerun" if st["ordered_rerun"] else "forced cut" if st["cut_overrides"] else "resolved" if st["tie_resolved"] else "reported")
         masks[key] = masks.get(key, 0) + 1
     rerun += st["ordered_rerun"]
     resolved += st["tie_resolved"] > 0
@@ -51,7 +56,7 @@ for t in range(trials):
         print(f"trial {t}: MISMATCH gen={gen} crop {ch}x{cw}/{step} n={px.size} U={u} k={k} tie_flags={st['tie_flags']} "
               f"palette entries differing {int((pal != r_pal).sum()) if pal.size == r_pal.size else -1}", flush=True)
 hu = np.array(hist_u)
-print(f"{trials} mid-size inputs against the reference: {bad} mismatches; U min/median/max {hu.min()}/{int(np.median(hu))}/{hu.max()}, "
+print(f"{len(hist_u)} mid-size inputs against the reference: {bad} mismatches; U min/median/max {hu.min()}/{int(np.median(hu))}/{hu.max()}, "
       f"{int((hu > 4096).sum())} above the ordered path's default limit; tie audit flagged {flagged} "
       f"({resolved} resolved in place, {rerun} re-run in the reference's order)")
 for key in sorted(masks):
