@@ -55,6 +55,7 @@ def build(verbose=False):
 
 
 def load_library(path=LIB_PATH):
+    path = os.environ.get("DIVQUANT_B200_LIB", path)  # (A/B timing of two builds on one box: tools/)
     if not os.path.exists(path):
         raise FileNotFoundError(
             f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (there is no CPU fallback)")

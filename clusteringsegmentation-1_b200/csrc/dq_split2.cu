@@ -49,7 +49,6 @@ struct JobConst {
   double tw, tm[3], cut;
   int32_t axis, buf;
   uint32_t begin, size;
-  int32_t forced, pad;  // forced: the cut comes from SplitArgs::cut_overrides (not audited: it IS the reference's)
 };
 // Tie audit: what the bounds of a job's passes need from its node (dq_tie.cuh).  Lives in shared memory only; warp 1 and
 // thread 0 read it, nobody keeps it in registers.  eM < 0 = audit off.
@@ -422,7 +421,11 @@ __device__ __forceinline__ void derive_audit_warp1(Shared2 &S, const JobConst &j
 __device__ __forceinline__ void set_split_params(Shared2 &S, const JobConst &jc, const JobAudit *aud) {
   if (threadIdx.x == 0) {
     S.pp.a = jc.cut;
-    const double eM = jc.forced ? -1.0 : (aud ? aud->eM : __longlong_as_double(0x7ff0000000000000ll));
+    // a cut taken from SplitArgs::cut_overrides is the reference's own comparison: not audited
+    bool forced = false;
+    for (uint32_t i = 0; i < S.n_ovr; ++i)
+      forced = forced || (S.ovr[i].begin == jc.begin && S.ovr[i].size == jc.size && S.ovr[i].mean_ref == jc.cut);
+    const double eM = forced ? -1.0 : (aud ? aud->eM : __longlong_as_double(0x7ff0000000000000ll));
     S.ext.tol = eM;  // tie audit of the cut test (:473): the cut is the node's mean (a forced cut is the reference's own)
     S.pp.tol_hi = __double2hiint(eM) + (eM >= 0.0 ? 1 : 0);
     S.pp.r[0] = S.pp.r[1] = S.pp.r[2] = 0.0;
@@ -449,7 +452,6 @@ __device__ __forceinline__ JobConst job_const_of(const SplitNode &nd) {
   jc.buf = nd.buf;
   jc.begin = nd.begin;
   jc.size = nd.size;
-  jc.forced = 0, jc.pad = 0;
   return jc;
 }
 __device__ __forceinline__ JobConst job_const_of(const Shared2 &S, const SplitNode &nd) {
@@ -457,7 +459,6 @@ __device__ __forceinline__ JobConst job_const_of(const Shared2 &S, const SplitNo
   for (uint32_t i = 0; i < S.n_ovr; ++i) {
     if (S.ovr[i].begin == jc.begin && S.ovr[i].size == jc.size && S.ovr[i].mean_here == jc.cut) {
       jc.cut = S.ovr[i].mean_ref;
-      jc.forced = 1;
     }
   }
   return jc;
