@@ -742,7 +742,8 @@ QuantStepResult quantize_step(dq_context *ctx, uint32_t *k_inout, uint32_t *colo
     }
     if (differs && q.resplits < 8) {
       // status-3 cut entries whose range is not inside another one's (a cut below a cut that changes is decided next time)
-      const CutOverride *rec = reinterpret_cast<const CutOverride *>(ctx->h_small + K + 2 * kTieListCap);
+      CutOverride rec[kTieListCap];  // (copied out: K odd leaves the doubles inside h_small unaligned)
+      memcpy(rec, ctx->h_small + K + 2 * kTieListCap, q.cut_count * sizeof(CutOverride));
       const uint32_t *st = ctx->h_small + K + q.tie_count;
       uint32_t added = 0;
       for (uint32_t i = 0; i < q.cut_count; ++i) {
