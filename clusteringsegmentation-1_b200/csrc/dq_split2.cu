@@ -1054,8 +1054,9 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
       }
       __syncthreads();
       exact_first_seen(X.exact_src, X.exact_first_seen, (uint32_t)(b * T + tid), (uint32_t)(G * T));
-      if (X.exact_fused == 2u && (U > (uint32_t)exact::kSmemPoints || K >= 32)) {
-        // (few splits of a small input: CTA 0 alone, with everything in shared memory, is quicker)
+      if (X.exact_fused == 2u && (U > (uint32_t)exact::kSmemPoints || (K >= 32 && U >= 32u))) {
+        // (few splits of a small input -- few clusters or few colours: CTA 0 alone, with everything in shared memory, is
+        // quicker)
         // all CTAs: controller on CTA 0, the others split leaves ahead of it (dq_split_ordered.cuh)
         const ordered::Scratch og = ordered::carve(X.exact_scratch, A.node_cap);
         for (uint32_t i = (uint32_t)(b * T + tid); i < A.node_cap; i += (uint32_t)(G * T)) og.state[i] = ordered::kInvalid;

@@ -60,7 +60,7 @@ struct Shared {
   int32_t warp_tmp[32];
   double red_val[32];
   int32_t red_idx[32];
-  int32_t cur_n, old_index, new_size, emitted;
+  int32_t cur_n, old_index, new_size, emitted, steady;
   // scalars of the current split
   double tw, tm[3], tv[3], nw, ow, nm[3], om[3], nv[3];
   double lhs, rr[3], cut;
@@ -91,6 +91,13 @@ __device__ __forceinline__ double chan(uint32_t p, int c) { return byte_to_doubl
 __device__ __forceinline__ double chan_sq(uint32_t p, int c) {
   const uint32_t v = (p >> (16 - 8 * c)) & 0xFFu;
   return u52_to_double((uint64_t)(v * v));  // the reference squares in int, then converts (:98-100, :741-743)
+}
+
+// Do two values act alike as inputs of a split?  Equal bits -- or both NaN: sign and payload of a NaN reach no comparison
+// (all false), no non-NaN result and no conversion (NaN -> 0), and the empty clusters of a K > U tail do carry NaNs whose
+// sign flips from one split to the next.
+__device__ __forceinline__ bool same_input(double a, double b) {
+  return __double_as_longlong(a) == __double_as_longlong(b) || (a != a && b != b);
 }
 
 template <bool SOLO>
@@ -708,6 +715,45 @@ __device__ __noinline__ void split_exact_body(const SplitArgs &A, int U, unsigne
         if (best_i >= 0) S.old_index = best_i;
       }
       __syncthreads();
+    }
+    // ---- steady state: the split just made put every point on the old side, left the old cluster's statistics bit for bit
+    //      as they were and the same cluster is up again -- so the next split starts from the very inputs this one had and
+    //      every split that is left repeats it (K far above the number of colours: the tail of empty clusters, :876-887
+    //      with no TSE above DBL_MIN).  The arg-max cannot change either: the only new entry of tse[] equals the one that did
+    //      not win this time.  The remaining clusters are filled in instead of computed ----
+    if (tid == 0) {
+      bool steady = S.new_size == 0 && S.old_index == old_index;
+      if (steady) {
+        steady = same_input(weight[old_index], S.tw);
+        for (int c = 0; c < 3; ++c)
+          steady = steady && same_input(mean[3 * old_index + c], S.tm[c]) && same_input(var[3 * old_index + c], S.tv[c]);
+      }
+      S.steady = steady ? 1 : 0;
+    }
+    __syncthreads();
+    if (S.steady) {
+      for (int ni = new_index + 1 + tid; ni < K; ni += THREADS) {
+        const bool last = (ni == K - 1);
+        size[ni] = 0;
+        for (int c = 0; c < 3; ++c) mean[3 * ni + c] = mean[3 * new_index + c];
+        if (!last) {  // (the last split touches neither var nor weight nor tse, :823-832)
+          for (int c = 0; c < 3; ++c) var[3 * ni + c] = var[3 * new_index + c];
+          weight[ni] = weight[new_index];
+          tse[ni] = tse[new_index];
+        }
+        if (A.records != nullptr) {
+          SplitRecord r = A.records[new_index - 1];
+          r.new_index = ni;
+          r.is_last = last;
+          if (last) {
+            for (int c = 0; c < 3; ++c) r.new_var[c] = r.old_var[c] = 0.0;
+            r.new_tse = r.old_tse = 0.0;
+          }
+          A.records[ni - 1] = r;
+        }
+      }
+      __syncthreads();
+      break;
     }
     // ---- gather its points in ascending original order (:929-1019): contiguous pieces + exclusive scan ----
     {

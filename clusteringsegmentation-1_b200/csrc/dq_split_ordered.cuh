@@ -412,6 +412,7 @@ __device__ __noinline__ void run(const SplitArgs &A, const Split2Extra &X, int U
     if (failed) break;
     __threadfence();
     __shared__ int s_child2;
+    __shared__ int s_steady;
     if (tid == 0) {
       const SplitNode nd = load_node_cg(A.nodes, node);
       const int child = nd.child;
@@ -419,6 +420,13 @@ __device__ __noinline__ void run(const SplitArgs &A, const Split2Extra &X, int U
       cnode[old_index] = child;
       cnode[new_index] = child + 1;
       const SplitNode o = load_node_cg(A.nodes, child), n = load_node_cg(A.nodes, child + 1);
+      {
+        // steady state (see dq_split_exact.cuh): nothing went to the new side and the old side's statistics are the
+        // parent's bit for bit -- if the same cluster is up again, every split that is left repeats this one
+        bool same = n.size == 0u && exact::same_input(o.tw, nd.tw);
+        for (int c = 0; c < 3; ++c) same = same && exact::same_input(o.tm[c], nd.tm[c]) && exact::same_input(o.tv[c], nd.tv[c]);
+        s_steady = same ? 1 : 0;
+      }
       if (new_index < K - 1) {  // the last split leaves tse[] alone (:823-832)
         ctse[old_index] = o.tse;
         ctse[new_index] = n.tse;
@@ -462,8 +470,28 @@ __device__ __noinline__ void run(const SplitArgs &A, const Split2Extra &X, int U
         S.old_index = (best_i >= 0) ? best_i : old_index;
       }
       __syncthreads();
+      const bool repeats = s_steady != 0 && S.old_index == old_index;
       old_index = S.old_index;
       __syncthreads();
+      if (repeats) {
+        // the remaining clusters are all this split's empty new side; the old cluster keeps the old child (same statistics)
+        for (int ni = new_index + 1 + tid; ni < K; ni += T) {
+          cnode[ni] = cnode[new_index];
+          if (ni < K - 1) ctse[ni] = ctse[new_index];
+          if (A.records != nullptr) {
+            SplitRecord r = A.records[new_index - 1];
+            r.new_index = ni;
+            r.is_last = (ni == K - 1);
+            if (r.is_last) {
+              for (int c = 0; c < 3; ++c) r.new_var[c] = r.old_var[c] = 0.0;
+              r.new_tse = r.old_tse = 0.0;
+            }
+            A.records[ni - 1] = r;
+          }
+        }
+        __syncthreads();
+        break;
+      }
     }
   }
   if (tid == 0) {
