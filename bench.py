@@ -555,13 +555,49 @@ def run_ours(args, rank, world, local_rank):
             dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
             b_ok = bool(t_ok.item() > 0.5)
         lib.dq_pipeline_destroy(pipe)
+        # the same batch with the frames resident in HBM when the clock starts (what `value` is for the 4K workload):
+        # this is the part that shards -- the host-fed figure above is bounded by the box's host memory and PCIe
+        d_in_b = [f.cuda() for f in b_in]
+        d_lanes = args.lanes
+        pipe_d = lib.dq_pipeline_create_lanes(local_rank, 0, d_lanes, 0)
+        lib.dq_pipeline_set_blocking_wait(pipe_d, blocking)
+        d_outs_b = [torch.empty(bpix, dtype=torch.int32, device="cuda") for _ in range(d_lanes + 2)]
+
+        def run_batch_device(n_frames):
+            nks_b = [C.c_uint32(BK) for _ in range(n_frames)]
+            cts_b = [np.zeros(BK, np.uint32) for _ in range(n_frames)]
+            tickets = []
+            nbuf = len(d_outs_b)
+            for i in range(n_frames):
+                if i >= nbuf:
+                    lib.dq_pipeline_wait(pipe_d, tickets[i - nbuf])
+                tickets.append(lib.dq_pipeline_submit_device(pipe_d, bpix, d_in_b[frame_slot[i]].data_ptr(), d_outs_b[i % nbuf].data_ptr(),
+                                                             C.byref(nks_b[i]), cts_b[i].ctypes.data_as(u32p), 0))
+            lib.dq_pipeline_flush(pipe_d)
+            return float(lib.dq_pipeline_last_elapsed_ms(pipe_d)), cts_b[n_frames - 1][:nks_b[n_frames - 1].value].copy()
+
+        run_batch_device(min(len(mine), 64))
+        barrier()
+        ms_batch_dev, last_pal = run_batch_device(len(mine))
+        barrier()
+        last_f = distinct[frame_slot[len(mine) - 1]]
+        dev_ok = bgold is None or o.hash_words(last_pal) == int(bgold["c4_pal_hash"][last_f])
+        if dist:
+            t = torch.tensor([ms_batch_dev], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_batch_dev = float(t.item())
+        lib.dq_pipeline_destroy(pipe_d)
+        del d_in_b, d_outs_b
         batch_info = {"workload": f"BASELINE config 4: {BN} frames {BW}x{BH} G1 (frame f: seed 12345+f), K={BK}, frame-sharded over {world} GPU(s), no collective, host-fed (pinned)",
                       "value": BN * bpix / (ms_batch * 1e-3) / 1e6, "unit": "Mpixels/s", "ms_total": ms_batch, "ms_per_frame": ms_batch / BN,
                       "frames_per_rank": len(mine), "distinct_frames_per_rank": len(distinct),
                       "ring_note": "frames cycle through the first ring slots of the rank's range; the frames the tie audit flags (f = 65, 485, 487, 779) are in the batch exactly once each, as in the real batch",
                       "h2d_bytes_per_frame": bpix * 4, "d2h_bytes_per_frame": bpix * 4 + BK * 4 + 4,
                       "every_distinct_frame_matches_reference": bool(b_ok) if b_checked else None, "frames_checked_rank0": b_checked,
-                      "tie_flagged_frames_in_check_pass_rank0": int(flagged0), "lanes": b_lanes, "scaling": "strong (fixed batch)"}
+                      "tie_flagged_frames_in_check_pass_rank0": int(flagged0), "lanes": b_lanes, "scaling": "strong (fixed batch)",
+                      "device_resident": {"value": BN * bpix / (ms_batch_dev * 1e-3) / 1e6, "unit": "Mpixels/s", "ms_total": ms_batch_dev,
+                                          "ms_per_frame": ms_batch_dev / BN, "lanes": d_lanes, "last_palette_matches_reference": bool(dev_ok),
+                                          "note": "the same 1024-frame batch, frame-sharded, with each rank's frames already in HBM when the clock starts (CUDA events, max over ranks)"}}
         del b_in, b_outs
 
     if rank != 0:
