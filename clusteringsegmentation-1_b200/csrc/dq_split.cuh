@@ -224,7 +224,7 @@ constexpr uint32_t kSplit2MaxColors = 512;
 struct Split2Extra {
   unsigned long long *slots;  // [2][slot_cap][kAccWords] tagged words, zeroed by the kernel
   uint32_t slot_cap;
-  uint32_t *cursors;          // [2][K][2] scatter cursors of wide jobs
+  uint32_t *cursors;          // (unused since the partition takes its destinations from the exchanged counts)
   uint32_t *progress;         // [grid] last stage each CTA reached (diagnostics of an expired wait)
   // when non-null the root pass also builds the points from the histogram (fused hist_collect):
   // pts[0][i] = (uniq[i], table[uniq[i]]) and the counter is zeroed

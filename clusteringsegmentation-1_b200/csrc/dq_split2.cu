@@ -1112,7 +1112,6 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
       atomicAdd(reinterpret_cast<unsigned long long *>(A.root_acc + tid), (unsigned long long)S.tot[tid]);
     const size_t slot_words = (size_t)2 * X.slot_cap * kAccWords;
     for (size_t i = (size_t)b * T + tid; i < slot_words; i += (size_t)G * T) X.slots[i] = 0ull;
-    for (size_t i = (size_t)b * T + tid; i < (size_t)4 * K; i += (size_t)G * T) X.cursors[i] = 0u;
   }
   trace2(A, kTraceReduced, 0);
   grid_barrier2(A, bar_target);
@@ -1322,11 +1321,6 @@ __global__ void __launch_bounds__(T, 65536 / (128 * T)) split2_kernel(const Spli
         A.ctl[kCtlSplits] += (uint32_t)njobs;
         A.ctl[kCtlJobs] = (uint32_t)njobs;
       }
-    }
-    // scatter cursors of the next round are cleared now (nobody touches that parity in this round)
-    {
-      uint32_t *other = X.cursors + (size_t)((round & 1) ^ 1) * 2 * K;
-      for (int i = b * T + tid; i < 2 * K; i += G * T) other[i] = 0u;
     }
     const int n_mywide = S.n_mywide, n_mynarrow = S.n_mynarrow;
     for (int mw = tid; mw < min(n_mywide, kAudCache); mw += T) {
