@@ -90,6 +90,7 @@ struct dq_context {
   DevBuf<uint32_t> d_ovr;       // cuts taken from the resolver (SplitArgs::cut_overrides) of the call in flight
   CutOverride h_ovr[kCutOverrideCap];
   uint32_t n_ovr = 0;
+  bool ovr_active = false;
   DevBuf<uint64_t> d_keys;
   // sized by K
   DevBuf<SplitNode> d_nodes;
@@ -312,7 +313,7 @@ uint32_t run_split(dq_context *ctx, uint32_t point_capacity, double norm, uint32
   if (a.tie_audit) {
     ctx->d_tie.ensure(kTieListWords);
     a.tie_list = ctx->d_tie.ptr;
-    if (ctx->n_ovr) {
+    if (ctx->ovr_active && ctx->n_ovr) {  // (only the re-split of quantize_step: other callers never inherit a frame's cuts)
       a.cut_overrides = reinterpret_cast<const CutOverride *>(ctx->d_ovr.ptr);
       a.num_cut_overrides = ctx->n_ovr;
     }
@@ -642,8 +643,10 @@ QuantStepResult quantize_step(dq_context *ctx, uint32_t *k_inout, uint32_t *colo
     reset_control(ctx);
     run_histogram(ctx, q.d_in, q.n, q.rows, q.cols, (uint32_t)q.dec, q.num_bits);
     uint32_t unused = 0;
+    ctx->ovr_active = true;
     run_split(ctx, q.point_cap, q.norm, K, q.max_iters, q.num_bits, &unused, q.records, q.mean_out, q.size_out, true, &src, true,
               false, /*defer=*/true);
+    ctx->ovr_active = false;
     q.resplits++;
     q.phase = 0;
   };
