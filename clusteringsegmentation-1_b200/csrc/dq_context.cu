@@ -611,6 +611,26 @@ void quantize_begin(dq_context *ctx, uint32_t n, const uint32_t *d_in, uint32_t 
 // quantize_step() advances one phase and says what to poll next; quantize_pending_ready() is the non-blocking poll.
 enum QuantStepResult { kQuantDone = 0, kQuantPending = 1 };
 
+// Which of the resolver's cut entries become forced cuts of the next run of the split (host logic of the re-split, pure):
+// those the resolver found the reference cuts elsewhere (status 3) whose range of positions is not inside another such
+// entry's -- a cut below a cut that changes is decided by the next run -- as long as there is room.  Appends to
+// out[*n_out..cap) and returns how many it added.
+uint32_t select_cut_overrides(const CutOverride *rec, const uint32_t *status, uint32_t n, CutOverride *out, uint32_t *n_out,
+                              uint32_t cap) {
+  uint32_t added = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    if (status[i] != 3u) continue;
+    bool nested = false;
+    for (uint32_t j = 0; j < n; ++j)
+      nested = nested || (j != i && status[j] == 3u && rec[j].begin <= rec[i].begin &&
+                          rec[i].begin + rec[i].size <= rec[j].begin + rec[j].size && (rec[j].size > rec[i].size || j < i));
+    if (nested || *n_out >= cap) continue;
+    out[(*n_out)++] = rec[i];
+    ++added;
+  }
+  return added;
+}
+
 bool quantize_pending_ready(dq_context *ctx) {
   if (ctx->qs.phase == 1 || ctx->qs.phase == 3) return cudaEventQuery(ctx->tie_ev) != cudaErrorNotReady;
   return split_ready(ctx);
@@ -748,18 +768,7 @@ QuantStepResult quantize_step(dq_context *ctx, uint32_t *k_inout, uint32_t *colo
       CutOverride rec[kTieListCap];  // (copied out: K odd leaves the doubles inside h_small unaligned)
       memcpy(rec, ctx->h_small + K + 2 * kTieListCap, q.cut_count * sizeof(CutOverride));
       const uint32_t *st = ctx->h_small + K + q.tie_count;
-      uint32_t added = 0;
-      for (uint32_t i = 0; i < q.cut_count; ++i) {
-        if (st[i] != 3u) continue;
-        bool nested = false;
-        for (uint32_t j = 0; j < q.cut_count; ++j)
-          nested = nested || (j != i && st[j] == 3u && rec[j].begin <= rec[i].begin &&
-                              rec[i].begin + rec[i].size <= rec[j].begin + rec[j].size &&
-                              (rec[j].size > rec[i].size || j < i));
-        if (nested || ctx->n_ovr >= kCutOverrideCap) continue;
-        ctx->h_ovr[ctx->n_ovr++] = rec[i];
-        ++added;
-      }
+      const uint32_t added = select_cut_overrides(rec, st, q.cut_count, ctx->h_ovr, &ctx->n_ovr, kCutOverrideCap);
       if (added) {
         queue_resplit();
         return kQuantPending;
@@ -955,6 +964,18 @@ uint32_t dq_host_dedup_palette(uint32_t *colortable, uint32_t num_colors) { retu
 
 void dq_host_build_search_tables(const uint32_t *colortable, int num_colors, uint32_t *sorted_out, int32_t *lut_init_out) {
   build_search_tables(colortable, num_colors, sorted_out, lut_init_out);
+}
+
+uint32_t dq_host_select_cut_overrides(const uint32_t *begin, const uint32_t *size, const uint32_t *status, uint32_t n,
+                                      uint32_t already, uint32_t *picked_out) {
+  if (n > kTieListCap) n = kTieListCap;
+  CutOverride rec[kTieListCap], out[kCutOverrideCap];
+  for (uint32_t i = 0; i < n; ++i) rec[i].begin = begin[i], rec[i].size = size[i], rec[i].mean_here = (double)i, rec[i].mean_ref = 0.0;
+  uint32_t n_out = std::min(already, kCutOverrideCap);
+  const uint32_t first = n_out;
+  const uint32_t added = select_cut_overrides(rec, status, n, out, &n_out, kCutOverrideCap);
+  for (uint32_t k = 0; k < added; ++k) picked_out[k] = (uint32_t)out[first + k].mean_here;  // the entry's index
+  return added;
 }
 
 void dq_host_sort_permutation(const uint32_t *keys, int n, int use_replay, uint32_t *perm_out) {

@@ -349,6 +349,13 @@ uint32_t dq_host_dedup_palette(uint32_t *colortable, uint32_t num_colors);
  * must agree for every input, equal keys included -- tests/test_stdsort.py. */
 void dq_host_sort_permutation(const uint32_t *keys, int n, int use_replay, uint32_t *perm_out);
 void dq_host_build_search_tables(const uint32_t *colortable, int num_colors, uint32_t *sorted_out, int32_t *lut_init_out);
+/* Host logic of the re-split with forced cuts (dq_call_stats::cut_overrides): of n <= 16 flagged cut entries, each a range
+ * [begin, begin + size) of point positions with the resolver's status (3 = the reference cuts this node elsewhere), which
+ * ones are forced in the next run -- the status-3 entries whose range does not lie inside another status-3 entry's, while
+ * fewer than 16 cuts are forced in all (`already` = those forced by earlier runs).  Writes their indices to picked_out,
+ * returns how many. */
+uint32_t dq_host_select_cut_overrides(const uint32_t *begin, const uint32_t *size, const uint32_t *status, uint32_t n,
+                                      uint32_t already, uint32_t *picked_out);
 
 const char *dq_version(void);
 
