@@ -37,9 +37,12 @@ def test_our_arm_line(name, gpus):
     assert d["ms_per_step"] * d["steps"] >= 500.0              # the timed region is at least half a second
     b = d["batch1080"]                                         # BASELINE config 4, host-fed, at every N
     assert b["every_distinct_frame_matches_reference"] is True and b["value"] > 0 and "1024 frames" in b["workload"]
+    assert b["device_resident"]["value"] > b["value"] and b["device_resident"]["last_palette_matches_reference"] is True
     if gpus == 1:
         assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"]) and d["cpu_baseline"]["kind"] in ("reference", "port")
         assert len(d["small_inputs"]["rows"]) == 6 and d["e2e"]["pageable_single_call_ms"] > 0
+        assert d["g2_stress"]["parity"] is True and d["g2_stress"]["unique_colours"] > 1_000_000   # SURVEY 8c stress input
+        assert d["single_call"]["calls_timed"] >= 32                                                # every ring frame once
     else:
         r = d["row_sharded"]
         assert r["matches_single_gpu_call"] is True and len(r["sizes"]) == 2
