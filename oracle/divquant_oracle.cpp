@@ -233,6 +233,13 @@ inline void derive_err(ClusterErr &b, double tw, const Vec3 &tm, const Vec3 &tv,
 }
 struct TieAudit {
   uint32_t flags[6];  // [1..5] = D1..D5 counts, [0] = total
+  // CPU model of the device's tie resolver (csrc/dq_resolve.cu + the forced cuts of csrc/dq_context.cu): next to the exact
+  // integer sums, the reference's own sequential double sums are carried for the SAME memberships ("shadow" statistics:
+  // what the resolver recomputes from the split tree).  A flagged cut is taken from the shadow mean when the two means
+  // have different floors, a flagged rounding rounds the shadow mean.  [0] roundings taken from the shadow, [1] cuts
+  // confirmed (same floor), [2] cuts forced.
+  bool resolve;
+  uint32_t resolved[3];
   void hit(int d) {
     flags[d]++;
     flags[0]++;
@@ -313,7 +320,15 @@ static int varpart_impl(uint32_t num_pixels, const uint32_t *in, uint32_t num_ro
   std::vector<Vec3> mean(K, Vec3{0, 0, 0}), var(K, Vec3{0, 0, 0});
   std::vector<uint32_t> member(U, 0u);
   std::vector<ClusterErr> cerr(K, ClusterErr{0, 0, 0, 0, 0, 0});
-  if (audit) memset(audit, 0, sizeof(*audit));
+  const bool resolve = audit != nullptr && audit->resolve && exact_counts && s.counts != nullptr;
+  if (audit) {
+    memset(audit, 0, sizeof(*audit));
+    audit->resolve = resolve;
+  }
+  // shadow statistics of the resolver model: the reference's weight and mean of every cluster for the model's memberships
+  std::vector<double> s_weight(resolve ? K : 0, 0.0);
+  std::vector<Vec3> s_mean(resolve ? K : 0, Vec3{0, 0, 0});
+  if (resolve) s_weight[0] = 1.0;
 
   // The cluster being split: `cur` lists original point indices in ascending order (the reference
   // keeps tmp_data/point_index, :929-1019; before the first gather it is the identity).
@@ -359,6 +374,40 @@ static int varpart_impl(uint32_t num_pixels, const uint32_t *in, uint32_t num_ro
       cut = tm.b;
     }
 
+    // resolver model: the reference's own mean of this cluster (root: the sequential weighted sums of :60-104)
+    double s_tw = 0.0;
+    Vec3 s_tm{0, 0, 0};
+    if (resolve) {
+      s_tw = s_weight[old_index];
+      if (new_index == 1) {
+        DivisiveState ref_state = s;
+        ref_state.uniform = false;
+        ref_state.counts = nullptr;
+        ref_state.w = weights.data();
+        Vec3 unused_var;
+        initial_mean_and_var(ref_state, &s_tm, &unused_var);
+      } else {
+        s_tm = s_mean[old_index];
+      }
+      // a flagged cut (some point within the bound of the cut): the points are integers, so the two cuts separate the same
+      // points iff they have the same floor; otherwise the reference's cut is taken (the device's forced cut)
+      const double s_cut = (axis == 0) ? s_tm.r : ((axis == 1) ? s_tm.g : s_tm.b);
+      bool flagged = false;
+      for (int j = 0; j < cur_n && !flagged; ++j) {
+        const uint32_t p = s.data[cur[j]];
+        const double proj = (axis == 0) ? chan_r(p) : ((axis == 1) ? chan_g(p) : chan_b(p));
+        flagged = std::fabs(proj - cut) <= pe.eM;
+      }
+      if (flagged) {
+        if (std::floor(s_cut) == std::floor(cut)) {
+          audit->resolved[1]++;
+        } else {
+          audit->resolved[2]++;
+          cut = s_cut;
+        }
+      }
+    }
+
     Vec3 &nm = mean[new_index];
     Vec3 &nv = var[new_index];
     Vec3 &om = mean[old_index];
@@ -374,7 +423,7 @@ static int varpart_impl(uint32_t num_pixels, const uint32_t *in, uint32_t num_ro
         uint32_t p = s.data[idx];
         uint32_t R = chan_r(p), G = chan_g(p), B = chan_b(p);
         double proj = (axis == 0) ? R : ((axis == 1) ? G : B);
-        if (audit && std::fabs(proj - cut) <= pe.eM) audit->hit(2);
+        if (audit && !resolve && std::fabs(proj - cut) <= pe.eM) audit->hit(2);
         if (cut < proj) {
           ++cut_new;
           if (s.uniform) {
@@ -432,6 +481,8 @@ static int varpart_impl(uint32_t num_pixels, const uint32_t *in, uint32_t num_ro
       nm = Vec3{0, 0, 0};
       nv = Vec3{0, 0, 0};
       uint64_t ir = 0, ig = 0, ib = 0, irr = 0, igg = 0, ibb = 0, cnt = 0;
+      double s_nw = 0.0;  // resolver model: the reference's sums of the new side, term by term in emission order
+      Vec3 s_nm{0, 0, 0};
       for (int j = 0; j < cur_n; ++j) {
         int idx = cur[j];
         uint32_t p = s.data[idx];
@@ -458,6 +509,13 @@ static int varpart_impl(uint32_t num_pixels, const uint32_t *in, uint32_t num_ro
               irr += c * (R * R);
               igg += c * (G * G);
               ibb += c * (B * B);
+              if (resolve) {
+                const double wt = weights[idx];
+                s_nm.r += wt * red;
+                s_nm.g += wt * green;
+                s_nm.b += wt * blue;
+                s_nw += wt;
+              }
             }
           } else {
             double wt = s.w[idx];
@@ -504,6 +562,20 @@ static int varpart_impl(uint32_t num_pixels, const uint32_t *in, uint32_t num_ro
       om.r = (tw * tm.r - nw * nm.r) / ow;
       om.g = (tw * tm.g - nw * nm.g) / ow;
       om.b = (tw * tm.b - nw * nm.b) / ow;
+      if (resolve && it == last_it) {
+        // the reference's centres after its last pass (:780-810), from its own sums over the model's memberships
+        s_nm.r /= s_nw;
+        s_nm.g /= s_nw;
+        s_nm.b /= s_nw;
+        const double s_ow = s_tw - s_nw;
+        s_mean[new_index] = s_nm;
+        s_mean[old_index] = Vec3{(s_tw * s_tm.r - s_nw * s_nm.r) / s_ow, (s_tw * s_tm.g - s_nw * s_nm.g) / s_ow,
+                                 (s_tw * s_tm.b - s_nw * s_nm.b) / s_ow};
+        if (new_index < K - 1) {  // (the last split leaves the weights alone, :823-832)
+          s_weight[old_index] = s_ow;
+          s_weight[new_index] = s_nw;
+        }
+      }
     }
 
     size[old_index] = cur_n - new_size;
@@ -609,17 +681,26 @@ static int varpart_impl(uint32_t num_pixels, const uint32_t *in, uint32_t num_ro
   int empty = 0, emitted = 0;
   for (int ic = 0; ic < K; ++ic) {
     if (size[ic] > 0) {
-      uint32_t R = ((uint8_t)(mean[ic].r + 0.5)) << shift;
-      uint32_t G = ((uint8_t)(mean[ic].g + 0.5)) << shift;
-      uint32_t B = ((uint8_t)(mean[ic].b + 0.5)) << shift;
-      colortable[emitted++] = (R << 16) | (G << 8) | B;
+      Vec3 m = mean[ic];
       if (audit) {
         const double mm[3] = {mean[ic].r, mean[ic].g, mean[ic].b};
+        bool flagged = false;
         for (int c = 0; c < 3; ++c) {
           const double v = mm[c] + 0.5;
-          if (std::fabs(v - std::rint(v)) <= cerr[ic].eM + 512.0 * kU) audit->hit(5);
+          if (std::fabs(v - std::rint(v)) <= cerr[ic].eM + 512.0 * kU) {
+            flagged = true;
+            if (!resolve) audit->hit(5);
+          }
+        }
+        if (flagged && resolve && K > 1) {  // the resolver's answer: the reference's own mean decides the rounding
+          m = s_mean[ic];
+          audit->resolved[0]++;
         }
       }
+      uint32_t R = ((uint8_t)(m.r + 0.5)) << shift;
+      uint32_t G = ((uint8_t)(m.g + 0.5)) << shift;
+      uint32_t B = ((uint8_t)(m.b + 0.5)) << shift;
+      colortable[emitted++] = (R << 16) | (G << 8) | B;
     } else {
       ++empty;
     }
@@ -642,9 +723,26 @@ extern "C" int oracle_quant_varpart_fast_exact_audit(uint32_t num_pixels, const 
                                                      int num_bits, int dec_factor, int max_iters, int all_pixels_unique,
                                                      uint32_t *flags_out) {
   TieAudit audit;
+  audit.resolve = false;
   int rc = varpart_impl(num_pixels, in, num_rows, num_cols, num_clusters, colortable, num_bits, dec_factor, max_iters,
                         all_pixels_unique, nullptr, nullptr, true, &audit);
   for (int i = 0; i < 6; ++i) flags_out[i] = audit.flags[i];
+  return rc;
+}
+
+// The device-arithmetic model WITH the resolver model (see TieAudit): flags_out[0..5] as above for what is left flagged
+// (axis / hyperplane / TSE: the memberships may differ from the reference's, nothing is resolved then), [6] roundings taken
+// from the reference's mean, [7] cuts confirmed, [8] cuts forced.  With flags_out[0] == 0 the palette is the reference's.
+extern "C" int oracle_quant_varpart_fast_exact_resolved(uint32_t num_pixels, const uint32_t *in, uint32_t num_rows,
+                                                        uint32_t num_cols, uint32_t *num_clusters, uint32_t *colortable,
+                                                        int num_bits, int dec_factor, int max_iters, int all_pixels_unique,
+                                                        uint32_t *flags_out) {
+  TieAudit audit;
+  audit.resolve = true;
+  int rc = varpart_impl(num_pixels, in, num_rows, num_cols, num_clusters, colortable, num_bits, dec_factor, max_iters,
+                        all_pixels_unique, nullptr, nullptr, true, &audit);
+  for (int i = 0; i < 6; ++i) flags_out[i] = audit.flags[i];
+  for (int i = 0; i < 3; ++i) flags_out[6 + i] = audit.resolved[i];
   return rc;
 }
 

@@ -53,6 +53,18 @@ int oracle_quant_varpart_fast_exact(uint32_t num_pixels, const uint32_t *in, uin
                                     uint32_t num_cols, uint32_t *num_clusters, uint32_t *colortable,
                                     int num_bits, int dec_factor, int max_iters, int all_pixels_unique,
                                     oracle_split_record *records, int *num_records);
+/* The same model with the device's tie audit (csrc/dq_tie.cuh): flags_out[0] = decisions inside the reference's rounding
+ * noise in all, [1..5] = by kind (axis :388-403, cut :473, hyperplane :683, TSE arg-max :876-887, rounding :1050-1052). */
+int oracle_quant_varpart_fast_exact_audit(uint32_t num_pixels, const uint32_t *in, uint32_t num_rows, uint32_t num_cols,
+                                          uint32_t *num_clusters, uint32_t *colortable, int num_bits, int dec_factor,
+                                          int max_iters, int all_pixels_unique, uint32_t *flags_out);
+/* ... and with the model of the device's resolver (csrc/dq_resolve.cu, forced cuts of csrc/dq_context.cu): the reference's
+ * own sequential sums are carried for the model's memberships; a flagged rounding rounds the reference's mean, a flagged
+ * cut is the reference's when the two means have different floors.  flags_out[0..5] = what is LEFT flagged (kinds 1, 3, 4),
+ * [6] roundings resolved, [7] cuts confirmed, [8] cuts forced.  flags_out[0] == 0 => the palette is the reference's. */
+int oracle_quant_varpart_fast_exact_resolved(uint32_t num_pixels, const uint32_t *in, uint32_t num_rows, uint32_t num_cols,
+                                             uint32_t *num_clusters, uint32_t *colortable, int num_bits, int dec_factor,
+                                             int max_iters, int all_pixels_unique, uint32_t *flags_out);
 
 /* map_colors_mps (DivQuantMapColors.cpp:243-539), restated as the reference's pruned two-way search. */
 void oracle_map_colors_mps(const uint32_t *in, uint32_t num_pixels, uint32_t *out, const uint32_t *colortable,
