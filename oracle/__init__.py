@@ -138,7 +138,8 @@ class Oracle:
         fn.argtypes = [C.c_uint32, _u32p, C.c_uint32, C.c_uint32, _u32p, _u32p, C.c_int, C.c_int, C.c_int, C.c_int, _u32p]
         fn(px.size, _ptr(px), 1, px.size, C.byref(nk), _ptr(ct), num_bits, dec_factor, max_iters, 0, _ptr(flags))
         return ct[:nk.value].copy(), {"left": int(flags[0]), "roundings": int(flags[6]), "cuts_confirmed": int(flags[7]),
-                                      "cuts_forced": int(flags[8])}
+                                      "cuts_forced": int(flags[8]), "left_axis": int(flags[1]), "left_hyperplane": int(flags[3]),
+                                      "left_tse": int(flags[4])}
 
     def quant_varpart_fast(self, pixels, k, num_bits=8, dec_factor=1, max_iters=10, all_unique=0,
                            with_records=False, exact_counts=False, rows=1, cols=None):

@@ -33,4 +33,4 @@ def test_resolver_model_equals_reference(oracle, seed, kind):
     elif kind == "cut":
         assert info["cuts_forced"] == 1
     else:
-        assert np.array_equal(plain, ref_pal) and info == {"left": 0, "roundings": 0, "cuts_confirmed": 0, "cuts_forced": 0}
+        assert np.array_equal(plain, ref_pal) and not any(info.values())
